@@ -1,0 +1,165 @@
+"""Generate tests/golden/*.npz|json by running the UNMODIFIED reference
+(/root/reference) on seeded synthetic inputs and weights.
+
+Run once in the build container (the reference cannot travel to the GPU box):
+    python tests/golden/make_golden.py
+The shims are harness-side only: force
+pretrained=False (sedt/backbone.py:98-100 hard-codes a download), stub
+dcase_util (utilities/BoxEncoder.py:4-5 imports it, never uses it), build
+SetCriterion/matcher directly, and make Tensor.cuda the identity for
+SPSEDT.forward (sedt/spsedt.py:37-38 hard-codes .cuda()).
+
+Fixtures hold outputs in full (small) and strided samples of intermediates.
+"""
+import json
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+import torchvision
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+warnings.filterwarnings("ignore")
+
+_r50 = torchvision.models.resnet50
+torchvision.models.resnet50 = lambda *a, **k: _r50(*a, **{**k, "pretrained": False})
+for name in ("dcase_util", "dcase_util.data"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["dcase_util.data"].DecisionEncoder = sys.modules["dcase_util.data"].ProbabilityEncoder = object
+
+from sedt import build_model, build_matcher  # noqa: E402  (the reference package)
+from sedt.sedt import PostProcess  # noqa: E402
+from utilities.BoxEncoder import BoxEncoder  # noqa: E402
+
+from sound_event_detection_transformer_b200 import spec, synth  # noqa: E402
+
+CLASSES = [f"class{i}" for i in range(10)]
+SAMPLE = 97
+
+
+def sample(t):
+    return t.detach().flatten()[::SAMPLE].contiguous().numpy()
+
+
+def build_ref(args, seed):
+    model, _, _ = build_model(args)
+    sd = synth.synth_state_dict(args, seed)
+    missing = model.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert list(model.state_dict().keys()) == list(sd.keys()) or set(model.state_dict()) == set(sd)
+    model.eval()
+    return model
+
+
+def run_sedt(tag, args, clips, seed):
+    model = build_ref(args, seed)
+    taps = {}
+    body = model.backbone[0].body
+    hooks = [body.maxpool.register_forward_hook(lambda m, i, o: taps.__setitem__("stem", o))]
+    for li in range(1, 5):
+        hooks.append(getattr(body, f"layer{li}").register_forward_hook(
+            lambda m, i, o, li=li: taps.__setitem__(f"layer{li}", o)))
+    hooks.append(model.transformer.encoder.register_forward_hook(lambda m, i, o: taps.__setitem__("memory_sbc", o)))
+    hooks.append(model.transformer.decoder.register_forward_hook(lambda m, i, o: taps.__setitem__("hs_dqbc", o)))
+    with torch.no_grad():
+        out = model(clips)
+    for h in hooks:
+        h.remove()
+    fx = {"pred_logits": out["pred_logits"].numpy(), "pred_boxes": out["pred_boxes"].numpy()}
+    if "at" in out:
+        fx["at"] = out["at"].numpy()
+    for i, aux in enumerate(out.get("aux_outputs", [])):
+        fx[f"aux{i}_pred_logits"] = aux["pred_logits"].numpy()
+        fx[f"aux{i}_pred_boxes"] = aux["pred_boxes"].numpy()
+    for k in ("stem", "layer1", "layer2", "layer3", "layer4"):
+        fx["tap_" + k] = sample(taps[k])
+    fx["tap_memory"] = sample(taps["memory_sbc"].permute(1, 0, 2))          # [B,S,C]
+    fx["tap_hs"] = sample(taps["hs_dqbc"].transpose(1, 2))                 # [D,B,Q,C]
+    np.savez_compressed(os.path.join(HERE, f"sedt_{tag}.npz"), **fx)
+
+    # decoded events through the reference's own PostProcess + BoxEncoder (engine.py:264-291)
+    if "at" in out:
+        B = out["pred_logits"].shape[0]
+        sizes = torch.full((B,), 10.0)
+        tags = (out["at"].reshape(B, -1) > 0.5).long()
+        enc = BoxEncoder(list(CLASSES), seconds=10.0)
+        events = {}
+        for at_m in (1, 2, 3):
+            res = PostProcess()({k: v.clone() for k, v in out.items() if k != "aux_outputs"}, sizes, tags, at_m)
+            per_clip = []
+            for r in res:
+                r = {k: v.numpy() for k, v in r.items()}
+                per_clip.append([[e[0], float(e[1]), float(e[2]), float(e[3])] for e in enc.decode_strong(r, 0.5)])
+            events[str(at_m)] = per_clip
+        with open(os.path.join(HERE, f"events_{tag}.json"), "w") as f:
+            json.dump(events, f)
+        n_ev = sum(len(c) for c in events["2"])
+        print(f"  events at_m=2: {n_ev}")
+    print(f"sedt_{tag}: logits std {out['pred_logits'].std():.4f} boxes std {out['pred_boxes'].std():.4f}")
+
+
+def run_spsedt(tag, args, clips, patches, seed):
+    torch.Tensor.cuda = lambda self, *a, **k: self          # spsedt.py:37-38
+    model = build_ref(args, seed)
+    mask = torch.zeros(clips.shape[0], clips.shape[2], clips.shape[3], dtype=torch.bool)
+    with torch.no_grad():
+        out = model((clips, mask), patches)
+    fx = {"pred_logits": out["pred_logits"].numpy(), "pred_boxes": out["pred_boxes"].numpy(),
+          "pred_feature": sample(out["pred_feature"]), "gt_feature": sample(out["gt_feature"])}
+    for i, aux in enumerate(out.get("aux_outputs", [])):
+        fx[f"aux{i}_pred_logits"] = aux["pred_logits"].numpy()
+        fx[f"aux{i}_pred_boxes"] = aux["pred_boxes"].numpy()
+    np.savez_compressed(os.path.join(HERE, f"spsedt_{tag}.npz"), **fx)
+    print(f"spsedt_{tag}: logits std {out['pred_logits'].std():.4f}")
+
+
+def run_matcher(tag, B, Q, C, kmin, kmax, seed, chunk=32, normalize=False):
+    args = spec.default_args()
+    matcher = build_matcher(args)
+    outputs, targets = synth.synth_matcher_case(B, Q, C, kmin, kmax, seed)
+    rows, cols, counts = [], [], []
+    for s in range(0, B, chunk):
+        o = {k: v[s:s + chunk] for k, v in outputs.items()}
+        idx, coef = matcher(o, targets[s:s + chunk], normalize=normalize)
+        for (r, c), cf in zip(idx, coef):
+            rows.append(r.numpy()); cols.append(c.numpy()); counts.append(len(r))
+            assert cf.shape[0] == len(r)
+    np.savez_compressed(os.path.join(HERE, f"matcher_{tag}.npz"),
+                        rows=np.concatenate(rows) if rows else np.zeros(0, np.int64),
+                        cols=np.concatenate(cols) if cols else np.zeros(0, np.int64),
+                        counts=np.asarray(counts, np.int32),
+                        meta=np.asarray([B, Q, C, kmin, kmax, seed], np.int64))
+    print(f"matcher_{tag}: {B} clips, {int(np.sum(counts))} pairs")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    # config-1 shape (URBAN-SED: T=500, E=3, Q=10) and config-2 shape (DCASE: T=496, E=6, Q=20), batch 2
+    run_sedt("c1_b2", spec.config_args("c1"), synth.synth_clips(2, 500, 64, seed=1), seed=11)
+    run_sedt("c2_b2", spec.config_args("c2"), synth.synth_clips(2, 496, 64, seed=2), seed=12)
+    # ragged list input -> real padding mask (utilities/utils.py:470-492), B=1 squeeze quirk (sedt.py:92)
+    rag = [synth.synth_clips(1, 500, 64, seed=3)[0], synth.synth_clips(1, 333, 64, seed=4)[0],
+           synth.synth_clips(1, 420, 64, seed=5)[0]]
+    run_sedt("c1_ragged", spec.config_args("c1"), rag, seed=11)
+    run_sedt("c1_b1", spec.config_args("c1"), synth.synth_clips(1, 500, 64, seed=6), seed=11)
+    # no audio query / no aux variants of the head wiring (sedt.py:107-123)
+    a = spec.config_args("c1"); a.dec_at = False; a.aux_loss = False
+    run_sedt("c1_plain", a, synth.synth_clips(2, 256, 64, seed=7), seed=13)
+    # post-norm transformer (--pre_norm flag flips it, train_sedt.py:98)
+    a = spec.config_args("c1"); a.pre_norm = False
+    run_sedt("c1_postnorm", a, synth.synth_clips(2, 256, 64, seed=8), seed=14)
+    # SP-SEDT (config 5 shape, batch 2, 10 patches)
+    run_spsedt("c5_b2", spec.config_args("c5"), synth.synth_clips(2, 496, 64, seed=9),
+               synth.synth_patches(2, 10, 128, 64, seed=9), seed=15)
+    # matcher: config-3 distribution, plus K=0 and K>Q edge set
+    run_matcher("c3_small", 256, 20, 10, 0, 10, seed=3)
+    run_matcher("c3_edges", 64, 20, 10, 18, 28, seed=4)
+    run_matcher("urban_q10", 64, 10, 10, 0, 12, seed=5)
+    run_matcher("c3_normalize", 32, 20, 10, 0, 10, seed=6, normalize=True)

@@ -1,0 +1,111 @@
+"""The oracle restatement vs fixtures produced by the real reference
+(tests/golden/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import decode_oracle, matcher_oracle, sedt_oracle
+from sound_event_detection_transformer_b200 import spec, synth
+
+torch.set_num_threads(max(1, os.cpu_count() or 1))
+TOL = 2e-6   # x max(1,|ref|max): intermediates are bit-identical (diff 0.0); the head Linear on a strided view differs by a few ulp
+SAMPLE = 97
+
+
+def _sample(t):
+    return t.detach().flatten()[::SAMPLE].numpy()
+
+
+def _cases():
+    c1, c2 = spec.config_args("c1"), spec.config_args("c2")
+    plain = spec.config_args("c1"); plain.dec_at = False; plain.aux_loss = False
+    post = spec.config_args("c1"); post.pre_norm = False
+    rag = [synth.synth_clips(1, 500, 64, seed=3)[0], synth.synth_clips(1, 333, 64, seed=4)[0],
+           synth.synth_clips(1, 420, 64, seed=5)[0]]
+    return {
+        "c1_b2": (c1, synth.synth_clips(2, 500, 64, seed=1), 11),
+        "c2_b2": (c2, synth.synth_clips(2, 496, 64, seed=2), 12),
+        "c1_ragged": (c1, rag, 11),
+        "c1_b1": (c1, synth.synth_clips(1, 500, 64, seed=6), 11),
+        "c1_plain": (plain, synth.synth_clips(2, 256, 64, seed=7), 13),
+        "c1_postnorm": (post, synth.synth_clips(2, 256, 64, seed=8), 14),
+    }
+
+
+@pytest.mark.parametrize("tag", list(_cases().keys()))
+def test_sedt_oracle_matches_reference(tag):
+    args, clips, seed = _cases()[tag]
+    fx = np.load(os.path.join(GOLDEN, f"sedt_{tag}.npz"))
+    sd = synth.synth_state_dict(args, seed)
+    taps = {}
+    out = sedt_oracle.sedt_forward(sd, args, clips, taps=taps)
+    for k in ("pred_logits", "pred_boxes", "at"):
+        if k in fx:
+            assert out[k].shape == fx[k].shape, k
+            assert np.abs(out[k].numpy() - fx[k]).max() <= TOL * max(1.0, np.abs(fx[k]).max()), k
+    for i, aux in enumerate(out.get("aux_outputs", [])):
+        assert np.abs(aux["pred_logits"].numpy() - fx[f"aux{i}_pred_logits"]).max() <= TOL * max(1.0, np.abs(fx[f"aux{i}_pred_logits"]).max())
+        assert np.abs(aux["pred_boxes"].numpy() - fx[f"aux{i}_pred_boxes"]).max() <= TOL
+    for k in ("stem", "layer1", "layer2", "layer3", "layer4", "memory", "hs"):
+        ref = fx["tap_" + k]
+        got = _sample(taps[k])
+        assert got.shape == ref.shape, k
+        assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), k
+
+    ev_path = os.path.join(GOLDEN, f"events_{tag}.json")
+    if os.path.exists(ev_path):
+        gold = json.load(open(ev_path))
+        B = out["pred_logits"].shape[0]
+        sizes = torch.full((B,), 10.0)
+        tags = (out["at"].reshape(B, -1) > 0.5).long()
+        names = [f"class{i}" for i in range(10)]
+        total = 0
+        for at_m in (1, 2, 3):
+            res = sedt_oracle.post_process({k: v.clone() for k, v in out.items() if k != "aux_outputs"}, sizes, tags, at_m)
+            for clip_res, clip_gold in zip(res, gold[str(at_m)]):
+                ev = decode_oracle.decode_strong({k: v.numpy() for k, v in clip_res.items()}, names, 0.5)
+                assert [e[0] for e in ev] == [e[0] for e in clip_gold]
+                for e, g in zip(ev, clip_gold):
+                    assert abs(float(e[1]) - g[1]) < 1e-5 and abs(float(e[2]) - g[2]) < 1e-5 and abs(float(e[3]) - g[3]) < 1e-5
+                total += len(ev)
+        assert total > 0, "golden event lists must not be empty (SURVEY 7.2c)"
+
+
+def test_spsedt_oracle_matches_reference():
+    args = spec.config_args("c5")
+    fx = np.load(os.path.join(GOLDEN, "spsedt_c5_b2.npz"))
+    sd = synth.synth_state_dict(args, 15)
+    x = synth.synth_clips(2, 496, 64, seed=9)
+    patches = synth.synth_patches(2, 10, 128, 64, seed=9)
+    mask = torch.zeros(2, 496, 64, dtype=torch.bool)
+    out = sedt_oracle.spsedt_forward(sd, args, x, mask, patches)
+    for k in ("pred_logits", "pred_boxes"):
+        assert np.abs(out[k].numpy() - fx[k]).max() <= TOL * max(1.0, np.abs(fx[k]).max()), k
+    for k in ("pred_feature", "gt_feature"):
+        ref = fx[k]
+        assert np.abs(_sample(out[k]) - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), k
+    for i, aux in enumerate(out["aux_outputs"]):
+        assert np.abs(aux["pred_logits"].numpy() - fx[f"aux{i}_pred_logits"]).max() <= TOL * max(1.0, np.abs(fx[f"aux{i}_pred_logits"]).max())
+
+
+@pytest.mark.parametrize("tag,normalize", [("c3_small", False), ("c3_edges", False), ("urban_q10", False),
+                                           ("c3_normalize", True)])
+@pytest.mark.parametrize("solver", ["scipy", "c"])
+def test_matcher_oracle_matches_reference(tag, normalize, solver):
+    fx = np.load(os.path.join(GOLDEN, f"matcher_{tag}.npz"))
+    B, Q, C, kmin, kmax, seed = [int(v) for v in fx["meta"]]
+    outputs, targets = synth.synth_matcher_case(B, Q, C, kmin, kmax, seed)
+    idx, coef = matcher_oracle.hungarian_matcher(
+        {k: v.numpy() for k, v in outputs.items()},
+        [{k: v.numpy() for k, v in t.items()} for t in targets], normalize=normalize, solver=solver)
+    counts = np.asarray([len(r) for r, _ in idx], np.int32)
+    assert np.array_equal(counts, fx["counts"])
+    assert np.array_equal(np.concatenate([r for r, _ in idx]), fx["rows"])
+    assert np.array_equal(np.concatenate([c for _, c in idx]), fx["cols"])
+    for (r, c), cf, t in zip(idx, coef, targets):
+        assert len(r) == min(Q, len(t["boxes"])) and cf.shape == c.shape
+        assert np.all(np.diff(r) > 0)
