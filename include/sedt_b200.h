@@ -1,0 +1,151 @@
+/* sedt_b200 — C ABI of the B200-native SEDT hot path.
+ *
+ * The reference (Anaesthesiaye/sound_event_detection_transformer) is pure
+ * Python and has no FFI; its seam is the Python module API of package `sedt`
+ * (SURVEY.md section 8b).  This header is the layer directly beneath that
+ * seam: the Python mirror in sound_event_detection_transformer_b200/sedt/
+ * keeps the reference's classes and binds these entry points with ctypes
+ * (INTEGRATION.md shows the stub).  Each entry point names the reference
+ * code it replaces (paths relative to the reference root).
+ *
+ * Conventions: every pointer is a raw CUDA device pointer unless marked
+ * [host]; all memory is owned by the caller (PyTorch); `stream` is a
+ * cudaStream_t passed as void*; functions return 0 on success or a negative
+ * sedt_status and never throw, exit or synchronise the device unless stated;
+ * sedt_last_error() returns the message for the calling thread.
+ */
+#ifndef SEDT_B200_H
+#define SEDT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEDT_ABI_VERSION 1
+#if defined(__GNUC__)
+#define SEDT_API __attribute__((visibility("default")))
+#else
+#define SEDT_API
+#endif
+
+enum sedt_status {
+    SEDT_STATUS_OK = 0,
+    SEDT_STATUS_INVALID = -1,
+    SEDT_STATUS_CUDA = -2,
+    SEDT_STATUS_WORKSPACE = -3,
+    SEDT_STATUS_NUMERIC = -4,      /* NaN / -inf cost entries: scipy raises ValueError here */
+    SEDT_STATUS_INFEASIBLE = -5,
+    SEDT_STATUS_UNSUPPORTED = -6
+};
+
+enum sedt_dtype { SEDT_F32 = 0, SEDT_BF16 = 1 };
+
+/* Model hyper-parameters `build_model(args)` reads (sedt/__init__.py:8-63,
+ * sedt/transformer.py:409-420, sedt/backbone.py:135-141). */
+typedef struct sedt_config {
+    int32_t enc_layers, dec_layers;
+    int32_t num_queries;          /* event queries, without the audio query */
+    int32_t num_classes;
+    int32_t hidden_dim, nheads, dim_feedforward;
+    int32_t dec_at, pre_norm, dilation;
+    int32_t self_sup, feature_recon, num_patches;
+    int32_t aux_loss;
+    int32_t precision;            /* 0: fp32 CUDA-core tier; 1: bf16 operands, fp32 accumulate, tcgen05 */
+    int32_t use_tensor_cores;     /* precision 1 only; 0 routes every GEMM to the CUDA-core kernel */
+} sedt_config;
+
+typedef struct sedt_model sedt_model;
+
+/* fp32 outputs of one forward; null members are skipped. */
+typedef struct sedt_outputs {
+    float* hs;            /* [D, B, Qall, 256]  decoder states (transformer.py:140-150); required */
+    float* logits;        /* [D, B, Q, C+1]     class_embed on every decoder layer (sedt.py:90); required */
+    float* boxes;         /* [D, B, Q, 2]       sigmoid(bbox_embed) = (center, width) (sedt.py:91); required */
+    float* at;            /* [B, C]             sigmoid(weak_class_embed(hs[-1,:,0])) (sedt.py:92); dec_at only */
+    float* memory;        /* [B, S, 256]        encoder output, optional */
+    float* pred_feature;  /* [D, B, Q, 2048]    feature_align(hs) (spsedt.py:80), SP-SEDT only, optional */
+    float* gt_feature;    /* [B*P, 2048]        avgpool(backbone(patches)) (spsedt.py:50), SP-SEDT only, optional */
+    float* feat;          /* [B, H, W, 2048]    layer4 output, fp32 tier only, optional (parity tests) */
+} sedt_outputs;
+
+SEDT_API const char* sedt_last_error(void);
+SEDT_API int sedt_abi_version(void);
+/* number of kernels this library has launched since load (bench.py reports the delta) */
+SEDT_API unsigned long long sedt_launch_count(void);
+
+/* ---- model lifecycle: replaces SEDT.__init__/SPSEDT.__init__ state (sedt/sedt.py:20-61) ---- */
+SEDT_API int sedt_model_create(const sedt_config* cfg, sedt_model** out);
+SEDT_API void sedt_model_destroy(sedt_model* m);
+/* The weight table: slot i is the reference state_dict entry sedt_model_weight_name(m, i)
+ * (fp32, contiguous, reference shape).  SURVEY.md section 8b lists the names. */
+SEDT_API int sedt_model_num_weights(const sedt_model* m);
+SEDT_API const char* sedt_model_weight_name(const sedt_model* m, int i);
+SEDT_API int64_t sedt_model_weight_numel(const sedt_model* m, int i);
+SEDT_API int64_t sedt_model_packed_bytes(const sedt_model* m);
+/* Snapshot the weights into `packed` (256-byte aligned): OIHW -> O(HW)I repack in the tier's
+ * dtype, FrozenBatchNorm2d fold (sedt/backbone.py:43-53), conv0-into-conv1 fold.  Call again
+ * whenever a parameter changes.  `weights` is a [host] array of device pointers. */
+SEDT_API int sedt_model_pack(sedt_model* m, const void* const* weights, void* packed, int64_t packed_bytes, void* stream);
+
+/* Spatial size of the layer4 feature map for a [T, F] clip (backbone.py + resnet strides). */
+SEDT_API int sedt_feature_shape(int T, int F, int dilation, int* H, int* W);
+/* Bytes of scratch sedt_forward needs for this shape (P = PT = 0 unless SP-SEDT). */
+SEDT_API int64_t sedt_workspace_bytes(sedt_model* m, int B, int T, int F, int P, int PT);
+
+/* The forward hot path: replaces SEDT.forward (sedt/sedt.py:64-123) and, with patches,
+ * SPSEDT.forward's eval branch (sedt/spsedt.py:34-91).
+ *   x       [B, 1, T, F] fp32 log-mel clips (already zero-padded to the batch maximum)
+ *   mask    [B, T, F] uint8, 1 = padding (utilities/utils.py:470-492), or null if nothing is padded
+ *   patches [B, P, 1, PT, F] fp32 or null */
+SEDT_API int sedt_forward(sedt_model* m, const float* x, const uint8_t* mask, int B, int T, int F,
+                 const float* patches, int P, int PT, void* workspace, int64_t workspace_bytes,
+                 const sedt_outputs* out, void* stream);
+
+/* ---- HungarianMatcher.forward default path (sedt/matcher.py:41-97; utilities/box_ops.py:9-56)
+ *   logits [B, Q, C1] fp32, boxes [B, Q, 2] fp32 (center, width)
+ *   tgt_labels [sumK] int64, tgt_boxes [sumK, 2] fp32, offsets [B+1] int32 (clip b owns targets
+ *   offsets[b] .. offsets[b+1]); kmax >= max_b K_b.
+ *   rows, cols [B, Q] int64 (first counts[b] entries valid, rows ascending; rest -1), counts [B] int32,
+ *   status [1] int32 (must be zeroed by the caller; set to a negative sedt_status on NaN/-inf costs).
+ *   cost_out: optional [B, Q, ld_cost] fp32 copy of the cost blocks. */
+SEDT_API int sedt_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
+                 const int32_t* offsets, int B, int Q, int C1, int kmax,
+                 float cost_class, float cost_bbox, float cost_giou,
+                 float* cost_out, int ld_cost, int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status,
+                 void* stream);
+/* Only the per-clip assignment (scipy.optimize.linear_sum_assignment, sedt/matcher.py:95) on caller
+ * supplied fp32 cost blocks cost[B, Q, ld_cost]; clip b uses its first offsets[b+1]-offsets[b] columns. */
+SEDT_API int sedt_lsap(const float* cost, int ld_cost, const int32_t* offsets, int B, int Q, int kmax,
+              int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status, void* stream);
+
+/* ---- single operators, exported so the parity tests can pin each kernel against the oracle ---- */
+typedef struct sedt_conv_desc {
+    const void* in; const void* w; const float* scale; const float* bias; const void* residual; void* out;
+    int32_t in_dtype, out_dtype;
+    int32_t B, H, W, Cin, lda, Ho, Wo, Cout, ldc, ld_res, R, S, stride, dil, pad, relu;
+} sedt_conv_desc;
+/* Conv/linear + FrozenBN scale/bias + residual + ReLU as implicit GEMM (NHWC in, [Cout][R][S][Cin] weights).
+ * engine: 0 = CUDA-core kernel, 1 = TMA + tcgen05 kernel (bf16 in). */
+SEDT_API int sedt_op_conv(const sedt_conv_desc* d, int engine, void* stream);
+SEDT_API int sedt_op_conv_tc_supported(const sedt_conv_desc* d);
+/* OIHW fp32 -> O(HW)I in `dtype` */
+SEDT_API int sedt_op_repack_conv(const float* w_oihw, void* out, int dtype, int Cout, int Cin, int R, int S, void* stream);
+SEDT_API int sedt_op_cast(const float* in, void* out, int dtype, int64_t n, void* stream);
+/* conv0 + conv1 + bn1 + relu + maxpool (sedt/backbone.py:102 + resnet stem); out NHWC [B, Hp, 16, 64] */
+SEDT_API int sedt_op_stem(const float* x, const float* conv0_w, const float* conv0_b, const float* conv1_w,
+                 const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var,
+                 void* scratch /* >= 32 KiB */, void* out, int out_dtype, int B, int T, int F, void* stream);
+SEDT_API int sedt_op_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int64_t pos_rows,
+                      void* y, void* ypos, float* y32, int dtype, int64_t rows, void* stream);
+SEDT_API int sedt_op_attention(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo,
+                      int dtype, const uint8_t* key_padding_mask, const float* attn_mask,
+                      int B, int nheads, int Lq, int Lk, float scale, void* stream);
+SEDT_API int sedt_op_pos_table(const uint8_t* mask /* [B,T,F] or null */, uint8_t* mask_ds /* [B,H*W] scratch or null */,
+                      float* pos, int B, int T, int F, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEDT_B200_H */

@@ -1,0 +1,111 @@
+"""ctypes binding of libsedt_b200.so (include/sedt_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is
+missing or does not export the ABI this module raises, and every product
+entry point above it fails with it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsedt_b200.so")
+ABI_VERSION = 1
+
+F32, BF16 = 0, 1
+
+
+class SedtConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "enc_layers", "dec_layers", "num_queries", "num_classes", "hidden_dim", "nheads", "dim_feedforward",
+        "dec_at", "pre_norm", "dilation", "self_sup", "feature_recon", "num_patches", "aux_loss",
+        "precision", "use_tensor_cores")]
+
+
+class SedtOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("hs", "logits", "boxes", "at", "memory", "pred_feature", "gt_feature", "feat")]
+
+
+class SedtConvDesc(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("in_", "w", "scale", "bias", "residual", "out")] + \
+               [(n, C.c_int32) for n in ("in_dtype", "out_dtype", "B", "H", "W", "Cin", "lda", "Ho", "Wo", "Cout", "ldc",
+                                         "ld_res", "R", "S", "stride", "dil", "pad", "relu")]
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/sedt_b200.h declares
+SIGNATURES = {
+    "sedt_last_error": (C.c_char_p, []),
+    "sedt_abi_version": (_i, []),
+    "sedt_launch_count": (C.c_ulonglong, []),
+    "sedt_model_create": (_i, [C.POINTER(SedtConfig), C.POINTER(_vp)]),
+    "sedt_model_destroy": (None, [_vp]),
+    "sedt_model_num_weights": (_i, [_vp]),
+    "sedt_model_weight_name": (C.c_char_p, [_vp, _i]),
+    "sedt_model_weight_numel": (_i64, [_vp, _i]),
+    "sedt_model_packed_bytes": (_i64, [_vp]),
+    "sedt_model_pack": (_i, [_vp, C.POINTER(_vp), _vp, _i64, _vp]),
+    "sedt_feature_shape": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "sedt_workspace_bytes": (_i64, [_vp, _i, _i, _i, _i, _i]),
+    "sedt_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i64, C.POINTER(SedtOutputs), _vp]),
+    "sedt_matcher": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sedt_lsap": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sedt_op_conv": (_i, [C.POINTER(SedtConvDesc), _i, _vp]),
+    "sedt_op_conv_tc_supported": (_i, [C.POINTER(SedtConvDesc)]),
+    "sedt_op_repack_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "sedt_op_cast": (_i, [_vp, _vp, _i, _i64, _vp]),
+    "sedt_op_stem": (_i, [_vp] * 10 + [_i, _i, _i, _i, _vp]),
+    "sedt_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i64, _vp]),
+    "sedt_op_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "sedt_op_pos_table": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class SedtError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sedt_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    """Load the library (once).  Raises if it is missing: build it with
+    `python -m sound_event_detection_transformer_b200.build` or __graft_entry__.build()."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension has not been built "
+                "(run `python -m sound_event_detection_transformer_b200.build`). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if lib.sedt_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"libsedt_b200.so ABI {lib.sedt_abi_version()} != expected {ABI_VERSION}; rebuild")
+        _lib = lib
+        return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().sedt_last_error()
+        raise SedtError(rc, msg.decode() if msg else "")
+
+
+def ptr(t) -> int:
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

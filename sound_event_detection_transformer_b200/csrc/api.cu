@@ -1,0 +1,192 @@
+// extern "C" surface declared in include/sedt_b200.h.
+#include "../../include/sedt_b200.h"
+#include "model.h"
+
+using namespace sedt;
+
+struct sedt_model { Model* impl; };
+
+static_assert(sizeof(sedt_config) == sizeof(Config), "sedt_config and sedt::Config must stay in lock-step");
+
+static ConvGemm to_gemm(const sedt_conv_desc* d)
+{
+    ConvGemm g;
+    g.in = d->in; g.w = d->w; g.scale = d->scale; g.bias = d->bias; g.residual = d->residual; g.out = d->out;
+    g.in_dt = d->in_dtype; g.out_dt = d->out_dtype;
+    g.B = d->B; g.H = d->H; g.W = d->W; g.Cin = d->Cin; g.lda = d->lda; g.Ho = d->Ho; g.Wo = d->Wo; g.Cout = d->Cout;
+    g.ldc = d->ldc; g.ld_res = d->ld_res; g.R = d->R; g.S = d->S; g.stride = d->stride; g.dil = d->dil; g.pad = d->pad;
+    g.relu = d->relu;
+    return g;
+}
+
+extern "C" {
+
+const char* sedt_last_error(void) { return get_error(); }
+int sedt_abi_version(void) { return SEDT_ABI_VERSION; }
+unsigned long long sedt_launch_count(void) { return g_launch_count; }
+
+int sedt_model_create(const sedt_config* cfg, sedt_model** out)
+{
+    SEDT_REQUIRE(cfg != nullptr && out != nullptr, "model_create: null argument");
+    SEDT_REQUIRE(cfg->hidden_dim == 256 && cfg->nheads == 8, "model_create: kernels are built for hidden_dim=256, nheads=8 "
+                 "(train_sedt.py:86,95 defaults); got %d / %d", cfg->hidden_dim, cfg->nheads);
+    SEDT_REQUIRE(cfg->dim_feedforward % 64 == 0 && cfg->dim_feedforward >= 64, "model_create: dim_feedforward=%d", cfg->dim_feedforward);
+    SEDT_REQUIRE(cfg->enc_layers >= 0 && cfg->dec_layers >= 1 && cfg->num_queries >= 1 && cfg->num_classes >= 1,
+                 "model_create: bad layer/query/class counts");
+    SEDT_REQUIRE(cfg->precision == 0 || cfg->precision == 1, "model_create: precision must be 0 (fp32) or 1 (bf16)");
+    SEDT_REQUIRE(!(cfg->self_sup && cfg->dec_at), "model_create: SP-SEDT has no audio query");
+    SEDT_REQUIRE(!cfg->self_sup || (cfg->num_patches >= 1 && cfg->num_queries % cfg->num_patches == 0),
+                 "model_create: num_queries must be a multiple of num_patches (sedt/spsedt.py:27)");
+    Config c;
+    memcpy(&c, cfg, sizeof(c));
+    sedt_model* m = new sedt_model;
+    m->impl = new Model(c);
+    *out = m;      // the TMA driver entry point is resolved lazily at the first tensor-core launch
+    return SEDT_OK;
+}
+
+void sedt_model_destroy(sedt_model* m)
+{
+    if (m == nullptr) return;
+    delete m->impl;
+    delete m;
+}
+
+int sedt_model_num_weights(const sedt_model* m) { return m ? (int)m->impl->slots().size() : 0; }
+const char* sedt_model_weight_name(const sedt_model* m, int i)
+{
+    if (m == nullptr || i < 0 || i >= (int)m->impl->slots().size()) return nullptr;
+    return m->impl->slots()[i].name.c_str();
+}
+int64_t sedt_model_weight_numel(const sedt_model* m, int i)
+{
+    if (m == nullptr || i < 0 || i >= (int)m->impl->slots().size()) return -1;
+    return m->impl->slots()[i].numel;
+}
+int64_t sedt_model_packed_bytes(const sedt_model* m) { return m ? (int64_t)m->impl->packed_bytes() : -1; }
+
+int sedt_model_pack(sedt_model* m, const void* const* weights, void* packed, int64_t packed_bytes, void* stream)
+{
+    SEDT_REQUIRE(m != nullptr && weights != nullptr && packed != nullptr, "model_pack: null argument");
+    return m->impl->pack(weights, packed, (size_t)packed_bytes, (cudaStream_t)stream);
+}
+
+int sedt_feature_shape(int T, int F, int dilation, int* H, int* W)
+{
+    SEDT_REQUIRE(H != nullptr && W != nullptr && T >= 1 && F >= 1, "feature_shape: bad argument");
+    Model::feature_shape(T, F, dilation != 0, H, W);
+    return SEDT_OK;
+}
+
+int64_t sedt_workspace_bytes(sedt_model* m, int B, int T, int F, int P, int PT)
+{
+    if (m == nullptr) { set_error("workspace_bytes: null model"); return SEDT_ERR_INVALID; }
+    Arena a(nullptr, 0);
+    ForwardOut o{};
+    int rc = m->impl->forward(nullptr, nullptr, B, T, F, nullptr, P, PT, a, o, nullptr, true);
+    if (rc != 0) return rc;
+    return (int64_t)((a.off + 255) & ~(size_t)255);
+}
+
+int sedt_forward(sedt_model* m, const float* x, const uint8_t* mask, int B, int T, int F, const float* patches, int P,
+                 int PT, void* workspace, int64_t workspace_bytes, const sedt_outputs* out, void* stream)
+{
+    SEDT_REQUIRE(m != nullptr && x != nullptr && out != nullptr, "forward: null argument");
+    SEDT_REQUIRE(out->hs != nullptr && out->logits != nullptr && out->boxes != nullptr, "forward: hs/logits/boxes outputs are required");
+    SEDT_REQUIRE(!m->impl->cfg().dec_at || out->at != nullptr, "forward: dec_at model needs the `at` output");
+    SEDT_REQUIRE(((uintptr_t)workspace & 255) == 0, "forward: workspace must be 256-byte aligned");
+    const int64_t need = sedt_workspace_bytes(m, B, T, F, P, PT);
+    if (need < 0) return (int)need;
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("forward: workspace too small (%lld bytes needed, %lld given)", (long long)need, (long long)workspace_bytes);
+        return SEDT_ERR_WORKSPACE;
+    }
+    Arena a(workspace, (size_t)workspace_bytes);
+    ForwardOut o{out->hs, out->logits, out->boxes, out->at, out->memory, out->pred_feature, out->gt_feature, out->feat};
+    return m->impl->forward(x, mask, B, T, F, patches, P, PT, a, o, (cudaStream_t)stream, false);
+}
+
+int sedt_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
+                 const int32_t* offsets, int B, int Q, int C1, int kmax, float cost_class, float cost_bbox, float cost_giou,
+                 float* cost_out, int ld_cost, int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status, void* stream)
+{
+    SEDT_REQUIRE(B == 0 || (logits && boxes && offsets && rows && cols && counts && status), "matcher: null argument");
+    SEDT_REQUIRE(cost_out == nullptr || ld_cost >= kmax, "matcher: ld_cost=%d < kmax=%d", ld_cost, kmax);
+    return launch_matcher(logits, boxes, tgt_labels, tgt_boxes, offsets, B, Q, C1, kmax, cost_class, cost_bbox, cost_giou,
+                          nullptr, 0, cost_out, ld_cost, rows, cols, counts, status, 1, (cudaStream_t)stream);
+}
+
+int sedt_lsap(const float* cost, int ld_cost, const int32_t* offsets, int B, int Q, int kmax, int64_t* rows, int64_t* cols,
+              int32_t* counts, int32_t* status, void* stream)
+{
+    SEDT_REQUIRE(B == 0 || (cost && offsets && rows && cols && counts && status), "lsap: null argument");
+    SEDT_REQUIRE(ld_cost >= kmax, "lsap: ld_cost=%d < kmax=%d", ld_cost, kmax);
+    return launch_matcher(nullptr, nullptr, nullptr, nullptr, offsets, B, Q, 1, kmax, 0.f, 0.f, 0.f, cost, ld_cost, nullptr, 0,
+                          rows, cols, counts, status, 1, (cudaStream_t)stream);
+}
+
+int sedt_op_conv(const sedt_conv_desc* d, int engine, void* stream)
+{
+    SEDT_REQUIRE(d != nullptr, "op_conv: null descriptor");
+    ConvGemm g = to_gemm(d);
+    if (engine == 0) return launch_conv_simt(g, (cudaStream_t)stream);
+    SEDT_TRY(tc_init());
+    if (!conv_tc_supported(g)) {
+        set_error("op_conv: shape not supported by the tcgen05 kernel");
+        return SEDT_ERR_UNSUPPORTED;
+    }
+    return launch_conv_tc(g, (cudaStream_t)stream);
+}
+
+int sedt_op_conv_tc_supported(const sedt_conv_desc* d) { return d != nullptr && conv_tc_supported(to_gemm(d)) ? 1 : 0; }
+
+int sedt_op_repack_conv(const float* w_oihw, void* out, int dtype, int Cout, int Cin, int R, int S, void* stream)
+{
+    return launch_repack_conv(w_oihw, out, dtype, Cout, Cin, R, S, (cudaStream_t)stream);
+}
+
+int sedt_op_cast(const float* in, void* out, int dtype, int64_t n, void* stream)
+{
+    return launch_cast(in, out, dtype, n, (cudaStream_t)stream);
+}
+
+int sedt_op_stem(const float* x, const float* conv0_w, const float* conv0_b, const float* conv1_w, const float* bn_w,
+                 const float* bn_b, const float* bn_mean, const float* bn_var, void* scratch, void* out, int out_dtype, int B,
+                 int T, int F, void* stream)
+{
+    SEDT_REQUIRE(scratch != nullptr && ((uintptr_t)scratch & 255) == 0, "op_stem: scratch must be 256-byte aligned");
+    float* weff = (float*)scratch;              // 49*64
+    float* sat = weff + 49 * 64 + 64;           // 64*64 (offset keeps 16-byte alignment)
+    float* scale = sat + 64 * 64;
+    float* bias = scale + 64;
+    cudaStream_t s = (cudaStream_t)stream;
+    SEDT_TRY(launch_stem_pack(conv0_w, conv0_b, conv1_w, weff, sat, s));
+    SEDT_TRY(launch_bn_fold(bn_w, bn_b, bn_mean, bn_var, scale, bias, 64, s));
+    StemWeights w{weff, sat, scale, bias};
+    return launch_stem(x, w, out, out_dtype, B, T, F, s);
+}
+
+int sedt_op_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int64_t pos_rows, void* y,
+                      void* ypos, float* y32, int dtype, int64_t rows, void* stream)
+{
+    return launch_layernorm(x, gamma, beta, pos, pos_rows < 1 ? 1 : pos_rows, y, ypos, y32, dtype, rows, (cudaStream_t)stream);
+}
+
+int sedt_op_attention(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int dtype,
+                      const uint8_t* key_padding_mask, const float* attn_mask, int B, int nheads, int Lq, int Lk, float scale,
+                      void* stream)
+{
+    return launch_attention(Q, ldq, K, ldk, V, ldv, O, ldo, dtype, key_padding_mask, attn_mask, B, nheads, Lq, Lk, scale,
+                            (cudaStream_t)stream);
+}
+
+int sedt_op_pos_table(const uint8_t* mask, uint8_t* mask_ds, float* pos, int B, int T, int F, int H, int W, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mask == nullptr) return launch_pos_table(nullptr, pos, 1, H, W, s);
+    SEDT_REQUIRE(mask_ds != nullptr, "op_pos_table: mask_ds scratch required with a mask");
+    SEDT_TRY(launch_mask_downsample(mask, mask_ds, B, T, F, H, W, s));
+    return launch_pos_table(mask_ds, pos, B, H, W, s);
+}
+
+}  // extern "C"

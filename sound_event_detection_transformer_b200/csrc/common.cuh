@@ -1,0 +1,76 @@
+// Shared helpers for the sedt_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace sedt {
+
+// ---- error plumbing: C-ABI functions return int and never throw -------------
+enum : int {
+    SEDT_OK = 0,
+    SEDT_ERR_INVALID = -1,      // bad argument / unsupported shape
+    SEDT_ERR_CUDA = -2,         // a CUDA runtime/driver call failed
+    SEDT_ERR_WORKSPACE = -3,    // workspace or packed buffer too small
+    SEDT_ERR_NUMERIC = -4,      // NaN/-inf cost entries (matcher) -> ValueError upstream
+    SEDT_ERR_INFEASIBLE = -5,   // LSAP infeasible
+    SEDT_ERR_UNSUPPORTED = -6,
+};
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SEDT_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ::sedt::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,            \
+                              cudaGetErrorString(_e));                                         \
+            return ::sedt::SEDT_ERR_CUDA;                                                      \
+        }                                                                                      \
+    } while (0)
+
+#define SEDT_REQUIRE(cond, ...)                                                                \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            ::sedt::set_error(__VA_ARGS__);                                                    \
+            return ::sedt::SEDT_ERR_INVALID;                                                   \
+        }                                                                                      \
+    } while (0)
+
+#define SEDT_TRY(expr)                                                                         \
+    do {                                                                                       \
+        int _rc = (expr);                                                                      \
+        if (_rc != 0) return _rc;                                                              \
+    } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// launch counter: bench.py reports how many of OUR kernels ran in the timed region
+extern unsigned long long g_launch_count;
+#define SEDT_COUNT_LAUNCH() (++::sedt::g_launch_count)
+
+// ---- device-side conversions -------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace sedt

@@ -1,0 +1,91 @@
+// Internal launcher declarations shared by the kernel translation units and
+// the host runtime (model.cu / api.cu).  Nothing here is exported.
+#pragma once
+#include "common.cuh"
+
+namespace sedt {
+
+enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+static inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+// One convolution / linear layer as an implicit GEMM over NHWC activations:
+//   out[m, n] = act( (sum_k A[m,k] * W[n,k]) * scale[n] + bias[n] + residual[m,n] )
+// with m = (b, ho, wo), k = (r, s, c), W stored [Cout][R][S][Cin].
+// A linear layer on [rows, K] is B=rows, H=W=Ho=Wo=1, R=S=1.
+struct ConvGemm {
+    const void* in = nullptr;      // activation, dtype in_dt, pixel stride lda elements
+    const void* w = nullptr;       // weights, dtype in_dt
+    const float* scale = nullptr;  // per-Cout (FrozenBN fold) or nullptr (=1)
+    const float* bias = nullptr;   // per-Cout or nullptr (=0)
+    const void* residual = nullptr;  // dtype out_dt, row stride ld_res, or nullptr
+    void* out = nullptr;           // dtype out_dt, row stride ldc
+    int in_dt = DT_F32, out_dt = DT_F32;
+    int B = 0, H = 1, W = 1, Cin = 0, lda = 0;
+    int Ho = 1, Wo = 1, Cout = 0, ldc = 0, ld_res = 0;
+    int R = 1, S = 1, stride = 1, dil = 1, pad = 0;
+    int relu = 0;
+};
+
+// ---- conv_simt.cu : fp32-accumulate CUDA-core implicit GEMM (precise tier + small shapes)
+int launch_conv_simt(const ConvGemm& g, cudaStream_t stream);
+
+// ---- gemm_tc.cu : TMA + tcgen05/TMEM implicit GEMM (bf16 tier)
+bool conv_tc_supported(const ConvGemm& g);
+int launch_conv_tc(const ConvGemm& g, cudaStream_t stream);
+int tc_init();     // resolves cuTensorMapEncodeTiled once; safe without a GPU
+
+// ---- stem.cu : conv0(1x1,bias) + conv1(7x7 s2 p3) + FrozenBN + ReLU + maxpool(3x3 s2 p1), F == 64
+struct StemWeights {
+    const float* weff;   // [49][64]   sum_c conv1[o][c][tap] * conv0.w[c]
+    const float* sat;    // [8][8][64] inclusive 2-D prefix sums of sum_c conv1[o][c][tap] * conv0.b[c]
+    const float* scale;  // [64] bn1 fold
+    const float* bias;   // [64]
+};
+int launch_stem_pack(const float* conv0_w, const float* conv0_b, const float* conv1_w, float* weff, float* sat,
+                     cudaStream_t stream);
+int launch_stem(const float* x, const StemWeights& w, void* out, int out_dt, int B, int T, int F, cudaStream_t stream);
+
+// ---- pack.cu
+int launch_bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* bias,
+                   int n, cudaStream_t stream);
+// OIHW fp32 -> O(HW)I in dtype dt
+int launch_repack_conv(const float* w_oihw, void* out, int dt, int Cout, int Cin, int R, int S, cudaStream_t stream);
+int launch_cast(const float* in, void* out, int dt, int64_t n, cudaStream_t stream);
+
+// ---- transformer.cu
+// LayerNorm over D=256, eps 1e-5.  Any of y / ypos / y32 may be null.
+//   y    = LN(x)                      (dtype dt)
+//   ypos = LN(x) + pos[row % pos_rows] (dtype dt)
+//   y32  = LN(x)                      (fp32)
+int launch_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int64_t pos_rows,
+                     void* y, void* ypos, float* y32, int dt, int64_t rows, cudaStream_t stream);
+// y = x (cast), ypos = x + pos[row % pos_rows]  (post-norm path and memory+pos)
+int launch_cast_addpos(const float* x, const float* pos, int64_t pos_rows, void* y, void* ypos, int dt, int64_t rows,
+                       cudaStream_t stream);
+// Multi-head attention core, head_dim 32: O = softmax(Q K^T * scale + amask + kpm) V
+int launch_attention(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int dt,
+                     const uint8_t* kpm, const float* amask, int B, int nheads, int Lq, int Lk, float scale,
+                     cudaStream_t stream);
+int launch_mask_downsample(const uint8_t* mask, uint8_t* out, int B, int T, int F, int H, int W, cudaStream_t stream);
+// sine position table: [nb][H*W][256] fp32; mask_ds null => unpadded (nb must be 1)
+int launch_pos_table(const uint8_t* mask_ds, float* pos, int nb, int H, int W, cudaStream_t stream);
+int launch_fill_zero(void* p, size_t bytes, cudaStream_t stream);
+// slice decoder slots and apply sigmoid: see model.cu
+int launch_heads_finalize(const float* cls_raw, const float* box_raw, const float* weak_raw, float* logits, float* boxes,
+                          float* at, int D, int B, int Qall, int start, int C1, int C, cudaStream_t stream);
+// [N, HW, C] -> [N, C] mean (SP-SEDT avgpool), fp32 out
+int launch_avgpool(const void* x, int dt, float* out, int N, int HW, int C, cudaStream_t stream);
+// query_pos[b, q, :] = pq[b, q / qpp, :] + query_embed[start + q, :]
+int launch_patch_query(const float* pq, const float* query_embed, float* out, int B, int P, int qpp, int start,
+                       cudaStream_t stream);
+
+// additive block-diagonal 0/-inf decoder mask [Q,Q] (sedt/spsedt.py:27-32)
+int launch_blockdiag_mask(float* m, int Q, int qpp, cudaStream_t stream);
+
+// ---- matcher.cu
+int launch_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
+                   const int32_t* offsets, int B, int Q, int C1, int Kmax, float w_class, float w_bbox, float w_giou,
+                   const float* cost_in, int ld_in, float* cost_out, int ld_out,
+                   int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status, int solve, cudaStream_t stream);
+
+}  // namespace sedt

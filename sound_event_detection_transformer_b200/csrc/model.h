@@ -1,0 +1,120 @@
+// Host-side runtime of the SEDT forward hot path: owns the layer table (which
+// reference state_dict entry feeds which kernel), the packed-weight layout and
+// the launch sequence.  All device memory belongs to the caller (PyTorch):
+// weights, the packed buffer, the workspace and the outputs are raw pointers.
+#pragma once
+#include "kernels.h"
+#include <string>
+#include <vector>
+
+namespace sedt {
+
+struct Config {                 // mirrors include/sedt_b200.h : sedt_config
+    int enc_layers, dec_layers, num_queries, num_classes, hidden_dim, nheads, dim_feedforward;
+    int dec_at, pre_norm, dilation, self_sup, feature_recon, num_patches, aux_loss;
+    int precision;              // 0 = fp32 CUDA-core tier, 1 = bf16 tcgen05 tier
+    int use_tensor_cores;       // bf16 tier only: 0 forces the CUDA-core kernels (debug / A-B tests)
+};
+
+struct WeightSlot {
+    std::string name;           // reference state_dict key
+    int64_t numel;
+};
+
+struct ConvLayer {
+    int cin, cout, k, stride, dil, pad, relu;
+    int w_slot, bn_slot;        // bn_slot: weight, +1 bias, +2 running_mean, +3 running_var
+    size_t off_w, off_scale, off_bias;
+};
+
+struct Block { ConvLayer c1, c2, c3, ds; bool has_ds; };
+
+struct Linear {                 // y = x W^T + b ; W [out, in]
+    int in, out, w_slot, b_slot;
+    size_t off_w, off_b;        // off_w in tier dtype (or fp32 when f32_only)
+    bool f32_only;
+};
+
+struct Norm { int w_slot, b_slot; size_t off_g, off_b; };
+
+struct Mha { Linear in_proj, out_proj; };        // in_proj rows: [Wq; Wk; Wv]
+
+struct EncLayer { Mha attn; Linear lin1, lin2; Norm n1, n2; };
+struct DecLayer { Mha self_attn, cross_attn; Linear lin1, lin2; Norm n1, n2, n3; };
+
+struct Arena {
+    char* base; size_t off, cap; bool overflow;
+    Arena(void* b, size_t c) : base((char*)b), off(0), cap(c), overflow(false) {}
+    void* alloc(size_t bytes) {
+        size_t o = (off + 255) & ~(size_t)255;
+        off = o + bytes;
+        if (base == nullptr || off > cap) { overflow = true; return base == nullptr ? nullptr : base; }
+        return base + o;
+    }
+};
+
+struct ForwardOut {             // all fp32, caller-allocated
+    float* hs;                  // [D, B, Qall, 256] decoder states after decoder.norm
+    float* logits;              // [D, B, Q, C+1]
+    float* boxes;               // [D, B, Q, 2]   sigmoid(center, width)
+    float* at;                  // [B, C] or null (dec_at only)
+    float* memory;              // optional [B, S, 256] encoder output (fp32 copy) or null
+    float* pred_feature;        // SP-SEDT: [D, B, Q, 2048] or null
+    float* gt_feature;          // SP-SEDT: [B*P, 2048] or null
+    float* feat;                // optional backbone feature map copy [B, H, W, 2048] fp32 (tests) or null
+};
+
+class Model {
+public:
+    explicit Model(const Config& c);
+    const Config& cfg() const { return cfg_; }
+    const std::vector<WeightSlot>& slots() const { return slots_; }
+    size_t packed_bytes() const { return packed_bytes_; }
+    int act_dt() const { return cfg_.precision ? DT_BF16 : DT_F32; }
+
+    int pack(const void* const* weights, void* packed, size_t bytes, cudaStream_t stream);
+    // dry = true only sizes the workspace (no launches)
+    int forward(const float* x, const uint8_t* mask, int B, int T, int F, const float* patches, int P, int PT,
+                Arena& ws, const ForwardOut& out, cudaStream_t stream, bool dry);
+    static void feature_shape(int T, int F, bool dilation, int* H, int* W);
+
+private:
+    int add_slot(const std::string& name, int64_t numel);
+    size_t reserve(size_t bytes);
+    ConvLayer make_conv(const std::string& conv, const std::string& bn, int cin, int cout, int k, int stride, int dil,
+                        int pad, int relu);
+    Linear make_linear(const std::string& name, int in, int out, bool f32_only);
+    Linear make_linear_slots(int w_slot, int b_slot, int in, int out, bool f32_only);
+    Norm make_norm(const std::string& name);
+    Mha make_mha(const std::string& name);
+
+    int gemm(const ConvGemm& g, cudaStream_t s, bool dry);
+    int conv(const ConvLayer& L, const void* in, int N, int H, int W, const void* residual, void* out, int* Ho, int* Wo,
+             cudaStream_t s, bool dry);
+    // rows x L.in -> rows x L.out.  row0/nrows select a slice of W's rows (packed in_proj).
+    int linear(const Linear& L, int row0, int nrows, const void* in, int in_dt, int lda, int64_t rows, const void* residual,
+               void* out, int out_dt, int ldc, int relu, cudaStream_t s, bool dry);
+    int backbone(const float* x, int N, int T, int F, Arena& ws, void** feat, int* H, int* W, cudaStream_t s, bool dry);
+    int mha(const Mha& A, const void* q_in, const void* k_in, const void* v_in, int64_t B, int Lq, int Lk,
+            const uint8_t* kpm, const float* amask, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry);
+
+    Config cfg_;
+    std::vector<WeightSlot> slots_;
+    size_t packed_bytes_ = 0;
+    char* packed_ = nullptr;
+
+    // layer table
+    int s_conv0_w, s_conv0_b, s_conv1_w, s_bn1;
+    size_t off_weff, off_sat, off_stem_scale, off_stem_bias;
+    std::vector<Block> blocks_;
+    Linear input_proj_;
+    std::vector<EncLayer> enc_;
+    Norm enc_norm_;
+    std::vector<DecLayer> dec_;
+    Norm dec_norm_;
+    Linear class_embed_, bbox0_, bbox1_, bbox2_, weak_, patch2query_, falign0_, falign1_;
+    int s_query_embed; size_t off_query_embed;
+    int qall_;
+};
+
+}  // namespace sedt

@@ -1,0 +1,393 @@
+// Transformer-side kernels that are bandwidth / latency bound (no contraction
+// large enough for a tensor-core tile): LayerNorm(+pos), the sine position
+// table, padding-mask resize, the multi-head attention core on <=128-token
+// sequences, head finalisation, and the two SP-SEDT glue ops.
+// Numerical recipe: SURVEY.md Appendix A.3, A.5-A.9 (sedt/transformer.py,
+// sedt/position_encoding.py:28-47, torch functional.py:6630-6659).
+#include "kernels.h"
+#include <math_constants.h>
+
+namespace sedt {
+namespace {
+
+constexpr int D = 256;   // hidden_dim of every documented recipe (train_sedt.py:86)
+
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// ---- LayerNorm: one warp per row, 8 contiguous elements per lane -------------
+template <typename T, bool kNorm>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const float* __restrict__ pos, int64_t pos_rows, T* __restrict__ y, T* __restrict__ ypos,
+                 float* __restrict__ y32, int64_t rows)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float v[8];
+    load8(x + row * D + lane * 8, v);
+    if (kNorm) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[i];
+        const float mean = warp_sum(s) * (1.f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
+        float g[8], bt[8];
+        load8(gamma + lane * 8, g);
+        load8(beta + lane * 8, bt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * g[i] + bt[i];
+    }
+    if (y != nullptr) store8<T>(y + row * D + lane * 8, v);
+    if (y32 != nullptr) store8<float>(y32 + row * D + lane * 8, v);
+    if (ypos != nullptr) {
+        float p[8];
+        load8(pos + (row % pos_rows) * D + lane * 8, p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] += v[i];
+        store8<T>(ypos + row * D + lane * 8, p);
+    }
+}
+
+// ---- attention core ------------------------------------------------------------
+// CTA = (query block, head group, clip); thread = (head in group, query row).
+// K/V head slices of one 128-key tile are staged in shared memory as fp32 and
+// read as warp-wide broadcasts; softmax is the online (running max / sum) form
+// updated every 8 keys, all in fp32.
+constexpr int KT = 128;   // keys per shared-memory tile
+constexpr int HD = 32;    // head_dim
+
+template <typename T, int HG, int QB>
+__global__ void __launch_bounds__(HG * QB)
+attention_kernel(const T* __restrict__ Q, int ldq, const T* __restrict__ K, int ldk, const T* __restrict__ V, int ldv,
+                 T* __restrict__ O, int ldo, const uint8_t* __restrict__ kpm, const float* __restrict__ amask,
+                 int Lq, int Lk, float scale)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* Ks = smem;                       // [HG][KT][HD]
+    float* Vs = smem + HG * KT * HD;
+    const int tid = threadIdx.x;
+    const int hl = tid / QB, ql = tid % QB;
+    const int b = blockIdx.z, h0 = blockIdx.y * HG;
+    const int qrow = blockIdx.x * QB + ql;
+    const bool active = qrow < Lq;
+
+    float q[HD], o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) { q[d] = 0.f; o[d] = 0.f; }
+    if (active) {
+        const T* qp = Q + ((size_t)b * Lq + qrow) * ldq + (h0 + hl) * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) q[d] = to_f32<T>(qp[d]) * scale;     // q * sqrt(1/hd) first (functional.py:6636)
+    }
+    float m = -CUDART_INF_F, l = 0.f;
+
+    for (int k0 = 0; k0 < Lk; k0 += KT) {
+        const int kt = min(KT, Lk - k0);
+        __syncthreads();
+        for (int i = tid; i < HG * kt * (HD / 4); i += HG * QB) {
+            const int d4 = i % (HD / 4);
+            const int j = (i / (HD / 4)) % kt;
+            const int hh = i / ((HD / 4) * kt);
+            const T* kp = K + ((size_t)b * Lk + k0 + j) * ldk + (h0 + hh) * HD + d4 * 4;
+            const T* vp = V + ((size_t)b * Lk + k0 + j) * ldv + (h0 + hh) * HD + d4 * 4;
+            float4 kv = make_float4(to_f32<T>(kp[0]), to_f32<T>(kp[1]), to_f32<T>(kp[2]), to_f32<T>(kp[3]));
+            float4 vv = make_float4(to_f32<T>(vp[0]), to_f32<T>(vp[1]), to_f32<T>(vp[2]), to_f32<T>(vp[3]));
+            *reinterpret_cast<float4*>(Ks + ((size_t)hh * KT + j) * HD + d4 * 4) = kv;
+            *reinterpret_cast<float4*>(Vs + ((size_t)hh * KT + j) * HD + d4 * 4) = vv;
+        }
+        __syncthreads();
+        if (!active) continue;
+        const float* kh = Ks + (size_t)hl * KT * HD;
+        const float* vh = Vs + (size_t)hl * KT * HD;
+        for (int j0 = 0; j0 < kt; j0 += 8) {
+            float s[8];
+            float mb = -CUDART_INF_F;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int j = j0 + t;
+                float acc = -CUDART_INF_F;
+                if (j < kt) {
+                    acc = 0.f;
+                    const float4* kr = reinterpret_cast<const float4*>(kh + j * HD);
+#pragma unroll
+                    for (int d4 = 0; d4 < HD / 4; ++d4) {
+                        const float4 kk = kr[d4];
+                        acc = fmaf(q[4 * d4 + 0], kk.x, acc); acc = fmaf(q[4 * d4 + 1], kk.y, acc);
+                        acc = fmaf(q[4 * d4 + 2], kk.z, acc); acc = fmaf(q[4 * d4 + 3], kk.w, acc);
+                    }
+                    if (amask != nullptr) acc += amask[(size_t)qrow * Lk + k0 + j];
+                    if (kpm != nullptr && kpm[(size_t)b * Lk + k0 + j]) acc = -CUDART_INF_F;
+                }
+                s[t] = acc;
+                mb = fmaxf(mb, acc);
+            }
+            const float mn = fmaxf(m, mb);
+            if (mn == -CUDART_INF_F) continue;            // everything masked so far
+            const float corr = expf(m - mn);              // m = -inf -> 0
+            l *= corr;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) o[d] *= corr;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int j = j0 + t;
+                if (j >= kt) break;
+                const float p = expf(s[t] - mn);
+                l += p;
+                const float4* vr = reinterpret_cast<const float4*>(vh + j * HD);
+#pragma unroll
+                for (int d4 = 0; d4 < HD / 4; ++d4) {
+                    const float4 vv = vr[d4];
+                    o[4 * d4 + 0] = fmaf(p, vv.x, o[4 * d4 + 0]); o[4 * d4 + 1] = fmaf(p, vv.y, o[4 * d4 + 1]);
+                    o[4 * d4 + 2] = fmaf(p, vv.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(p, vv.w, o[4 * d4 + 3]);
+                }
+            }
+            m = mn;
+        }
+    }
+    if (active) {
+        const float inv = 1.f / l;
+        T* op = O + ((size_t)b * Lq + qrow) * ldo + (h0 + hl) * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) op[d] = from_f32<T>(o[d] * inv);
+    }
+}
+
+// ---- padding mask nearest-resize (sedt/backbone.py:81) ----------------------------
+__global__ void mask_downsample_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ out, int B, int T, int F,
+                                       int H, int W)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * H * W) return;
+    const int w = i % W, h = (i / W) % H, b = i / (W * H);
+    // torch nearest: src = min(floor(dst * (float)in / out), in - 1), in fp32
+    const float sh = (float)T / (float)H, sw = (float)F / (float)W;
+    const int th = min((int)floorf((float)h * sh), T - 1);
+    const int tw = min((int)floorf((float)w * sw), F - 1);
+    out[i] = mask[((size_t)b * T + th) * F + tw];
+}
+
+// ---- sine position table (sedt/position_encoding.py:28-47) -------------------------
+__global__ void pos_table_kernel(const uint8_t* __restrict__ mask_ds, float* __restrict__ pos, int H, int W)
+{
+    // grid (H*W, nb); block 256 = feature index
+    const int s = blockIdx.x, b = blockIdx.y, i = threadIdx.x;
+    const int h = s / W, w = s % W;
+    float y = (float)(h + 1), last = (float)H;
+    if (mask_ds != nullptr) {
+        int cy = 0, cl = 0;
+        for (int hh = 0; hh < H; ++hh) {
+            const int nm = mask_ds[((size_t)b * H + hh) * W + w] ? 0 : 1;
+            cl += nm;
+            if (hh <= h) cy += nm;
+        }
+        y = (float)cy; last = (float)cl;
+    }
+    const float ye = __fmul_rn(__fdiv_rn(y, __fadd_rn(last, 1e-6f)), 6.283185307179586f);
+    const float expo = __fdiv_rn(2.f * (float)(i / 2), 256.f);
+    const float dim_t = powf(10000.f, expo);
+    const float v = __fdiv_rn(ye, dim_t);
+    pos[((size_t)b * H * W + s) * D + i] = (i & 1) ? cosf(v) : sinf(v);
+}
+
+// ---- heads: slice decoder slots, sigmoid (sedt/sedt.py:89-95) ----------------------
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void heads_finalize_kernel(const float* __restrict__ cls_raw, const float* __restrict__ box_raw,
+                                      const float* __restrict__ weak_raw, float* __restrict__ logits,
+                                      float* __restrict__ boxes, float* __restrict__ at, int D_, int B, int Qall, int start,
+                                      int C1, int C)
+{
+    const int Q = Qall - start;
+    const int64_t nl = (int64_t)D_ * B * Q * C1, nb = (int64_t)D_ * B * Q * 2, na = (at != nullptr) ? (int64_t)B * C : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nl + nb + na; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < nl) {
+            const int c = (int)(i % C1);
+            const int64_t r = i / C1;                 // (d*B + b)*Q + q
+            const int q = (int)(r % Q);
+            const int64_t db = r / Q;
+            logits[i] = cls_raw[(db * Qall + q + start) * C1 + c];
+        } else if (i < nl + nb) {
+            const int64_t k = i - nl;
+            const int c = (int)(k % 2);
+            const int64_t r = k / 2;
+            const int q = (int)(r % Q);
+            const int64_t db = r / Q;
+            boxes[k] = sigmoidf(box_raw[(db * Qall + q + start) * 2 + c]);
+        } else {
+            const int64_t k = i - nl - nb;
+            at[k] = sigmoidf(weak_raw[k]);
+        }
+    }
+}
+
+template <typename T>
+__global__ void avgpool_kernel(const T* __restrict__ x, float* __restrict__ out, int HW, int C)
+{
+    // grid (C/256, N); thread = channel
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += to_f32<T>(x[((size_t)n * HW + p) * C + c]);
+    out[(size_t)n * C + c] = s / (float)HW;
+}
+
+__global__ void patch_query_kernel(const float* __restrict__ pq, const float* __restrict__ qe, float* __restrict__ out,
+                                   int B, int P, int qpp, int start)
+{
+    const int Q = P * qpp;
+    const int64_t total = (int64_t)B * Q * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const int q = (int)((i / D) % Q);
+        const int b = (int)(i / ((int64_t)D * Q));
+        out[i] = pq[((size_t)b * P + q / qpp) * D + d] + qe[(size_t)(start + q) * D + d];
+    }
+}
+
+__global__ void blockdiag_mask_kernel(float* __restrict__ m, int Q, int qpp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q * Q) return;
+    m[i] = ((i / Q) / qpp == (i % Q) / qpp) ? 0.f : -CUDART_INF_F;      // sedt/spsedt.py:27-32
+}
+
+}  // namespace
+
+int launch_blockdiag_mask(float* m, int Q, int qpp, cudaStream_t stream)
+{
+    blockdiag_mask_kernel<<<(unsigned)ceil_div((int64_t)Q * Q, 256), 256, 0, stream>>>(m, Q, qpp);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int64_t pos_rows,
+                     void* y, void* ypos, float* y32, int dt, int64_t rows, cudaStream_t stream)
+{
+    if (rows == 0) return SEDT_OK;
+    dim3 grid((unsigned)ceil_div(rows, 8)), block(256);
+    if (dt == DT_F32) layernorm_kernel<float, true><<<grid, block, 0, stream>>>(x, gamma, beta, pos, pos_rows, (float*)y, (float*)ypos, y32, rows);
+    else layernorm_kernel<__nv_bfloat16, true><<<grid, block, 0, stream>>>(x, gamma, beta, pos, pos_rows, (__nv_bfloat16*)y, (__nv_bfloat16*)ypos, y32, rows);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_cast_addpos(const float* x, const float* pos, int64_t pos_rows, void* y, void* ypos, int dt, int64_t rows,
+                       cudaStream_t stream)
+{
+    if (rows == 0) return SEDT_OK;
+    dim3 grid((unsigned)ceil_div(rows, 8)), block(256);
+    if (dt == DT_F32) layernorm_kernel<float, false><<<grid, block, 0, stream>>>(x, nullptr, nullptr, pos, pos_rows, (float*)y, (float*)ypos, nullptr, rows);
+    else layernorm_kernel<__nv_bfloat16, false><<<grid, block, 0, stream>>>(x, nullptr, nullptr, pos, pos_rows, (__nv_bfloat16*)y, (__nv_bfloat16*)ypos, nullptr, rows);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+template <typename T, int HG, int QB>
+static int attention_launch(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo,
+                            const uint8_t* kpm, const float* amask, int B, int nheads, int Lq, int Lk, float scale,
+                            cudaStream_t stream)
+{
+    const size_t smem = (size_t)2 * HG * KT * HD * sizeof(float);
+    SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<T, HG, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)ceil_div(Lq, QB), (unsigned)(nheads / HG), (unsigned)B), block(HG * QB);
+    attention_kernel<T, HG, QB><<<grid, block, smem, stream>>>((const T*)Q, ldq, (const T*)K, ldk, (const T*)V, ldv,
+                                                               (T*)O, ldo, kpm, amask, Lq, Lk, scale);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_attention(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int dt,
+                     const uint8_t* kpm, const float* amask, int B, int nheads, int Lq, int Lk, float scale,
+                     cudaStream_t stream)
+{
+    if (B == 0 || Lq == 0) return SEDT_OK;
+    SEDT_REQUIRE(Lk >= 1, "attention: Lk=%d", Lk);
+    SEDT_REQUIRE(nheads % 4 == 0, "attention: nheads=%d must be a multiple of 4", nheads);
+    const bool small_q = Lq <= 32;      // decoder: 11 / 21 queries
+#define SEDT_ATT(T)                                                                                                   \
+    (small_q ? attention_launch<T, 4, 32>(Q, ldq, K, ldk, V, ldv, O, ldo, kpm, amask, B, nheads, Lq, Lk, scale, stream) \
+             : attention_launch<T, 1, 128>(Q, ldq, K, ldk, V, ldv, O, ldo, kpm, amask, B, nheads, Lq, Lk, scale, stream))
+    return dt == DT_F32 ? SEDT_ATT(float) : SEDT_ATT(__nv_bfloat16);
+#undef SEDT_ATT
+}
+
+int launch_mask_downsample(const uint8_t* mask, uint8_t* out, int B, int T, int F, int H, int W, cudaStream_t stream)
+{
+    const int n = B * H * W;
+    if (n == 0) return SEDT_OK;
+    mask_downsample_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(mask, out, B, T, F, H, W);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_pos_table(const uint8_t* mask_ds, float* pos, int nb, int H, int W, cudaStream_t stream)
+{
+    SEDT_REQUIRE(mask_ds != nullptr || nb == 1, "pos_table: an unpadded table is batch-invariant (nb must be 1)");
+    dim3 grid((unsigned)(H * W), (unsigned)nb), block(D);
+    pos_table_kernel<<<grid, block, 0, stream>>>(mask_ds, pos, H, W);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_heads_finalize(const float* cls_raw, const float* box_raw, const float* weak_raw, float* logits, float* boxes,
+                          float* at, int D_, int B, int Qall, int start, int C1, int C, cudaStream_t stream)
+{
+    const int64_t n = (int64_t)D_ * B * (Qall - start) * (C1 + 2) + (at ? (int64_t)B * C : 0);
+    if (n == 0) return SEDT_OK;
+    int64_t g = ceil_div(n, 256); if (g > 148 * 8) g = 148 * 8;
+    heads_finalize_kernel<<<(unsigned)g, 256, 0, stream>>>(cls_raw, box_raw, weak_raw, logits, boxes, at, D_, B, Qall, start, C1, C);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_avgpool(const void* x, int dt, float* out, int N, int HW, int C, cudaStream_t stream)
+{
+    if (N == 0) return SEDT_OK;
+    dim3 grid((unsigned)ceil_div(C, 256), (unsigned)N), block(256);
+    if (dt == DT_F32) avgpool_kernel<float><<<grid, block, 0, stream>>>((const float*)x, out, HW, C);
+    else avgpool_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, out, HW, C);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_patch_query(const float* pq, const float* query_embed, float* out, int B, int P, int qpp, int start,
+                       cudaStream_t stream)
+{
+    const int64_t n = (int64_t)B * P * qpp * D;
+    if (n == 0) return SEDT_OK;
+    int64_t g = ceil_div(n, 256); if (g > 148 * 8) g = 148 * 8;
+    patch_query_kernel<<<(unsigned)g, 256, 0, stream>>>(pq, query_embed, out, B, P, qpp, start);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+}  // namespace sedt

@@ -1,0 +1,127 @@
+"""Python owner of one native model handle: collects the module's parameters
+into the library's weight table, keeps the packed-weight snapshot fresh,
+caches the workspace and drives sedt_forward on the current CUDA stream.
+PyTorch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+
+class ForwardRuntime:
+    def __init__(self, cfg: Dict[str, int]):
+        self.lib = _lib.load()
+        self.cfg = _lib.SedtConfig(**cfg)
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.sedt_model_create(C.byref(self.cfg), C.byref(self.handle)))
+        n = self.lib.sedt_model_num_weights(self.handle)
+        self.names = [self.lib.sedt_model_weight_name(self.handle, i).decode() for i in range(n)]
+        self.numels = [self.lib.sedt_model_weight_numel(self.handle, i) for i in range(n)]
+        self.packed_bytes = self.lib.sedt_model_packed_bytes(self.handle)
+        self.packed: Optional[torch.Tensor] = None
+        self._stamp = None
+        self._ws: Optional[torch.Tensor] = None
+        self._keep = None
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.sedt_model_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- weights -------------------------------------------------------------
+    def ensure_packed(self, tensors: Dict[str, torch.Tensor]) -> None:
+        """tensors: reference state_dict name -> live parameter/buffer (CUDA, fp32)."""
+        stamp = tuple((tensors[n].data_ptr(), tensors[n]._version) for n in self.names)
+        if stamp == self._stamp and self.packed is not None:
+            return
+        dev = None
+        ptrs = (C.c_void_p * len(self.names))()
+        keep = []
+        for i, n in enumerate(self.names):
+            t = tensors[n]
+            if not t.is_cuda:
+                raise RuntimeError(f"parameter {n} lives on {t.device}: move the model to a CUDA device "
+                                   "(there is no CPU path)")
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.detach().to(torch.float32).contiguous()
+                keep.append(t)
+            if t.numel() != self.numels[i]:
+                raise RuntimeError(f"parameter {n} has {t.numel()} elements, expected {self.numels[i]}")
+            dev = t.device
+            ptrs[i] = t.data_ptr()
+        if self.packed is None or self.packed.device != dev:
+            self.packed = torch.empty(self.packed_bytes + 256, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.sedt_model_pack(self.handle, ptrs, self._aligned(self.packed), self.packed_bytes,
+                                                _lib.current_stream()))
+        self._keep = keep
+        self._stamp = stamp
+
+    @staticmethod
+    def _aligned(buf: torch.Tensor) -> int:
+        return (buf.data_ptr() + 255) & ~255
+
+    # ---- forward -------------------------------------------------------------
+    def feature_shape(self, T: int, F: int):
+        h, w = C.c_int(), C.c_int()
+        _lib.check(self.lib.sedt_feature_shape(T, F, self.cfg.dilation, C.byref(h), C.byref(w)))
+        return h.value, w.value
+
+    def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor], patches: Optional[torch.Tensor] = None,
+                want_memory: bool = False, want_feat: bool = False) -> Dict[str, torch.Tensor]:
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 1
+        x = x.contiguous()
+        B, _, T, F = x.shape
+        dev = x.device
+        cfg = self.cfg
+        P = PT = 0
+        if cfg.self_sup:
+            assert patches is not None and patches.dim() == 5
+            patches = patches.to(dev, torch.float32).contiguous()
+            P, PT = patches.shape[1], patches.shape[3]
+        D = cfg.dec_layers
+        if cfg.self_sup:
+            qall = q = P * (cfg.num_queries // cfg.num_patches)
+        else:
+            q = cfg.num_queries
+            qall = q + (1 if cfg.dec_at else 0)
+        ncls = 1 if cfg.self_sup else cfg.num_classes
+        f32 = dict(dtype=torch.float32, device=dev)
+        res = {
+            "hs": torch.empty(D, B, qall, cfg.hidden_dim, **f32),
+            "logits": torch.empty(D, B, q, ncls + 1, **f32),
+            "boxes": torch.empty(D, B, q, 2, **f32),
+        }
+        if cfg.dec_at:
+            res["at"] = torch.empty(B, ncls, **f32)
+        H, W = self.feature_shape(T, F)
+        if want_memory:
+            res["memory"] = torch.empty(B, H * W, cfg.hidden_dim, **f32)
+        if want_feat:
+            res["feat"] = torch.empty(B, H, W, 2048, **f32)
+        if cfg.self_sup:
+            res["gt_feature"] = torch.empty(B * P, 2048, **f32)
+            if cfg.feature_recon:
+                res["pred_feature"] = torch.empty(D, B, q, 2048, **f32)
+        need = self.lib.sedt_workspace_bytes(self.handle, B, T, F, P, PT)
+        if need < 0:
+            _lib.check(int(need))
+        if self._ws is None or self._ws.numel() < need + 256 or self._ws.device != dev:
+            self._ws = None
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        m8 = None
+        if mask is not None:
+            m8 = mask.to(dev).contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(dev, torch.uint8).contiguous()
+        outs = _lib.SedtOutputs(**{k: _lib.ptr(res.get(k)) or None for k, _ in _lib.SedtOutputs._fields_})
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.sedt_forward(self.handle, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
+                                             _lib.ptr(patches) or None, P, PT, self._aligned(self._ws),
+                                             self._ws.numel() - 256, C.byref(outs), _lib.current_stream()))
+        return res

@@ -1,0 +1,162 @@
+"""SetCriterion and PostProcess with the reference's call contracts
+(sedt/sedt.py:134-352 and :355-396).  Matching runs in the CUDA matcher; the
+scalar losses themselves are small batched torch expressions over the matched
+pairs -- they are the consumer right after the hot
+path, not part of it, and get fused kernels together with the training
+backward."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+def _se(boxes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(center, width) -> (onset, offset); utilities/box_ops.py:9-19."""
+    c, l = boxes.unbind(-1)
+    return c - l / 2, c + l / 2
+
+
+def paired_l1_giou(src: torch.Tensor, tgt: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-pair L1 on (s,0,e,1) and 1-D GIoU of matched intervals: the diagonal of the
+    reference's N x N generalized_box_iou (sedt/sedt.py:249-254) without forming the matrix."""
+    s1, e1 = _se(src)
+    s2, e2 = _se(tgt)
+    l1 = (s1 - s2).abs() + (e1 - e2).abs()
+    inter = (torch.min(e1, e2) - torch.max(s1, s2)).clamp(min=0)
+    union = (e1 - s1) + (e2 - s2) - inter
+    enc = (torch.max(e1, e2) - torch.min(s1, s2)).clamp(min=0)
+    giou = inter / union - (enc - union) / enc
+    return l1, giou
+
+
+class SetCriterion(nn.Module):
+    def __init__(self, num_classes, matcher, weight_dict, eos_coef, losses):
+        super().__init__()
+        self.num_classes, self.matcher, self.weight_dict = num_classes, matcher, weight_dict
+        self.eos_coef, self.losses = eos_coef, losses
+        empty_weight = torch.ones(num_classes + 1)
+        empty_weight[-1] = eos_coef
+        self.register_buffer("empty_weight", empty_weight)
+
+    # -- helpers ------------------------------------------------------------
+    @staticmethod
+    def _pairs(indices, device):
+        batch = torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(indices)]).to(device)
+        src = torch.cat([src for src, _ in indices]).to(device)
+        return batch, src
+
+    def _layer_losses(self, out, targets, indices, coef, num_boxes, strong_mask, log: bool):
+        res = {}
+        dev = out["pred_logits"].device
+        tg = targets[strong_mask]
+        coef_cat = torch.cat(coef).to(dev)
+        bi, si = self._pairs(indices, dev)
+        if "labels" in self.losses:
+            logits = out["pred_logits"][strong_mask]
+            matched = torch.cat([t["labels"].to(dev)[j.to(dev)] for t, (_, j) in zip(tg, indices)])
+            cls = torch.full(logits.shape[:2], self.num_classes, dtype=torch.int64, device=dev)
+            wq = torch.ones(logits.shape[:2], dtype=torch.float32, device=dev)
+            cls[bi, si] = matched
+            wq[bi, si] = coef_cat
+            ce = F.cross_entropy(logits.transpose(1, 2), cls, self.empty_weight, reduction="none")
+            res["loss_ce"] = (ce * wq).sum() / num_boxes
+            if log:
+                if matched.numel() == 0:
+                    res["class_error"] = torch.zeros([], device=dev)
+                else:
+                    acc = (logits[bi, si].argmax(-1) == matched).float().mean() * 100.0
+                    res["class_error"] = 100 - acc
+        if "cardinality" in self.losses:
+            with torch.no_grad():
+                pl = out["pred_logits"]
+                n_tgt = torch.as_tensor([len(v["labels"]) for v in targets], device=dev, dtype=torch.float32)
+                n_pred = (pl.argmax(-1) != pl.shape[-1] - 1).sum(1).float()
+                res["cardinality_error"] = F.l1_loss(n_pred, n_tgt)
+        if "boxes" in self.losses:
+            src = out["pred_boxes"][bi, si]
+            tgt = torch.cat([t["boxes"].to(dev)[j.to(dev)] for t, (_, j) in zip(targets, indices)], dim=0)
+            l1, giou = paired_l1_giou(src, tgt.reshape(-1, 2))
+            res["loss_bbox"] = (l1 * coef_cat).sum() / num_boxes
+            res["loss_giou"] = ((1 - giou) * coef_cat).sum() / num_boxes
+        if "feature" in self.losses:
+            gt = out["gt_feature"]
+            nb = len(indices)
+            gt = gt.view(nb, gt.shape[0] // nb, -1)
+            src = F.normalize(out["pred_feature"][bi, si], dim=1)
+            tgt = F.normalize(torch.cat([t[j.to(dev)] for t, (_, j) in zip(gt, indices)], dim=0), dim=1)
+            res["loss_feature"] = F.mse_loss(src, tgt, reduction="none").sum() / num_boxes
+        return res
+
+    def _weak_loss(self, outputs, targets, strong_mask, weak_mask):
+        if "at" not in outputs:
+            return {}
+        labeled = slice(weak_mask.stop) if weak_mask is not None else slice(strong_mask.stop)
+        pred = outputs["at"][labeled]
+        dev = pred.device
+        gt = torch.zeros(pred.shape, device=dev)
+        rows, cols, vals = [], [], []
+        for i in range(pred.shape[0]):
+            lab = targets[i]["labels"]
+            if len(lab) == 0:
+                continue
+            rows.append(torch.full((len(lab),), i, dtype=torch.int64))
+            cols.append(torch.as_tensor(lab, dtype=torch.int64).cpu())
+            vals.append(targets[i]["ratio"].float().cpu() if "ratio" in targets[i] else torch.ones(len(lab)))
+        if rows:
+            gt.index_put_((torch.cat(rows).to(dev), torch.cat(cols).to(dev)), torch.cat(vals).to(dev), accumulate=True)
+        return {"loss_weak": F.binary_cross_entropy(pred, gt.clamp(0, 1))}
+
+    # -- reference entry point ---------------------------------------------------
+    def forward(self, outputs, targets, weak_mask=None, strong_mask=None, fine_tune=False, normalize=False, fl=False):
+        if fl:
+            raise NotImplementedError("focal-loss branch (semi-supervised only) is out of scope (SURVEY.md section 2, #9)")
+        losses = {}
+        indices = None
+        if strong_mask is not None:
+            top = {k: v[strong_mask] for k, v in outputs.items() if k != "aux_outputs"}
+            indices, coef = self.matcher(top, targets[strong_mask], fine_tune=fine_tune, normalize=normalize, fl=fl)
+            num_boxes = torch.cat(coef).sum()
+            num_boxes = torch.as_tensor([num_boxes], dtype=torch.float, device=outputs["pred_boxes"].device)
+            losses.update(self._layer_losses(outputs, targets, indices, coef, num_boxes, strong_mask, log=True))
+        if "weak" in self.losses:
+            losses.update(self._weak_loss(outputs, targets, strong_mask, weak_mask))
+        if "aux_outputs" in outputs and strong_mask is not None:
+            for i, aux in enumerate(outputs["aux_outputs"]):
+                sub = {k: v[strong_mask] for k, v in aux.items()}
+                sub_idx, sub_coef = self.matcher(sub, targets[strong_mask], fl=fl)
+                part = self._layer_losses(aux, targets, sub_idx, sub_coef, num_boxes, strong_mask, log=False)
+                losses.update({f"{k}_{i}": v for k, v in part.items()})
+        return losses, indices
+
+
+class PostProcess(nn.Module):
+    """outputs -> per-clip {'scores','labels','boxes'} in seconds (sedt/sedt.py:359-396)."""
+
+    @torch.no_grad()
+    def forward(self, outputs, target_sizes, audio_tags=None, at_m=2, is_semi=False, threshold=0.5):
+        logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
+        prob = F.softmax(logits, -1)
+        nq = prob.shape[1]
+        if audio_tags is not None:
+            ev = prob[..., :-1]                                   # view: writes go through to prob
+            best = ev.argmax(1, keepdim=True)                     # per (clip, class): the strongest query
+            tags = audio_tags.to(prob.device)
+            if at_m in (2, 3):
+                top = ev.gather(1, best)
+                lift = top < threshold
+                if at_m == 3:
+                    lift = lift & tags.bool().unsqueeze(1)
+                ev.scatter_(1, best, torch.where(lift, torch.full_like(top, threshold), top))
+            if at_m in (1, 2):
+                ev.mul_(tags.unsqueeze(1).expand(-1, nq, -1).to(ev.dtype))
+        scores, labels = prob[..., :-1].max(-1)
+        if not is_semi:
+            c, l = boxes.unbind(-1)
+            se = torch.stack([c - l / 2, c + l / 2], dim=-1)
+            se = se * target_sizes.to(se.device).unsqueeze(-1)[:, None, :]
+        else:
+            se = boxes
+        return [{"scores": s, "labels": lb, "boxes": b} for s, lb, b in zip(scores, labels, se)]

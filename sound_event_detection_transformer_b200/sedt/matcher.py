@@ -1,0 +1,120 @@
+"""HungarianMatcher with the reference's call contract (sedt/matcher.py:41-133)
+running on the GPU: one sedt_matcher launch builds every clip's cost block and
+solves it (one warp per clip), replacing the [B*Q, sum K] cross-batch matrix,
+the .cpu() copy and the serial scipy loop."""
+from __future__ import annotations
+
+import ctypes as C
+from collections import Counter
+from typing import List, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from .. import _lib
+
+
+class HungarianMatcher(nn.Module):
+    def __init__(self, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1, epsilon=0, alpha=100):
+        super().__init__()
+        self.cost_class, self.cost_bbox, self.cost_giou = cost_class, cost_bbox, cost_giou
+        self.epsilon, self.alpha = epsilon, alpha
+        assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0, "all costs cant be 0"
+        self.device_indices = False      # True: keep index tensors on the GPU (skips the D2H copy + sync)
+
+    @torch.no_grad()
+    def forward(self, outputs, targets: Sequence[dict], fine_tune=False, normalize=False, fl=False):
+        """Returns (indices, Coef): indices[i] = (int64 rows ascending, int64 cols) with
+        len = min(num_queries, K_i); Coef[i] fp32 (ones | 1/multiplicity | targets[i]['ratio'])."""
+        if fl or fine_tune:
+            raise NotImplementedError("the focal-loss class cost (fl) and the fine_tune relaxation "
+                                      "(sedt/matcher.py:77-82,99-121) are not on the B200 hot path yet (SURVEY 8f.3)")
+        rows, cols, counts = self.match(outputs["pred_logits"], outputs["pred_boxes"], targets)
+        if not self.device_indices:
+            rows, cols = rows.cpu(), cols.cpu()
+        idx: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        coef: List[torch.Tensor] = []
+        for i, n in enumerate(counts):
+            r, c = rows[i, :n], cols[i, :n]
+            idx.append((r, c))
+            if normalize:
+                cur = c.tolist()
+                num = Counter(cur)
+                coef.append(torch.tensor([1 / num[j] for j in cur], dtype=torch.float32))
+            elif "ratio" in targets[i]:
+                coef.append(targets[i]["ratio"].cpu())
+            else:
+                coef.append(torch.ones(n, dtype=torch.float32))
+        return idx, coef
+
+    @torch.no_grad()
+    def match(self, pred_logits: torch.Tensor, pred_boxes: torch.Tensor, targets: Sequence[dict],
+              return_cost: bool = False):
+        """Raw batched call: returns rows [B,Q] int64, cols [B,Q] int64 (padded with -1) on the device and
+        the per-clip pair counts as a Python list (known on the host: min(Q, K_i))."""
+        lib = _lib.load()
+        if not pred_logits.is_cuda:
+            raise RuntimeError("HungarianMatcher needs CUDA tensors (there is no CPU path)")
+        dev = pred_logits.device
+        B, Q, C1 = pred_logits.shape
+        assert len(targets) == B
+        sizes = [int(len(v["boxes"])) for v in targets]
+        kmax = max(sizes) if sizes else 0
+        logits = pred_logits.detach().to(torch.float32).contiguous()
+        boxes = pred_boxes.detach().to(torch.float32).contiguous()
+        if sum(sizes) > 0:
+            tgt_ids = torch.cat([v["labels"][:len(v["boxes"])].reshape(-1) for v in targets]).to(dev, torch.int64).contiguous()
+            tgt_box = torch.cat([v["boxes"].reshape(-1, 2) for v in targets]).to(dev, torch.float32).contiguous()
+        else:
+            tgt_ids = torch.zeros(1, dtype=torch.int64, device=dev)
+            tgt_box = torch.zeros(1, 2, dtype=torch.float32, device=dev)
+        off = [0]
+        for k in sizes:
+            off.append(off[-1] + k)
+        offsets = torch.tensor(off, dtype=torch.int32).to(dev, non_blocking=True)
+        rows = torch.empty(B, Q, dtype=torch.int64, device=dev)
+        cols = torch.empty(B, Q, dtype=torch.int64, device=dev)
+        counts = torch.empty(B, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        cost = torch.full((B, Q, max(kmax, 1)), float("nan"), dtype=torch.float32, device=dev) if return_cost else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.sedt_matcher(logits.data_ptr(), boxes.data_ptr(), tgt_ids.data_ptr(), tgt_box.data_ptr(),
+                                        offsets.data_ptr(), B, Q, C1, kmax, float(self.cost_class), float(self.cost_bbox),
+                                        float(self.cost_giou), _lib.ptr(cost) or None, max(kmax, 1), rows.data_ptr(),
+                                        cols.data_ptr(), counts.data_ptr(), status.data_ptr(), _lib.current_stream()))
+        if not self.device_indices:
+            st = int(status.item())
+            if st == -4:
+                raise ValueError("matrix contains invalid numeric entries")      # scipy's message (matcher.py:95)
+            if st != 0:
+                raise ValueError("cost matrix is infeasible")
+        n = [min(Q, k) for k in sizes]
+        if return_cost:
+            return rows, cols, n, cost
+        return rows, cols, n
+
+
+def lsap_batched(cost: torch.Tensor, sizes: Sequence[int]):
+    """scipy.optimize.linear_sum_assignment on every cost[b, :, :sizes[b]] in one launch (test hook)."""
+    lib = _lib.load()
+    dev = cost.device
+    B, Q, ld = cost.shape
+    cost = cost.to(torch.float32).contiguous()
+    off = [0]
+    for k in sizes:
+        off.append(off[-1] + int(k))
+    offsets = torch.tensor(off, dtype=torch.int32, device=dev)
+    rows = torch.empty(B, Q, dtype=torch.int64, device=dev)
+    cols = torch.empty(B, Q, dtype=torch.int64, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sedt_lsap(cost.data_ptr(), ld, offsets.data_ptr(), B, Q, max([int(k) for k in sizes] + [0]),
+                                 rows.data_ptr(), cols.data_ptr(), counts.data_ptr(), status.data_ptr(),
+                                 _lib.current_stream()))
+    return rows, cols, counts, int(status.item())
+
+
+def build_matcher(args):
+    return HungarianMatcher(cost_class=args.set_cost_class, cost_bbox=args.set_cost_bbox,
+                            cost_giou=args.set_cost_giou, epsilon=args.epsilon, alpha=args.alpha)

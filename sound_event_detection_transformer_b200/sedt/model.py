@@ -1,0 +1,165 @@
+"""SEDT / SPSEDT with the reference's constructor, state_dict and forward()
+contract (sedt/sedt.py:17-131, sedt/spsedt.py:14-95); the forward itself is
+one call into the native runtime (hand-written sm_100a kernels)."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from ..runtime import ForwardRuntime
+from ..utils import NestedTensor, nested_tensor_from_tensor_list
+from .modules import MLP
+
+PRECISIONS = {"fp32": 0, "bf16": 1}
+
+
+class SEDT(nn.Module):
+    """Drop-in for sedt.sedt.SEDT.  Extra keyword `precision`: "bf16" (default: bf16 operands,
+    fp32 accumulation on tcgen05 tensor cores) or "fp32" (CUDA-core tier held to 1e-4 parity)."""
+
+    def __init__(self, backbone, transformer, num_classes, num_queries, aux_loss=False, dec_at=False, pooling=None,
+                 precision: str = "bf16", use_tensor_cores: bool = True):
+        super().__init__()
+        if pooling is not None:
+            raise NotImplementedError("pooling/at_p heads (sedt/sedt.py:47-61,96-106) are unused by every documented "
+                                      "recipe (default None) and are not part of the B200 hot path")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.num_queries = num_queries
+        self.transformer = transformer
+        hidden_dim = transformer.d_model
+        self.class_embed = nn.Linear(hidden_dim, num_classes + 1)
+        self.bbox_embed = MLP(hidden_dim, hidden_dim, 2, 3)
+        self.input_proj = nn.Conv2d(backbone.num_channels, hidden_dim, kernel_size=1)
+        self.backbone = backbone
+        self.aux_loss = aux_loss
+        self.dec_at = dec_at
+        self.pooling = pooling
+        self.num_classes = num_classes
+        if self.dec_at:
+            self.query_embed = nn.Embedding(num_queries + 1, hidden_dim)
+            self.weak_class_embed = nn.Linear(hidden_dim, num_classes)
+        else:
+            self.query_embed = nn.Embedding(num_queries, hidden_dim)
+        self.precision = precision
+        self.use_tensor_cores = use_tensor_cores
+        self._rt: Optional[ForwardRuntime] = None
+        self._self_sup = False
+        self._feature_recon = False
+        self._num_patches = 1
+
+    # ---- native runtime plumbing ----------------------------------------------
+    def _native_config(self) -> Dict[str, int]:
+        tr = self.transformer
+        lin1 = tr.encoder.layers[0].linear1 if len(tr.encoder.layers) else tr.decoder.layers[0].linear1
+        return dict(enc_layers=len(tr.encoder.layers), dec_layers=len(tr.decoder.layers), num_queries=self.num_queries,
+                    num_classes=self.num_classes, hidden_dim=tr.d_model, nheads=tr.nhead,
+                    dim_feedforward=lin1.out_features, dec_at=int(self.dec_at), pre_norm=int(tr.normalize_before),
+                    dilation=int(self._dilation),
+                    self_sup=int(self._self_sup), feature_recon=int(self._feature_recon),
+                    num_patches=int(self._num_patches), aux_loss=int(self.aux_loss),
+                    precision=PRECISIONS[self.precision], use_tensor_cores=int(self.use_tensor_cores))
+
+    @property
+    def _dilation(self) -> bool:
+        return bool(getattr(self.backbone[0], "dilation", True))
+
+    def set_precision(self, precision: str, use_tensor_cores: bool = True) -> "SEDT":
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.precision, self.use_tensor_cores = precision, use_tensor_cores
+        self._rt = None
+        return self
+
+    def runtime(self) -> ForwardRuntime:
+        if self._rt is None:
+            self._rt = ForwardRuntime(self._native_config())
+        tensors = dict(self.named_parameters())
+        tensors.update(dict(self.named_buffers()))
+        self._rt.ensure_packed(tensors)
+        return self._rt
+
+    def _check_mode(self):
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "the B200 path currently implements the forward (eval / no_grad); the backward kernels for the "
+                "training step (SURVEY.md section 8, config 4) are not built yet. Call model.eval() or wrap in "
+                "torch.no_grad().")
+
+    def _device(self):
+        return self.query_embed.weight.device
+
+    def _prepare(self, samples):
+        if isinstance(samples, (list, torch.Tensor)):
+            samples = nested_tensor_from_tensor_list(samples)
+        x, mask = samples.decompose()
+        assert mask is not None
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("model parameters are on the CPU: call model.cuda() first (there is no CPU path)")
+        x = x.to(dev, torch.float32, non_blocking=True)
+        unpadded = getattr(samples, "unpadded", None)
+        if unpadded is None:
+            unpadded = not bool(mask.any().item())
+        return x, (None if unpadded else mask.to(dev, non_blocking=True))
+
+    # ---- forward ------------------------------------------------------------------
+    def forward(self, samples: NestedTensor):
+        """Same contract as sedt/sedt.py:64-123: returns pred_logits [B,Q,C+1], pred_boxes [B,Q,2]
+        (center, width), `at` [B,C] under dec_at, and aux_outputs for the earlier decoder layers."""
+        self._check_mode()
+        x, mask = self._prepare(samples)
+        res = self.runtime().forward(x, mask)
+        out = {"pred_logits": res["logits"][-1], "pred_boxes": res["boxes"][-1]}
+        if self.dec_at:
+            out["at"] = res["at"].squeeze()              # sedt.py:92 squeezes: [C] when B == 1
+        if self.aux_loss:
+            out["aux_outputs"] = [{"pred_logits": a, "pred_boxes": b}
+                                  for a, b in zip(res["logits"][:-1], res["boxes"][:-1])]
+        return out
+
+
+class SPSEDT(SEDT):
+    """Drop-in for sedt.spsedt.SPSEDT (eval branch of forward; the training branch draws a random
+    query-drop mask and needs the backward kernels, see SEDT._check_mode)."""
+
+    def __init__(self, backbone, transformer, num_classes, num_queries, aux_loss=False, dec_at=False, feature_recon=True,
+                 query_shuffle=False, mask_ratio=0.1, num_patches=10, pooling=None, precision: str = "bf16",
+                 use_tensor_cores: bool = True):
+        super().__init__(backbone, transformer, num_classes, num_queries, aux_loss, dec_at, pooling, precision,
+                         use_tensor_cores)
+        if dec_at:
+            raise NotImplementedError("SP-SEDT with an audio query is not a valid reference configuration "
+                                      "(sedt/spsedt.py:59,72 shapes do not line up)")
+        if query_shuffle:
+            raise NotImplementedError("query_shuffle is off in every documented recipe (train_spsedt.py:42)")
+        hidden_dim = transformer.d_model
+        self.patch2query = nn.Linear(backbone.num_channels, hidden_dim)
+        self.num_patches = num_patches
+        self.mask_ratio = mask_ratio
+        self.feature_recon = feature_recon
+        if feature_recon:
+            self.feature_align = MLP(hidden_dim, hidden_dim, backbone.num_channels, 2)
+        self.query_shuffle = query_shuffle
+        assert num_queries % num_patches == 0
+        self._self_sup, self._feature_recon, self._num_patches = True, bool(feature_recon), num_patches
+
+    def forward(self, samples, patches: torch.Tensor):
+        self._check_mode()
+        if isinstance(samples, (list, tuple)) and len(samples) == 2 and torch.is_tensor(samples[0]) and samples[0].dim() == 4:
+            samples = NestedTensor(samples[0], samples[1])          # engine.py:59 passes .decompose()
+        x, mask = self._prepare(samples)
+        res = self.runtime().forward(x, mask, patches=patches)
+        out = {"pred_logits": res["logits"][-1], "pred_boxes": res["boxes"][-1]}
+        if self.feature_recon:
+            out["pred_feature"] = res["pred_feature"][-1]
+            out["gt_feature"] = res["gt_feature"]
+            if self.aux_loss:
+                out["aux_outputs"] = [{"pred_logits": a, "pred_boxes": b, "pred_feature": c, "gt_feature": res["gt_feature"]}
+                                      for a, b, c in zip(res["logits"][:-1], res["boxes"][:-1], res["pred_feature"][:-1])]
+        elif self.aux_loss:
+            out["aux_outputs"] = [{"pred_logits": a, "pred_boxes": b}
+                                  for a, b in zip(res["logits"][:-1], res["boxes"][:-1])]
+        return out

@@ -1,0 +1,122 @@
+"""CUDA matcher (through the reference-shaped HungarianMatcher and the raw C ABI) against the
+oracle, scipy and the golden indices produced by the reference.  GPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from scipy.optimize import linear_sum_assignment
+
+from conftest import GOLDEN
+from oracle import matcher_oracle
+from sound_event_detection_transformer_b200 import spec, synth
+from sound_event_detection_transformer_b200.sedt import build_matcher
+from sound_event_detection_transformer_b200.sedt.matcher import lsap_batched
+
+pytestmark = pytest.mark.gpu
+
+
+def _to_cuda(outputs, targets):
+    return ({k: v.cuda() for k, v in outputs.items()}, [{k: v.cuda() for k, v in t.items()} for t in targets])
+
+
+@pytest.mark.parametrize("tag,normalize", [("c3_small", False), ("c3_edges", False), ("urban_q10", False),
+                                           ("c3_normalize", True)])
+def test_matcher_matches_reference_golden(tag, normalize):
+    fx = np.load(os.path.join(GOLDEN, f"matcher_{tag}.npz"))
+    B, Q, C, kmin, kmax, seed = [int(v) for v in fx["meta"]]
+    outputs, targets = synth.synth_matcher_case(B, Q, C, kmin, kmax, seed)
+    matcher = build_matcher(spec.default_args())
+    idx, coef = matcher(*_to_cuda(outputs, targets), normalize=normalize)
+    assert all(not r.is_cuda and r.dtype == torch.int64 and c.dtype == torch.int64 for r, c in idx)   # matcher.py:97
+    assert np.array_equal(np.asarray([len(r) for r, _ in idx], np.int32), fx["counts"])
+    assert np.array_equal(torch.cat([r for r, _ in idx]).numpy(), fx["rows"])
+    assert np.array_equal(torch.cat([c for _, c in idx]).numpy(), fx["cols"])
+    oidx, ocoef = matcher_oracle.hungarian_matcher({k: v.numpy() for k, v in outputs.items()},
+                                                   [{k: v.numpy() for k, v in t.items()} for t in targets],
+                                                   normalize=normalize)
+    for cf, ocf in zip(coef, ocoef):
+        assert cf.dtype == torch.float32 and np.allclose(cf.numpy(), ocf)
+
+
+def test_matcher_cost_matrix_matches_oracle():
+    outputs, targets = synth.synth_matcher_case(97, 20, 10, 0, 12, seed=11)
+    matcher = build_matcher(spec.default_args())
+    o, t = _to_cuda(outputs, targets)
+    rows, cols, n, cost = matcher.match(o["pred_logits"], o["pred_boxes"], t, return_cost=True)
+    cost = cost.cpu().numpy()
+    prob = matcher_oracle.softmax_f32(outputs["pred_logits"].numpy())
+    for b, tg in enumerate(targets):
+        k = len(tg["boxes"])
+        ref = matcher_oracle.cost_block(prob[b], outputs["pred_boxes"][b].numpy(), tg["labels"].numpy(), tg["boxes"].numpy())
+        assert np.abs(cost[b, :, :k] - ref).max() <= 2e-6          # expf vs numpy exp: a few ulp on the class term
+        # the solve on the device's own cost block is scipy's solve, bit for bit
+        r, c = linear_sum_assignment(cost[b, :, :k])
+        assert np.array_equal(rows[b, :n[b]].cpu().numpy(), r) and np.array_equal(cols[b, :n[b]].cpu().numpy(), c)
+
+
+@pytest.mark.parametrize("Q,K", [(20, 10), (20, 28), (10, 10), (32, 32), (40, 17), (17, 40), (100, 64), (5, 128)])
+def test_lsap_bit_exact_vs_scipy_random(Q, K):
+    rng = np.random.default_rng(Q * 1000 + K)
+    B = 64
+    cost = rng.standard_normal((B, Q, K)).astype(np.float32)
+    sizes = rng.integers(0, K + 1, size=B)
+    sizes[0], sizes[1] = 0, K
+    rows, cols, counts, status = lsap_batched(torch.from_numpy(cost).cuda(), sizes.tolist())
+    assert status == 0
+    rows, cols, counts = rows.cpu().numpy(), cols.cpu().numpy(), counts.cpu().numpy()
+    for b in range(B):
+        r, c = linear_sum_assignment(cost[b, :, :sizes[b]])
+        assert counts[b] == len(r)
+        assert np.array_equal(rows[b, :len(r)], r) and np.array_equal(cols[b, :len(r)], c)
+        assert (rows[b, len(r):] == -1).all()
+
+
+@pytest.mark.parametrize("Q,K", [(20, 10), (8, 8), (6, 15), (20, 28), (40, 40)])
+def test_lsap_bit_exact_vs_scipy_ties(Q, K):
+    """Integer costs with heavy ties: the tie rule replays scipy's remaining[] order."""
+    rng = np.random.default_rng(17)
+    B = 128
+    cost = rng.integers(0, 3, size=(B, Q, K)).astype(np.float32)
+    cost[0] = 1.0                                    # constant matrix (scipy #11602)
+    rows, cols, counts, status = lsap_batched(torch.from_numpy(cost).cuda(), [K] * B)
+    assert status == 0
+    rows, cols = rows.cpu().numpy(), cols.cpu().numpy()
+    for b in range(B):
+        r, c = linear_sum_assignment(cost[b])
+        assert np.array_equal(rows[b, :len(r)], r) and np.array_equal(cols[b, :len(r)], c)
+
+
+def test_matcher_nan_raises_like_scipy():
+    outputs, targets = synth.synth_matcher_case(4, 20, 10, 3, 5, seed=2)
+    outputs["pred_boxes"][2, 3, 0] = float("nan")
+    matcher = build_matcher(spec.default_args())
+    with pytest.raises(ValueError):
+        matcher(*_to_cuda(outputs, targets))
+
+
+def test_matcher_empty_batch_targets():
+    outputs, _ = synth.synth_matcher_case(5, 20, 10, 0, 0, seed=2)
+    targets = [{"labels": torch.zeros(0, dtype=torch.int64), "boxes": torch.zeros(0, 2)} for _ in range(5)]
+    matcher = build_matcher(spec.default_args())
+    idx, coef = matcher(*_to_cuda(outputs, targets))
+    assert all(len(r) == 0 and len(c) == 0 for r, c in idx) and all(len(c) == 0 for c in coef)
+
+
+def test_matcher_full_size_properties():
+    """Config 3 at full size (8192 clips): permutation validity and optimality vs scipy on a sample."""
+    B, Q = 8192, 20
+    outputs, targets = synth.synth_matcher_case(B, Q, 10, 0, 10, seed=3)
+    matcher = build_matcher(spec.default_args())
+    o, t = _to_cuda(outputs, targets)
+    rows, cols, n, cost = matcher.match(o["pred_logits"], o["pred_boxes"], t, return_cost=True)
+    rows, cols, cost = rows.cpu().numpy(), cols.cpu().numpy(), cost.cpu().numpy()
+    for b in range(B):
+        k = len(targets[b]["boxes"])
+        assert n[b] == min(Q, k)
+        r, c = rows[b, :n[b]], cols[b, :n[b]]
+        assert np.all(np.diff(r) > 0) and len(set(c.tolist())) == len(c) and (c >= 0).all() and (c < max(k, 1)).all()
+    for b in range(0, B, 37):
+        k = len(targets[b]["boxes"])
+        r, c = linear_sum_assignment(cost[b, :, :k])
+        assert np.array_equal(rows[b, :n[b]], r) and np.array_equal(cols[b, :n[b]], c)
