@@ -83,9 +83,11 @@ int64_t sedt_workspace_bytes(sedt_model* m, int B, int T, int F, int P, int PT)
     if (m == nullptr) { set_error("workspace_bytes: null model"); return SEDT_ERR_INVALID; }
     Arena a(nullptr, 0);
     ForwardOut o{};
-    int rc = m->impl->forward(nullptr, nullptr, B, T, F, nullptr, P, PT, a, o, nullptr, true);
+    // sized for the padded case (per-clip position table), an upper bound for the unpadded one
+    static const uint8_t kAnyMask = 0;
+    int rc = m->impl->forward(nullptr, &kAnyMask, B, T, F, nullptr, P, PT, a, o, nullptr, true);
     if (rc != 0) return rc;
-    return (int64_t)((a.off + 255) & ~(size_t)255);
+    return (int64_t)((a.peak + 255) & ~(size_t)255);
 }
 
 int sedt_forward(sedt_model* m, const float* x, const uint8_t* mask, int B, int T, int F, const float* patches, int P,

@@ -324,7 +324,7 @@ int Model::backbone(const float* x, int N, int T, int F, Arena& ws, void** feat,
     return SEDT_OK;
 }
 
-int Model::mha(const Mha& A, const void* q_in, const void* k_in, const void* v_in, int64_t B, int Lq, int Lk,
+int Model::mha(const Mha& A, bool self_attn, const void* q_in, const void* k_in, const void* v_in, int64_t B, int Lq, int Lk,
                const uint8_t* kpm, const float* amask, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry)
 {
     const int d = cfg_.hidden_dim, dt = act_dt();
@@ -335,7 +335,7 @@ int Model::mha(const Mha& A, const void* q_in, const void* k_in, const void* v_i
     void* vbuf = ws.alloc((size_t)B * Lk * d * es);
     SEDT_TRY(linear(A.in_proj, 2 * d, d, v_in, dt, d, B * Lk, nullptr, vbuf, dt, d, 0, s, dry));
     Vp = vbuf;
-    if (q_in == k_in) {        // self-attention: one GEMM for Q and K (N = 512)
+    if (self_attn) {           // q and k share their input: one GEMM for Q and K (N = 512)
         void* qk = ws.alloc((size_t)B * Lq * 2 * d * es);
         SEDT_TRY(linear(A.in_proj, 0, 2 * d, q_in, dt, d, B * Lq, nullptr, qk, dt, 2 * d, 0, s, dry));
         Qp = qk; Kp = (const char*)qk + (size_t)d * es; ldq = ldk = 2 * d;
@@ -430,13 +430,13 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
     for (auto& e : enc_) {
         if (cfg_.pre_norm) {
             SEDT_TRY(LN(e.n1, x32, pos, pos_rows, na, nap, nullptr, rows));
-            SEDT_TRY(mha(e.attn, nap, nap, na, B, S, S, mask_ds, nullptr, x32, x32, ws, s, dry));
+            SEDT_TRY(mha(e.attn, true, nap, nap, na, B, S, S, mask_ds, nullptr, x32, x32, ws, s, dry));
             SEDT_TRY(LN(e.n2, x32, nullptr, 1, na, nullptr, nullptr, rows));
             SEDT_TRY(linear(e.lin1, 0, ff, na, dt, d, rows, nullptr, ffh, dt, ff, 1, s, dry));
             SEDT_TRY(linear(e.lin2, 0, d, ffh, dt, ff, rows, x32, x32, DT_F32, d, 0, s, dry));
         } else {
             if (!dry) SEDT_TRY(launch_cast_addpos(x32, pos, pos_rows, na, nap, dt, rows, s));
-            SEDT_TRY(mha(e.attn, nap, nap, na, B, S, S, mask_ds, nullptr, x32, x32, ws, s, dry));
+            SEDT_TRY(mha(e.attn, true, nap, nap, na, B, S, S, mask_ds, nullptr, x32, x32, ws, s, dry));
             SEDT_TRY(LN(e.n1, x32, nullptr, 1, na, nullptr, x32, rows));
             SEDT_TRY(linear(e.lin1, 0, ff, na, dt, d, rows, nullptr, ffh, dt, ff, 1, s, dry));
             SEDT_TRY(linear(e.lin2, 0, d, ffh, dt, ff, rows, x32, x32, DT_F32, d, 0, s, dry));
@@ -471,17 +471,17 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
         float* hs_l = out.hs + l * (size_t)qrows * d;
         if (cfg_.pre_norm) {
             SEDT_TRY(LN(e.n1, t32, qpos, qpos_rows, da, dap, nullptr, qrows));
-            SEDT_TRY(mha(e.self_attn, dap, dap, da, B, Qall, Qall, nullptr, amask, t32, t32, ws, s, dry));
+            SEDT_TRY(mha(e.self_attn, true, dap, dap, da, B, Qall, Qall, nullptr, amask, t32, t32, ws, s, dry));
             SEDT_TRY(LN(e.n2, t32, qpos, qpos_rows, nullptr, dap, nullptr, qrows));
-            SEDT_TRY(mha(e.cross_attn, dap, mempos, mem, B, Qall, S, mask_ds, nullptr, t32, t32, ws, s, dry));
+            SEDT_TRY(mha(e.cross_attn, false, dap, mempos, mem, B, Qall, S, mask_ds, nullptr, t32, t32, ws, s, dry));
             SEDT_TRY(LN(e.n3, t32, nullptr, 1, da, nullptr, nullptr, qrows));
             SEDT_TRY(linear(e.lin1, 0, ff, da, dt, d, qrows, nullptr, dffh, dt, ff, 1, s, dry));
             SEDT_TRY(linear(e.lin2, 0, d, dffh, dt, ff, qrows, t32, t32, DT_F32, d, 0, s, dry));
         } else {
             if (!dry) SEDT_TRY(launch_cast_addpos(t32, qpos, qpos_rows, da, dap, dt, qrows, s));
-            SEDT_TRY(mha(e.self_attn, dap, dap, da, B, Qall, Qall, nullptr, amask, t32, t32, ws, s, dry));
+            SEDT_TRY(mha(e.self_attn, true, dap, dap, da, B, Qall, Qall, nullptr, amask, t32, t32, ws, s, dry));
             SEDT_TRY(LN(e.n1, t32, qpos, qpos_rows, nullptr, dap, t32, qrows));
-            SEDT_TRY(mha(e.cross_attn, dap, mempos, mem, B, Qall, S, mask_ds, nullptr, t32, t32, ws, s, dry));
+            SEDT_TRY(mha(e.cross_attn, false, dap, mempos, mem, B, Qall, S, mask_ds, nullptr, t32, t32, ws, s, dry));
             SEDT_TRY(LN(e.n2, t32, nullptr, 1, da, nullptr, t32, qrows));
             SEDT_TRY(linear(e.lin1, 0, ff, da, dt, d, qrows, nullptr, dffh, dt, ff, 1, s, dry));
             SEDT_TRY(linear(e.lin2, 0, d, dffh, dt, ff, qrows, t32, t32, DT_F32, d, 0, s, dry));
@@ -515,7 +515,7 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
         SEDT_TRY(linear(falign1_, 0, 2048, h1, DT_F32, d, hrows, nullptr, out.pred_feature, DT_F32, 2048, 0, s, dry));
     }
     if (ws.overflow && !dry) {
-        set_error("forward: workspace too small (%zu bytes needed, %zu given)", ws.off, ws.cap);
+        set_error("forward: workspace too small (%zu bytes needed, %zu given)", ws.peak, ws.cap);
         return SEDT_ERR_WORKSPACE;
     }
     return SEDT_OK;

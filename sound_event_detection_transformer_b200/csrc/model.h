@@ -43,11 +43,12 @@ struct EncLayer { Mha attn; Linear lin1, lin2; Norm n1, n2; };
 struct DecLayer { Mha self_attn, cross_attn; Linear lin1, lin2; Norm n1, n2, n3; };
 
 struct Arena {
-    char* base; size_t off, cap; bool overflow;
-    Arena(void* b, size_t c) : base((char*)b), off(0), cap(c), overflow(false) {}
+    char* base; size_t off, cap, peak; bool overflow;
+    Arena(void* b, size_t c) : base((char*)b), off(0), cap(c), peak(0), overflow(false) {}
     void* alloc(size_t bytes) {
         size_t o = (off + 255) & ~(size_t)255;
         off = o + bytes;
+        if (off > peak) peak = off;
         if (base == nullptr || off > cap) { overflow = true; return base == nullptr ? nullptr : base; }
         return base + o;
     }
@@ -95,7 +96,7 @@ private:
     int linear(const Linear& L, int row0, int nrows, const void* in, int in_dt, int lda, int64_t rows, const void* residual,
                void* out, int out_dt, int ldc, int relu, cudaStream_t s, bool dry);
     int backbone(const float* x, int N, int T, int F, Arena& ws, void** feat, int* H, int* W, cudaStream_t s, bool dry);
-    int mha(const Mha& A, const void* q_in, const void* k_in, const void* v_in, int64_t B, int Lq, int Lk,
+    int mha(const Mha& A, bool self_attn, const void* q_in, const void* k_in, const void* v_in, int64_t B, int Lq, int Lk,
             const uint8_t* kpm, const float* amask, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry);
 
     Config cfg_;
