@@ -75,6 +75,15 @@ SEDT_API int sedt_abi_version(void);
 /* number of kernels this library has launched since load (bench.py reports the delta) */
 SEDT_API unsigned long long sedt_launch_count(void);
 
+/* Per-kernel-class device timing for roofline evidence (bench.py).  While enabled every launch is
+ * bracketed by CUDA events on its stream; sedt_profile_read synchronises the device and returns
+ * the summed milliseconds and launch counts per class since the last read, indexed by
+ * sedt_kernel_class ([host] arrays of SEDT_KC_COUNT entries). */
+enum sedt_kernel_class { SEDT_KC_GEMM_TCGEN05 = 0, SEDT_KC_GEMM_CUDA_CORE, SEDT_KC_STEM, SEDT_KC_ATTENTION, SEDT_KC_NORM,
+                         SEDT_KC_MATCHER, SEDT_KC_OTHER, SEDT_KC_COUNT };
+SEDT_API int sedt_profile_enable(int on);
+SEDT_API int sedt_profile_read(double* ms_per_class, long long* launches_per_class);
+
 /* ---- model lifecycle: replaces SEDT.__init__/SPSEDT.__init__ state (sedt/sedt.py:20-61) ---- */
 SEDT_API int sedt_model_create(const sedt_config* cfg, sedt_model** out);
 SEDT_API void sedt_model_destroy(sedt_model* m);

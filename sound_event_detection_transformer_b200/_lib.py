@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsedt_b200.so")
 ABI_VERSION = 1
 
 F32, BF16 = 0, 1
+KERNEL_CLASSES = ("gemm_tcgen05", "gemm_cuda_core", "stem", "attention", "norm", "matcher", "other")
 
 
 class SedtConfig(C.Structure):
@@ -41,6 +42,8 @@ SIGNATURES = {
     "sedt_last_error": (C.c_char_p, []),
     "sedt_abi_version": (_i, []),
     "sedt_launch_count": (C.c_ulonglong, []),
+    "sedt_profile_enable": (_i, [_i]),
+    "sedt_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "sedt_model_create": (_i, [C.POINTER(SedtConfig), C.POINTER(_vp)]),
     "sedt_model_destroy": (None, [_vp]),
     "sedt_model_num_weights": (_i, [_vp]),

@@ -25,6 +25,13 @@ const char* sedt_last_error(void) { return get_error(); }
 int sedt_abi_version(void) { return SEDT_ABI_VERSION; }
 unsigned long long sedt_launch_count(void) { return g_launch_count; }
 
+int sedt_profile_enable(int on) { g_prof_on = on != 0; return SEDT_OK; }
+int sedt_profile_read(double* ms_per_class, long long* launches_per_class)
+{
+    SEDT_REQUIRE(ms_per_class != nullptr && launches_per_class != nullptr, "profile_read: null argument");
+    return prof_read(ms_per_class, launches_per_class);
+}
+
 int sedt_model_create(const sedt_config* cfg, sedt_model** out)
 {
     SEDT_REQUIRE(cfg != nullptr && out != nullptr, "model_create: null argument");

@@ -53,6 +53,20 @@ static inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b
 extern unsigned long long g_launch_count;
 #define SEDT_COUNT_LAUNCH() (++::sedt::g_launch_count)
 
+// ---- optional per-kernel-class device timing (bench.py roofline evidence) ---------------
+// When enabled, every launcher brackets its kernel with two CUDA events on the launching
+// stream; sedt_profile_read() synchronises and sums elapsed time per class.  Off by default
+// (no events are recorded and nothing is synchronised).
+enum ProfClass : int { PROF_GEMM_TC = 0, PROF_GEMM_SIMT, PROF_STEM, PROF_ATTENTION, PROF_NORM, PROF_MATCHER, PROF_OTHER, PROF_NCLASS };
+extern bool g_prof_on;
+void prof_begin(int cls, cudaStream_t s);
+void prof_end(cudaStream_t s);
+struct ProfScope {
+    cudaStream_t s; bool on;
+    ProfScope(int cls, cudaStream_t st) : s(st), on(g_prof_on) { if (on) prof_begin(cls, s); }
+    ~ProfScope() { if (on) prof_end(s); }
+};
+
 // ---- device-side conversions -------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

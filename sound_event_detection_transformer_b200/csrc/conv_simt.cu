@@ -123,6 +123,7 @@ int launch_conv_simt(const ConvGemm& c, cudaStream_t stream)
     if (M == 0 || c.Cout == 0) return SEDT_OK;
     Geo g{c.B, c.H, c.W, c.Cin, c.lda, c.Ho, c.Wo, c.Cout, c.ldc, c.ld_res, c.R, c.S, c.stride, c.dil, c.pad, c.relu};
     dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(c.Cout, BN)), block(NT);
+    ProfScope _prof(PROF_GEMM_SIMT, stream);
     if (c.in_dt == DT_F32 && c.out_dt == DT_F32) {
         conv_simt_kernel<float, float><<<grid, block, 0, stream>>>(
             (const float*)c.in, (const float*)c.w, c.scale, c.bias, (const float*)c.residual, (float*)c.out, g);

@@ -334,6 +334,7 @@ int launch_variant(const CUtensorMap* maps, const CUtensorMap& mb, const TcParam
         SEDT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
+    ProfScope _prof(PROF_GEMM_TC, stream);
     kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(maps[0], maps[1], maps[2], maps[3], mb, p);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());

@@ -82,6 +82,8 @@ int launch_patch_query(const float* pq, const float* query_embed, float* out, in
 // additive block-diagonal 0/-inf decoder mask [Q,Q] (sedt/spsedt.py:27-32)
 int launch_blockdiag_mask(float* m, int Q, int qpp, cudaStream_t stream);
 
+int prof_read(double* ms, long long* counts);   // model.cu
+
 // ---- matcher.cu
 int launch_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
                    const int32_t* offsets, int B, int Q, int C1, int Kmax, float w_class, float w_bbox, float w_giou,

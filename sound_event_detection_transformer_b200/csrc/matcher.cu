@@ -290,6 +290,7 @@ int launch_matcher(const float* logits, const float* boxes, const int64_t* tgt_l
     const size_t smem = (size_t)kWarpsPerCta * (Q * kpad + Q * C1) * sizeof(float);
     SEDT_REQUIRE(smem <= 200 * 1024, "matcher: cost block too large for shared memory (%zu bytes)", smem);
     dim3 grid((unsigned)ceil_div(B, kWarpsPerCta)), block(kWarpsPerCta * 32);
+    ProfScope _prof(PROF_MATCHER, stream);
 #define SEDT_MATCHER_LAUNCH(CPL)                                                                          \
     do {                                                                                                  \
         if (smem > 48 * 1024)                                                                             \

@@ -21,6 +21,39 @@ void set_error(const char* fmt, ...)
 }
 const char* get_error() { return g_err; }
 
+// ---- per-class kernel timing -----------------------------------------------------------
+bool g_prof_on = false;
+namespace {
+struct ProfRec { int cls; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event()
+{
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+void prof_begin(int cls, cudaStream_t s)
+{
+    ProfRec r{cls, prof_event(), prof_event()};
+    cudaEventRecord(r.a, s);
+    g_prof_recs.push_back(r);
+}
+void prof_end(cudaStream_t s) { cudaEventRecord(g_prof_recs.back().b, s); }
+int prof_read(double* ms, long long* counts)
+{
+    for (int i = 0; i < PROF_NCLASS; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    SEDT_CHECK_CUDA(cudaDeviceSynchronize());
+    for (auto& r : g_prof_recs) {
+        float t = 0.f;
+        SEDT_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.cls] += t; counts[r.cls] += 1;
+        g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+    return SEDT_OK;
+}
+
 // ---- layer table ------------------------------------------------------------------
 static const char* kBody = "backbone.0.body.";
 

@@ -85,6 +85,7 @@ int launch_fill_zero(void* p, size_t bytes, cudaStream_t stream)
     if (bytes == 0) return SEDT_OK;
     SEDT_REQUIRE(((uintptr_t)p & 15) == 0, "fill_zero: pointer must be 16-byte aligned");
     const size_t n16 = bytes / 16, ntail = bytes % 16;
+    ProfScope _prof(PROF_OTHER, stream);
     fill_zero_kernel<<<grid_for((int64_t)(n16 ? n16 : 1)), 256, 0, stream>>>((uint4*)p, n16, (unsigned char*)p + n16 * 16, ntail);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());

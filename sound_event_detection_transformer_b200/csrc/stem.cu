@@ -169,6 +169,7 @@ int launch_stem(const float* x, const StemWeights& w, void* out, int out_dt, int
     const int Hc = (T - 1) / 2 + 1;
     const int Hp = (Hc - 1) / 2 + 1;
     dim3 grid((unsigned)ceil_div(Hp, PH), (unsigned)B), block(NTHREADS);
+    ProfScope _prof(PROF_STEM, stream);
     if (out_dt == DT_F32) {
         SEDT_CHECK_CUDA(cudaFuncSetAttribute(stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kStemSmem));

@@ -275,6 +275,7 @@ __global__ void blockdiag_mask_kernel(float* __restrict__ m, int Q, int qpp)
 
 int launch_blockdiag_mask(float* m, int Q, int qpp, cudaStream_t stream)
 {
+    ProfScope _prof(PROF_OTHER, stream);
     blockdiag_mask_kernel<<<(unsigned)ceil_div((int64_t)Q * Q, 256), 256, 0, stream>>>(m, Q, qpp);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
@@ -286,6 +287,7 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, cons
 {
     if (rows == 0) return SEDT_OK;
     dim3 grid((unsigned)ceil_div(rows, 8)), block(256);
+    ProfScope _prof(PROF_NORM, stream);
     if (dt == DT_F32) layernorm_kernel<float, true><<<grid, block, 0, stream>>>(x, gamma, beta, pos, pos_rows, (float*)y, (float*)ypos, y32, rows);
     else layernorm_kernel<__nv_bfloat16, true><<<grid, block, 0, stream>>>(x, gamma, beta, pos, pos_rows, (__nv_bfloat16*)y, (__nv_bfloat16*)ypos, y32, rows);
     SEDT_COUNT_LAUNCH();
@@ -298,6 +300,7 @@ int launch_cast_addpos(const float* x, const float* pos, int64_t pos_rows, void*
 {
     if (rows == 0) return SEDT_OK;
     dim3 grid((unsigned)ceil_div(rows, 8)), block(256);
+    ProfScope _prof(PROF_NORM, stream);
     if (dt == DT_F32) layernorm_kernel<float, false><<<grid, block, 0, stream>>>(x, nullptr, nullptr, pos, pos_rows, (float*)y, (float*)ypos, nullptr, rows);
     else layernorm_kernel<__nv_bfloat16, false><<<grid, block, 0, stream>>>(x, nullptr, nullptr, pos, pos_rows, (__nv_bfloat16*)y, (__nv_bfloat16*)ypos, nullptr, rows);
     SEDT_COUNT_LAUNCH();
@@ -313,6 +316,7 @@ static int attention_launch(const void* Q, int ldq, const void* K, int ldk, cons
     const size_t smem = (size_t)2 * HG * KT * HD * sizeof(float);
     SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<T, HG, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)ceil_div(Lq, QB), (unsigned)(nheads / HG), (unsigned)B), block(HG * QB);
+    ProfScope _prof(PROF_ATTENTION, stream);
     attention_kernel<T, HG, QB><<<grid, block, smem, stream>>>((const T*)Q, ldq, (const T*)K, ldk, (const T*)V, ldv,
                                                                (T*)O, ldo, kpm, amask, Lq, Lk, scale);
     SEDT_COUNT_LAUNCH();
@@ -339,6 +343,7 @@ int launch_mask_downsample(const uint8_t* mask, uint8_t* out, int B, int T, int 
 {
     const int n = B * H * W;
     if (n == 0) return SEDT_OK;
+    ProfScope _prof(PROF_OTHER, stream);
     mask_downsample_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(mask, out, B, T, F, H, W);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
@@ -349,6 +354,7 @@ int launch_pos_table(const uint8_t* mask_ds, float* pos, int nb, int H, int W, c
 {
     SEDT_REQUIRE(mask_ds != nullptr || nb == 1, "pos_table: an unpadded table is batch-invariant (nb must be 1)");
     dim3 grid((unsigned)(H * W), (unsigned)nb), block(D);
+    ProfScope _prof(PROF_OTHER, stream);
     pos_table_kernel<<<grid, block, 0, stream>>>(mask_ds, pos, H, W);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
@@ -361,6 +367,7 @@ int launch_heads_finalize(const float* cls_raw, const float* box_raw, const floa
     const int64_t n = (int64_t)D_ * B * (Qall - start) * (C1 + 2) + (at ? (int64_t)B * C : 0);
     if (n == 0) return SEDT_OK;
     int64_t g = ceil_div(n, 256); if (g > 148 * 8) g = 148 * 8;
+    ProfScope _prof(PROF_OTHER, stream);
     heads_finalize_kernel<<<(unsigned)g, 256, 0, stream>>>(cls_raw, box_raw, weak_raw, logits, boxes, at, D_, B, Qall, start, C1, C);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
@@ -371,6 +378,7 @@ int launch_avgpool(const void* x, int dt, float* out, int N, int HW, int C, cuda
 {
     if (N == 0) return SEDT_OK;
     dim3 grid((unsigned)ceil_div(C, 256), (unsigned)N), block(256);
+    ProfScope _prof(PROF_OTHER, stream);
     if (dt == DT_F32) avgpool_kernel<float><<<grid, block, 0, stream>>>((const float*)x, out, HW, C);
     else avgpool_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, out, HW, C);
     SEDT_COUNT_LAUNCH();
@@ -384,6 +392,7 @@ int launch_patch_query(const float* pq, const float* query_embed, float* out, in
     const int64_t n = (int64_t)B * P * qpp * D;
     if (n == 0) return SEDT_OK;
     int64_t g = ceil_div(n, 256); if (g > 148 * 8) g = 148 * 8;
+    ProfScope _prof(PROF_OTHER, stream);
     patch_query_kernel<<<(unsigned)g, 256, 0, stream>>>(pq, query_embed, out, B, P, qpp, start);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());

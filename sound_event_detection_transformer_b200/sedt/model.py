@@ -92,13 +92,16 @@ class SEDT(nn.Module):
         return self.query_embed.weight.device
 
     def _prepare(self, samples):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("model parameters are on the CPU: call model.cuda() first (there is no CPU path)")
+        if isinstance(samples, torch.Tensor) and samples.dim() == 4:
+            # a dense [B,1,T,F] batch has no padding: skip building the all-False mask (utils.py:470-492)
+            return samples.to(dev, torch.float32, non_blocking=True), None
         if isinstance(samples, (list, torch.Tensor)):
             samples = nested_tensor_from_tensor_list(samples)
         x, mask = samples.decompose()
         assert mask is not None
-        dev = self._device()
-        if dev.type != "cuda":
-            raise RuntimeError("model parameters are on the CPU: call model.cuda() first (there is no CPU path)")
         x = x.to(dev, torch.float32, non_blocking=True)
         unpadded = getattr(samples, "unpadded", None)
         if unpadded is None:
