@@ -1,0 +1,330 @@
+// Persistent TMA + tcgen05 implicit-GEMM convolution / linear (production kernel).
+//
+// Same math and operand path as gemm_tc.cu (4-D TMA boxes per filter tap, zero padding by TMA
+// out-of-bounds fill, stride-2 through phase views, 128B-swizzled K-major operands, fp32
+// accumulation in TMEM) with the three things the one-tile-per-CTA kernel lacks:
+//   * one CTA per SM loops over output tiles (static round-robin, N tiles adjacent so CTAs that
+//     run together share the same A box through L2);
+//   * the accumulator is double-buffered in TMEM (2 x BLOCK_N columns): the epilogue warps drain
+//     tile i while the producer / MMA warps already run the main loop of tile i+1;
+//   * the epilogue is staged through shared memory: the residual tile arrives by TMA (prefetched
+//     one tile ahead), results are written back with TMA stores (coalesced, asynchronous, rows
+//     outside the tensor are clipped by the store), so no thread ever waits on a global load.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (one TMEM lane quadrant each; thread = one row of the 128-row tile).
+#include "tc_common.cuh"
+#include <cstdlib>
+
+namespace sedt {
+namespace {
+
+using namespace tc;
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO>
+struct Smem2 {
+    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int CHUNK_COLS = 128 / (int)sizeof(TO);              // columns per 128-byte staging row
+    static constexpr int NCHUNK = BLOCK_N / CHUNK_COLS;
+    static constexpr int CHUNK_BYTES = BLOCK_M * 128;                     // 16 KiB, keeps 1024-B alignment
+    static constexpr int OUT_BYTES = NCHUNK * CHUNK_BYTES;
+    static constexpr int OUT_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFFSET = OUT_OFFSET + OUT_BUFS * OUT_BYTES;
+    static constexpr int NBARS = 2 * STAGES + 4 + OUT_BUFS;
+    static constexpr int TOTAL = BAR_OFFSET + NBARS * 8 + 16 + 1024;
+};
+
+template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
+                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+                const __grid_constant__ CUtensorMap map_res, const __grid_constant__ TcParams p,
+                const int tiles_nc, const int total_tiles)
+{
+    using L = Smem2<BLOCK_N, STAGES, OUT_BUFS, TO>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = (uint64_t*)(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;          // [2]
+    uint64_t* acc_empty = acc_full + 2;               // [2]
+    uint64_t* res_full = acc_empty + 2;               // [OUT_BUFS]
+    uint32_t* tmem_slot = (uint32_t*)(res_full + OUT_BUFS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cpb = p.Cin / BLOCK_K;
+    const int num_kb = p.ntaps * cpb;
+    const bool has_res = p.residual != nullptr;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a0); prefetch_tmap(&map_b); prefetch_tmap(&map_out);
+        if (has_res) prefetch_tmap(&map_res);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < OUT_BUFS; ++s) mbar_init(&res_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> coordinates.  N tiles are adjacent in the schedule: t = m_tile * tiles_nc + n_tile.
+    auto tile_coords = [&](int t, int& w0, int& h0, int& n0, int& col0) {
+        const int n_tile = t % tiles_nc, m_tile = t / tiles_nc;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        w0 = tw * p.bw; h0 = th * p.bh; n0 = tn * p.bn; col0 = n_tile * BLOCK_N;
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int w0, h0, n0, col0;
+                tile_coords(t, w0, h0, n0, col0);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / cpb, c0 = (kb - tap * cpb) * BLOCK_K;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    const int mi = p.tap_map[tap];
+                    const CUtensorMap* ma = mi == 0 ? &map_a0 : (mi == 1 ? &map_a1 : (mi == 2 ? &map_a2 : &map_a3));
+                    tma_load_4d(ma, sa, &full_bar[stage], c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+                    tma_load_2d(&map_b, sb, &full_bar[stage], tap * p.Cin + c0, col0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+            int stage = 0; uint32_t phase = 0;
+            int li = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+                const int as = li & 1;
+                mbar_wait(&acc_empty[as], ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        umma_bf16(tmem_d, make_smem_desc(sa + k * UMMA_K * 2), make_smem_desc(sb + k * UMMA_K * 2), idesc,
+                                  (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[as]);
+            }
+        }
+    } else {
+        // ===== epilogue =====
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;                          // tile row owned by this thread
+        const bool leader = (warp == 2 && lane == 0);
+        uint8_t* out_base = smem + L::OUT_OFFSET;
+        const int sw = r & 7;
+        constexpr int LOOKAHEAD = OUT_BUFS - 1;
+
+        auto issue_residual = [&](int t, int buf) {
+            int w0, h0, n0, col0;
+            tile_coords(t, w0, h0, n0, col0);
+            mbar_expect_tx(&res_full[buf], L::OUT_BYTES);
+#pragma unroll
+            for (int c = 0; c < L::NCHUNK; ++c)
+                tma_load_4d(&map_res, out_base + buf * L::OUT_BYTES + c * L::CHUNK_BYTES, &res_full[buf],
+                            col0 + c * L::CHUNK_COLS, w0, h0, n0);
+        };
+
+        if (leader && has_res && LOOKAHEAD > 0) {
+            int t = blockIdx.x;
+            for (int k = 0; k < LOOKAHEAD && t < total_tiles; ++k, t += gridDim.x) issue_residual(t, k % OUT_BUFS);
+        }
+
+        int li = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+            const int as = li & 1, ob = li % OUT_BUFS;
+            int w0, h0, n0, col0;
+            tile_coords(t, w0, h0, n0, col0);
+            // the staging buffer that tile li+LOOKAHEAD will use was last read by the store of tile
+            // li+LOOKAHEAD-OUT_BUFS = li-1: drain it, then prefetch that tile's residual into it
+            if (leader) {
+                tma_store_wait_read0();
+                const int tn = t + LOOKAHEAD * (int)gridDim.x;
+                if (has_res && tn < total_tiles) issue_residual(tn, (li + LOOKAHEAD) % OUT_BUFS);
+            }
+            if (OUT_BUFS == 1) epi_bar_sync();                   // nobody may overwrite the buffer before the drain
+            mbar_wait(&acc_full[as], (li >> 1) & 1);
+            tc_fence_after();
+            if (has_res) mbar_wait(&res_full[ob], (li / OUT_BUFS) & 1);
+            uint8_t* ostage = out_base + ob * L::OUT_BYTES;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c * 32), acc);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                const int nb = col0 + c * 32;
+                if (p.scale != nullptr) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + nb) + j4);
+                        v[4 * j4] *= s4.x; v[4 * j4 + 1] *= s4.y; v[4 * j4 + 2] *= s4.z; v[4 * j4 + 3] *= s4.w;
+                    }
+                }
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j4);
+                        v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+                    }
+                }
+                if constexpr (sizeof(TO) == 2) {
+                    // 32 columns = 64 bytes = pieces (c&1)*4 .. +3 of the 128-byte row of chunk c/2
+                    uint8_t* row = ostage + (c >> 1) * L::CHUNK_BYTES + r * 128;
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        uint4* slot = reinterpret_cast<uint4*>(row + ((((c & 1) * 4 + j8) ^ sw) << 4));
+                        if (has_res) {
+                            const uint4 u = *slot;
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+                                v[8 * j8 + 2 * q] += __low2float(h); v[8 * j8 + 2 * q + 1] += __high2float(h);
+                            }
+                        }
+                        uint32_t w[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float a = v[8 * j8 + 2 * q], b = v[8 * j8 + 2 * q + 1];
+                            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                            w[q] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        *slot = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                } else {
+                    // 32 columns = 128 bytes = the whole staging row of chunk c
+                    uint8_t* row = ostage + c * L::CHUNK_BYTES + r * 128;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4* slot = reinterpret_cast<float4*>(row + ((j4 ^ sw) << 4));
+                        float4 o4 = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                        if (has_res) { const float4 r4 = *slot; o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w; }
+                        if (p.relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
+                        *slot = o4;
+                    }
+                }
+            }
+            // accumulator stage is free again
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+            // publish the staged tile to the async proxy and store it
+            fence_async_smem();
+            epi_bar_sync();
+            if (leader) {
+#pragma unroll
+                for (int c = 0; c < L::NCHUNK; ++c)
+                    tma_store_4d(&map_out, ostage + c * L::CHUNK_BYTES, col0 + c * L::CHUNK_COLS, w0, h0, n0);
+                tma_store_commit();
+            }
+        }
+        if (leader) tma_store_wait_read0();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * BLOCK_N>(tmem_base);
+    }
+}
+
+template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO>
+int launch_v2(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr, cudaStream_t stream)
+{
+    using L = Smem2<BLOCK_N, STAGES, OUT_BUFS, TO>;
+    static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
+    auto kern = conv_tc2_kernel<BLOCK_N, STAGES, OUT_BUFS, TO>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    const int total = pr.tiles_m * pr.tiles_nc;
+    const int grid = std::min(total, num_sms());
+    ProfScope _prof(PROF_GEMM_TC, stream);
+    kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(pr.map_a[0], pr.map_a[1], pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p,
+                                                  pr.tiles_nc, total);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int encode_out_map(CUtensorMap* m, const void* base, int ld, bool f32, const ConvGemm& g, const TcParams& p)
+{
+    const int es = f32 ? 4 : 2;
+    const uint64_t dims[4] = {(uint64_t)g.Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)ld * es, (uint64_t)g.Wo * ld * es, (uint64_t)g.Ho * g.Wo * ld * es};
+    const uint32_t box[4] = {(uint32_t)(128 / es), (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    return encode_map(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, 4, dims, strides, box);
+}
+
+}  // namespace
+
+int launch_conv_tc(const ConvGemm& g, cudaStream_t stream)
+{
+    static const bool force_v1 = [] { const char* e = getenv("SEDT_TC_V1"); return e != nullptr && e[0] == '1'; }();
+    if (force_v1) return launch_conv_tc_v1(g, stream);
+    SEDT_REQUIRE(conv_tc_supported(g), "conv_tc: unsupported shape");
+    const bool f32 = g.out_dt == DT_F32;
+    // BLOCK_N: the widest tile that divides Cout and still leaves about two tiles per SM
+    int block_n = 64;
+    if (g.Cout % 128 == 0) block_n = 128;
+    if (!f32 && g.Cout % 256 == 0) {
+        const int64_t m_tiles = ceil_div((int64_t)g.B * g.Ho * g.Wo, BLOCK_M);
+        if (m_tiles * (g.Cout / 256) >= 2 * num_sms()) block_n = 256;
+    }
+    TcProblem pr;
+    SEDT_TRY(build_problem(g, block_n, &pr));
+    CUtensorMap mo, mr;
+    SEDT_TRY(encode_out_map(&mo, g.out, g.ldc, f32, g, pr.p));
+    if (g.residual != nullptr) SEDT_TRY(encode_out_map(&mr, g.residual, g.ld_res, f32, g, pr.p));
+    else mr = mo;
+    if (f32) {
+        if (block_n == 128) return launch_v2<128, 4, 1, float>(pr, mo, mr, stream);
+        return launch_v2<64, 4, 2, float>(pr, mo, mr, stream);
+    }
+    if (block_n == 256) return launch_v2<256, 3, 1, __nv_bfloat16>(pr, mo, mr, stream);
+    if (block_n == 128) return launch_v2<128, 4, 2, __nv_bfloat16>(pr, mo, mr, stream);
+    return launch_v2<64, 6, 2, __nv_bfloat16>(pr, mo, mr, stream);
+}
+
+}  // namespace sedt

@@ -29,6 +29,9 @@ TC_SHAPES = [
     (5, 32, 4, 512, 2048, 1, 1, 1, True, True),      # layer4 conv3 + residual
     (6, 8, 4, 256, 256, 3, 1, 1, False, True),       # SP-SEDT patch at layer3 (4 images per tile)
     (1, 1, 1, 256, 512, 1, 1, 1, False, False),      # degenerate: a single row
+    (40, 31, 4, 512, 2048, 1, 1, 1, True, True),     # enough tiles for the BLOCK_N=256 variant, with residual
+    (20, 124, 16, 64, 256, 1, 1, 1, True, True),     # BLOCK_N=256, K=64 (one k-block per tile), many tiles per CTA
+    (20, 124, 16, 64, 64, 3, 1, 1, False, True),     # BLOCK_N=64, many tiles per CTA
 ]
 
 
