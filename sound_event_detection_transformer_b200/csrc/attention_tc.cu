@@ -1,0 +1,225 @@
+// Fused multi-head attention core on tcgen05 / TMEM for sequences of up to 128 tokens
+// (encoder: S = 124 / 128 tokens; decoder: 11 / 21 queries x 21 / 124 keys), head_dim 32.
+//
+// One CTA of 128 threads per (clip, head); thread t owns query row t = TMEM lane t.
+//   1. Q_h, K_h rows are copied into shared memory in the 128B-swizzled K-major operand layout
+//      (head_dim 32 fills the first 64 bytes of each 128-byte row), V_h is transposed on the fly
+//      into [head_dim][keys] so that it is a K-major B operand as well.
+//   2. S = Q K^T       one 128x128x32 tcgen05.mma chain, fp32 accumulator in TMEM.
+//   3. softmax         two passes over the thread's own TMEM lane (max, then exp2 / sum), masks
+//      (additive attn_mask, key_padding_mask, keys >= Lk) applied in fp32; P is written as bf16
+//      into shared memory in A-operand layout.
+//   4. O = P V         128x32x128 tcgen05.mma chain into the same TMEM columns, scaled by 1/sum
+//      and stored as bf16.
+// Replaces the need_weights=True eager path of nn.MultiheadAttention
+// (torch/nn/functional.py:6630-6659: q*sqrt(1/hd), baddbmm, softmax, bmm).
+#include "tc_common.cuh"
+#include <math_constants.h>
+
+namespace sedt {
+namespace {
+
+using namespace tc;
+
+constexpr int ATT_THREADS = 128;
+constexpr int HD = 32;
+constexpr int SQ_OFF = 0;                   // [128 rows][128 B]
+constexpr int SK_OFF = 16384;
+constexpr int SP_OFF = 0;                   // 2 chunks of [128 rows][64 keys]; reuses Q/K once S = QK^T has retired
+constexpr int SV_OFF = 32768;               // 2 chunks of [32 rows][64 keys]
+constexpr int SM_OFF = 32768 + 8192;        // key mask as float [128]
+constexpr int BAR_OFF = SM_OFF + 512;
+constexpr int ATT_SMEM = BAR_OFF + 64 + 1024;
+
+__device__ __forceinline__ uint32_t swz(int row, int byte_in_row) {
+    // 128-byte swizzle: 16-byte piece index XOR (row mod 8)
+    return (uint32_t)(row * 128 + ((((byte_in_row >> 4) ^ (row & 7)) << 4) | (byte_in_row & 15)));
+}
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ K, int ldk,
+                    const __nv_bfloat16* __restrict__ V, int ldv, __nv_bfloat16* __restrict__ O, int ldo,
+                    const uint8_t* __restrict__ kpm, const float* __restrict__ amask, int Lq, int Lk, float scale)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* s_mask = (float*)(smem + SM_OFF);
+    uint64_t* bar_s = (uint64_t*)(smem + BAR_OFF);
+    uint64_t* bar_o = bar_s + 1;
+    uint32_t* tmem_slot = (uint32_t*)(bar_o + 1);
+
+    const int t = threadIdx.x, warp = t >> 5;
+    const int h = blockIdx.x, b = blockIdx.y;
+
+    if (t == 0) {
+        mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc<128>(tmem_slot);
+
+    // ---- stage Q, K (row t) and V^T (column t) ----------------------------------------------
+    {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        uint4 q4[4] = {z, z, z, z}, k4[4] = {z, z, z, z}, v4[4] = {z, z, z, z};
+        if (t < Lq) {
+            const uint4* src = reinterpret_cast<const uint4*>(Q + ((size_t)b * Lq + t) * ldq + h * HD);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) q4[j] = src[j];
+        }
+        if (t < Lk) {
+            const uint4* ks = reinterpret_cast<const uint4*>(K + ((size_t)b * Lk + t) * ldk + h * HD);
+            const uint4* vs = reinterpret_cast<const uint4*>(V + ((size_t)b * Lk + t) * ldv + h * HD);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { k4[j] = ks[j]; v4[j] = vs[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            *reinterpret_cast<uint4*>(smem + SQ_OFF + swz(t, j * 16)) = j < 4 ? q4[j] : z;
+            *reinterpret_cast<uint4*>(smem + SK_OFF + swz(t, j * 16)) = j < 4 ? k4[j] : z;
+        }
+        // V^T: element (d, key t) -> chunk t/64, row d, column t%64
+        const __nv_bfloat16* vh = reinterpret_cast<const __nv_bfloat16*>(v4);
+        uint8_t* vbase = smem + SV_OFF + (t >> 6) * 4096;
+        const int col_b = (t & 63) * 2;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) *reinterpret_cast<__nv_bfloat16*>(vbase + swz(d, col_b)) = vh[d];
+        float mk = 0.f;
+        if (t >= Lk) mk = -CUDART_INF_F;
+        else if (kpm != nullptr && kpm[(size_t)b * Lk + t]) mk = -CUDART_INF_F;
+        s_mask[t] = mk;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- S = Q K^T -----------------------------------------------------------------------------
+    if (t == 0) {
+        constexpr uint32_t idesc = make_idesc(128, 128);
+        const uint32_t sq = smem_u32(smem + SQ_OFF), sk = smem_u32(smem + SK_OFF);
+#pragma unroll
+        for (int k = 0; k < HD / UMMA_K; ++k)
+            umma_bf16(tmem_base, make_smem_desc(sq + k * UMMA_K * 2), make_smem_desc(sk + k * UMMA_K * 2), idesc, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+
+    // ---- softmax over this thread's row -------------------------------------------------------
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float* arow = (amask != nullptr && t < Lq) ? amask + (size_t)t * Lk : nullptr;
+    float m = -CUDART_INF_F;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        uint32_t acc[32];
+        tmem_ld32(lane_addr + c * 32, acc);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float s = __uint_as_float(acc[j]) * scale + s_mask[c * 32 + j];
+            if (arow != nullptr && c * 32 + j < Lk) s += arow[c * 32 + j];
+            m = fmaxf(m, s);
+        }
+    }
+    const float mm = (m == -CUDART_INF_F) ? 0.f : m;
+    float l = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        uint32_t acc[32];
+        tmem_ld32(lane_addr + c * 32, acc);
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            float s0 = __uint_as_float(acc[j]) * scale + s_mask[c * 32 + j];
+            float s1 = __uint_as_float(acc[j + 1]) * scale + s_mask[c * 32 + j + 1];
+            if (arow != nullptr) {
+                if (c * 32 + j < Lk) s0 += arow[c * 32 + j];
+                if (c * 32 + j + 1 < Lk) s1 += arow[c * 32 + j + 1];
+            }
+            const float p0 = exp2f((s0 - mm) * 1.4426950408889634f), p1 = exp2f((s1 - mm) * 1.4426950408889634f);
+            l += p0 + p1;
+            const __nv_bfloat162 hp = __floats2bfloat162_rn(p0, p1);
+            packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        // 32 keys = 64 bytes = pieces (c&1)*4 .. +3 of row t in P chunk c/2
+        uint8_t* prow = smem + SP_OFF + (c >> 1) * 16384;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+            *reinterpret_cast<uint4*>(prow + swz(t, ((c & 1) * 4 + j4) * 16)) =
+                make_uint4(packed[4 * j4], packed[4 * j4 + 1], packed[4 * j4 + 2], packed[4 * j4 + 3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- O = P V (accumulates into TMEM columns 0..31, S is dead) ------------------------------
+    if (t == 0) {
+        constexpr uint32_t idesc = make_idesc(128, HD);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t sp = smem_u32(smem + SP_OFF + c * 16384), sv = smem_u32(smem + SV_OFF + c * 4096);
+#pragma unroll
+            for (int k = 0; k < 64 / UMMA_K; ++k)
+                umma_bf16(tmem_base, make_smem_desc(sp + k * UMMA_K * 2), make_smem_desc(sv + k * UMMA_K * 2), idesc,
+                          (c > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_o);
+    }
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    {
+        uint32_t acc[32];
+        tmem_ld32(lane_addr, acc);
+        if (t < Lq) {
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const __nv_bfloat162 ho = __floats2bfloat162_rn(__uint_as_float(acc[j]) * inv, __uint_as_float(acc[j + 1]) * inv);
+                w[j >> 1] = *reinterpret_cast<const uint32_t*>(&ho);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(O + ((size_t)b * Lq + t) * ldo + h * HD);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_uint4(w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<128>(tmem_base);
+    }
+}
+
+}  // namespace
+
+bool attention_tc_supported(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* O, int ldo,
+                            int dt, int nheads, int Lq, int Lk)
+{
+    if (dt != DT_BF16 || Lq < 1 || Lk < 1 || Lq > 128 || Lk > 128 || nheads < 1) return false;
+    if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return false;
+    if (((uintptr_t)Q & 15) || ((uintptr_t)K & 15) || ((uintptr_t)V & 15) || ((uintptr_t)O & 15)) return false;
+    return true;
+}
+
+int launch_attention_tc(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo,
+                        const uint8_t* kpm, const float* amask, int B, int nheads, int Lq, int Lk, float scale,
+                        cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)nheads, (unsigned)B), block(ATT_THREADS);
+    ProfScope _prof(PROF_ATTENTION, stream);
+    attention_tc_kernel<<<grid, block, ATT_SMEM, stream>>>((const __nv_bfloat16*)Q, ldq, (const __nv_bfloat16*)K, ldk,
+                                                           (const __nv_bfloat16*)V, ldv, (__nv_bfloat16*)O, ldo, kpm, amask,
+                                                           Lq, Lk, scale);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+}  // namespace sedt

@@ -67,6 +67,12 @@ int launch_cast_addpos(const float* x, const float* pos, int64_t pos_rows, void*
 int launch_attention(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int dt,
                      const uint8_t* kpm, const float* amask, int B, int nheads, int Lq, int Lk, float scale,
                      cudaStream_t stream);
+// attention_tc.cu: tcgen05 version for bf16, Lq, Lk <= 128 (SEDT_ATT_SIMT=1 disables it)
+bool attention_tc_supported(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* O, int ldo,
+                            int dt, int nheads, int Lq, int Lk);
+int launch_attention_tc(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo,
+                        const uint8_t* kpm, const float* amask, int B, int nheads, int Lq, int Lk, float scale,
+                        cudaStream_t stream);
 int launch_mask_downsample(const uint8_t* mask, uint8_t* out, int B, int T, int F, int H, int W, cudaStream_t stream);
 // sine position table: [nb][H*W][256] fp32; mask_ds null => unpadded (nb must be 1)
 int launch_pos_table(const uint8_t* mask_ds, float* pos, int nb, int H, int W, cudaStream_t stream);

@@ -6,6 +6,7 @@
 // sedt/position_encoding.py:28-47, torch functional.py:6630-6659).
 #include "kernels.h"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace sedt {
 namespace {
@@ -331,6 +332,9 @@ int launch_attention(const void* Q, int ldq, const void* K, int ldk, const void*
     if (B == 0 || Lq == 0) return SEDT_OK;
     SEDT_REQUIRE(Lk >= 1, "attention: Lk=%d", Lk);
     SEDT_REQUIRE(nheads % 4 == 0, "attention: nheads=%d must be a multiple of 4", nheads);
+    static const bool force_simt = [] { const char* e = getenv("SEDT_ATT_SIMT"); return e != nullptr && e[0] == '1'; }();
+    if (!force_simt && attention_tc_supported(Q, ldq, K, ldk, V, ldv, O, ldo, dt, nheads, Lq, Lk))
+        return launch_attention_tc(Q, ldq, K, ldk, V, ldv, O, ldo, kpm, amask, B, nheads, Lq, Lk, scale, stream);
     const bool small_q = Lq <= 32;      // decoder: 11 / 21 queries
 #define SEDT_ATT(T)                                                                                                   \
     (small_q ? attention_launch<T, 4, 32>(Q, ldq, K, ldk, V, ldv, O, ldo, kpm, amask, B, nheads, Lq, Lk, scale, stream) \
