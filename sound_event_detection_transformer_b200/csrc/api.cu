@@ -151,7 +151,7 @@ int sedt_op_conv_tc_supported(const sedt_conv_desc* d) { return d != nullptr && 
 
 int sedt_op_repack_conv(const float* w_oihw, void* out, int dtype, int Cout, int Cin, int R, int S, void* stream)
 {
-    return launch_repack_conv(w_oihw, out, dtype, Cout, Cin, R, S, (cudaStream_t)stream);
+    return launch_repack_conv(w_oihw, nullptr, out, dtype, Cout, Cin, R, S, (cudaStream_t)stream);
 }
 
 int sedt_op_cast(const float* in, void* out, int dtype, int64_t n, void* stream)

@@ -41,8 +41,8 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
                     const __nv_bfloat16* __restrict__ V, int ldv, __nv_bfloat16* __restrict__ O, int ldo,
                     const uint8_t* __restrict__ kpm, const float* __restrict__ amask, int Lq, int Lk, float scale)
 {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS)
     float* s_mask = (float*)(smem + SM_OFF);
     uint64_t* bar_s = (uint64_t*)(smem + BAR_OFF);
     uint64_t* bar_o = bar_s + 1;

@@ -28,10 +28,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+constexpr int NUM_THREADS2 = 224;      // 7 warps: producer, MMA, 4 x epilogue, store
 
 template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO>
 struct Smem2 {
@@ -43,12 +44,87 @@ struct Smem2 {
     static constexpr int OUT_BYTES = NCHUNK * CHUNK_BYTES;
     static constexpr int OUT_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int BAR_OFFSET = OUT_OFFSET + OUT_BUFS * OUT_BYTES;
-    static constexpr int NBARS = 2 * STAGES + 4 + OUT_BUFS;
+    static constexpr int NBARS = 2 * STAGES + 4 + 2 * OUT_BUFS;
     static constexpr int TOTAL = BAR_OFFSET + NBARS * 8 + 16 + 1024;
 };
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// One 32-column slab of the tile row owned by this thread: bias (+scale), residual, ReLU, convert, stage.
+template <typename TO, int CHUNK_BYTES>
+__device__ __forceinline__ void epilogue_slab(uint32_t (&acc)[32], int c, int nb, const float* __restrict__ scale,
+                                              const float* __restrict__ bias, bool has_res, int relu, uint8_t* ostage,
+                                              int r, int sw)
+{
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    if (scale != nullptr) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + nb) + j4);
+            v[4 * j4] *= s4.x; v[4 * j4 + 1] *= s4.y; v[4 * j4 + 2] *= s4.z; v[4 * j4 + 3] *= s4.w;
+        }
+    }
+    if (bias != nullptr) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb) + j4);
+            v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+        }
+    }
+    if constexpr (sizeof(TO) == 2) {
+        // 32 columns = 64 bytes = pieces (c&1)*4 .. +3 of the 128-byte row of chunk c/2
+        uint8_t* row = ostage + (c >> 1) * CHUNK_BYTES + r * 128;
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+            uint4* slot = reinterpret_cast<uint4*>(row + ((((c & 1) * 4 + j8) ^ sw) << 4));
+            if (has_res) {
+                const uint4 u = *slot;
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+                    v[8 * j8 + 2 * q] += __low2float(h); v[8 * j8 + 2 * q + 1] += __high2float(h);
+                }
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float a = v[8 * j8 + 2 * q], b = v[8 * j8 + 2 * q + 1];
+                if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                w[q] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *slot = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    } else {
+        // 32 columns = 128 bytes = the whole staging row of chunk c
+        uint8_t* row = ostage + c * CHUNK_BYTES + r * 128;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            float4* slot = reinterpret_cast<float4*>(row + ((j4 ^ sw) << 4));
+            float4 o4 = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+            if (has_res) { const float4 r4 = *slot; o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w; }
+            if (relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
+            *slot = o4;
+        }
+    }
+}
+
 template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                 const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
@@ -56,14 +132,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                 const int tiles_nc, const int total_tiles)
 {
     using L = Smem2<BLOCK_N, STAGES, OUT_BUFS, TO>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // keep the pointer derived from the __shared__ symbol so that staging traffic compiles to LDS/STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = (uint64_t*)(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* acc_full = empty_bar + STAGES;          // [2]
-    uint64_t* acc_empty = acc_full + 2;               // [2]
-    uint64_t* res_full = acc_empty + 2;               // [OUT_BUFS]
-    uint32_t* tmem_slot = (uint32_t*)(res_full + OUT_BUFS);
+    uint64_t* acc_full = empty_bar + STAGES;          // [2]  MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 2;               // [2]  epilogue -> MMA
+    uint64_t* buf_ready = acc_empty + 2;              // [OUT_BUFS] store warp / residual TMA -> epilogue
+    uint64_t* buf_full = buf_ready + OUT_BUFS;        // [OUT_BUFS] epilogue -> store warp
+    uint32_t* tmem_slot = (uint32_t*)(buf_full + OUT_BUFS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cpb = p.Cin / BLOCK_K;
@@ -75,7 +153,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         if (has_res) prefetch_tmap(&map_res);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
-        for (int s = 0; s < OUT_BUFS; ++s) mbar_init(&res_full[s], 1);
+        for (int s = 0; s < OUT_BUFS; ++s) { mbar_init(&buf_ready[s], 1); mbar_init(&buf_full[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_slot);
@@ -141,122 +219,72 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                 umma_commit(&acc_full[as]);
             }
         }
+    } else if (warp == 6) {
+        // ===== store warp: TMA stores of finished tiles, residual prefetch, staging-buffer recycling =====
+        if (lane == 0) {
+            uint8_t* out_base = smem + L::OUT_OFFSET;
+            auto make_ready = [&](int t, int buf) {      // staging buffer `buf` becomes usable for tile t
+                if (has_res) {
+                    int w0, h0, n0, col0;
+                    tile_coords(t, w0, h0, n0, col0);
+                    mbar_expect_tx(&buf_ready[buf], L::OUT_BYTES);
+#pragma unroll
+                    for (int c = 0; c < L::NCHUNK; ++c)
+                        tma_load_4d(&map_res, out_base + buf * L::OUT_BYTES + c * L::CHUNK_BYTES, &buf_ready[buf],
+                                    col0 + c * L::CHUNK_COLS, w0, h0, n0);
+                } else {
+                    mbar_arrive(&buf_ready[buf]);
+                }
+            };
+            {
+                int t = blockIdx.x;
+                for (int k = 0; k < OUT_BUFS && t < total_tiles; ++k, t += gridDim.x) make_ready(t, k);
+            }
+            int li = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+                const int ob = li % OUT_BUFS;
+                int w0, h0, n0, col0;
+                tile_coords(t, w0, h0, n0, col0);
+                mbar_wait(&buf_full[ob], (li / OUT_BUFS) & 1);
+#pragma unroll
+                for (int c = 0; c < L::NCHUNK; ++c)
+                    tma_store_4d(&map_out, out_base + ob * L::OUT_BYTES + c * L::CHUNK_BYTES, col0 + c * L::CHUNK_COLS, w0, h0, n0);
+                tma_store_commit();
+                tma_store_wait_read0();                  // staging buffer has been read out
+                const int tn = t + OUT_BUFS * (int)gridDim.x;
+                if (tn < total_tiles) make_ready(tn, ob);
+            }
+        }
     } else {
-        // ===== epilogue =====
+        // ===== epilogue warps 2..5 =====
         const int quad = warp & 3;
         const int r = quad * 32 + lane;                          // tile row owned by this thread
-        const bool leader = (warp == 2 && lane == 0);
         uint8_t* out_base = smem + L::OUT_OFFSET;
         const int sw = r & 7;
-        constexpr int LOOKAHEAD = OUT_BUFS - 1;
-
-        auto issue_residual = [&](int t, int buf) {
-            int w0, h0, n0, col0;
-            tile_coords(t, w0, h0, n0, col0);
-            mbar_expect_tx(&res_full[buf], L::OUT_BYTES);
-#pragma unroll
-            for (int c = 0; c < L::NCHUNK; ++c)
-                tma_load_4d(&map_res, out_base + buf * L::OUT_BYTES + c * L::CHUNK_BYTES, &res_full[buf],
-                            col0 + c * L::CHUNK_COLS, w0, h0, n0);
-        };
-
-        if (leader && has_res && LOOKAHEAD > 0) {
-            int t = blockIdx.x;
-            for (int k = 0; k < LOOKAHEAD && t < total_tiles; ++k, t += gridDim.x) issue_residual(t, k % OUT_BUFS);
-        }
-
         int li = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
             const int as = li & 1, ob = li % OUT_BUFS;
-            int w0, h0, n0, col0;
-            tile_coords(t, w0, h0, n0, col0);
-            // the staging buffer that tile li+LOOKAHEAD will use was last read by the store of tile
-            // li+LOOKAHEAD-OUT_BUFS = li-1: drain it, then prefetch that tile's residual into it
-            if (leader) {
-                tma_store_wait_read0();
-                const int tn = t + LOOKAHEAD * (int)gridDim.x;
-                if (has_res && tn < total_tiles) issue_residual(tn, (li + LOOKAHEAD) % OUT_BUFS);
-            }
-            if (OUT_BUFS == 1) epi_bar_sync();                   // nobody may overwrite the buffer before the drain
+            const int col0 = (t % tiles_nc) * BLOCK_N;
+            mbar_wait(&buf_ready[ob], (li / OUT_BUFS) & 1);      // staging free (and residual landed)
             mbar_wait(&acc_full[as], (li >> 1) & 1);
             tc_fence_after();
-            if (has_res) mbar_wait(&res_full[ob], (li / OUT_BUFS) & 1);
             uint8_t* ostage = out_base + ob * L::OUT_BYTES;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N);
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                uint32_t acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c * 32), acc);
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                const int nb = col0 + c * 32;
-                if (p.scale != nullptr) {
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + nb) + j4);
-                        v[4 * j4] *= s4.x; v[4 * j4 + 1] *= s4.y; v[4 * j4 + 2] *= s4.z; v[4 * j4 + 3] *= s4.w;
-                    }
-                }
-                if (p.bias != nullptr) {
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j4);
-                        v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
-                    }
-                }
-                if constexpr (sizeof(TO) == 2) {
-                    // 32 columns = 64 bytes = pieces (c&1)*4 .. +3 of the 128-byte row of chunk c/2
-                    uint8_t* row = ostage + (c >> 1) * L::CHUNK_BYTES + r * 128;
-#pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        uint4* slot = reinterpret_cast<uint4*>(row + ((((c & 1) * 4 + j8) ^ sw) << 4));
-                        if (has_res) {
-                            const uint4 u = *slot;
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
-                                v[8 * j8 + 2 * q] += __low2float(h); v[8 * j8 + 2 * q + 1] += __high2float(h);
-                            }
-                        }
-                        uint32_t w[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float a = v[8 * j8 + 2 * q], b = v[8 * j8 + 2 * q + 1];
-                            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-                            w[q] = *reinterpret_cast<const uint32_t*>(&h);
-                        }
-                        *slot = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                } else {
-                    // 32 columns = 128 bytes = the whole staging row of chunk c
-                    uint8_t* row = ostage + c * L::CHUNK_BYTES + r * 128;
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        float4* slot = reinterpret_cast<float4*>(row + ((j4 ^ sw) << 4));
-                        float4 o4 = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-                        if (has_res) { const float4 r4 = *slot; o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w; }
-                        if (p.relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
-                        *slot = o4;
-                    }
-                }
+            for (int c = 0; c < BLOCK_N / 32; c += 2) {
+                uint32_t acc0[32], acc1[32];
+                tmem_ld32_nowait(taddr + (uint32_t)(c * 32), acc0);
+                tmem_ld32_nowait(taddr + (uint32_t)(c * 32 + 32), acc1);
+                tmem_ld_wait();
+                epilogue_slab<TO, L::CHUNK_BYTES>(acc0, c, col0 + c * 32, p.scale, p.bias, has_res, p.relu, ostage, r, sw);
+                epilogue_slab<TO, L::CHUNK_BYTES>(acc1, c + 1, col0 + c * 32 + 32, p.scale, p.bias, has_res, p.relu, ostage, r, sw);
             }
-            // accumulator stage is free again
+            // accumulator stage is free again; staged tile is visible to the async proxy
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);
-            // publish the staged tile to the async proxy and store it
             fence_async_smem();
-            epi_bar_sync();
-            if (leader) {
-#pragma unroll
-                for (int c = 0; c < L::NCHUNK; ++c)
-                    tma_store_4d(&map_out, ostage + c * L::CHUNK_BYTES, col0 + c * L::CHUNK_COLS, w0, h0, n0);
-                tma_store_commit();
-            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&acc_empty[as]); mbar_arrive(&buf_full[ob]); }
         }
-        if (leader) tma_store_wait_read0();
     }
 
     tc_fence_before();
@@ -281,7 +309,7 @@ int launch_v2(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr,
     const int total = pr.tiles_m * pr.tiles_nc;
     const int grid = std::min(total, num_sms());
     ProfScope _prof(PROF_GEMM_TC, stream);
-    kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(pr.map_a[0], pr.map_a[1], pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p,
+    kern<<<grid, NUM_THREADS2, L::TOTAL, stream>>>(pr.map_a[0], pr.map_a[1], pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p,
                                                   pr.tiles_nc, total);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
@@ -305,10 +333,14 @@ int launch_conv_tc(const ConvGemm& g, cudaStream_t stream)
     if (force_v1) return launch_conv_tc_v1(g, stream);
     SEDT_REQUIRE(conv_tc_supported(g), "conv_tc: unsupported shape");
     const bool f32 = g.out_dt == DT_F32;
-    // BLOCK_N: the widest tile that divides Cout and still leaves about two tiles per SM
+    // BLOCK_N: the widest tile that divides Cout, still leaves about two tiles per SM and has a main
+    // loop long enough (num_kb >= min_kb256) to hide the single-buffered 256-wide epilogue
+    static const int min_kb256 = [] { const char* e = getenv("SEDT_BN256_MIN_KB"); return e ? atoi(e) : 16; }();
+    static const int f32_bn = [] { const char* e = getenv("SEDT_F32_BN"); return e ? atoi(e) : 128; }();
+    const int num_kb = g.R * g.S * g.Cin / BLOCK_K;
     int block_n = 64;
-    if (g.Cout % 128 == 0) block_n = 128;
-    if (!f32 && g.Cout % 256 == 0) {
+    if (g.Cout % 128 == 0 && !(f32 && f32_bn == 64)) block_n = 128;
+    if (!f32 && g.Cout % 256 == 0 && num_kb >= min_kb256) {
         const int64_t m_tiles = ceil_div((int64_t)g.B * g.Ho * g.Wo, BLOCK_M);
         if (m_tiles * (g.Cout / 256) >= 2 * num_sms()) block_n = 256;
     }

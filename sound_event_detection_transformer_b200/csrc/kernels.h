@@ -49,8 +49,9 @@ int launch_stem(const float* x, const StemWeights& w, void* out, int out_dt, int
 // ---- pack.cu
 int launch_bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* bias,
                    int n, cudaStream_t stream);
-// OIHW fp32 -> O(HW)I in dtype dt
-int launch_repack_conv(const float* w_oihw, void* out, int dt, int Cout, int Cin, int R, int S, cudaStream_t stream);
+// OIHW fp32 -> O(HW)I in dtype dt; optional per-output-channel scale folded into the weights
+int launch_repack_conv(const float* w_oihw, const float* scale, void* out, int dt, int Cout, int Cin, int R, int S,
+                       cudaStream_t stream);
 int launch_cast(const float* in, void* out, int dt, int64_t n, cudaStream_t stream);
 
 // ---- transformer.cu

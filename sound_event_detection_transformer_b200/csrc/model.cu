@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 
 namespace sedt {
 
@@ -217,9 +218,12 @@ int Model::pack(const void* const* weights, void* packed, size_t bytes, cudaStre
     const int dt = act_dt();
 
     auto pack_conv = [&](const ConvLayer& L) -> int {
-        SEDT_TRY(launch_repack_conv(W(L.w_slot), P(L.off_w), dt, L.cout, L.cin, L.k, L.k, s));
-        return launch_bn_fold(W(L.bn_slot), W(L.bn_slot + 1), W(L.bn_slot + 2), W(L.bn_slot + 3),
-                              (float*)P(L.off_scale), (float*)P(L.off_bias), L.cout, s);
+        SEDT_TRY(launch_bn_fold(W(L.bn_slot), W(L.bn_slot + 1), W(L.bn_slot + 2), W(L.bn_slot + 3),
+                                (float*)P(L.off_scale), (float*)P(L.off_bias), L.cout, s));
+        // bf16 tier: the FrozenBN scale is folded into the weights before rounding (one rounding instead of
+        // two, and the epilogue only adds the bias); the fp32 tier keeps x*scale+bias like the reference
+        return launch_repack_conv(W(L.w_slot), fold_scale() ? (const float*)P(L.off_scale) : nullptr, P(L.off_w), dt, L.cout,
+                                  L.cin, L.k, L.k, s);
     };
     auto pack_linear = [&](const Linear& L) -> int {
         SEDT_TRY(launch_cast(W(L.w_slot), P(L.off_w), L.f32_only ? DT_F32 : dt, (int64_t)L.in * L.out, s));
@@ -274,7 +278,7 @@ int Model::conv(const ConvLayer& L, const void* in, int N, int H, int W, const v
                 cudaStream_t s, bool dry)
 {
     ConvGemm g;
-    g.in = in; g.w = packed_ + L.off_w; g.scale = (const float*)(packed_ + L.off_scale);
+    g.in = in; g.w = packed_ + L.off_w; g.scale = fold_scale() ? nullptr : (const float*)(packed_ + L.off_scale);
     g.bias = (const float*)(packed_ + L.off_bias); g.residual = residual; g.out = out;
     g.in_dt = g.out_dt = act_dt();
     g.B = N; g.H = H; g.W = W; g.Cin = L.cin; g.lda = L.cin;
@@ -308,52 +312,98 @@ void Model::feature_shape(int T, int F, bool dilation, int* H, int* W)
     *H = h; *W = w;
 }
 
+// Blocks [b0, b1) of the trunk on N images of size H x W held in `in`.  The last block writes to
+// `final_out` when given (otherwise to one of the ping-pong buffers); *out receives that pointer.
+int Model::run_blocks(size_t b0, size_t b1, const void* in, int N, int* H, int* W, const BlockBufs& bb, void* final_out,
+                      void** out, cudaStream_t s, bool dry)
+{
+    const void* cur = in;
+    void* ping = bb.ping; void* pong = bb.pong;
+    for (size_t i = b0; i < b1; ++i) {
+        const Block& b = blocks_[i];
+        int h1, w1, ho, wo, h3, w3;
+        void* dst = (i + 1 == b1 && final_out != nullptr) ? final_out : ping;
+        SEDT_TRY(conv(b.c1, cur, N, *H, *W, nullptr, bb.t1, &h1, &w1, s, dry));
+        SEDT_TRY(conv(b.c2, bb.t1, N, *H, *W, nullptr, bb.t2, &ho, &wo, s, dry));
+        const void* idn = cur;
+        if (b.has_ds) {
+            int hd, wd;
+            SEDT_TRY(conv(b.ds, cur, N, *H, *W, nullptr, bb.ds, &hd, &wd, s, dry));
+            idn = bb.ds;
+        }
+        SEDT_TRY(conv(b.c3, bb.t2, N, ho, wo, idn, dst, &h3, &w3, s, dry));
+        cur = dst;
+        std::swap(ping, pong);
+        *H = ho; *W = wo;
+    }
+    *out = const_cast<void*>(cur);
+    return SEDT_OK;
+}
+
+// scratch for blocks [b0, b1) on N images entering at h x w (in_elems: the stage input if it must live in ping/pong)
+Model::BlockBufs Model::alloc_block_bufs(size_t b0, size_t b1, int N, int h, int w, size_t extra_out_elems, Arena& ws,
+                                         int* Hout, int* Wout, size_t* last_elems)
+{
+    const size_t es = dtype_size(act_dt());
+    size_t max_out = extra_out_elems, max_t1 = 0, max_t2 = 0, max_ds = 0, last = 0;
+    for (size_t i = b0; i < b1; ++i) {
+        const Block& b = blocks_[i];
+        const int ho = conv_out_dim(h, 3, b.c2.stride, b.c2.pad, b.c2.dil), wo = conv_out_dim(w, 3, b.c2.stride, b.c2.pad, b.c2.dil);
+        max_t1 = std::max(max_t1, (size_t)N * h * w * b.c1.cout);
+        max_t2 = std::max(max_t2, (size_t)N * ho * wo * b.c2.cout);
+        last = (size_t)N * ho * wo * b.c3.cout;
+        max_out = std::max(max_out, last);
+        if (b.has_ds) max_ds = std::max(max_ds, (size_t)N * ho * wo * b.ds.cout);
+        h = ho; w = wo;
+    }
+    BlockBufs bb;
+    bb.ping = ws.alloc(max_out * es);
+    bb.pong = ws.alloc(max_out * es);
+    bb.t1 = ws.alloc(max_t1 * es);
+    bb.t2 = ws.alloc(max_t2 * es);
+    bb.ds = ws.alloc(max_ds * es);
+    *Hout = h; *Wout = w; *last_elems = last;
+    return bb;
+}
+
+// Backbone: stem -> layer1..layer4.  The bandwidth-bound front (stem, layer1, layer2: 9-10 MB of bf16
+// activations per clip between convolutions) runs in chunks of clips small enough for the tensors
+// handed from one convolution to the next to stay in the 126 MB L2; layer3/4 (compute-bound) run
+// on the whole batch.
 int Model::backbone(const float* x, int N, int T, int F, Arena& ws, void** feat, int* Hout, int* Wout, cudaStream_t s, bool dry)
 {
     const int dt = act_dt();
     const size_t es = dtype_size(dt);
-    int H = conv_out_dim(conv_out_dim(T, 7, 2, 3, 1), 3, 2, 1, 1), W = conv_out_dim(conv_out_dim(F, 7, 2, 3, 1), 3, 2, 1, 1);
-    // size the ping-pong / scratch buffers
-    size_t max_out = (size_t)N * H * W * 64, max_t1 = 0, max_t2 = 0, max_ds = 0;
-    {
-        int h = H, w = W;
-        for (auto& b : blocks_) {
-            const int ho = conv_out_dim(h, 3, b.c2.stride, b.c2.pad, b.c2.dil), wo = conv_out_dim(w, 3, b.c2.stride, b.c2.pad, b.c2.dil);
-            max_t1 = std::max(max_t1, (size_t)N * h * w * b.c1.cout);
-            max_t2 = std::max(max_t2, (size_t)N * ho * wo * b.c2.cout);
-            max_out = std::max(max_out, (size_t)N * ho * wo * b.c3.cout);
-            if (b.has_ds) max_ds = std::max(max_ds, (size_t)N * ho * wo * b.ds.cout);
-            h = ho; w = wo;
-        }
+    SEDT_REQUIRE(F == 64, "stem: the fused stem kernel needs 64 mel bins (config.py n_mels), got F=%d", F);
+    const int H0 = conv_out_dim(conv_out_dim(T, 7, 2, 3, 1), 3, 2, 1, 1), W0 = conv_out_dim(conv_out_dim(F, 7, 2, 3, 1), 3, 2, 1, 1);
+    static const int env_chunk = [] { const char* e = getenv("SEDT_CHUNK_MB"); return e ? atoi(e) : 0; }();   // 0 = off: measured slower on B200
+    // clips per chunk: keep one layer1 output (H0*W0*256 elements per clip) within ~env_chunk MB
+    const size_t l1_bytes = (size_t)H0 * W0 * 256 * es;
+    int chunk = (int)std::max<size_t>(1, ((size_t)env_chunk << 20) / l1_bytes);
+    const size_t n_front = 7;                                   // layer1 (3 blocks) + layer2 (4 blocks)
+    if (env_chunk <= 0 || chunk >= N) chunk = N;
+    const int nchunks = (int)ceil_div(N, chunk);
+
+    int H2, W2, H4, W4; size_t front_last, back_last;
+    // full-batch layer2 output, then layer3/4 scratch; per-chunk front scratch
+    BlockBufs fb = alloc_block_bufs(0, n_front, chunk, H0, W0, (size_t)chunk * H0 * W0 * 64, ws, &H2, &W2, &front_last);
+    const size_t l2_per_clip = front_last / chunk;
+    void* l2_out = ws.alloc((size_t)N * l2_per_clip * es);
+    BlockBufs bk = alloc_block_bufs(n_front, blocks_.size(), N, H2, W2, 0, ws, &H4, &W4, &back_last);
+
+    StemWeights sw{(const float*)(packed_ + off_weff), (const float*)(packed_ + off_sat),
+                   (const float*)(packed_ + off_stem_scale), (const float*)(packed_ + off_stem_bias)};
+    for (int c = 0; c < nchunks; ++c) {
+        const int n0 = c * chunk, nc = std::min(chunk, N - n0);
+        if (!dry) SEDT_TRY(launch_stem(x + (size_t)n0 * T * F, sw, fb.pong, dt, nc, T, F, s));
+        int h = H0, w = W0;
+        void* o = nullptr;
+        // stem output sits in `pong`; the first block writes to `ping`
+        SEDT_TRY(run_blocks(0, n_front, fb.pong, nc, &h, &w, fb, (char*)l2_out + (size_t)n0 * l2_per_clip * es, &o, s, dry));
     }
-    void* bufA = ws.alloc(max_out * es);
-    void* bufB = ws.alloc(max_out * es);
-    void* t1 = ws.alloc(max_t1 * es);
-    void* t2 = ws.alloc(max_t2 * es);
-    void* dsb = ws.alloc(max_ds * es);
-    if (!dry) {
-        StemWeights sw{(const float*)(packed_ + off_weff), (const float*)(packed_ + off_sat),
-                       (const float*)(packed_ + off_stem_scale), (const float*)(packed_ + off_stem_bias)};
-        SEDT_TRY(launch_stem(x, sw, bufA, dt, N, T, F, s));
-    } else {
-        SEDT_REQUIRE(F == 64, "stem: the fused stem kernel needs 64 mel bins (config.py n_mels), got F=%d", F);
-    }
-    void* cur = bufA; void* nxt = bufB;
-    for (auto& b : blocks_) {
-        int h1, w1, ho, wo, h3, w3;
-        SEDT_TRY(conv(b.c1, cur, N, H, W, nullptr, t1, &h1, &w1, s, dry));
-        SEDT_TRY(conv(b.c2, t1, N, H, W, nullptr, t2, &ho, &wo, s, dry));
-        const void* idn = cur;
-        if (b.has_ds) {
-            int hd, wd;
-            SEDT_TRY(conv(b.ds, cur, N, H, W, nullptr, dsb, &hd, &wd, s, dry));
-            idn = dsb;
-        }
-        SEDT_TRY(conv(b.c3, t2, N, ho, wo, idn, nxt, &h3, &w3, s, dry));
-        std::swap(cur, nxt);
-        H = ho; W = wo;
-    }
-    *feat = cur; *Hout = H; *Wout = W;
+    int h = H2, w = W2;
+    SEDT_TRY(run_blocks(n_front, blocks_.size(), l2_out, N, &h, &w, bk, nullptr, feat, s, dry));
+    *Hout = h; *Wout = w;
     return SEDT_OK;
 }
 

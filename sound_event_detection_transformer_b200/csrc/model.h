@@ -72,6 +72,7 @@ public:
     const std::vector<WeightSlot>& slots() const { return slots_; }
     size_t packed_bytes() const { return packed_bytes_; }
     int act_dt() const { return cfg_.precision ? DT_BF16 : DT_F32; }
+    bool fold_scale() const { return cfg_.precision != 0; }
 
     int pack(const void* const* weights, void* packed, size_t bytes, cudaStream_t stream);
     // dry = true only sizes the workspace (no launches)
@@ -95,6 +96,11 @@ private:
     // rows x L.in -> rows x L.out.  row0/nrows select a slice of W's rows (packed in_proj).
     int linear(const Linear& L, int row0, int nrows, const void* in, int in_dt, int lda, int64_t rows, const void* residual,
                void* out, int out_dt, int ldc, int relu, cudaStream_t s, bool dry);
+    struct BlockBufs { void *ping, *pong, *t1, *t2, *ds; };
+    BlockBufs alloc_block_bufs(size_t b0, size_t b1, int N, int h, int w, size_t extra_out_elems, Arena& ws, int* Hout, int* Wout,
+                               size_t* last_elems);
+    int run_blocks(size_t b0, size_t b1, const void* in, int N, int* H, int* W, const BlockBufs& bb, void* final_out, void** out,
+                   cudaStream_t s, bool dry);
     int backbone(const float* x, int N, int T, int F, Arena& ws, void** feat, int* H, int* W, cudaStream_t s, bool dry);
     int mha(const Mha& A, bool self_attn, const void* q_in, const void* k_in, const void* v_in, int64_t B, int Lq, int Lk,
             const uint8_t* kpm, const float* amask, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry);

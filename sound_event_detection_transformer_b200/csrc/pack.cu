@@ -17,7 +17,8 @@ __global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restr
 }
 
 template <typename T>
-__global__ void repack_conv_kernel(const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int RS)
+__global__ void repack_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale, T* __restrict__ out, int Cout,
+                                   int Cin, int RS)
 {
     // out[o][tap][c] = w[o][c][tap]; consecutive threads -> consecutive c (coalesced writes)
     const int64_t total = (int64_t)Cout * Cin * RS;
@@ -25,7 +26,8 @@ __global__ void repack_conv_kernel(const float* __restrict__ w, T* __restrict__ 
         const int c = (int)(i % Cin);
         const int tap = (int)((i / Cin) % RS);
         const int o = (int)(i / ((int64_t)Cin * RS));
-        out[i] = from_f32<T>(w[((int64_t)o * Cin + c) * RS + tap]);
+        const float v = w[((int64_t)o * Cin + c) * RS + tap];
+        out[i] = from_f32<T>(scale != nullptr ? v * scale[o] : v);
     }
 }
 
@@ -60,11 +62,12 @@ int launch_bn_fold(const float* w, const float* b, const float* mean, const floa
     return SEDT_OK;
 }
 
-int launch_repack_conv(const float* w_oihw, void* out, int dt, int Cout, int Cin, int R, int S, cudaStream_t stream)
+int launch_repack_conv(const float* w_oihw, const float* scale, void* out, int dt, int Cout, int Cin, int R, int S,
+                       cudaStream_t stream)
 {
     const int64_t total = (int64_t)Cout * Cin * R * S;
-    if (dt == DT_F32) repack_conv_kernel<float><<<grid_for(total), 256, 0, stream>>>(w_oihw, (float*)out, Cout, Cin, R * S);
-    else repack_conv_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, stream>>>(w_oihw, (__nv_bfloat16*)out, Cout, Cin, R * S);
+    if (dt == DT_F32) repack_conv_kernel<float><<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, (float*)out, Cout, Cin, R * S);
+    else repack_conv_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, (__nv_bfloat16*)out, Cout, Cin, R * S);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
