@@ -61,6 +61,7 @@ SIGNATURES = {
     "sedt_op_repack_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sedt_op_cast": (_i, [_vp, _vp, _i, _i64, _vp]),
     "sedt_op_stem": (_i, [_vp] * 10 + [_i, _i, _i, _i, _vp]),
+    "sedt_op_stem_tc": (_i, [_vp] * 10 + [_i, _i, _i, _vp]),
     "sedt_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i64, _vp]),
     "sedt_op_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "sedt_op_pos_table": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

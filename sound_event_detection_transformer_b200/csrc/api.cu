@@ -175,6 +175,20 @@ int sedt_op_stem(const float* x, const float* conv0_w, const float* conv0_b, con
     return launch_stem(x, w, out, out_dtype, B, T, F, s);
 }
 
+int sedt_op_stem_tc(const float* x, const float* conv0_w, const float* conv0_b, const float* conv1_w, const float* bn_w,
+                    const float* bn_b, const float* bn_mean, const float* bn_var, void* scratch, void* out, int B, int T, int F,
+                    void* stream)
+{
+    SEDT_REQUIRE(scratch != nullptr && ((uintptr_t)scratch & 255) == 0, "op_stem_tc: scratch must be 256-byte aligned");
+    uint8_t* wtc = (uint8_t*)scratch;                 // 16 KiB
+    float* scale = (float*)(wtc + 16384);
+    float* bias = scale + 64;
+    cudaStream_t s = (cudaStream_t)stream;
+    SEDT_TRY(launch_bn_fold(bn_w, bn_b, bn_mean, bn_var, scale, bias, 64, s));
+    SEDT_TRY(launch_stem_tc_pack(conv0_w, conv0_b, conv1_w, scale, wtc, s));
+    return launch_stem_tc(x, wtc, bias, out, B, T, F, s);
+}
+
 int sedt_op_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int64_t pos_rows, void* y,
                       void* ypos, float* y32, int dtype, int64_t rows, void* stream)
 {

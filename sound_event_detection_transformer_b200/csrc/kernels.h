@@ -46,6 +46,11 @@ int launch_stem_pack(const float* conv0_w, const float* conv0_b, const float* co
                      cudaStream_t stream);
 int launch_stem(const float* x, const StemWeights& w, void* out, int out_dt, int B, int T, int F, cudaStream_t stream);
 
+// stem_tc.cu: the same stem on tcgen05 (bf16 output).  wtc: 16 KiB pre-swizzled weight image, bn_scale folded in
+int launch_stem_tc_pack(const float* conv0_w, const float* conv0_b, const float* conv1_w, const float* bn_scale, void* wtc,
+                        cudaStream_t stream);
+int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, void* out, int B, int T, int F, cudaStream_t stream);
+
 // ---- pack.cu
 int launch_bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* bias,
                    int n, cudaStream_t stream);

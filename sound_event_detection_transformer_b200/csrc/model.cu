@@ -170,6 +170,7 @@ Model::Model(const Config& c) : cfg_(c)
     off_sat = reserve(64 * 64 * 4);
     off_stem_scale = reserve(64 * 4);
     off_stem_bias = reserve(64 * 4);
+    off_stem_wtc = reserve(16384);
 
     // torchvision resnet50 (resnet.py:225-262) with replace_stride_with_dilation=[F,F,dilation]
     static const int planes_[4] = {64, 128, 256, 512}, nblk_[4] = {3, 4, 6, 3}, stride_[4] = {1, 2, 2, 2};
@@ -251,6 +252,8 @@ int Model::pack(const void* const* weights, void* packed, size_t bytes, cudaStre
     SEDT_TRY(launch_stem_pack(W(s_conv0_w), W(s_conv0_b), W(s_conv1_w), (float*)P(off_weff), (float*)P(off_sat), s));
     SEDT_TRY(launch_bn_fold(W(s_bn1), W(s_bn1 + 1), W(s_bn1 + 2), W(s_bn1 + 3), (float*)P(off_stem_scale),
                             (float*)P(off_stem_bias), 64, s));
+    if (cfg_.precision == 1)
+        SEDT_TRY(launch_stem_tc_pack(W(s_conv0_w), W(s_conv0_b), W(s_conv1_w), (const float*)P(off_stem_scale), P(off_stem_wtc), s));
     for (auto& b : blocks_) {
         SEDT_TRY(pack_conv(b.c1)); SEDT_TRY(pack_conv(b.c2)); SEDT_TRY(pack_conv(b.c3));
         if (b.has_ds) SEDT_TRY(pack_conv(b.ds));
@@ -395,7 +398,13 @@ int Model::backbone(const float* x, int N, int T, int F, Arena& ws, void** feat,
                    (const float*)(packed_ + off_stem_scale), (const float*)(packed_ + off_stem_bias)};
     for (int c = 0; c < nchunks; ++c) {
         const int n0 = c * chunk, nc = std::min(chunk, N - n0);
-        if (!dry) SEDT_TRY(launch_stem(x + (size_t)n0 * T * F, sw, fb.pong, dt, nc, T, F, s));
+        if (!dry) {
+            if (cfg_.precision == 1 && cfg_.use_tensor_cores)
+                SEDT_TRY(launch_stem_tc(x + (size_t)n0 * T * F, packed_ + off_stem_wtc, (const float*)(packed_ + off_stem_bias),
+                                        fb.pong, nc, T, F, s));
+            else
+                SEDT_TRY(launch_stem(x + (size_t)n0 * T * F, sw, fb.pong, dt, nc, T, F, s));
+        }
         int h = H0, w = W0;
         void* o = nullptr;
         // stem output sits in `pong`; the first block writes to `ping`

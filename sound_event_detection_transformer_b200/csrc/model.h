@@ -112,7 +112,7 @@ private:
 
     // layer table
     int s_conv0_w, s_conv0_b, s_conv1_w, s_bn1;
-    size_t off_weff, off_sat, off_stem_scale, off_stem_bias;
+    size_t off_weff, off_sat, off_stem_scale, off_stem_bias, off_stem_wtc;
     std::vector<Block> blocks_;
     Linear input_proj_;
     std::vector<EncLayer> enc_;

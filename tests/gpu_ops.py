@@ -58,7 +58,7 @@ def tc_supported(x_nhwc, w_krsc, stride=1, dil=1, pad=0, out_dtype=None) -> bool
     return bool(lib.sedt_op_conv_tc_supported(C.byref(d)))
 
 
-def stem(x, sd, body, out_dtype=torch.float32):
+def stem(x, sd, body, out_dtype=torch.float32, engine=0):
     lib = _lib.load()
     B, _, T, F = x.shape
     hc = (T - 1) // 2 + 1
@@ -69,6 +69,13 @@ def stem(x, sd, body, out_dtype=torch.float32):
     sp = (scratch.data_ptr() + 255) & ~255
     out = torch.empty(B, hp, 16, 64, dtype=out_dtype, device="cuda")
     xx = x.cuda().float().contiguous()
+    if engine == 1:
+        assert out_dtype == torch.bfloat16
+        _lib.check(lib.sedt_op_stem_tc(xx.data_ptr(), g["conv0.weight"].data_ptr(), g["conv0.bias"].data_ptr(),
+                                       g["conv1.weight"].data_ptr(), g["bn1.weight"].data_ptr(), g["bn1.bias"].data_ptr(),
+                                       g["bn1.running_mean"].data_ptr(), g["bn1.running_var"].data_ptr(), sp, out.data_ptr(),
+                                       B, T, F, _lib.current_stream()))
+        return out
     _lib.check(lib.sedt_op_stem(xx.data_ptr(), g["conv0.weight"].data_ptr(), g["conv0.bias"].data_ptr(),
                                 g["conv1.weight"].data_ptr(), g["bn1.weight"].data_ptr(), g["bn1.bias"].data_ptr(),
                                 g["bn1.running_mean"].data_ptr(), g["bn1.running_var"].data_ptr(), sp, out.data_ptr(),

@@ -95,6 +95,26 @@ def test_stem(T, dtype):
         assert rel_err(o[:, :, :, sl], ref[:, :, :, sl]) < tol * 2
 
 
+@pytest.mark.parametrize("T", [500, 496, 128, 333, 61, 7])
+def test_stem_tcgen05(T):
+    """tcgen05 stem (im2col in smem + indicator channel for the conv0-bias border term)."""
+    args = spec.config_args("c1")
+    sd = synth.synth_state_dict(args, 21)
+    x = synth.synth_clips(3, T, 64, seed=T)
+    body = sedt_oracle.BODY
+    ref = F.conv2d(x, sd[body + "conv0.weight"], sd[body + "conv0.bias"])
+    ref = F.conv2d(ref, sd[body + "conv1.weight"], stride=2, padding=3)
+    ref = F.max_pool2d(F.relu(sedt_oracle.frozen_bn(ref, sd, body + "bn1")), 3, 2, 1)
+    out = gpu_ops.stem(x, sd, body, torch.bfloat16, engine=1)
+    torch.cuda.synchronize()
+    assert out.shape == (3, ref.shape[2], 16, 64)
+    o = out.permute(0, 3, 1, 2).float().cpu()
+    assert rel_err(o, ref) < 8e-3                    # bf16 operands (x, folded weights) and bf16 output
+    for sl in (slice(0, 1), slice(-1, None)):
+        assert rel_err(o[:, :, sl, :], ref[:, :, sl, :]) < 1.6e-2
+        assert rel_err(o[:, :, :, sl], ref[:, :, :, sl]) < 1.6e-2
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_layernorm(dtype):
     g = torch.Generator().manual_seed(3)
