@@ -109,9 +109,13 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
     // ---- softmax over this thread's row -------------------------------------------------------
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const float* arow = (amask != nullptr && t < Lq) ? amask + (size_t)t * Lk : nullptr;
+    // only key chunks that hold real keys, and only warps that own real query rows, do softmax work
+    // (decoder: 11 / 21 queries, 21 keys in self-attention)
+    const int nkc = (Lk + 31) >> 5;
+    const bool row_warp = warp * 32 < Lq;
     float m = -CUDART_INF_F;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < (row_warp ? nkc : 0); ++c) {
         uint32_t acc[32];
         tmem_ld32(lane_addr + c * 32, acc);
 #pragma unroll
@@ -124,7 +128,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
     const float mm = (m == -CUDART_INF_F) ? 0.f : m;
     float l = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < (row_warp ? nkc : 0); ++c) {
         uint32_t acc[32];
         tmem_ld32(lane_addr + c * 32, acc);
         uint32_t packed[16];
@@ -156,13 +160,11 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
     // ---- O = P V (accumulates into TMEM columns 0..31, S is dead) ------------------------------
     if (t == 0) {
         constexpr uint32_t idesc = make_idesc(128, HD);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        const int ksteps = (Lk + UMMA_K - 1) / UMMA_K;          // P is exactly 0 beyond Lk inside a processed chunk
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int c = ks >> 2, k = ks & 3;
             const uint32_t sp = smem_u32(smem + SP_OFF + c * 16384), sv = smem_u32(smem + SV_OFF + c * 4096);
-#pragma unroll
-            for (int k = 0; k < 64 / UMMA_K; ++k)
-                umma_bf16(tmem_base, make_smem_desc(sp + k * UMMA_K * 2), make_smem_desc(sv + k * UMMA_K * 2), idesc,
-                          (c > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_base, make_smem_desc(sp + k * UMMA_K * 2), make_smem_desc(sv + k * UMMA_K * 2), idesc, ks > 0 ? 1u : 0u);
         }
         umma_commit(bar_o);
     }

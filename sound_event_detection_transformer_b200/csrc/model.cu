@@ -195,6 +195,11 @@ Model::Model(const Config& c) : cfg_(c)
     qall_ = cfg_.num_queries + (cfg_.dec_at ? 1 : 0);
     s_query_embed = add_slot("query_embed.weight", (int64_t)qall_ * d);
     off_query_embed = reserve((size_t)qall_ * d * 4);
+    {
+        const size_t nd = (size_t)cfg_.dec_layers;
+        off_ck_w = reserve(nd * d * d * dtype_size(act_dt())); off_ck_b = reserve(nd * d * 4);
+        off_cv_w = reserve(nd * d * d * dtype_size(act_dt())); off_cv_b = reserve(nd * d * 4);
+    }
     if (cfg_.dec_at) weak_ = make_linear("weak_class_embed", d, ncls, true);
     if (cfg_.self_sup) {
         patch2query_ = make_linear("patch2query", 2048, d, true);
@@ -247,6 +252,16 @@ int Model::pack(const void* const* weights, void* packed, size_t bytes, cudaStre
         SEDT_TRY(pack_norm(e.n1)); SEDT_TRY(pack_norm(e.n2)); SEDT_TRY(pack_norm(e.n3));
     }
     SEDT_TRY(pack_norm(dec_norm_));
+    for (size_t l = 0; l < dec_.size(); ++l) {          // [Wk_0; Wk_1; ...] and [Wv_0; Wv_1; ...]
+        const int d = cfg_.hidden_dim;
+        const size_t es = dtype_size(dt);
+        const float* w = W(dec_[l].cross_attn.in_proj.w_slot);
+        const float* b = W(dec_[l].cross_attn.in_proj.b_slot);
+        SEDT_TRY(launch_cast(w + (size_t)d * d, (char*)P(off_ck_w) + l * d * d * es, dt, (int64_t)d * d, s));
+        SEDT_TRY(launch_cast(w + (size_t)2 * d * d, (char*)P(off_cv_w) + l * d * d * es, dt, (int64_t)d * d, s));
+        SEDT_TRY(launch_cast(b + d, (float*)P(off_ck_b) + l * d, DT_F32, d, s));
+        SEDT_TRY(launch_cast(b + 2 * d, (float*)P(off_cv_b) + l * d, DT_F32, d, s));
+    }
     SEDT_TRY(pack_linear(class_embed_)); SEDT_TRY(pack_linear(bbox0_)); SEDT_TRY(pack_linear(bbox1_));
     SEDT_TRY(pack_linear(bbox2_)); SEDT_TRY(pack_linear(input_proj_));
     SEDT_TRY(launch_stem_pack(W(s_conv0_w), W(s_conv0_b), W(s_conv1_w), (float*)P(off_weff), (float*)P(off_sat), s));
@@ -416,6 +431,23 @@ int Model::backbone(const float* x, int N, int T, int F, Arena& ws, void** feat,
     return SEDT_OK;
 }
 
+// Cross attention with K / V already projected (all decoder layers at once, see forward()).
+int Model::cross_mha(const Mha& A, const void* q_in, const void* Kp, const void* Vp, int ldkv, int64_t B, int Lq, int Lk,
+                     const uint8_t* kpm, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry)
+{
+    const int d = cfg_.hidden_dim, dt = act_dt();
+    const size_t es = dtype_size(dt);
+    const size_t mark = ws.off;
+    const float scale = (float)std::sqrt(1.0 / (double)(d / cfg_.nheads));
+    void* qb = ws.alloc((size_t)B * Lq * d * es);
+    void* ao = ws.alloc((size_t)B * Lq * d * es);
+    SEDT_TRY(linear(A.in_proj, 0, d, q_in, dt, d, B * Lq, nullptr, qb, dt, d, 0, s, dry));
+    if (!dry) SEDT_TRY(launch_attention(qb, d, Kp, ldkv, Vp, ldkv, ao, d, dt, kpm, nullptr, (int)B, cfg_.nheads, Lq, Lk, scale, s));
+    SEDT_TRY(linear(A.out_proj, 0, d, ao, dt, d, B * Lq, resid32, out32, DT_F32, d, 0, s, dry));
+    ws.off = mark;
+    return SEDT_OK;
+}
+
 int Model::mha(const Mha& A, bool self_attn, const void* q_in, const void* k_in, const void* v_in, int64_t B, int Lq, int Lk,
                const uint8_t* kpm, const float* amask, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry)
 {
@@ -544,6 +576,20 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
         if (out.memory != nullptr) SEDT_CHECK_CUDA(cudaMemcpyAsync(out.memory, x32, (size_t)rows * d * 4, cudaMemcpyDeviceToDevice, s));
     }
 
+    // cross-attention keys / values of every decoder layer: K_l = (memory + pos) Wk_l^T, V_l = memory Wv_l^T
+    const int Dn_ = (int)dec_.size();
+    void* ck_all = ws.alloc((size_t)rows * Dn_ * d * es);
+    void* cv_all = ws.alloc((size_t)rows * Dn_ * d * es);
+    {
+        ConvGemm g;
+        g.in_dt = g.out_dt = dt; g.B = (int)rows; g.H = g.W = g.Ho = g.Wo = 1; g.Cin = d; g.lda = d;
+        g.Cout = Dn_ * d; g.ldc = Dn_ * d; g.ld_res = Dn_ * d;
+        g.in = mempos; g.w = packed_ + off_ck_w; g.bias = (const float*)(packed_ + off_ck_b); g.out = ck_all;
+        SEDT_TRY(gemm(g, s, dry));
+        g.in = mem; g.w = packed_ + off_cv_w; g.bias = (const float*)(packed_ + off_cv_b); g.out = cv_all;
+        SEDT_TRY(gemm(g, s, dry));
+    }
+
     // ---- decoder (transformer.py:123-152, :240-284)
     const int64_t qrows = (int64_t)B * Qall;
     const float* qpos = cfg_.self_sup ? qpos_batched : P_(off_query_embed);
@@ -565,7 +611,8 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
             SEDT_TRY(LN(e.n1, t32, qpos, qpos_rows, da, dap, nullptr, qrows));
             SEDT_TRY(mha(e.self_attn, true, dap, dap, da, B, Qall, Qall, nullptr, amask, t32, t32, ws, s, dry));
             SEDT_TRY(LN(e.n2, t32, qpos, qpos_rows, nullptr, dap, nullptr, qrows));
-            SEDT_TRY(mha(e.cross_attn, false, dap, mempos, mem, B, Qall, S, mask_ds, nullptr, t32, t32, ws, s, dry));
+            SEDT_TRY(cross_mha(e.cross_attn, dap, (const char*)ck_all + l * d * es, (const char*)cv_all + l * d * es, Dn_ * d, B, Qall, S,
+                               mask_ds, t32, t32, ws, s, dry));
             SEDT_TRY(LN(e.n3, t32, nullptr, 1, da, nullptr, nullptr, qrows));
             SEDT_TRY(linear(e.lin1, 0, ff, da, dt, d, qrows, nullptr, dffh, dt, ff, 1, s, dry));
             SEDT_TRY(linear(e.lin2, 0, d, dffh, dt, ff, qrows, t32, t32, DT_F32, d, 0, s, dry));
@@ -573,7 +620,8 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
             if (!dry) SEDT_TRY(launch_cast_addpos(t32, qpos, qpos_rows, da, dap, dt, qrows, s));
             SEDT_TRY(mha(e.self_attn, true, dap, dap, da, B, Qall, Qall, nullptr, amask, t32, t32, ws, s, dry));
             SEDT_TRY(LN(e.n1, t32, qpos, qpos_rows, nullptr, dap, t32, qrows));
-            SEDT_TRY(mha(e.cross_attn, false, dap, mempos, mem, B, Qall, S, mask_ds, nullptr, t32, t32, ws, s, dry));
+            SEDT_TRY(cross_mha(e.cross_attn, dap, (const char*)ck_all + l * d * es, (const char*)cv_all + l * d * es, Dn_ * d, B, Qall, S,
+                               mask_ds, t32, t32, ws, s, dry));
             SEDT_TRY(LN(e.n2, t32, nullptr, 1, da, nullptr, t32, qrows));
             SEDT_TRY(linear(e.lin1, 0, ff, da, dt, d, qrows, nullptr, dffh, dt, ff, 1, s, dry));
             SEDT_TRY(linear(e.lin2, 0, d, dffh, dt, ff, qrows, t32, t32, DT_F32, d, 0, s, dry));

@@ -102,6 +102,8 @@ private:
     int run_blocks(size_t b0, size_t b1, const void* in, int N, int* H, int* W, const BlockBufs& bb, void* final_out, void** out,
                    cudaStream_t s, bool dry);
     int backbone(const float* x, int N, int T, int F, Arena& ws, void** feat, int* H, int* W, cudaStream_t s, bool dry);
+    int cross_mha(const Mha& A, const void* q_in, const void* Kp, const void* Vp, int ldkv, int64_t B, int Lq, int Lk,
+                  const uint8_t* kpm, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry);
     int mha(const Mha& A, bool self_attn, const void* q_in, const void* k_in, const void* v_in, int64_t B, int Lq, int Lk,
             const uint8_t* kpm, const float* amask, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry);
 
@@ -121,6 +123,9 @@ private:
     Norm dec_norm_;
     Linear class_embed_, bbox0_, bbox1_, bbox2_, weak_, patch2query_, falign0_, falign1_;
     int s_query_embed; size_t off_query_embed;
+    // cross-attention K / V projection weights of all decoder layers, concatenated ([D*256, 256]) so that the
+    // encoder memory is projected by two GEMMs instead of 2*D
+    size_t off_ck_w, off_ck_b, off_cv_w, off_cv_b;
     int qall_;
 };
 

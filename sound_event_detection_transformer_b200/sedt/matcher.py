@@ -30,21 +30,26 @@ class HungarianMatcher(nn.Module):
             raise NotImplementedError("the focal-loss class cost (fl) and the fine_tune relaxation "
                                       "(sedt/matcher.py:77-82,99-121) are not on the B200 hot path yet (SURVEY 8f.3)")
         rows, cols, counts = self.match(outputs["pred_logits"], outputs["pred_boxes"], targets)
+        # compact the padded [B,Q] index matrices once on the device, then one split on the host
+        valid = rows >= 0
+        flat_r, flat_c = rows[valid], cols[valid]
         if not self.device_indices:
-            rows, cols = rows.cpu(), cols.cpu()
-        idx: List[Tuple[torch.Tensor, torch.Tensor]] = []
+            flat_r, flat_c = flat_r.cpu(), flat_c.cpu()
+        rs, cs = flat_r.split(counts), flat_c.split(counts)
+        idx: List[Tuple[torch.Tensor, torch.Tensor]] = list(zip(rs, cs))
         coef: List[torch.Tensor] = []
-        for i, n in enumerate(counts):
-            r, c = rows[i, :n], cols[i, :n]
-            idx.append((r, c))
-            if normalize:
-                cur = c.tolist()
-                num = Counter(cur)
-                coef.append(torch.tensor([1 / num[j] for j in cur], dtype=torch.float32))
-            elif "ratio" in targets[i]:
-                coef.append(targets[i]["ratio"].cpu())
-            else:
-                coef.append(torch.ones(n, dtype=torch.float32))
+        if normalize or any("ratio" in t for t in targets):
+            for i, n in enumerate(counts):
+                if normalize:
+                    cur = cs[i].tolist()
+                    num = Counter(cur)
+                    coef.append(torch.tensor([1 / num[j] for j in cur], dtype=torch.float32))
+                elif "ratio" in targets[i]:
+                    coef.append(targets[i]["ratio"].cpu())
+                else:
+                    coef.append(torch.ones(n, dtype=torch.float32))
+        else:
+            coef = list(torch.ones(sum(counts), dtype=torch.float32).split(counts))
         return idx, coef
 
     @torch.no_grad()
@@ -63,8 +68,10 @@ class HungarianMatcher(nn.Module):
         logits = pred_logits.detach().to(torch.float32).contiguous()
         boxes = pred_boxes.detach().to(torch.float32).contiguous()
         if sum(sizes) > 0:
-            tgt_ids = torch.cat([v["labels"][:len(v["boxes"])].reshape(-1) for v in targets]).to(dev, torch.int64).contiguous()
-            tgt_box = torch.cat([v["boxes"].reshape(-1, 2) for v in targets]).to(dev, torch.float32).contiguous()
+            # matcher.py:69 slices labels to the number of boxes; skip the per-clip slice when they already agree
+            labs = [v["labels"] if v["labels"].shape[0] == k else v["labels"][:k] for v, k in zip(targets, sizes)]
+            tgt_ids = torch.cat(labs).reshape(-1).to(dev, torch.int64).contiguous()
+            tgt_box = torch.cat([v["boxes"] for v in targets]).reshape(-1, 2).to(dev, torch.float32).contiguous()
         else:
             tgt_ids = torch.zeros(1, dtype=torch.int64, device=dev)
             tgt_box = torch.zeros(1, 2, dtype=torch.float32, device=dev)
