@@ -136,7 +136,8 @@ typedef struct sedt_conv_desc {
     int32_t B, H, W, Cin, lda, Ho, Wo, Cout, ldc, ld_res, R, S, stride, dil, pad, relu;
 } sedt_conv_desc;
 /* Conv/linear + FrozenBN scale/bias + residual + ReLU as implicit GEMM (NHWC in, [Cout][R][S][Cin] weights).
- * engine: 0 = CUDA-core kernel, 1 = TMA + tcgen05 kernel (bf16 in). */
+ * engine: 0 = CUDA-core kernel, 1 = TMA + tcgen05 kernel (bf16 in; picks the 1-SM or 2-SM variant),
+ *         2 = force the cta_group::2 variant (bf16 out, Cout % 256 == 0, enough tiles). */
 SEDT_API int sedt_op_conv(const sedt_conv_desc* d, int engine, void* stream);
 SEDT_API int sedt_op_conv_tc_supported(const sedt_conv_desc* d);
 /* OIHW fp32 -> O(HW)I in `dtype` */

@@ -249,7 +249,7 @@ int encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int r
     return SEDT_OK;
 }
 
-int build_problem(const ConvGemm& g, int block_n, TcProblem* out)
+int build_problem(const ConvGemm& g, int block_n, TcProblem* out, int b_split)
 {
     TcParams& p = out->p;
     memset(out, 0, sizeof(*out));
@@ -296,9 +296,19 @@ int build_problem(const ConvGemm& g, int block_n, TcProblem* out)
     const uint64_t K = (uint64_t)g.R * g.S * g.Cin;
     const uint64_t bdims[2] = {K, (uint64_t)g.Cout};
     const uint64_t bstrides[1] = {K * 2};
-    const uint32_t bbox[2] = {(uint32_t)BLOCK_K, (uint32_t)block_n};
+    const uint32_t bbox[2] = {(uint32_t)BLOCK_K, (uint32_t)(block_n / b_split)};     // b_split = 2: each CTA of a pair loads half
     return encode_map(&out->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, g.w, 2, bdims, bstrides, bbox);
 }
+
+int encode_out_map(CUtensorMap* m, const void* base, int ld, bool f32, const ConvGemm& g, const TcParams& p)
+{
+    const int es = f32 ? 4 : 2;
+    const uint64_t dims[4] = {(uint64_t)g.Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)ld * es, (uint64_t)g.Wo * ld * es, (uint64_t)g.Ho * g.Wo * ld * es};
+    const uint32_t box[4] = {(uint32_t)(128 / es), (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    return encode_map(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, 4, dims, strides, box);
+}
+
 
 }  // namespace tc
 

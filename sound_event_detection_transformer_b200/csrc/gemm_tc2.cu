@@ -21,18 +21,7 @@ namespace {
 
 using namespace tc;
 
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                 ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-constexpr int NUM_THREADS2 = 224;      // 7 warps: producer, MMA, 4 x epilogue, store
+constexpr int NUM_THREADS2 = 352;      // 11 warps: producer, MMA, 8 x epilogue (two per TMEM lane quadrant), store
 
 template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO>
 struct Smem2 {
@@ -48,82 +37,10 @@ struct Smem2 {
     static constexpr int TOTAL = BAR_OFFSET + NBARS * 8 + 16 + 1024;
 };
 
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// One 32-column slab of the tile row owned by this thread: bias (+scale), residual, ReLU, convert, stage.
-template <typename TO, int CHUNK_BYTES>
-__device__ __forceinline__ void epilogue_slab(uint32_t (&acc)[32], int c, int nb, const float* __restrict__ scale,
-                                              const float* __restrict__ bias, bool has_res, int relu, uint8_t* ostage,
-                                              int r, int sw)
-{
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-    if (scale != nullptr) {
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + nb) + j4);
-            v[4 * j4] *= s4.x; v[4 * j4 + 1] *= s4.y; v[4 * j4 + 2] *= s4.z; v[4 * j4 + 3] *= s4.w;
-        }
-    }
-    if (bias != nullptr) {
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb) + j4);
-            v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
-        }
-    }
-    if constexpr (sizeof(TO) == 2) {
-        // 32 columns = 64 bytes = pieces (c&1)*4 .. +3 of the 128-byte row of chunk c/2
-        uint8_t* row = ostage + (c >> 1) * CHUNK_BYTES + r * 128;
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-            uint4* slot = reinterpret_cast<uint4*>(row + ((((c & 1) * 4 + j8) ^ sw) << 4));
-            if (has_res) {
-                const uint4 u = *slot;
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
-                    v[8 * j8 + 2 * q] += __low2float(h); v[8 * j8 + 2 * q + 1] += __high2float(h);
-                }
-            }
-            uint32_t w[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float a = v[8 * j8 + 2 * q], b = v[8 * j8 + 2 * q + 1];
-                if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-                w[q] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            *slot = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-    } else {
-        // 32 columns = 128 bytes = the whole staging row of chunk c
-        uint8_t* row = ostage + c * CHUNK_BYTES + r * 128;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            float4* slot = reinterpret_cast<float4*>(row + ((j4 ^ sw) << 4));
-            float4 o4 = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-            if (has_res) { const float4 r4 = *slot; o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w; }
-            if (relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
-            *slot = o4;
-        }
-    }
-}
-
-template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO>
+// PAIR = 2: launched as clusters of two CTAs that work on vertically adjacent M tiles of the same N tile.
+// Each CTA fetches half of the B (weight) tile and multicasts it to both, so the weight stream is read
+// from L2 once per pair; smem stages are recycled only when BOTH MMA warps have released them.
+template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO, int PAIR>
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                 const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
@@ -151,20 +68,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a0); prefetch_tmap(&map_b); prefetch_tmap(&map_out);
         if (has_res) prefetch_tmap(&map_res);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
-        for (int s = 0; s < OUT_BUFS; ++s) { mbar_init(&buf_ready[s], 1); mbar_init(&buf_full[s], 4); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+        for (int s = 0; s < OUT_BUFS; ++s) { mbar_init(&buf_ready[s], 1); mbar_init(&buf_full[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if (PAIR == 2) cluster_sync_all();                // the peer's barriers are initialised before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int crank = PAIR == 2 ? (int)cluster_ctarank() : 0;
+    // schedule: work item t = (pair-row pm, n_tile); with PAIR == 2 the two CTAs of a cluster take M tiles 2pm, 2pm+1
+    const int first_item = PAIR == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int item_stride = PAIR == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-    // tile -> coordinates.  N tiles are adjacent in the schedule: t = m_tile * tiles_nc + n_tile.
+    // item -> coordinates.  N tiles are adjacent in the schedule: t = m_item * tiles_nc + n_tile.
     auto tile_coords = [&](int t, int& w0, int& h0, int& n0, int& col0) {
-        const int n_tile = t % tiles_nc, m_tile = t / tiles_nc;
+        const int n_tile = t % tiles_nc, m_tile = (t / tiles_nc) * PAIR + crank;
         const int tw = m_tile % p.tiles_w;
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
         const int tn = m_tile / (p.tiles_w * p.tiles_h);
@@ -175,7 +97,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = first_item; t < total_tiles; t += item_stride) {
                 int w0, h0, n0, col0;
                 tile_coords(t, w0, h0, n0, col0);
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -187,7 +109,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                     const int mi = p.tap_map[tap];
                     const CUtensorMap* ma = mi == 0 ? &map_a0 : (mi == 1 ? &map_a1 : (mi == 2 ? &map_a2 : &map_a3));
                     tma_load_4d(ma, sa, &full_bar[stage], c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-                    tma_load_2d(&map_b, sb, &full_bar[stage], tap * p.Cin + c0, col0);
+                    if (PAIR == 2)      // my half of the weight tile, delivered to both CTAs of the pair
+                        tma_load_2d_mcast(&map_b, sb + crank * (L::B_STAGE_BYTES / 2), &full_bar[stage], tap * p.Cin + c0,
+                                          col0 + crank * (BLOCK_N / 2), (uint16_t)0x3);
+                    else
+                        tma_load_2d(&map_b, sb, &full_bar[stage], tap * p.Cin + c0, col0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -198,7 +124,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
             int stage = 0; uint32_t phase = 0;
             int li = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+            for (int t = first_item; t < total_tiles; t += item_stride, ++li) {
                 const int as = li & 1;
                 mbar_wait(&acc_empty[as], ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
@@ -213,13 +139,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                         umma_bf16(tmem_d, make_smem_desc(sa + k * UMMA_K * 2), make_smem_desc(sb + k * UMMA_K * 2), idesc,
                                   (kb > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if (PAIR == 2) umma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);   // both producers wait for both MMA warps
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&acc_full[as]);
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 10) {
         // ===== store warp: TMA stores of finished tiles, residual prefetch, staging-buffer recycling =====
         if (lane == 0) {
             uint8_t* out_base = smem + L::OUT_OFFSET;
@@ -237,11 +164,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                 }
             };
             {
-                int t = blockIdx.x;
-                for (int k = 0; k < OUT_BUFS && t < total_tiles; ++k, t += gridDim.x) make_ready(t, k);
+                int t = first_item;
+                for (int k = 0; k < OUT_BUFS && t < total_tiles; ++k, t += item_stride) make_ready(t, k);
             }
             int li = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+            for (int t = first_item; t < total_tiles; t += item_stride, ++li) {
                 const int ob = li % OUT_BUFS;
                 int w0, h0, n0, col0;
                 tile_coords(t, w0, h0, n0, col0);
@@ -251,18 +178,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                     tma_store_4d(&map_out, out_base + ob * L::OUT_BYTES + c * L::CHUNK_BYTES, col0 + c * L::CHUNK_COLS, w0, h0, n0);
                 tma_store_commit();
                 tma_store_wait_read0();                  // staging buffer has been read out
-                const int tn = t + OUT_BUFS * (int)gridDim.x;
+                const int tn = t + OUT_BUFS * item_stride;
                 if (tn < total_tiles) make_ready(tn, ob);
             }
         }
     } else {
-        // ===== epilogue warps 2..5 =====
+        // ===== epilogue warps 2..9: warp & 3 = TMEM lane quadrant, (warp - 2) >> 2 = column half of the tile =====
         const int quad = warp & 3;
+        const int colhalf = (warp - 2) >> 2;
         const int r = quad * 32 + lane;                          // tile row owned by this thread
         uint8_t* out_base = smem + L::OUT_OFFSET;
         const int sw = r & 7;
+        constexpr int NS = BLOCK_N / 64;                         // 32-column slabs per warp
         int li = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+        for (int t = first_item; t < total_tiles; t += item_stride, ++li) {
             const int as = li & 1, ob = li % OUT_BUFS;
             const int col0 = (t % tiles_nc) * BLOCK_N;
             mbar_wait(&buf_ready[ob], (li / OUT_BUFS) & 1);      // staging free (and residual landed)
@@ -270,14 +199,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             tc_fence_after();
             uint8_t* ostage = out_base + ob * L::OUT_BYTES;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N);
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; c += 2) {
-                uint32_t acc0[32], acc1[32];
+            if constexpr (NS == 1) {
+                const int c = colhalf;
+                uint32_t acc0[32];
                 tmem_ld32_nowait(taddr + (uint32_t)(c * 32), acc0);
-                tmem_ld32_nowait(taddr + (uint32_t)(c * 32 + 32), acc1);
                 tmem_ld_wait();
                 epilogue_slab<TO, L::CHUNK_BYTES>(acc0, c, col0 + c * 32, p.scale, p.bias, has_res, p.relu, ostage, r, sw);
-                epilogue_slab<TO, L::CHUNK_BYTES>(acc1, c + 1, col0 + c * 32 + 32, p.scale, p.bias, has_res, p.relu, ostage, r, sw);
+            } else {
+#pragma unroll 1
+                for (int c = colhalf * NS; c < (colhalf + 1) * NS; c += 2) {
+                    uint32_t acc0[32], acc1[32];
+                    tmem_ld32_nowait(taddr + (uint32_t)(c * 32), acc0);
+                    tmem_ld32_nowait(taddr + (uint32_t)(c * 32 + 32), acc1);
+                    tmem_ld_wait();
+                    epilogue_slab<TO, L::CHUNK_BYTES>(acc0, c, col0 + c * 32, p.scale, p.bias, has_res, p.relu, ostage, r, sw);
+                    epilogue_slab<TO, L::CHUNK_BYTES>(acc1, c + 1, col0 + c * 32 + 32, p.scale, p.bias, has_res, p.relu, ostage, r, sw);
+                }
             }
             // accumulator stage is free again; staged tile is visible to the async proxy
             tc_fence_before();
@@ -289,40 +226,41 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR == 2) cluster_sync_all();                // no CTA leaves while its peer may still multicast to it / signal it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<2 * BLOCK_N>(tmem_base);
     }
 }
 
-template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO>
+template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO, int PAIR>
 int launch_v2(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr, cudaStream_t stream)
 {
     using L = Smem2<BLOCK_N, STAGES, OUT_BUFS, TO>;
     static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-    auto kern = conv_tc2_kernel<BLOCK_N, STAGES, OUT_BUFS, TO>;
+    auto kern = conv_tc2_kernel<BLOCK_N, STAGES, OUT_BUFS, TO, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
         SEDT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    const int total = pr.tiles_m * pr.tiles_nc;
-    const int grid = std::min(total, num_sms());
+    // work items: (M tile, N tile) or, for PAIR == 2, (pair of vertically adjacent M tiles, N tile)
+    const int m_items = (pr.tiles_m + PAIR - 1) / PAIR;
+    const int total = m_items * pr.tiles_nc;
+    int grid = std::min(total * PAIR, num_sms());
+    if (PAIR == 2) grid &= ~1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NUM_THREADS2); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = PAIR == 2 ? 1 : 0;
     ProfScope _prof(PROF_GEMM_TC, stream);
-    kern<<<grid, NUM_THREADS2, L::TOTAL, stream>>>(pr.map_a[0], pr.map_a[1], pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p,
-                                                  pr.tiles_nc, total);
+    SEDT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pr.map_a[0], pr.map_a[1], pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p,
+                                       pr.tiles_nc, total));
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
-}
-
-int encode_out_map(CUtensorMap* m, const void* base, int ld, bool f32, const ConvGemm& g, const TcParams& p)
-{
-    const int es = f32 ? 4 : 2;
-    const uint64_t dims[4] = {(uint64_t)g.Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.B};
-    const uint64_t strides[3] = {(uint64_t)ld * es, (uint64_t)g.Wo * ld * es, (uint64_t)g.Ho * g.Wo * ld * es};
-    const uint32_t box[4] = {(uint32_t)(128 / es), (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-    return encode_map(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, 4, dims, strides, box);
 }
 
 }  // namespace
@@ -332,6 +270,9 @@ int launch_conv_tc(const ConvGemm& g, cudaStream_t stream)
     static const bool force_v1 = [] { const char* e = getenv("SEDT_TC_V1"); return e != nullptr && e[0] == '1'; }();
     if (force_v1) return launch_conv_tc_v1(g, stream);
     SEDT_REQUIRE(conv_tc_supported(g), "conv_tc: unsupported shape");
+    static const int use_2sm = [] { const char* e = getenv("SEDT_TC_2SM"); return e ? atoi(e) : 1; }();
+    // two SMs per tile pay once the main loop is long (K >= 512); short-K layers are epilogue / HBM bound
+    if (use_2sm && g.R * g.S * g.Cin >= 512 && conv_tc_2sm_preferred(g)) return launch_conv_tc_2sm(g, stream);
     const bool f32 = g.out_dt == DT_F32;
     // BLOCK_N: the widest tile that divides Cout, still leaves about two tiles per SM and has a main
     // loop long enough (num_kb >= min_kb256) to hide the single-buffered 256-wide epilogue
@@ -344,19 +285,25 @@ int launch_conv_tc(const ConvGemm& g, cudaStream_t stream)
         const int64_t m_tiles = ceil_div((int64_t)g.B * g.Ho * g.Wo, BLOCK_M);
         if (m_tiles * (g.Cout / 256) >= 2 * num_sms()) block_n = 256;
     }
+    // clusters of two CTAs sharing the weight tile by TMA multicast (SEDT_TC_PAIR=0 disables)
+    static const int pair_env = [] { const char* e = getenv("SEDT_TC_PAIR"); return e ? atoi(e) : 0; }();     // measured: no gain on B200 (loads are latency-, not bandwidth-bound)
+    const int64_t m_tiles_all = ceil_div((int64_t)g.B * g.Ho * g.Wo, BLOCK_M);
+    const bool pair = pair_env != 0 && m_tiles_all * (g.Cout / block_n) >= 2 * num_sms();
     TcProblem pr;
-    SEDT_TRY(build_problem(g, block_n, &pr));
+    SEDT_TRY(build_problem(g, block_n, &pr, pair ? 2 : 1));
     CUtensorMap mo, mr;
     SEDT_TRY(encode_out_map(&mo, g.out, g.ldc, f32, g, pr.p));
     if (g.residual != nullptr) SEDT_TRY(encode_out_map(&mr, g.residual, g.ld_res, f32, g, pr.p));
     else mr = mo;
+#define SEDT_V2(BN, ST, OB, T) (pair ? launch_v2<BN, ST, OB, T, 2>(pr, mo, mr, stream) : launch_v2<BN, ST, OB, T, 1>(pr, mo, mr, stream))
     if (f32) {
-        if (block_n == 128) return launch_v2<128, 4, 1, float>(pr, mo, mr, stream);
-        return launch_v2<64, 4, 2, float>(pr, mo, mr, stream);
+        if (block_n == 128) return SEDT_V2(128, 4, 1, float);
+        return SEDT_V2(64, 4, 2, float);
     }
-    if (block_n == 256) return launch_v2<256, 3, 1, __nv_bfloat16>(pr, mo, mr, stream);
-    if (block_n == 128) return launch_v2<128, 4, 2, __nv_bfloat16>(pr, mo, mr, stream);
-    return launch_v2<64, 6, 2, __nv_bfloat16>(pr, mo, mr, stream);
+    if (block_n == 256) return SEDT_V2(256, 3, 1, __nv_bfloat16);
+    if (block_n == 128) return SEDT_V2(128, 5, 2, __nv_bfloat16);
+    return SEDT_V2(64, 8, 2, __nv_bfloat16);
+#undef SEDT_V2
 }
 
 }  // namespace sedt

@@ -33,6 +33,10 @@ int launch_conv_simt(const ConvGemm& g, cudaStream_t stream);
 bool conv_tc_supported(const ConvGemm& g);
 int launch_conv_tc(const ConvGemm& g, cudaStream_t stream);      // gemm_tc2.cu: persistent kernel (or v1 if SEDT_TC_V1=1)
 int launch_conv_tc_v1(const ConvGemm& g, cudaStream_t stream);
+// gemm_tc3.cu: cta_group::2 (two SMs per 256 x 256 tile) for bf16-out layers with Cout % 256 == 0
+bool conv_tc_2sm_supported(const ConvGemm& g);
+bool conv_tc_2sm_preferred(const ConvGemm& g);    // ... and enough tiles to fill the SM pairs
+int launch_conv_tc_2sm(const ConvGemm& g, cudaStream_t stream);
 int tc_init();     // resolves cuTensorMapEncodeTiled once; safe without a GPU
 
 // ---- stem.cu : conv0(1x1,bias) + conv1(7x7 s2 p3) + FrozenBN + ReLU + maxpool(3x3 s2 p1), F == 64

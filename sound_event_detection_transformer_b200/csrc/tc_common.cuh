@@ -64,6 +64,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* smem, 
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// same load delivered to every CTA of the cluster named in cta_mask (same smem / mbarrier offsets in each)
+__device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* map, void* smem, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -91,6 +97,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive on the barrier at the same offset in every CTA of cta_mask once this thread's MMAs have retired
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -117,6 +133,94 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 }
 
 
+// ---- epilogue helpers shared by the persistent kernels -------------------------------------
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// One 32-column slab of the tile row owned by this thread: bias (+scale), residual, ReLU, convert, stage.
+template <typename TO, int CHUNK_BYTES>
+__device__ __forceinline__ void epilogue_slab(uint32_t (&acc)[32], int c, int nb, const float* __restrict__ scale,
+                                              const float* __restrict__ bias, bool has_res, int relu, uint8_t* ostage,
+                                              int r, int sw)
+{
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    if (scale != nullptr) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + nb) + j4);
+            v[4 * j4] *= s4.x; v[4 * j4 + 1] *= s4.y; v[4 * j4 + 2] *= s4.z; v[4 * j4 + 3] *= s4.w;
+        }
+    }
+    if (bias != nullptr) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb) + j4);
+            v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+        }
+    }
+    if constexpr (sizeof(TO) == 2) {
+        // 32 columns = 64 bytes = pieces (c&1)*4 .. +3 of the 128-byte row of chunk c/2
+        uint8_t* row = ostage + (c >> 1) * CHUNK_BYTES + r * 128;
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+            uint4* slot = reinterpret_cast<uint4*>(row + ((((c & 1) * 4 + j8) ^ sw) << 4));
+            if (has_res) {
+                const uint4 u = *slot;
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+                    v[8 * j8 + 2 * q] += __low2float(h); v[8 * j8 + 2 * q + 1] += __high2float(h);
+                }
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float a = v[8 * j8 + 2 * q], b = v[8 * j8 + 2 * q + 1];
+                if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                w[q] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *slot = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    } else {
+        // 32 columns = 128 bytes = the whole staging row of chunk c
+        uint8_t* row = ostage + c * CHUNK_BYTES + r * 128;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            float4* slot = reinterpret_cast<float4*>(row + ((j4 ^ sw) << 4));
+            float4 o4 = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+            if (has_res) { const float4 r4 = *slot; o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w; }
+            if (relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
+            *slot = o4;
+        }
+    }
+}
+
+
 // ---- host side (gemm_tc.cu) ---------------------------------------------------------------
 struct TcProblem {
     TcParams p;
@@ -127,8 +231,10 @@ struct TcProblem {
 int encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
                const uint64_t* strides_bytes, const uint32_t* box);
 // fills p, the A phase maps / tap table and the B map for the chosen BLOCK_N
-int build_problem(const ConvGemm& g, int block_n, TcProblem* out);
+int build_problem(const ConvGemm& g, int block_n, TcProblem* out, int b_split = 1);
 int num_sms();
+// 4-D map over an NHWC output / residual tensor with 128-byte inner boxes (64 bf16 or 32 fp32 columns)
+int encode_out_map(CUtensorMap* m, const void* base, int ld, bool f32, const ConvGemm& g, const TcParams& p);
 
 }  // namespace tc
 }  // namespace sedt

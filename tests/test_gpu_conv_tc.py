@@ -91,3 +91,29 @@ def test_conv_tc_inplace_residual():
     _lib.check(lib.sedt_op_conv(C.byref(d), 1, _lib.current_stream()))
     torch.cuda.synchronize()
     assert rel_err(ad, ref) < 1e-5
+
+
+TC_2SM_SHAPES = [
+    (40, 31, 4, 512, 2048, 1, 1, 1, True, True),      # layer4 conv3 + residual
+    (40, 31, 4, 512, 512, 3, 1, 2, False, True),      # layer4 conv2, dilation 2, K = 4608
+    (20, 124, 16, 64, 256, 1, 1, 1, True, True),      # layer1 conv3: one k block per tile, many tiles per cluster
+    (37, 31, 4, 1024, 256, 1, 1, 1, False, True),     # odd number of M tiles: the peer CTA's last tile is out of range
+    (24, 62, 8, 256, 256, 3, 2, 1, False, True),      # stride 2 through phase views
+    (300, 1, 124, 256, 512, 1, 1, 1, False, False),   # token-major linear (QK projection shape), no ReLU
+]
+
+
+@pytest.mark.parametrize("shape", TC_2SM_SHAPES)
+def test_conv_tc_2sm(shape):
+    """cta_group::2 kernel (engine 2) against torch fp32 conv and against the 1-SM kernel."""
+    B, H, W, Cin, Cout, k, stride, dil, res, relu = shape
+    x, w, scale, bias, pad, r, ref = _conv_case(*shape, seed=9, dtype=torch.bfloat16)
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
+    wd = gpu_ops.repack(w, torch.bfloat16)
+    rd = r.permute(0, 2, 3, 1).contiguous().cuda().bfloat16() if res else None
+    out = gpu_ops.conv(xd, wd, scale.cuda(), bias.cuda(), rd, stride, dil, pad, relu, torch.bfloat16, engine=2)
+    torch.cuda.synchronize()
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < 4e-3
+    out0 = gpu_ops.conv(xd, wd, scale.cuda(), bias.cuda(), rd, stride, dil, pad, relu, torch.bfloat16, engine=0)
+    torch.cuda.synchronize()
+    assert rel_err(out, out0) < 4e-3
