@@ -1,5 +1,4 @@
-// 2-SM (cta_group::2) variant of the persistent implicit-GEMM kernel for wide layers (Cout % 256 == 0,
-// bf16 out).
+// 2-SM (cta_group::2) variant of the persistent implicit-GEMM kernel for wide layers (Cout % 256 == 0).
 //
 // A cluster of two CTAs computes a 256 x 256 output tile per step: CTA r owns M tile 2*pm + r (128 output
 // pixels) and loads, per 64-wide k block, its own A box (16 KiB) and rows [128 r, 128 r + 128) of the B
@@ -15,7 +14,7 @@
 //   acc_full[a]  both; multicast commit after the last k block of a tile
 //   acc_empty[a] leader only, count 16: the eight epilogue warps of both CTAs (peer arrives remotely)
 //   buf_ready / buf_full: per-CTA handshake between epilogue warps and the store warp (as in gemm_tc2.cu),
-//   on 128-column half tiles so that stores overlap the other half's epilogue.
+//   on 32 KiB sub-tiles (128 bf16 / 64 fp32 columns) so that stores overlap the next sub-tile's epilogue.
 #include "tc_common.cuh"
 #include <cstdlib>
 
@@ -26,9 +25,9 @@ using namespace tc;
 
 constexpr int T3_THREADS = 352;              // producer, MMA, 8 epilogue warps, store warp
 constexpr int T3_BN = 256;                   // columns per cluster tile
-constexpr int T3_HALF = 128;                 // B rows held per CTA, and epilogue half-tile width
+constexpr int T3_HALF = 128;                 // B rows held per CTA
 constexpr int T3_STAGE = A_STAGE_BYTES + T3_HALF * BLOCK_K * 2;     // 32 KiB
-constexpr int T3_OUT_BYTES = BLOCK_M * T3_HALF * 2;                 // 32 KiB per half tile (bf16)
+constexpr int T3_OUT_BYTES = 32768;          // one epilogue sub-tile: 128 rows x (128 bf16 | 64 fp32) columns
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the leader CTA
 
 template <int STAGES>
@@ -67,7 +66,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <int STAGES>
+template <int STAGES, typename TO>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                 const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
@@ -76,6 +75,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                 const int tiles_nc, const int total_items)
 {
     using L = Smem3<STAGES>;
+    constexpr int SUBW = T3_OUT_BYTES / (BLOCK_M * (int)sizeof(TO));      // columns per epilogue sub-tile: 128 | 64
+    constexpr int NSUB = T3_BN / SUBW;                                    // sub-tiles per tile: 2 | 4
+    constexpr int CCOLS = 128 / (int)sizeof(TO);                          // columns per 128-byte staging row: 64 | 32
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = (uint64_t*)(smem + L::BAR_OFFSET);
@@ -172,32 +174,37 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         // ===== store warp: half tiles of 128 columns =====
         if (lane == 0) {
             uint8_t* out_base = smem + L::OUT_OFFSET;
-            auto make_ready = [&](int t, int hh) {
+            // sub-tile q of this CTA's tile sequence uses staging buffer q & 1
+            auto make_ready = [&](int t, int st, int buf) {
                 if (has_res) {
                     int w0, h0, n0, col0;
                     tile_coords(t, w0, h0, n0, col0);
-                    mbar_expect_tx(&buf_ready[hh], T3_OUT_BYTES);
+                    mbar_expect_tx(&buf_ready[buf], T3_OUT_BYTES);
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
-                        tma_load_4d(&map_res, out_base + hh * T3_OUT_BYTES + c * 16384, &buf_ready[hh],
-                                    col0 + hh * T3_HALF + c * 64, w0, h0, n0);
+                        tma_load_4d(&map_res, out_base + buf * T3_OUT_BYTES + c * 16384, &buf_ready[buf],
+                                    col0 + st * SUBW + c * CCOLS, w0, h0, n0);
                 } else {
-                    mbar_arrive(&buf_ready[hh]);
+                    mbar_arrive(&buf_ready[buf]);
                 }
             };
-            if (first_item < total_items) { make_ready(first_item, 0); make_ready(first_item, 1); }
-            int li = 0;
-            for (int t = first_item; t < total_items; t += item_stride, ++li) {
+            if (first_item < total_items) { make_ready(first_item, 0, 0); make_ready(first_item, 1, 1); }
+            int q = 0;
+            for (int t = first_item; t < total_items; t += item_stride) {
                 int w0, h0, n0, col0;
                 tile_coords(t, w0, h0, n0, col0);
-                for (int hh = 0; hh < 2; ++hh) {
-                    mbar_wait(&buf_full[hh], li & 1);
+                for (int st = 0; st < NSUB; ++st, ++q) {
+                    const int buf = q & 1;
+                    mbar_wait(&buf_full[buf], (q >> 1) & 1);
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
-                        tma_store_4d(&map_out, out_base + hh * T3_OUT_BYTES + c * 16384, col0 + hh * T3_HALF + c * 64, w0, h0, n0);
+                        tma_store_4d(&map_out, out_base + buf * T3_OUT_BYTES + c * 16384, col0 + st * SUBW + c * CCOLS, w0, h0, n0);
                     tma_store_commit();
                     tma_store_wait_read0();
-                    if (t + item_stride < total_items) make_ready(t + item_stride, hh);
+                    // the sub-tile that will use this buffer next is two ahead in the sequence
+                    int t2 = t, st2 = st + 2;
+                    if (st2 >= NSUB) { st2 -= NSUB; t2 += item_stride; }
+                    if (t2 < total_items) make_ready(t2, st2, buf);
                 }
             }
         }
@@ -209,29 +216,36 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         const int r = quad * 32 + lane;
         uint8_t* out_base = smem + L::OUT_OFFSET;
         const int sw = r & 7;
-        int li = 0;
+        int li = 0, q = 0;
         for (int t = first_item; t < total_items; t += item_stride, ++li) {
             const int as = li & 1;
             const int col0 = (t % tiles_nc) * T3_BN;
             mbar_wait(&acc_full[as], (li >> 1) & 1);
             tc_fence_after();
-            for (int hh = 0; hh < 2; ++hh) {
-                mbar_wait(&buf_ready[hh], li & 1);
-                uint8_t* ostage = out_base + hh * T3_OUT_BYTES;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * T3_BN + hh * T3_HALF);
-                {
-                    const int c = colhalf * 2;
+            for (int st = 0; st < NSUB; ++st, ++q) {
+                const int buf = q & 1;
+                mbar_wait(&buf_ready[buf], (q >> 1) & 1);
+                uint8_t* ostage = out_base + buf * T3_OUT_BYTES;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * T3_BN + st * SUBW);
+                if constexpr (sizeof(TO) == 2) {
+                    const int c = colhalf * 2;                   // two 32-column slabs of the 128-column sub-tile
                     uint32_t acc0[32], acc1[32];
                     tmem_ld32_nowait(taddr + (uint32_t)(c * 32), acc0);
                     tmem_ld32_nowait(taddr + (uint32_t)(c * 32 + 32), acc1);
                     tmem_ld_wait();
-                    const int nb = col0 + hh * T3_HALF + c * 32;
-                    epilogue_slab<__nv_bfloat16, 16384>(acc0, c, nb, p.scale, p.bias, has_res, p.relu, ostage, r, sw);
-                    epilogue_slab<__nv_bfloat16, 16384>(acc1, c + 1, nb + 32, p.scale, p.bias, has_res, p.relu, ostage, r, sw);
+                    const int nb = col0 + st * SUBW + c * 32;
+                    epilogue_slab<TO, 16384>(acc0, c, nb, p.scale, p.bias, has_res, p.relu, ostage, r, sw);
+                    epilogue_slab<TO, 16384>(acc1, c + 1, nb + 32, p.scale, p.bias, has_res, p.relu, ostage, r, sw);
+                } else {
+                    const int c = colhalf;                       // one 32-column slab of the 64-column sub-tile
+                    uint32_t acc0[32];
+                    tmem_ld32_nowait(taddr + (uint32_t)(c * 32), acc0);
+                    tmem_ld_wait();
+                    epilogue_slab<TO, 16384>(acc0, c, col0 + st * SUBW + c * 32, p.scale, p.bias, has_res, p.relu, ostage, r, sw);
                 }
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&buf_full[hh]);
+                if (lane == 0) mbar_arrive(&buf_full[buf]);
             }
             tc_fence_before();
             __syncwarp();
@@ -248,12 +262,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     }
 }
 
-template <int STAGES>
+template <int STAGES, typename TO>
 int launch_v3(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr, cudaStream_t stream)
 {
     using L = Smem3<STAGES>;
     static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-    auto kern = conv_tc3_kernel<STAGES>;
+    auto kern = conv_tc3_kernel<STAGES, TO>;
     static bool attr_set = false;
     if (!attr_set) {
         SEDT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -280,7 +294,7 @@ int launch_v3(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr,
 bool conv_tc_2sm_supported(const ConvGemm& g)
 {
     if (!conv_tc_supported(g)) return false;
-    return g.out_dt == DT_BF16 && g.Cout % T3_BN == 0;
+    return g.Cout % T3_BN == 0;
 }
 
 bool conv_tc_2sm_preferred(const ConvGemm& g)
@@ -297,10 +311,11 @@ int launch_conv_tc_2sm(const ConvGemm& g, cudaStream_t stream)
     TcProblem pr;
     SEDT_TRY(build_problem(g, T3_BN, &pr, 2));          // B box = 128 rows: each CTA loads its half of the 256-wide tile
     CUtensorMap mo, mr;
-    SEDT_TRY(encode_out_map(&mo, g.out, g.ldc, false, g, pr.p));
-    if (g.residual != nullptr) SEDT_TRY(encode_out_map(&mr, g.residual, g.ld_res, false, g, pr.p));
+    const bool f32 = g.out_dt == DT_F32;
+    SEDT_TRY(encode_out_map(&mo, g.out, g.ldc, f32, g, pr.p));
+    if (g.residual != nullptr) SEDT_TRY(encode_out_map(&mr, g.residual, g.ld_res, f32, g, pr.p));
     else mr = mo;
-    return launch_v3<5>(pr, mo, mr, stream);
+    return f32 ? launch_v3<5, float>(pr, mo, mr, stream) : launch_v3<5, __nv_bfloat16>(pr, mo, mr, stream);
 }
 
 }  // namespace sedt

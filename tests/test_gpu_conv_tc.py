@@ -104,16 +104,39 @@ TC_2SM_SHAPES = [
 
 
 @pytest.mark.parametrize("shape", TC_2SM_SHAPES)
-def test_conv_tc_2sm(shape):
-    """cta_group::2 kernel (engine 2) against torch fp32 conv and against the 1-SM kernel."""
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_conv_tc_2sm(shape, out_dtype):
+    """cta_group::2 kernel (engine 2) against torch fp32 conv and against the CUDA-core kernel."""
     B, H, W, Cin, Cout, k, stride, dil, res, relu = shape
     x, w, scale, bias, pad, r, ref = _conv_case(*shape, seed=9, dtype=torch.bfloat16)
     xd = x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
     wd = gpu_ops.repack(w, torch.bfloat16)
-    rd = r.permute(0, 2, 3, 1).contiguous().cuda().bfloat16() if res else None
-    out = gpu_ops.conv(xd, wd, scale.cuda(), bias.cuda(), rd, stride, dil, pad, relu, torch.bfloat16, engine=2)
+    rd = r.permute(0, 2, 3, 1).contiguous().cuda().to(out_dtype) if res else None
+    out = gpu_ops.conv(xd, wd, scale.cuda(), bias.cuda(), rd, stride, dil, pad, relu, out_dtype, engine=2)
     torch.cuda.synchronize()
-    assert rel_err(out.permute(0, 3, 1, 2), ref) < 4e-3
-    out0 = gpu_ops.conv(xd, wd, scale.cuda(), bias.cuda(), rd, stride, dil, pad, relu, torch.bfloat16, engine=0)
+    tol = 4e-3 if out_dtype == torch.bfloat16 else 1e-5
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < tol
+    out0 = gpu_ops.conv(xd, wd, scale.cuda(), bias.cuda(), rd, stride, dil, pad, relu, out_dtype, engine=0)
     torch.cuda.synchronize()
-    assert rel_err(out, out0) < 4e-3
+    assert rel_err(out, out0) < tol
+
+
+def test_linear_tc_2sm_inplace_residual_f32():
+    """FFN2 shape: K = 2048, fp32 out aliased with the fp32 residual (x += f(x))."""
+    import ctypes as C
+    from sound_event_detection_transformer_b200 import _lib
+    g = torch.Generator().manual_seed(15)
+    rows, K, N = 31 * 124, 2048, 256
+    x = torch.randn(rows, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, generator=g)
+    acc = torch.randn(rows, N, generator=g)
+    ref = acc + F.linear(x.float(), w.float(), b)
+    lib = _lib.load()
+    xd, wd, ad, bd = x.cuda(), w.cuda(), acc.cuda(), b.cuda()
+    d = _lib.SedtConvDesc(in_=xd.data_ptr(), w=wd.data_ptr(), scale=None, bias=bd.data_ptr(), residual=ad.data_ptr(),
+                          out=ad.data_ptr(), in_dtype=1, out_dtype=0, B=rows, H=1, W=1, Cin=K, lda=K, Ho=1, Wo=1, Cout=N,
+                          ldc=N, ld_res=N, R=1, S=1, stride=1, dil=1, pad=0, relu=0)
+    _lib.check(lib.sedt_op_conv(C.byref(d), 2, _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert rel_err(ad, ref) < 1e-5
