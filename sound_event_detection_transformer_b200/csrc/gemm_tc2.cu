@@ -272,7 +272,8 @@ int launch_conv_tc(const ConvGemm& g, cudaStream_t stream)
     SEDT_REQUIRE(conv_tc_supported(g), "conv_tc: unsupported shape");
     static const int use_2sm = [] { const char* e = getenv("SEDT_TC_2SM"); return e ? atoi(e) : 1; }();
     // two SMs per tile pay once the main loop is long (K >= 512); short-K layers are epilogue / HBM bound
-    if (use_2sm && g.R * g.S * g.Cin >= 512 && conv_tc_2sm_preferred(g)) return launch_conv_tc_2sm(g, stream);
+    static const int min_k_2sm = [] { const char* e = getenv("SEDT_2SM_MIN_K"); return e ? atoi(e) : 512; }();
+    if (use_2sm && g.R * g.S * g.Cin >= min_k_2sm && conv_tc_2sm_preferred(g)) return launch_conv_tc_2sm(g, stream);
     const bool f32 = g.out_dt == DT_F32;
     // BLOCK_N: the widest tile that divides Cout, still leaves about two tiles per SM and has a main
     // loop long enough (num_kb >= min_kb256) to hide the single-buffered 256-wide epilogue

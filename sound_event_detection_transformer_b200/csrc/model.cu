@@ -154,8 +154,10 @@ Model::Model(const Config& c) : cfg_(c)
     dec_norm_ = make_norm("transformer.decoder.norm");
     const int ncls = cfg_.self_sup ? 1 : cfg_.num_classes;
     class_embed_ = make_linear("class_embed", d, ncls + 1, true);
-    bbox0_ = make_linear("bbox_embed.layers.0", d, d, true);
-    bbox1_ = make_linear("bbox_embed.layers.1", d, d, true);
+    // the 256x256 layers of the box MLP (and feature_align) run on the tensor cores in the bf16 tier; the narrow
+    // output layers (C+1, 2, C columns) stay fp32 CUDA-core GEMMs
+    bbox0_ = make_linear("bbox_embed.layers.0", d, d, false);
+    bbox1_ = make_linear("bbox_embed.layers.1", d, d, false);
     bbox2_ = make_linear("bbox_embed.layers.2", d, 2, true);
     input_proj_ = make_linear("input_proj", 2048, d, false);
 
@@ -204,8 +206,8 @@ Model::Model(const Config& c) : cfg_(c)
     if (cfg_.self_sup) {
         patch2query_ = make_linear("patch2query", 2048, d, true);
         if (cfg_.feature_recon) {
-            falign0_ = make_linear("feature_align.layers.0", d, d, true);
-            falign1_ = make_linear("feature_align.layers.1", d, 2048, true);
+            falign0_ = make_linear("feature_align.layers.0", d, d, false);
+            falign1_ = make_linear("feature_align.layers.1", d, 2048, false);
         }
     }
     packed_bytes_ = (packed_bytes_ + 255) & ~(size_t)255;
@@ -604,9 +606,12 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
     void* dap = ws.alloc((size_t)qrows * d * es);
     void* dffh = ws.alloc((size_t)qrows * ff * es);
     if (!dry) SEDT_TRY(launch_fill_zero(t32, (size_t)qrows * d * 4, s));
+    // decoder states in the tier dtype (GEMM operand of the box / feature MLPs) next to the fp32 copy the caller gets
+    void* hs_t = dt == DT_F32 ? (void*)out.hs : ws.alloc((size_t)dec_.size() * qrows * d * es);
     for (size_t l = 0; l < dec_.size(); ++l) {
         auto& e = dec_[l];
         float* hs_l = out.hs + l * (size_t)qrows * d;
+        void* hs_tl = dt == DT_F32 ? nullptr : (void*)((char*)hs_t + l * (size_t)qrows * d * es);
         if (cfg_.pre_norm) {
             SEDT_TRY(LN(e.n1, t32, qpos, qpos_rows, da, dap, nullptr, qrows));
             SEDT_TRY(mha(e.self_attn, true, dap, dap, da, B, Qall, Qall, nullptr, amask, t32, t32, ws, s, dry));
@@ -627,7 +632,7 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
             SEDT_TRY(linear(e.lin2, 0, d, dffh, dt, ff, qrows, t32, t32, DT_F32, d, 0, s, dry));
             SEDT_TRY(LN(e.n3, t32, nullptr, 1, nullptr, nullptr, t32, qrows));
         }
-        SEDT_TRY(LN(dec_norm_, t32, nullptr, 1, nullptr, nullptr, hs_l, qrows));     // transformer.py:140-147
+        SEDT_TRY(LN(dec_norm_, t32, nullptr, 1, hs_tl, nullptr, hs_l, qrows));     // transformer.py:140-147
     }
 
     // ---- heads (sedt.py:89-95, spsedt.py:77-85): fp32 CUDA-core GEMMs on the tiny [D*B*Q, 256] matrix
@@ -636,13 +641,13 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
     const int ncls = cfg_.self_sup ? 1 : cfg_.num_classes, C1 = ncls + 1;
     const int start = cfg_.dec_at ? 1 : 0;
     float* cls_raw = (float*)ws.alloc((size_t)hrows * C1 * 4);
-    float* h1 = (float*)ws.alloc((size_t)hrows * d * 4);
+    void* h1 = ws.alloc((size_t)hrows * d * es);
     float* h2 = (float*)ws.alloc((size_t)hrows * d * 4);
     float* box_raw = (float*)ws.alloc((size_t)hrows * 2 * 4);
     float* weak_raw = cfg_.dec_at ? (float*)ws.alloc((size_t)B * ncls * 4) : nullptr;
     SEDT_TRY(linear(class_embed_, 0, C1, out.hs, DT_F32, d, hrows, nullptr, cls_raw, DT_F32, C1, 0, s, dry));
-    SEDT_TRY(linear(bbox0_, 0, d, out.hs, DT_F32, d, hrows, nullptr, h1, DT_F32, d, 1, s, dry));
-    SEDT_TRY(linear(bbox1_, 0, d, h1, DT_F32, d, hrows, nullptr, h2, DT_F32, d, 1, s, dry));
+    SEDT_TRY(linear(bbox0_, 0, d, hs_t, dt, d, hrows, nullptr, h1, dt, d, 1, s, dry));
+    SEDT_TRY(linear(bbox1_, 0, d, h1, dt, d, hrows, nullptr, h2, DT_F32, d, 1, s, dry));
     SEDT_TRY(linear(bbox2_, 0, 2, h2, DT_F32, d, hrows, nullptr, box_raw, DT_F32, 2, 0, s, dry));
     if (cfg_.dec_at)     // slot 0 of the last layer: rows at stride Qall*d (sedt.py:92)
         SEDT_TRY(linear(weak_, 0, ncls, out.hs + (size_t)(Dn - 1) * qrows * d, DT_F32, Qall * d, B, nullptr, weak_raw,
@@ -651,8 +656,8 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
         SEDT_TRY(launch_heads_finalize(cls_raw, box_raw, weak_raw, out.logits, out.boxes, cfg_.dec_at ? out.at : nullptr,
                                        Dn, B, Qall, start, C1, ncls, s));
     if (cfg_.self_sup && cfg_.feature_recon && out.pred_feature != nullptr) {
-        SEDT_TRY(linear(falign0_, 0, d, out.hs, DT_F32, d, hrows, nullptr, h1, DT_F32, d, 1, s, dry));
-        SEDT_TRY(linear(falign1_, 0, 2048, h1, DT_F32, d, hrows, nullptr, out.pred_feature, DT_F32, 2048, 0, s, dry));
+        SEDT_TRY(linear(falign0_, 0, d, hs_t, dt, d, hrows, nullptr, h1, dt, d, 1, s, dry));
+        SEDT_TRY(linear(falign1_, 0, 2048, h1, dt, d, hrows, nullptr, out.pred_feature, DT_F32, 2048, 0, s, dry));
     }
     if (ws.overflow && !dry) {
         set_error("forward: workspace too small (%zu bytes needed, %zu given)", ws.peak, ws.cap);
