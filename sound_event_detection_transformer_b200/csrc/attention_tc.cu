@@ -28,7 +28,8 @@ constexpr int SK_OFF = 16384;
 constexpr int SP_OFF = 0;                   // 2 chunks of [128 rows][64 keys]; reuses Q/K once S = QK^T has retired
 constexpr int SV_OFF = 32768;               // 2 chunks of [32 rows][64 keys]
 constexpr int SM_OFF = 32768 + 8192;        // key mask as float [128]
-constexpr int BAR_OFF = SM_OFF + 512;
+constexpr int SN_OFF = SM_OFF + 512;         // 0 / -1e30 per key (keeps masked keys out of the row maximum)
+constexpr int BAR_OFF = SN_OFF + 512;
 constexpr int ATT_SMEM = BAR_OFF + 64 + 1024;
 
 __device__ __forceinline__ uint32_t swz(int row, int byte_in_row) {
@@ -36,6 +37,12 @@ __device__ __forceinline__ uint32_t swz(int row, int byte_in_row) {
     return (uint32_t)(row * 128 + ((((byte_in_row >> 4) ^ (row & 7)) << 4) | (byte_in_row & 15)));
 }
 
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <bool HAS_AMASK>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ K, int ldk,
                     const __nv_bfloat16* __restrict__ V, int ldv, __nv_bfloat16* __restrict__ O, int ldo,
@@ -44,6 +51,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS)
     float* s_mask = (float*)(smem + SM_OFF);
+    float* s_neg = (float*)(smem + SN_OFF);
     uint64_t* bar_s = (uint64_t*)(smem + BAR_OFF);
     uint64_t* bar_o = bar_s + 1;
     uint32_t* tmem_slot = (uint32_t*)(bar_o + 1);
@@ -83,10 +91,11 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
         const int col_b = (t & 63) * 2;
 #pragma unroll
         for (int d = 0; d < HD; ++d) *reinterpret_cast<__nv_bfloat16*>(vbase + swz(d, col_b)) = vh[d];
-        float mk = 0.f;
-        if (t >= Lk) mk = -CUDART_INF_F;
-        else if (kpm != nullptr && kpm[(size_t)b * Lk + t]) mk = -CUDART_INF_F;
+        float mk = 1.f;                                    // validity of key t
+        if (t >= Lk) mk = 0.f;
+        else if (kpm != nullptr && kpm[(size_t)b * Lk + t]) mk = 0.f;
         s_mask[t] = mk;
+        s_neg[t] = (mk - 1.f) * 1e30f;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
@@ -107,25 +116,36 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
     tc_fence_after();
 
     // ---- softmax over this thread's row -------------------------------------------------------
+    // p_j = 2^(c*(s_j + a_j) - c*m) * valid_j with c = scale*log2(e).  The row maximum m is taken over
+    // the scores of the valid keys;
+    // masked keys are kept out of the maximum by a 0 / -1e30 vector and zeroed by a 0 / 1 validity vector, both
+    // in shared memory.  Only key chunks that hold real keys, and only warps that
+    // own real query rows, do any work (decoder: 11 / 21 queries, 21 keys in self-attention).
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const float* arow = (amask != nullptr && t < Lq) ? amask + (size_t)t * Lk : nullptr;
-    // only key chunks that hold real keys, and only warps that own real query rows, do softmax work
-    // (decoder: 11 / 21 queries, 21 keys in self-attention)
     const int nkc = (Lk + 31) >> 5;
     const bool row_warp = warp * 32 < Lq;
+    const float cs = scale * 1.4426950408889634f;
+    const float* arow = nullptr;
+    if (HAS_AMASK) arow = amask + (size_t)min(t, Lq - 1) * Lk;
     float m = -CUDART_INF_F;
 #pragma unroll 1
     for (int c = 0; c < (row_warp ? nkc : 0); ++c) {
         uint32_t acc[32];
         tmem_ld32(lane_addr + c * 32, acc);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float s = __uint_as_float(acc[j]) * scale + s_mask[c * 32 + j];
-            if (arow != nullptr && c * 32 + j < Lk) s += arow[c * 32 + j];
-            m = fmaxf(m, s);
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 ng = *reinterpret_cast<const float4*>(s_neg + c * 32 + j4 * 4);
+            const float ngv[4] = {ng.x, ng.y, ng.z, ng.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j4 * 4 + q;
+                float sv = __uint_as_float(acc[j]) + ngv[q];
+                if (HAS_AMASK) { const int key = c * 32 + j; sv += key < Lk ? fmaxf(arow[key], -1e30f) / scale : 0.f; }
+                m = fmaxf(m, sv);
+            }
         }
     }
-    const float mm = (m == -CUDART_INF_F) ? 0.f : m;
+    const float mc = m * cs;
     float l = 0.f;
 #pragma unroll 1
     for (int c = 0; c < (row_warp ? nkc : 0); ++c) {
@@ -133,17 +153,22 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
         tmem_ld32(lane_addr + c * 32, acc);
         uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-            float s0 = __uint_as_float(acc[j]) * scale + s_mask[c * 32 + j];
-            float s1 = __uint_as_float(acc[j + 1]) * scale + s_mask[c * 32 + j + 1];
-            if (arow != nullptr) {
-                if (c * 32 + j < Lk) s0 += arow[c * 32 + j];
-                if (c * 32 + j + 1 < Lk) s1 += arow[c * 32 + j + 1];
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 vm = *reinterpret_cast<const float4*>(s_mask + c * 32 + j4 * 4);      // 1 = real key, 0 = masked
+            const float vmv[4] = {vm.x, vm.y, vm.z, vm.w};
+            float pv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j4 * 4 + q;
+                float sv = __uint_as_float(acc[j]);
+                if (HAS_AMASK) { const int key = c * 32 + j; sv += key < Lk ? fmaxf(arow[key], -1e30f) / scale : 0.f; }
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(sv, cs, -mc)));
+                pv[q] = e * vmv[q];
+                l += pv[q];
             }
-            const float p0 = exp2f((s0 - mm) * 1.4426950408889634f), p1 = exp2f((s1 - mm) * 1.4426950408889634f);
-            l += p0 + p1;
-            const __nv_bfloat162 hp = __floats2bfloat162_rn(p0, p1);
-            packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+            packed[j4 * 2] = pack2(pv[0], pv[1]);
+            packed[j4 * 2 + 1] = pack2(pv[2], pv[3]);
         }
         // 32 keys = 64 bytes = pieces (c&1)*4 .. +3 of row t in P chunk c/2
         uint8_t* prow = smem + SP_OFF + (c >> 1) * 16384;
@@ -211,14 +236,20 @@ int launch_attention_tc(const void* Q, int ldq, const void* K, int ldk, const vo
 {
     static bool attr_set = false;
     if (!attr_set) {
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         attr_set = true;
     }
     dim3 grid((unsigned)nheads, (unsigned)B), block(ATT_THREADS);
     ProfScope _prof(PROF_ATTENTION, stream);
-    attention_tc_kernel<<<grid, block, ATT_SMEM, stream>>>((const __nv_bfloat16*)Q, ldq, (const __nv_bfloat16*)K, ldk,
-                                                           (const __nv_bfloat16*)V, ldv, (__nv_bfloat16*)O, ldo, kpm, amask,
-                                                           Lq, Lk, scale);
+    if (amask != nullptr)
+        attention_tc_kernel<true><<<grid, block, ATT_SMEM, stream>>>((const __nv_bfloat16*)Q, ldq, (const __nv_bfloat16*)K, ldk,
+                                                                     (const __nv_bfloat16*)V, ldv, (__nv_bfloat16*)O, ldo, kpm,
+                                                                     amask, Lq, Lk, scale);
+    else
+        attention_tc_kernel<false><<<grid, block, ATT_SMEM, stream>>>((const __nv_bfloat16*)Q, ldq, (const __nv_bfloat16*)K, ldk,
+                                                                      (const __nv_bfloat16*)V, ldv, (__nv_bfloat16*)O, ldo, kpm,
+                                                                      amask, Lq, Lk, scale);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
