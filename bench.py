@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step (configs[1]: 256)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     opts = ap.parse_args()
     opts.warmup = max(opts.warmup, 3)
     if opts.impl == "reference":
@@ -197,6 +198,7 @@ def main():
     model, _, _ = build_model(args)
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).eval()
+    model.use_cuda_graph = not opts.no_graph           # the forward's launch sequence is replayed as one CUDA graph
     B, K, W = opts.batch, opts.steps, opts.warmup
 
     # inputs: rotate over enough distinct batches that they cannot stay L2-resident
@@ -215,7 +217,7 @@ def main():
         if rank == 0:
             sampler.start()
             time.sleep(0.3)
-        l0 = lib.sedt_launch_count()
+        l0 = model.runtime().kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -224,7 +226,7 @@ def main():
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        launches = int(lib.sedt_launch_count() - l0)
+        launches = int(model.runtime().kernel_launches() - l0)
         clocks = sampler.stop() if rank == 0 else None
     value = world * B * K / (ms / 1e3)
 
@@ -262,6 +264,7 @@ def main():
     n_cls = (C.c_longlong * len(_lib.KERNEL_CLASSES))()
     with torch.no_grad():
         barrier()
+        model.use_cuda_graph = False                       # per-kernel events need eager launches
         lib.sedt_profile_enable(1)
         for i in range(K):
             model(devx[i % nrot])
@@ -303,7 +306,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if opts.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": B, "global_batch": B * world, "parallelism": f"dp{world}",
+        "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": B, "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": not opts.no_graph,
                    "l2": f"inputs rotate over {nrot} distinct {in_bytes / 2**20:.1f} MiB batches; per-step activation traffic "
                          "(>1 GB) exceeds the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,

@@ -26,6 +26,9 @@ class ForwardRuntime:
         self._stamp = None
         self._ws: Optional[torch.Tensor] = None
         self._keep = None
+        # CUDA-graph replay of the whole forward (one graph per input shape); see forward(use_graph=True)
+        self._graphs: Dict[tuple, dict] = {}
+        self.graph_kernel_launches = 0     # kernels executed through graph replays (the library counter only sees eager launches)
 
     def __del__(self):
         try:
@@ -63,6 +66,7 @@ class ForwardRuntime:
                                                 _lib.current_stream()))
         self._keep = keep
         self._stamp = stamp
+        self._graphs.clear()          # graphs bake in the packed-weight pointers: re-capture after a repack
 
     @staticmethod
     def _aligned(buf: torch.Tensor) -> int:
@@ -75,17 +79,17 @@ class ForwardRuntime:
         return h.value, w.value
 
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor], patches: Optional[torch.Tensor] = None,
-                want_memory: bool = False, want_feat: bool = False) -> Dict[str, torch.Tensor]:
+                want_memory: bool = False, want_feat: bool = False, use_graph: bool = False) -> Dict[str, torch.Tensor]:
+        """One forward.  use_graph=True replays a CUDA graph of the launch sequence captured for this input
+        shape (static input / output buffers owned by the runtime; the returned tensors are only valid until
+        the next call with the same shape)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 1
-        x = x.contiguous()
-        B, _, T, F = x.shape
-        dev = x.device
+        if use_graph and not want_memory and not want_feat:
+            return self._forward_graph(x, mask, patches)
+        return self._forward_eager(x, mask, patches, want_memory, want_feat)
+
+    def _alloc_outputs(self, B, T, F, P, dev, want_memory=False, want_feat=False):
         cfg = self.cfg
-        P = PT = 0
-        if cfg.self_sup:
-            assert patches is not None and patches.dim() == 5
-            patches = patches.to(dev, torch.float32).contiguous()
-            P, PT = patches.shape[1], patches.shape[3]
         D = cfg.dec_layers
         if cfg.self_sup:
             qall = q = P * (cfg.num_queries // cfg.num_patches)
@@ -110,6 +114,25 @@ class ForwardRuntime:
             res["gt_feature"] = torch.empty(B * P, 2048, **f32)
             if cfg.feature_recon:
                 res["pred_feature"] = torch.empty(D, B, q, 2048, **f32)
+        return res
+
+    def _launch(self, x, m8, patches, P, PT, ws, res):
+        B, _, T, F = x.shape
+        outs = _lib.SedtOutputs(**{k: _lib.ptr(res.get(k)) or None for k, _ in _lib.SedtOutputs._fields_})
+        _lib.check(self.lib.sedt_forward(self.handle, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
+                                         _lib.ptr(patches) or None, P, PT, self._aligned(ws), ws.numel() - 256,
+                                         C.byref(outs), _lib.current_stream()))
+
+    def _forward_eager(self, x, mask, patches, want_memory, want_feat):
+        x = x.contiguous()
+        B, _, T, F = x.shape
+        dev = x.device
+        P = PT = 0
+        if self.cfg.self_sup:
+            assert patches is not None and patches.dim() == 5
+            patches = patches.to(dev, torch.float32).contiguous()
+            P, PT = patches.shape[1], patches.shape[3]
+        res = self._alloc_outputs(B, T, F, P, dev, want_memory, want_feat)
         need = self.lib.sedt_workspace_bytes(self.handle, B, T, F, P, PT)
         if need < 0:
             _lib.check(int(need))
@@ -119,9 +142,48 @@ class ForwardRuntime:
         m8 = None
         if mask is not None:
             m8 = mask.to(dev).contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(dev, torch.uint8).contiguous()
-        outs = _lib.SedtOutputs(**{k: _lib.ptr(res.get(k)) or None for k, _ in _lib.SedtOutputs._fields_})
         with torch.cuda.device(dev):
-            _lib.check(self.lib.sedt_forward(self.handle, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
-                                             _lib.ptr(patches) or None, P, PT, self._aligned(self._ws),
-                                             self._ws.numel() - 256, C.byref(outs), _lib.current_stream()))
+            self._launch(x, m8, patches, P, PT, self._ws, res)
         return res
+
+    def _forward_graph(self, x, mask, patches):
+        B, _, T, F = x.shape
+        dev = x.device
+        P = PT = 0
+        if self.cfg.self_sup:
+            assert patches is not None and patches.dim() == 5
+            P, PT = patches.shape[1], patches.shape[3]
+        key = (B, T, F, P, PT, mask is not None, dev.index)
+        g = self._graphs.get(key)
+        if g is None:
+            need = self.lib.sedt_workspace_bytes(self.handle, B, T, F, P, PT)
+            if need < 0:
+                _lib.check(int(need))
+            g = {"x": torch.empty(B, 1, T, F, dtype=torch.float32, device=dev),
+                 "mask": torch.empty(B, T, F, dtype=torch.uint8, device=dev) if mask is not None else None,
+                 "patches": torch.empty(B, P, 1, PT, F, dtype=torch.float32, device=dev) if P else None,
+                 "ws": torch.empty(need + 256, dtype=torch.uint8, device=dev),
+                 "res": self._alloc_outputs(B, T, F, P, dev)}
+            with torch.cuda.device(dev):
+                # one eager pass first: lazy one-time setup (driver entry point, kernel attributes) must not be captured
+                self._launch(g["x"], g["mask"], g["patches"], P, PT, g["ws"], g["res"])
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                n0 = self.lib.sedt_launch_count()
+                with torch.cuda.graph(graph):
+                    self._launch(g["x"], g["mask"], g["patches"], P, PT, g["ws"], g["res"])
+                g["nlaunch"] = int(self.lib.sedt_launch_count() - n0)
+            g["graph"] = graph
+            self._graphs[key] = g
+        g["x"].copy_(x, non_blocking=True)
+        if mask is not None:
+            g["mask"].copy_(mask.view(torch.uint8) if mask.dtype == torch.bool else mask, non_blocking=True)
+        if P:
+            g["patches"].copy_(patches, non_blocking=True)
+        g["graph"].replay()
+        self.graph_kernel_launches += g["nlaunch"]
+        return g["res"]
+
+    def kernel_launches(self) -> int:
+        """Kernels of this library executed so far on behalf of this process (eager + graph replays)."""
+        return int(self.lib.sedt_launch_count()) + self.graph_kernel_launches

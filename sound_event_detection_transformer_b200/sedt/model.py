@@ -45,6 +45,9 @@ class SEDT(nn.Module):
             self.query_embed = nn.Embedding(num_queries, hidden_dim)
         self.precision = precision
         self.use_tensor_cores = use_tensor_cores
+        # replay the forward as one CUDA graph per input shape (outputs then live in runtime-owned buffers that
+        # the next call with the same shape overwrites)
+        self.use_cuda_graph = False
         self._rt: Optional[ForwardRuntime] = None
         self._self_sup = False
         self._feature_recon = False
@@ -114,7 +117,7 @@ class SEDT(nn.Module):
         (center, width), `at` [B,C] under dec_at, and aux_outputs for the earlier decoder layers."""
         self._check_mode()
         x, mask = self._prepare(samples)
-        res = self.runtime().forward(x, mask)
+        res = self.runtime().forward(x, mask, use_graph=self.use_cuda_graph)
         out = {"pred_logits": res["logits"][-1], "pred_boxes": res["boxes"][-1]}
         if self.dec_at:
             out["at"] = res["at"].squeeze()              # sedt.py:92 squeezes: [C] when B == 1
@@ -154,7 +157,7 @@ class SPSEDT(SEDT):
         if isinstance(samples, (list, tuple)) and len(samples) == 2 and torch.is_tensor(samples[0]) and samples[0].dim() == 4:
             samples = NestedTensor(samples[0], samples[1])          # engine.py:59 passes .decompose()
         x, mask = self._prepare(samples)
-        res = self.runtime().forward(x, mask, patches=patches)
+        res = self.runtime().forward(x, mask, patches=patches, use_graph=self.use_cuda_graph)
         out = {"pred_logits": res["logits"][-1], "pred_boxes": res["boxes"][-1]}
         if self.feature_recon:
             out["pred_feature"] = res["pred_feature"][-1]

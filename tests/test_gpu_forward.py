@@ -187,3 +187,24 @@ def test_weights_repacked_after_update():
         b = model(x)["pred_logits"]
     torch.cuda.synchronize()
     assert torch.allclose(b, a + 1.0, atol=1e-5)
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    args, clips, seed = _cases()["c2_b2"]
+    model, _ = _model(args, seed, "bf16")
+    x = clips.cuda()
+    with torch.no_grad():
+        ref = {k: v.clone() for k, v in model(x).items() if k != "aux_outputs"}
+        model.use_cuda_graph = True
+        for _ in range(3):                                   # capture, then replays
+            out = model(x)
+        torch.cuda.synchronize()
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+        x2 = synth.synth_clips(2, 496, 64, seed=99).cuda()   # new data through the same graph
+        out2 = {k: v.clone() for k, v in model(x2).items() if k != "aux_outputs"}
+        model.use_cuda_graph = False
+        ref2 = model(x2)
+        torch.cuda.synchronize()
+        for k in out2:
+            assert torch.equal(out2[k], ref2[k]), k
