@@ -137,7 +137,8 @@ typedef struct sedt_conv_desc {
 } sedt_conv_desc;
 /* Conv/linear + FrozenBN scale/bias + residual + ReLU as implicit GEMM (NHWC in, [Cout][R][S][Cin] weights).
  * engine: 0 = CUDA-core kernel, 1 = TMA + tcgen05 kernel (bf16 in; picks the 1-SM or 2-SM variant),
- *         2 = force the cta_group::2 variant (bf16 out, Cout % 256 == 0, enough tiles). */
+ *         2 = force the cta_group::2 variant (Cout % 256 == 0), 3 = force the weight-stationary variant (K <= 256,
+ *         Cout % 128 == 0). */
 SEDT_API int sedt_op_conv(const sedt_conv_desc* d, int engine, void* stream);
 SEDT_API int sedt_op_conv_tc_supported(const sedt_conv_desc* d);
 /* OIHW fp32 -> O(HW)I in `dtype` */

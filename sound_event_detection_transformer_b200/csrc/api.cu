@@ -140,6 +140,10 @@ int sedt_op_conv(const sedt_conv_desc* d, int engine, void* stream)
     ConvGemm g = to_gemm(d);
     if (engine == 0) return launch_conv_simt(g, (cudaStream_t)stream);
     SEDT_TRY(tc_init());
+    if (engine == 3) {
+        if (!conv_tc_ws_supported(g)) { set_error("op_conv: shape not supported by the weight-stationary kernel"); return SEDT_ERR_UNSUPPORTED; }
+        return launch_conv_tc_ws(g, (cudaStream_t)stream);
+    }
     if (engine == 2) {
         if (!conv_tc_2sm_supported(g)) { set_error("op_conv: shape not supported by the cta_group::2 kernel"); return SEDT_ERR_UNSUPPORTED; }
         return launch_conv_tc_2sm(g, (cudaStream_t)stream);

@@ -129,18 +129,19 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             for (int t = first_item; t < total_items; t += item_stride) {
                 int w0, h0, n0, col0;
                 tile_coords(t, w0, h0, n0, col0);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const int tap = kb / cpb, c0 = (kb - tap * cpb) * BLOCK_K;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * T3_STAGE);
-                    const uint32_t lbar = smem_u32(&full_bar[stage]) & kPeerMask;
-                    uint8_t* sa = smem + stage * T3_STAGE;
-                    uint8_t* sb = sa + A_STAGE_BYTES;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
                     const int mi = p.tap_map[tap];
                     const CUtensorMap* ma = mi == 0 ? &map_a0 : (mi == 1 ? &map_a1 : (mi == 2 ? &map_a2 : &map_a3));
-                    tma_load_4d_2sm(ma, sa, lbar, c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-                    tma_load_2d_2sm(&map_b, sb, lbar, tap * p.Cin + c0, col0 + crank * T3_HALF);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], kbase = tap * p.Cin;
+                    for (int c0 = 0; c0 < p.Cin; c0 += BLOCK_K) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (leader) mbar_expect_tx(&full_bar[stage], 2 * T3_STAGE);
+                        const uint32_t lbar = smem_u32(&full_bar[stage]) & kPeerMask;
+                        uint8_t* sa = smem + stage * T3_STAGE;
+                        tma_load_4d_2sm(ma, sa, lbar, c0, cw, ch, n0);
+                        tma_load_2d_2sm(&map_b, sa + A_STAGE_BYTES, lbar, kbase + c0, col0 + crank * T3_HALF);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }

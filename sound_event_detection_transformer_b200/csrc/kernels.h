@@ -33,6 +33,9 @@ int launch_conv_simt(const ConvGemm& g, cudaStream_t stream);
 bool conv_tc_supported(const ConvGemm& g);
 int launch_conv_tc(const ConvGemm& g, cudaStream_t stream);      // gemm_tc2.cu: persistent kernel (or v1 if SEDT_TC_V1=1)
 int launch_conv_tc_v1(const ConvGemm& g, cudaStream_t stream);
+// gemm_tc4.cu: weight-stationary variant for K <= 256
+bool conv_tc_ws_supported(const ConvGemm& g);
+int launch_conv_tc_ws(const ConvGemm& g, cudaStream_t stream);
 // gemm_tc3.cu: cta_group::2 (two SMs per 256 x 256 tile) for bf16-out layers with Cout % 256 == 0
 bool conv_tc_2sm_supported(const ConvGemm& g);
 bool conv_tc_2sm_preferred(const ConvGemm& g);    // ... and enough tiles to fill the SM pairs

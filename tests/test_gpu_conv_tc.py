@@ -140,3 +140,31 @@ def test_linear_tc_2sm_inplace_residual_f32():
     _lib.check(lib.sedt_op_conv(C.byref(d), 2, _lib.current_stream()))
     torch.cuda.synchronize()
     assert rel_err(ad, ref) < 1e-5
+
+
+TC_WS_SHAPES = [
+    (20, 124, 16, 64, 256, 1, 1, 1, True, True),      # layer1 conv3: K = 64, residual
+    (9, 62, 8, 128, 512, 1, 1, 1, True, True),        # layer2 conv3: K = 128
+    (37, 31, 4, 256, 1024, 1, 1, 1, True, True),      # layer3 conv3: K = 256, 8 N tiles
+    (8, 124, 16, 256, 128, 1, 2, 1, False, False),    # stride-2 1x1 (downsample-like), single N tile
+    (3, 1, 1, 256, 2048, 1, 1, 1, False, True),       # fewer M tiles than CTAs per N tile
+    (600, 1, 1, 256, 2048, 1, 1, 1, False, True),     # FFN linear1 shape (rows as images)
+]
+
+
+@pytest.mark.parametrize("shape", TC_WS_SHAPES)
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_conv_tc_weight_stationary(shape, out_dtype):
+    """weight-stationary kernel (engine 3) against torch fp32 conv and the CUDA-core kernel."""
+    B, H, W, Cin, Cout, k, stride, dil, res, relu = shape
+    x, w, scale, bias, pad, r, ref = _conv_case(*shape, seed=11, dtype=torch.bfloat16)
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
+    wd = gpu_ops.repack(w, torch.bfloat16)
+    rd = r.permute(0, 2, 3, 1).contiguous().cuda().to(out_dtype) if res else None
+    out = gpu_ops.conv(xd, wd, scale.cuda(), bias.cuda(), rd, stride, dil, pad, relu, out_dtype, engine=3)
+    torch.cuda.synchronize()
+    tol = 4e-3 if out_dtype == torch.bfloat16 else 1e-5
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < tol
+    out0 = gpu_ops.conv(xd, wd, scale.cuda(), bias.cuda(), rd, stride, dil, pad, relu, out_dtype, engine=0)
+    torch.cuda.synchronize()
+    assert rel_err(out, out0) < tol
