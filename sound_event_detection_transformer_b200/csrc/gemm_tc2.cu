@@ -258,7 +258,7 @@ int launch_conv_tc(const ConvGemm& g, cudaStream_t stream)
     if (use_2sm && g.R * g.S * g.Cin >= min_k_2sm && conv_tc_2sm_preferred(g)) return launch_conv_tc_2sm(g, stream);
     // short reductions: weight-stationary kernel (each CTA keeps its N tile's weights in shared memory)
     static const int use_ws = [] { const char* e = getenv("SEDT_TC_WS"); return e ? atoi(e) : 1; }();
-    if (use_ws && conv_tc_ws_supported(g) && ceil_div((int64_t)g.B * g.Ho * g.Wo, BLOCK_M) >= 2 * (num_sms() / (g.Cout / 128)))
+    if (use_ws && conv_tc_ws_supported(g) && ceil_div((int64_t)g.B * g.Ho * g.Wo, BLOCK_M) >= 2 * (num_sms() / ceil_div(g.Cout, 128)))
         return launch_conv_tc_ws(g, stream);
     const bool f32 = g.out_dt == DT_F32;
     // BLOCK_N: the widest tile that divides Cout, still leaves about two tiles per SM and has a main

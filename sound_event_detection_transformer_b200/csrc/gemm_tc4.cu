@@ -16,9 +16,8 @@ namespace {
 using namespace tc;
 
 constexpr int NUM_THREADS4 = 352;
-constexpr int MAX_KB4 = 4;                // K <= 256
 
-template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO>
+template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO, int MAX_KB>
 struct Smem4 {
     static constexpr int B_KB_BYTES = BLOCK_N * BLOCK_K * 2;                // one 64-wide k block of the weight tile
     static constexpr int CHUNK_COLS = 128 / (int)sizeof(TO);
@@ -26,13 +25,13 @@ struct Smem4 {
     static constexpr int CHUNK_BYTES = BLOCK_M * 128;
     static constexpr int OUT_BYTES = NCHUNK * CHUNK_BYTES;
     static constexpr int B_OFFSET = STAGES * A_STAGE_BYTES;                 // A ring first, then the resident weights
-    static constexpr int OUT_OFFSET = B_OFFSET + MAX_KB4 * B_KB_BYTES;
+    static constexpr int OUT_OFFSET = B_OFFSET + MAX_KB * B_KB_BYTES;
     static constexpr int BAR_OFFSET = OUT_OFFSET + OUT_BUFS * OUT_BYTES;
     static constexpr int NBARS = 2 * STAGES + 4 + 2 * OUT_BUFS + 1;
     static constexpr int TOTAL = BAR_OFFSET + NBARS * 8 + 16 + 1024;
 };
 
-template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO>
+template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO, int MAX_KB>
 __global__ void __launch_bounds__(NUM_THREADS4, 1)
 conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                 const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
@@ -40,7 +39,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ TcParams p,
                 const int tiles_nc, const int total_tiles)
 {
-    using L = Smem4<BLOCK_N, STAGES, OUT_BUFS, TO>;
+    using L = Smem4<BLOCK_N, STAGES, OUT_BUFS, TO, MAX_KB>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // keep the pointer derived from the __shared__ symbol so that staging traffic compiles to LDS/STS
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -226,12 +225,12 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     }
 }
 
-template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO>
+template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO, int MAX_KB>
 int launch_v4(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr, cudaStream_t stream)
 {
-    using L = Smem4<BLOCK_N, STAGES, OUT_BUFS, TO>;
+    using L = Smem4<BLOCK_N, STAGES, OUT_BUFS, TO, MAX_KB>;
     static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-    auto kern = conv_tc4_kernel<BLOCK_N, STAGES, OUT_BUFS, TO>;
+    auto kern = conv_tc4_kernel<BLOCK_N, STAGES, OUT_BUFS, TO, MAX_KB>;
     static bool attr_set = false;
     if (!attr_set) {
         SEDT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -254,7 +253,9 @@ bool conv_tc_ws_supported(const ConvGemm& g)
 {
     if (!conv_tc_supported(g)) return false;
     const int num_kb = g.R * g.S * g.Cin / BLOCK_K;
-    return num_kb <= MAX_KB4 && g.Cout % 128 == 0 && g.Cout / 128 <= num_sms();
+    // 128-wide N tiles with K <= 256, or the 64-channel 3x3 convolutions of layer1 (K = 576, whole 72 KiB filter resident)
+    if (g.Cout == 64) return g.out_dt == DT_BF16 && num_kb <= 9;
+    return num_kb <= 4 && g.Cout % 128 == 0 && g.Cout / 128 <= num_sms();
 }
 
 int launch_conv_tc_ws(const ConvGemm& g, cudaStream_t stream)
@@ -262,12 +263,14 @@ int launch_conv_tc_ws(const ConvGemm& g, cudaStream_t stream)
     SEDT_REQUIRE(conv_tc_ws_supported(g), "conv_tc_ws: unsupported shape");
     const bool f32 = g.out_dt == DT_F32;
     TcProblem pr;
-    SEDT_TRY(build_problem(g, 128, &pr));
+    const int block_n = g.Cout == 64 ? 64 : 128;
+    SEDT_TRY(build_problem(g, block_n, &pr));
     CUtensorMap mo, mr;
     SEDT_TRY(encode_out_map(&mo, g.out, g.ldc, f32, g, pr.p));
     if (g.residual != nullptr) SEDT_TRY(encode_out_map(&mr, g.residual, g.ld_res, f32, g, pr.p));
     else mr = mo;
-    return f32 ? launch_v4<128, 6, 1, float>(pr, mo, mr, stream) : launch_v4<128, 6, 2, __nv_bfloat16>(pr, mo, mr, stream);
+    if (block_n == 64) return launch_v4<64, 6, 2, __nv_bfloat16, 9>(pr, mo, mr, stream);
+    return f32 ? launch_v4<128, 6, 1, float, 4>(pr, mo, mr, stream) : launch_v4<128, 6, 2, __nv_bfloat16, 4>(pr, mo, mr, stream);
 }
 
 }  // namespace sedt

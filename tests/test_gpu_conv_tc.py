@@ -149,6 +149,8 @@ TC_WS_SHAPES = [
     (8, 124, 16, 256, 128, 1, 2, 1, False, False),    # stride-2 1x1 (downsample-like), single N tile
     (3, 1, 1, 256, 2048, 1, 1, 1, False, True),       # fewer M tiles than CTAs per N tile
     (600, 1, 1, 256, 2048, 1, 1, 1, False, True),     # FFN linear1 shape (rows as images)
+    (6, 124, 16, 64, 64, 3, 1, 1, False, True),       # layer1 conv2: 3x3, whole 64 x 576 filter resident (bf16 out only)
+    (5, 124, 16, 256, 64, 1, 1, 1, False, True),      # layer1 conv1 of blocks 1-2: N = 64, K = 256
 ]
 
 
@@ -157,6 +159,8 @@ TC_WS_SHAPES = [
 def test_conv_tc_weight_stationary(shape, out_dtype):
     """weight-stationary kernel (engine 3) against torch fp32 conv and the CUDA-core kernel."""
     B, H, W, Cin, Cout, k, stride, dil, res, relu = shape
+    if Cout == 64 and out_dtype == torch.float32:
+        pytest.skip("the 64-wide weight-stationary variant only writes bf16")
     x, w, scale, bias, pad, r, ref = _conv_case(*shape, seed=11, dtype=torch.bfloat16)
     xd = x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
     wd = gpu_ops.repack(w, torch.bfloat16)
