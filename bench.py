@@ -55,12 +55,16 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.mark_at = gpu_index, [], None, 0
+
+    def mark(self):
+        """Samples from here on fall inside the timed region."""
+        self.mark_at = len(self.rows)
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
@@ -72,7 +76,8 @@ class ClockSampler(threading.Thread):
             self.proc.terminate()
         self.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        timed = self.rows[self.mark_at:]
+        for r in (timed if len(timed) >= 3 else self.rows):     # the GPU is under the same load before the mark
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -83,7 +88,8 @@ class ClockSampler(threading.Thread):
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         busy = [v for v in sm if v > 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "samples_in_timed_region": len(timed), "interval_ms": 20}
 
 
 def cpu_port_clips_per_sec(args, sd, sample_clips, repeats):
@@ -216,7 +222,12 @@ def main():
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-            time.sleep(0.3)
+        # keep every GPU under the bench load while nvidia-smi starts sampling (untimed extra warm-up, <= 1 s)
+        t_w = time.perf_counter()
+        while time.perf_counter() - t_w < 1.0 and (time.perf_counter() - t_w < 0.4 or (rank == 0 and len(sampler.rows) < 2)):
+            model(devx[0])
+            torch.cuda.synchronize()
+        sampler.mark()
         l0 = model.runtime().kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -286,9 +297,19 @@ def main():
     dom_flops = fl["tensor_core_gemm"] * B if dom == "gemm_tcgen05" else fl["total"] * B
     achieved = dom_flops / (dom_ms / 1e3) / 1e12
     step_tf = fl["total"] * B * K / (ms / 1e3) / 1e12 / world if world else 0.0
+    # DRAM bytes of that kernel class per step come from the committed ncu capture of this same command / batch
+    # (profiles/r1f_class_summary.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the class's launches)
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1f_class_summary.json")
+    if os.path.exists(tp) and B == 256 and opts.precision == "bf16":
+        c = json.load(open(tp)).get(dom)
+        if c:
+            traffic = (c["dram_read_MB"] + c["dram_write_MB"]) * 1e6
+            traffic_src = "profiles/r1f_class_summary.json (ncu, bytes per step over the class's launches)"
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": achieved / peak_tf, "traffic": None, "peak_source": f"{peak_src} bf16_tflops_sustained",
+        "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": f"{peak_src} bf16_tflops_sustained",
         "algorithmic_flops_per_clip": fl["total"], "kernel_flops_per_step": dom_flops, "kernel_ms_per_step": dom_ms,
         "kernel_share_of_step": dom_ms / sum(v["ms_per_step"] for v in per_class.values()),
         "whole_step": {"achieved": fl["total"] * B / ((ms / K) / 1e3) / 1e12, "frac": fl["total"] * B / ((ms / K) / 1e3) / 1e12 / peak_tf},
