@@ -140,6 +140,11 @@ typedef struct sedt_conv_desc {
  *         2 = force the cta_group::2 variant (Cout % 256 == 0), 3 = force the weight-stationary variant (K <= 256,
  *         Cout % 128 == 0). */
 SEDT_API int sedt_op_conv(const sedt_conv_desc* d, int engine, void* stream);
+/* Weight gradient of the same layer (autograd's conv2d / addmm weight backward for sedt/backbone.py,
+ * sedt/transformer.py): dw [Cout][k*k*Cin] fp32 += sum over output pixels of dy[m, co] * x[m shifted by tap, ci].
+ * x NHWC bf16 [B,H,W,Cin], dy NHWC bf16 [B,Ho,Wo,Cout]; dw must be zeroed (or hold a running sum) by the caller. */
+SEDT_API int sedt_op_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int k,
+                                int stride, int dil, int pad, void* stream);
 SEDT_API int sedt_op_conv_tc_supported(const sedt_conv_desc* d);
 /* OIHW fp32 -> O(HW)I in `dtype` */
 SEDT_API int sedt_op_repack_conv(const float* w_oihw, void* out, int dtype, int Cout, int Cin, int R, int S, void* stream);

@@ -58,6 +58,7 @@ SIGNATURES = {
     "sedt_lsap": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "sedt_op_conv": (_i, [C.POINTER(SedtConvDesc), _i, _vp]),
     "sedt_op_conv_tc_supported": (_i, [C.POINTER(SedtConvDesc)]),
+    "sedt_op_conv_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "sedt_op_repack_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sedt_op_cast": (_i, [_vp, _vp, _i, _i64, _vp]),
     "sedt_op_stem": (_i, [_vp] * 10 + [_i, _i, _i, _i, _vp]),

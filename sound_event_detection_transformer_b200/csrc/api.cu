@@ -155,6 +155,20 @@ int sedt_op_conv(const sedt_conv_desc* d, int engine, void* stream)
     return launch_conv_tc(g, (cudaStream_t)stream);
 }
 
+int sedt_op_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int k, int stride,
+                       int dil, int pad, void* stream)
+{
+    SEDT_REQUIRE(x != nullptr && dy != nullptr && dw != nullptr, "op_conv_wgrad: null argument");
+    WgradGemm g;
+    g.x = x; g.dy = dy; g.dw = dw;
+    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.lda = Cin; g.Cout = Cout; g.ldy = Cout;
+    g.R = g.S = k; g.stride = stride; g.dil = dil; g.pad = pad;
+    g.Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    g.Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    if (!conv_wgrad_tc_supported(g)) { set_error("op_conv_wgrad: shape not supported by the tcgen05 kernel"); return SEDT_ERR_UNSUPPORTED; }
+    return launch_conv_wgrad_tc(g, (cudaStream_t)stream);
+}
+
 int sedt_op_conv_tc_supported(const sedt_conv_desc* d) { return d != nullptr && conv_tc_supported(to_gemm(d)) ? 1 : 0; }
 
 int sedt_op_repack_conv(const float* w_oihw, void* out, int dtype, int Cout, int Cin, int R, int S, void* stream)

@@ -293,6 +293,7 @@ int build_problem(const ConvGemm& g, int block_n, TcProblem* out, int b_split)
         }
     }
     for (int i = nmaps; i < 4; ++i) out->map_a[i] = out->map_a[0];
+    if (g.w == nullptr) return SEDT_OK;                    // activation-side maps only (gemm_wgrad.cu)
     const uint64_t K = (uint64_t)g.R * g.S * g.Cin;
     const uint64_t bdims[2] = {K, (uint64_t)g.Cout};
     const uint64_t bstrides[1] = {K * 2};

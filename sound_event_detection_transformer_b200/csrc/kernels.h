@@ -42,6 +42,18 @@ bool conv_tc_2sm_preferred(const ConvGemm& g);    // ... and enough tiles to fil
 int launch_conv_tc_2sm(const ConvGemm& g, cudaStream_t stream);
 int tc_init();     // resolves cuTensorMapEncodeTiled once; safe without a GPU
 
+// ---- gemm_wgrad.cu : weight gradient dW[co,(r,s),ci] += sum_pixels dY[m,co] * X[shifted m, ci] on tcgen05 (MN-major operands)
+struct WgradGemm {
+    const void* x = nullptr;       // forward input, NHWC bf16, pixel stride lda
+    const void* dy = nullptr;      // gradient of the forward output, NHWC bf16, pixel stride ldy
+    float* dw = nullptr;           // fp32 [Cout][R*S*Cin], accumulated atomically (caller zeroes)
+    int B = 0, H = 1, W = 1, Cin = 0, lda = 0;
+    int Ho = 1, Wo = 1, Cout = 0, ldy = 0;
+    int R = 1, S = 1, stride = 1, dil = 1, pad = 0;
+};
+bool conv_wgrad_tc_supported(const WgradGemm& g);
+int launch_conv_wgrad_tc(const WgradGemm& g, cudaStream_t stream);
+
 // ---- stem.cu : conv0(1x1,bias) + conv1(7x7 s2 p3) + FrozenBN + ReLU + maxpool(3x3 s2 p1), F == 64
 struct StemWeights {
     const float* weff;   // [49][64]   sum_c conv1[o][c][tap] * conv0.w[c]

@@ -45,6 +45,18 @@ def conv(x_nhwc, w_krsc, scale=None, bias=None, residual=None, stride=1, dil=1, 
     return out
 
 
+def conv_wgrad(x_nhwc, dy_nhwc, k, stride=1, dil=1, pad=0):
+    """x [B,H,W,Cin] bf16, dy [B,Ho,Wo,Cout] bf16 -> dw [Cout,k,k,Cin] fp32."""
+    lib = _lib.load()
+    B, H, W, Cin = x_nhwc.shape
+    Cout = dy_nhwc.shape[-1]
+    dw = torch.zeros(Cout, k, k, Cin, dtype=torch.float32, device="cuda")
+    x_nhwc, dy_nhwc = x_nhwc.contiguous(), dy_nhwc.contiguous()
+    _lib.check(lib.sedt_op_conv_wgrad(x_nhwc.data_ptr(), dy_nhwc.data_ptr(), dw.data_ptr(), B, H, W, Cin, Cout, k, stride, dil,
+                                      pad, _lib.current_stream()))
+    return dw
+
+
 def tc_supported(x_nhwc, w_krsc, stride=1, dil=1, pad=0, out_dtype=None) -> bool:
     lib = _lib.load()
     B, H, W, Cin = x_nhwc.shape
