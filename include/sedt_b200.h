@@ -143,6 +143,23 @@ SEDT_API int sedt_op_conv(const sedt_conv_desc* d, int engine, void* stream);
 /* Weight gradient of the same layer (autograd's conv2d / addmm weight backward for sedt/backbone.py,
  * sedt/transformer.py): dw [Cout][k*k*Cin] fp32 += sum over output pixels of dy[m, co] * x[m shifted by tap, ci].
  * x NHWC bf16 [B,H,W,Cin], dy NHWC bf16 [B,Ho,Wo,Cout]; dw must be zeroed (or hold a running sum) by the caller. */
+/* Non-GEMM backward operators (bf16 activations / gradients, fp32 parameter gradients accumulated atomically).
+ * Data gradient of a conv / linear layer = sedt_op_conv on dy with the weights from sedt_op_repack_dgrad
+ * (wd[ci][r'][s'][co] = scale[co] * w[co][ci][R-1-r'][S-1-s']), after sedt_op_upsample2 when the layer had stride 2;
+ * relu = 2 in the conv descriptor turns the residual input into a ReLU mask (out = residual > 0 ? acc : 0). */
+SEDT_API int sedt_op_repack_dgrad(const float* w_oihw, const float* scale, void* out, int dtype, int Cout, int Cin, int R, int S,
+                                  void* stream);
+SEDT_API int sedt_op_upsample2(const void* dy, void* u, int B, int H, int W, int Ho, int Wo, int C, void* stream);
+SEDT_API int sedt_op_relu_mask(const void* act, const void* g1, const void* g2, void* out, int64_t n, void* stream);
+SEDT_API int sedt_op_colsum(const void* in, int dtype, int64_t ld, float* out, int64_t M, int N, void* stream);
+/* torch.nn.LayerNorm backward over 256 features (sedt/transformer.py norm1-3): g1, g2 bf16 and g3 fp32 are gradients of the
+ * forward's y / y+pos / fp32 outputs (NULL = none), dres is added to dx. */
+SEDT_API int sedt_op_layernorm_bwd(const float* x, const float* gamma, const void* g1, const void* g2, const float* g3,
+                                   const float* dres, float* dx, float* dgamma, float* dbeta, int64_t rows, void* stream);
+/* backward of the attention core of nn.MultiheadAttention (softmax(QK^T * scale + masks) V), bf16, head_dim 32 */
+SEDT_API int sedt_op_attention_bwd(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
+                                   void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm,
+                                   const float* amask, int B, int nheads, int Lq, int Lk, float scale, void* stream);
 SEDT_API int sedt_op_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int k,
                                 int stride, int dil, int pad, void* stream);
 SEDT_API int sedt_op_conv_tc_supported(const sedt_conv_desc* d);

@@ -58,6 +58,12 @@ SIGNATURES = {
     "sedt_lsap": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "sedt_op_conv": (_i, [C.POINTER(SedtConvDesc), _i, _vp]),
     "sedt_op_conv_tc_supported": (_i, [C.POINTER(SedtConvDesc)]),
+    "sedt_op_repack_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "sedt_op_upsample2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sedt_op_relu_mask": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "sedt_op_colsum": (_i, [_vp, _i, _i64, _vp, _i64, _i, _vp]),
+    "sedt_op_layernorm_bwd": (_i, [_vp] * 9 + [_i64, _vp]),
+    "sedt_op_attention_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "sedt_op_conv_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "sedt_op_repack_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sedt_op_cast": (_i, [_vp, _vp, _i, _i64, _vp]),

@@ -169,6 +169,40 @@ int sedt_op_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, i
     return launch_conv_wgrad_tc(g, (cudaStream_t)stream);
 }
 
+int sedt_op_repack_dgrad(const float* w_oihw, const float* scale, void* out, int dtype, int Cout, int Cin, int R, int S, void* stream)
+{
+    return launch_repack_dgrad(w_oihw, scale, out, dtype, Cout, Cin, R, S, (cudaStream_t)stream);
+}
+
+int sedt_op_upsample2(const void* dy, void* u, int B, int H, int W, int Ho, int Wo, int C, void* stream)
+{
+    return launch_upsample2(dy, u, B, H, W, Ho, Wo, C, (cudaStream_t)stream);
+}
+
+int sedt_op_relu_mask(const void* act, const void* g1, const void* g2, void* out, int64_t n, void* stream)
+{
+    return launch_relu_mask(act, g1, g2, out, n, (cudaStream_t)stream);
+}
+
+int sedt_op_colsum(const void* in, int dtype, int64_t ld, float* out, int64_t M, int N, void* stream)
+{
+    return launch_colsum(in, dtype, ld, out, M, N, (cudaStream_t)stream);
+}
+
+int sedt_op_layernorm_bwd(const float* x, const float* gamma, const void* g1, const void* g2, const float* g3, const float* dres,
+                          float* dx, float* dgamma, float* dbeta, int64_t rows, void* stream)
+{
+    return launch_layernorm_bwd(x, gamma, g1, g2, g3, dres, dx, dgamma, dbeta, rows, (cudaStream_t)stream);
+}
+
+int sedt_op_attention_bwd(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
+                          void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm, const float* amask,
+                          int B, int nheads, int Lq, int Lk, float scale, void* stream)
+{
+    return launch_attention_bwd(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, kpm, amask, B, nheads, Lq, Lk,
+                                scale, (cudaStream_t)stream);
+}
+
 int sedt_op_conv_tc_supported(const sedt_conv_desc* d) { return d != nullptr && conv_tc_supported(to_gemm(d)) ? 1 : 0; }
 
 int sedt_op_repack_conv(const float* w_oihw, void* out, int dtype, int Cout, int Cin, int R, int S, void* stream)

@@ -106,8 +106,12 @@ conv_simt_kernel(const TA* __restrict__ in, const TA* __restrict__ w, const floa
             float v = acc[i][j];
             if (scale != nullptr) v *= scale[n];
             if (bias != nullptr) v += bias[n];
-            if (residual != nullptr) v += to_f32<TO>(residual[(size_t)mo * g.ld_res + n]);
-            if (g.relu) v = fmaxf(v, 0.f);
+            if (residual != nullptr) {
+                const float rv = to_f32<TO>(residual[(size_t)mo * g.ld_res + n]);
+                if (g.relu == 2) { if (!(rv > 0.f)) v = 0.f; }        // residual is a ReLU mask (data-gradient GEMMs)
+                else v += rv;
+            }
+            if (g.relu == 1) v = fmaxf(v, 0.f);
             out[(size_t)mo * g.ldc + n] = from_f32<TO>(v);
         }
     }

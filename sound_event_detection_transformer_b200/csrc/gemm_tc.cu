@@ -350,6 +350,7 @@ bool conv_tc_supported(const ConvGemm& g)
 int launch_conv_tc_v1(const ConvGemm& g, cudaStream_t stream)
 {
     SEDT_REQUIRE(conv_tc_supported(g), "conv_tc: unsupported shape");
+    SEDT_REQUIRE(g.relu != 2, "conv_tc v1: the ReLU-mask epilogue is only implemented in the persistent kernels");
     const int block_n = g.Cout % 128 == 0 ? 128 : 64;
     TcProblem pr;
     SEDT_TRY(build_problem(g, block_n, &pr));

@@ -78,6 +78,25 @@ int launch_repack_conv(const float* w_oihw, const float* scale, void* out, int d
                        cudaStream_t stream);
 int launch_cast(const float* in, void* out, int dt, int64_t n, cudaStream_t stream);
 
+// ---- backward.cu : the non-GEMM kernels of the backward pass (bf16 tier)
+// dX = conv(dY, Wd):  Wd[ci][r'][s'][co] = scale[co] * W[co][ci][R-1-r'][S-1-s'] from the OIHW fp32 weights
+int launch_repack_dgrad(const float* w_oihw, const float* scale, void* out, int dt, int Cout, int Cin, int R, int S,
+                        cudaStream_t stream);
+// zero insertion for stride-2 transposed convolutions: u[b,2ho,2wo,:] = dy[b,ho,wo,:] (bf16, C % 8 == 0)
+int launch_upsample2(const void* dy, void* u, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t stream);
+// out = act > 0 ? g1 + g2 : 0 (bf16; g2 may be null; out may alias g1)
+int launch_relu_mask(const void* act, const void* g1, const void* g2, void* out, int64_t n, cudaStream_t stream);
+// out[n] += sum_m in[m*ld + n]
+int launch_colsum(const void* in, int dt, int64_t ld, float* out, int64_t M, int N, cudaStream_t stream);
+// LayerNorm (D = 256) backward; g1/g2 bf16 and g3 fp32 are the gradients of the forward's y / ypos / y32 outputs (any may
+// be null), dres an fp32 gradient added to dx (the residual branch); dgamma / dbeta accumulate atomically
+int launch_layernorm_bwd(const float* x, const float* gamma, const void* g1, const void* g2, const float* g3, const float* dres,
+                         float* dx, float* dgamma, float* dbeta, int64_t rows, cudaStream_t stream);
+// attention core backward (bf16, head_dim 32, Lq, Lk <= 128): recomputes P from Q, K and the masks
+int launch_attention_bwd(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
+                         void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm, const float* amask,
+                         int B, int nheads, int Lq, int Lk, float scale, cudaStream_t stream);
+
 // ---- transformer.cu
 // LayerNorm over D=256, eps 1e-5.  Any of y / ypos / y32 may be null.
 //   y    = LN(x)                      (dtype dt)

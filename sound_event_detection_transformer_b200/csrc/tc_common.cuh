@@ -159,6 +159,8 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // One 32-column slab of the tile row owned by this thread: bias (+scale), residual, ReLU, convert, stage.
+// relu: 0 none, 1 ReLU, 2 "the residual tile is a ReLU mask": v = residual > 0 ? v : 0 (data-gradient GEMMs,
+// where the tile prefetched through the residual map is the forward activation of the layer below).
 template <typename TO, int CHUNK_BYTES>
 __device__ __forceinline__ void epilogue_slab(uint32_t (&acc)[32], int c, int nb, const float* __restrict__ scale,
                                               const float* __restrict__ bias, bool has_res, int relu, uint8_t* ostage,
@@ -193,14 +195,19 @@ __device__ __forceinline__ void epilogue_slab(uint32_t (&acc)[32], int c, int nb
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
-                    v[8 * j8 + 2 * q] += __low2float(h); v[8 * j8 + 2 * q + 1] += __high2float(h);
+                    if (relu == 2) {
+                        if (!(__low2float(h) > 0.f)) v[8 * j8 + 2 * q] = 0.f;
+                        if (!(__high2float(h) > 0.f)) v[8 * j8 + 2 * q + 1] = 0.f;
+                    } else {
+                        v[8 * j8 + 2 * q] += __low2float(h); v[8 * j8 + 2 * q + 1] += __high2float(h);
+                    }
                 }
             }
             uint32_t w[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float a = v[8 * j8 + 2 * q], b = v[8 * j8 + 2 * q + 1];
-                if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                if (relu == 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                 const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
                 w[q] = *reinterpret_cast<const uint32_t*>(&h);
             }
@@ -213,8 +220,16 @@ __device__ __forceinline__ void epilogue_slab(uint32_t (&acc)[32], int c, int nb
         for (int j4 = 0; j4 < 8; ++j4) {
             float4* slot = reinterpret_cast<float4*>(row + ((j4 ^ sw) << 4));
             float4 o4 = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-            if (has_res) { const float4 r4 = *slot; o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w; }
-            if (relu) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
+            if (has_res) {
+                const float4 r4 = *slot;
+                if (relu == 2) {
+                    if (!(r4.x > 0.f)) o4.x = 0.f;
+                    if (!(r4.y > 0.f)) o4.y = 0.f;
+                    if (!(r4.z > 0.f)) o4.z = 0.f;
+                    if (!(r4.w > 0.f)) o4.w = 0.f;
+                } else { o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w; }
+            }
+            if (relu == 1) { o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f); }
             *slot = o4;
         }
     }

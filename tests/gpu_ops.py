@@ -137,3 +137,79 @@ def pos_table(mask, B, T, F, H, W):
     pos = torch.empty(B, H * W, 256, device="cuda")
     _lib.check(lib.sedt_op_pos_table(m.data_ptr(), ds.data_ptr(), pos.data_ptr(), B, T, F, H, W, _lib.current_stream()))
     return pos, ds
+
+
+# ---- backward building blocks -----------------------------------------------------------------
+def repack_dgrad(w_oihw: torch.Tensor, scale=None, dtype=torch.bfloat16) -> torch.Tensor:
+    """OIHW fp32 -> [Cin, R, S, Cout] (taps rotated by 180 degrees, optional per-Cout scale)."""
+    lib = _lib.load()
+    co, ci, r, s = w_oihw.shape
+    w = w_oihw.cuda().float().contiguous()
+    out = torch.empty(ci, r, s, co, dtype=dtype, device="cuda")
+    _lib.check(lib.sedt_op_repack_dgrad(w.data_ptr(), _lib.ptr(scale) or None, out.data_ptr(), DT[dtype], co, ci, r, s,
+                                        _lib.current_stream()))
+    return out
+
+
+def upsample2(dy_nhwc, H, W):
+    lib = _lib.load()
+    B, Ho, Wo, Cc = dy_nhwc.shape
+    u = torch.empty(B, H, W, Cc, dtype=dy_nhwc.dtype, device="cuda")
+    _lib.check(lib.sedt_op_upsample2(dy_nhwc.contiguous().data_ptr(), u.data_ptr(), B, H, W, Ho, Wo, Cc, _lib.current_stream()))
+    return u
+
+
+def conv_dgrad(dy_nhwc, w_oihw, in_hw, scale=None, stride=1, dil=1, mask=None, residual=None, out_dtype=torch.bfloat16, engine=1):
+    """Data gradient of conv(x, w) (k in {1,3}, pad = dil for k=3) through the forward kernels."""
+    H, W = in_hw
+    k = w_oihw.shape[-1]
+    wd = repack_dgrad(w_oihw, scale)
+    g = dy_nhwc
+    if stride == 2:
+        g = upsample2(dy_nhwc, H, W)
+    pad = dil if k == 3 else 0
+    assert mask is None or residual is None
+    return conv(g, wd, None, None, mask if mask is not None else residual, 1, dil, pad, 2 if mask is not None else 0, out_dtype,
+                engine=engine)
+
+
+def relu_mask(act, g1, g2=None):
+    lib = _lib.load()
+    out = torch.empty_like(g1)
+    _lib.check(lib.sedt_op_relu_mask(act.data_ptr(), g1.data_ptr(), _lib.ptr(g2) or None, out.data_ptr(), g1.numel(),
+                                     _lib.current_stream()))
+    return out
+
+
+def colsum(x2d):
+    lib = _lib.load()
+    M, N = x2d.shape
+    out = torch.zeros(N, dtype=torch.float32, device="cuda")
+    _lib.check(lib.sedt_op_colsum(x2d.data_ptr(), DT[x2d.dtype], x2d.stride(0), out.data_ptr(), M, N, _lib.current_stream()))
+    return out
+
+
+def layernorm_bwd(x, gamma, g1=None, g2=None, g3=None, dres=None):
+    lib = _lib.load()
+    rows = x.shape[0]
+    dx = torch.empty_like(x)
+    dg = torch.zeros(256, dtype=torch.float32, device="cuda")
+    db = torch.zeros(256, dtype=torch.float32, device="cuda")
+    _lib.check(lib.sedt_op_layernorm_bwd(x.data_ptr(), gamma.data_ptr(), _lib.ptr(g1) or None, _lib.ptr(g2) or None,
+                                         _lib.ptr(g3) or None, _lib.ptr(dres) or None, dx.data_ptr(), dg.data_ptr(),
+                                         db.data_ptr(), rows, _lib.current_stream()))
+    return dx, dg, db
+
+
+def attention_bwd(q, k, v, do, nheads, kpm=None, amask=None, scale=None):
+    """q, do [B, Lq, E]; k, v [B, Lk, E] bf16 -> dq, dk, dv."""
+    lib = _lib.load()
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    scale = scale if scale is not None else (E // nheads) ** -0.5
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    k8 = kpm.to(torch.uint8).contiguous() if kpm is not None else None
+    _lib.check(lib.sedt_op_attention_bwd(q.data_ptr(), E, k.data_ptr(), E, v.data_ptr(), E, do.data_ptr(), E, dq.data_ptr(), E,
+                                         dk.data_ptr(), E, dv.data_ptr(), E, _lib.ptr(k8) or None, _lib.ptr(amask) or None, B,
+                                         nheads, Lq, Lk, scale, _lib.current_stream()))
+    return dq, dk, dv
