@@ -112,6 +112,26 @@ SEDT_API int sedt_forward(sedt_model* m, const float* x, const uint8_t* mask, in
                  const float* patches, int P, int PT, void* workspace, int64_t workspace_bytes,
                  const sedt_outputs* out, void* stream);
 
+/* ---- Training step (bf16 tier, pre-norm supervised model, dropout = 0) ----------------------------------
+ * sedt_forward_train is sedt_forward in train mode (sedt/sedt.py:64-123 under model.train()): same outputs, and
+ * every activation the backward pass needs is kept in `tape` (sedt_train_tape_bytes, caller-owned).
+ * sedt_backward replaces loss.backward() through the model (engine.py:70-74): from the gradients of
+ * pred_logits [D,B,Q,C+1], pred_boxes [D,B,Q,2] (all decoder layers, aux_outputs included) and at [B,C]
+ * (any may be NULL = zero) it writes the gradient of every trainable state_dict entry, fp32, reference
+ * layout, at grads + sedt_grad_offset(slot) (one flat buffer of sedt_grad_numel floats = the data-parallel
+ * all-reduce bucket; frozen entries - conv1, layer1, FrozenBN buffers - stay zero).  `weights` is the
+ * array given to sedt_model_pack; train_backbone = 0 stops at input_proj (lr_backbone = 0,
+ * sedt/backbone.py:135-141). */
+SEDT_API int64_t sedt_train_tape_bytes(sedt_model* m, int B, int T, int F, int has_mask);
+SEDT_API int64_t sedt_backward_workspace_bytes(sedt_model* m, int B, int T, int F);
+SEDT_API int64_t sedt_grad_numel(const sedt_model* m);
+SEDT_API int64_t sedt_grad_offset(const sedt_model* m, int slot);
+SEDT_API int sedt_forward_train(sedt_model* m, const float* x, const uint8_t* mask, int B, int T, int F, void* tape,
+                                int64_t tape_bytes, const sedt_outputs* out, void* stream);
+SEDT_API int sedt_backward(sedt_model* m, const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F,
+                           void* tape, int64_t tape_bytes, void* workspace, int64_t workspace_bytes, const float* d_logits,
+                           const float* d_boxes, const float* d_at, float* grads, int train_backbone, void* stream);
+
 /* ---- HungarianMatcher.forward default path (sedt/matcher.py:41-97; utilities/box_ops.py:9-56)
  *   logits [B, Q, C1] fp32, boxes [B, Q, 2] fp32 (center, width)
  *   tgt_labels [sumK] int64, tgt_boxes [sumK, 2] fp32, offsets [B+1] int32 (clip b owns targets

@@ -54,6 +54,12 @@ SIGNATURES = {
     "sedt_feature_shape": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "sedt_workspace_bytes": (_i64, [_vp, _i, _i, _i, _i, _i]),
     "sedt_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i64, C.POINTER(SedtOutputs), _vp]),
+    "sedt_train_tape_bytes": (_i64, [_vp, _i, _i, _i, _i]),
+    "sedt_backward_workspace_bytes": (_i64, [_vp, _i, _i, _i]),
+    "sedt_grad_numel": (_i64, [_vp]),
+    "sedt_grad_offset": (_i64, [_vp, _i]),
+    "sedt_forward_train": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i64, C.POINTER(SedtOutputs), _vp]),
+    "sedt_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp]),
     "sedt_matcher": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sedt_lsap": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "sedt_op_conv": (_i, [C.POINTER(SedtConvDesc), _i, _vp]),

@@ -115,6 +115,50 @@ int sedt_forward(sedt_model* m, const float* x, const uint8_t* mask, int B, int 
     return m->impl->forward(x, mask, B, T, F, patches, P, PT, a, o, (cudaStream_t)stream, false);
 }
 
+// ---- training step ---------------------------------------------------------------------------------------
+int64_t sedt_train_tape_bytes(sedt_model* m, int B, int T, int F, int has_mask)
+{
+    if (m == nullptr) { set_error("train_tape_bytes: null model"); return SEDT_ERR_INVALID; }
+    return m->impl->tape_bytes(B, T, F, has_mask != 0);
+}
+
+int64_t sedt_backward_workspace_bytes(sedt_model* m, int B, int T, int F)
+{
+    if (m == nullptr) { set_error("backward_workspace_bytes: null model"); return SEDT_ERR_INVALID; }
+    return m->impl->backward_workspace_bytes(B, T, F);
+}
+
+int64_t sedt_grad_numel(const sedt_model* m) { return m == nullptr ? (int64_t)SEDT_ERR_INVALID : m->impl->grad_numel(); }
+
+int64_t sedt_grad_offset(const sedt_model* m, int slot)
+{
+    if (m == nullptr || slot < 0 || slot >= (int)m->impl->slots().size()) { set_error("grad_offset: bad argument"); return SEDT_ERR_INVALID; }
+    return m->impl->grad_offset(slot);
+}
+
+int sedt_forward_train(sedt_model* m, const float* x, const uint8_t* mask, int B, int T, int F, void* tape, int64_t tape_bytes,
+                       const sedt_outputs* out, void* stream)
+{
+    SEDT_REQUIRE(m != nullptr && x != nullptr && out != nullptr && tape != nullptr, "forward_train: null argument");
+    SEDT_REQUIRE(out->hs != nullptr && out->logits != nullptr && out->boxes != nullptr, "forward_train: hs/logits/boxes outputs are required");
+    SEDT_REQUIRE(!m->impl->cfg().dec_at || out->at != nullptr, "forward_train: dec_at model needs the `at` output");
+    SEDT_REQUIRE(((uintptr_t)tape & 255) == 0, "forward_train: tape must be 256-byte aligned");
+    ForwardOut o{out->hs, out->logits, out->boxes, out->at, out->memory, nullptr, nullptr, nullptr};
+    return m->impl->forward_train(x, mask, B, T, F, tape, (size_t)tape_bytes, o, (cudaStream_t)stream);
+}
+
+int sedt_backward(sedt_model* m, const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F, void* tape,
+                  int64_t tape_bytes, void* workspace, int64_t workspace_bytes, const float* d_logits, const float* d_boxes,
+                  const float* d_at, float* grads, int train_backbone, void* stream)
+{
+    SEDT_REQUIRE(m != nullptr && weights != nullptr && x != nullptr && tape != nullptr && workspace != nullptr && grads != nullptr,
+                 "backward: null argument");
+    SEDT_REQUIRE(((uintptr_t)tape & 255) == 0 && ((uintptr_t)workspace & 255) == 0 && ((uintptr_t)grads & 255) == 0,
+                 "backward: tape, workspace and grads must be 256-byte aligned");
+    return m->impl->backward(weights, x, mask, B, T, F, tape, (size_t)tape_bytes, workspace, (size_t)workspace_bytes, d_logits,
+                             d_boxes, d_at, grads, train_backbone, (cudaStream_t)stream);
+}
+
 int sedt_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
                  const int32_t* offsets, int B, int Q, int C1, int kmax, float cost_class, float cost_bbox, float cost_giou,
                  float* cost_out, int ld_cost, int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status, void* stream)
@@ -171,7 +215,7 @@ int sedt_op_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, i
 
 int sedt_op_repack_dgrad(const float* w_oihw, const float* scale, void* out, int dtype, int Cout, int Cin, int R, int S, void* stream)
 {
-    return launch_repack_dgrad(w_oihw, scale, out, dtype, Cout, Cin, R, S, (cudaStream_t)stream);
+    return launch_repack_dgrad(w_oihw, scale, out, dtype, Cout, Cout, Cin, R, S, (cudaStream_t)stream);
 }
 
 int sedt_op_upsample2(const void* dy, void* u, int B, int H, int W, int Ho, int Wo, int C, void* stream)

@@ -20,20 +20,79 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- weights for the data gradient -----------------------------------------------------------
 // dX = conv(dY, Wd) with Wd[ci][r'][s'][co] = scale[co] * W[co][ci][R-1-r'][S-1-s']   (W is OIHW fp32)
+// The Cout axis (the reduction axis of the data-gradient GEMM) is zero-padded to Cout_pad.
 template <typename T>
 __global__ void repack_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ scale, T* __restrict__ out, int Cout,
-                                    int Cin, int R, int S)
+                                    int Cout_pad, int Cin, int R, int S)
 {
-    const int64_t total = (int64_t)Cout * Cin * R * S;
+    const int64_t total = (int64_t)Cout_pad * Cin * R * S;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int co = (int)(i % Cout);
-        int64_t t = i / Cout;
+        const int co = (int)(i % Cout_pad);
+        int64_t t = i / Cout_pad;
         const int s = (int)(t % S); t /= S;
         const int r = (int)(t % R);
         const int ci = (int)(t / R);
-        float v = w[(((int64_t)co * Cin + ci) * R + (R - 1 - r)) * S + (S - 1 - s)];
-        if (scale != nullptr) v *= scale[co];
+        float v = 0.f;
+        if (co < Cout) {
+            v = w[(((int64_t)co * Cin + ci) * R + (R - 1 - r)) * S + (S - 1 - s)];
+            if (scale != nullptr) v *= scale[co];
+        }
         out[i] = from_f32<T>(v);
+    }
+}
+
+// grad[co][ci][r][s] = scale[co] * dw[co][(r,s)][ci]   (weight gradient back in the reference's OIHW layout)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, const float* __restrict__ scale, float* __restrict__ grad, int Cout,
+                                    int Cin, int RS)
+{
+    const int64_t total = (int64_t)Cout * Cin * RS;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % RS);
+        const int64_t t = i / RS;
+        const int ci = (int)(t % Cin), co = (int)(t / Cin);
+        float v = dw[((int64_t)co * RS + tap) * Cin + ci];
+        if (scale != nullptr) v *= scale[co];
+        grad[i] = v;
+    }
+}
+
+// Gradients of the head outputs -> zero-padded bf16 GEMM operands (128 columns each):
+//   dcls[(l,b,q), c]  = d_logits[l,b,q-start,c]                       (0 for the audio query slot)
+//   dbox[(l,b,q), c]  = d_boxes[l,b,q-start,c] * s(1-s), s = boxes   (sigmoid backward)
+//   dweak[b, c]       = d_at[b,c] * a(1-a)
+__global__ void heads_bwd_prepare_kernel(const float* __restrict__ d_logits, const float* __restrict__ d_boxes,
+                                         const float* __restrict__ d_at, const float* __restrict__ boxes,
+                                         const float* __restrict__ at, bf16* __restrict__ dcls, bf16* __restrict__ dbox,
+                                         bf16* __restrict__ dweak, int D_, int B, int Qall, int start, int C1, int C)
+{
+    const int Q = Qall - start;
+    const int64_t hrows = (int64_t)D_ * B * Qall;
+    const int64_t n1 = hrows * 128, n3 = dweak != nullptr ? (int64_t)B * 128 : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n1 + n3; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < 2 * n1) {
+            const bool is_box = i >= n1;
+            const int64_t k = is_box ? i - n1 : i;
+            const int c = (int)(k % 128);
+            const int64_t r = k / 128;
+            const int q = (int)(r % Qall) - start;
+            const int64_t db = r / Qall;
+            float v = 0.f;
+            if (q >= 0) {
+                if (!is_box) { if (c < C1 && d_logits != nullptr) v = d_logits[(db * Q + q) * C1 + c]; }
+                else if (c < 2 && d_boxes != nullptr) {
+                    const float sg = boxes[(db * Q + q) * 2 + c];
+                    v = d_boxes[(db * Q + q) * 2 + c] * sg * (1.f - sg);
+                }
+            }
+            (is_box ? dbox : dcls)[k] = __float2bfloat16_rn(v);
+        } else {
+            const int64_t k = i - 2 * n1;
+            const int c = (int)(k % 128);
+            const int64_t b = k / 128;
+            float v = 0.f;
+            if (c < C && d_at != nullptr) { const float a = at[b * C + c]; v = d_at[b * C + c] * a * (1.f - a); }
+            dweak[k] = __float2bfloat16_rn(v);
+        }
     }
 }
 
@@ -294,17 +353,154 @@ attention_bwd_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict
     }
 }
 
+// ---- stem backward: gradients of conv0 (1 -> 3 channels, 1x1, bias), the only trainable parameters below layer2 ---------
+// Forward (sedt/backbone.py:102 + resnet conv1/bn1/relu/maxpool): z[o] = sum_taps Weff[o][tap] x[tap] + sum_{taps inside
+// the image} Beff[o][tap], Weff = sum_c conv1[o][c][tap] w0[c], Beff = sum_c conv1[o][c][tap] b0[c]; a = z * bn_scale + bn_bias;
+// out = maxpool3x3s2(relu(a)).  Given G = d/d(out): the kernel recomputes the (up to) nine a values of every pooling
+// window in fp32, routes G to the first maximum (if positive) and accumulates dWeff[o][tap] += dz * x[tap],
+// dBeff[o][tap] += dz (dz = G * bn_scale) in registers; thread = output channel o, CTA = (clip, 8 pooled rows).
+constexpr int SB_PH = 8;            // pooled rows per CTA
+constexpr int SB_XC = 64 + 10;      // padded input row
+
+__global__ void __launch_bounds__(64)
+stem_bwd_kernel(const float* __restrict__ x, const float* __restrict__ conv0_w, const float* __restrict__ conv0_b,
+                const float* __restrict__ conv1_w, const float* __restrict__ bn_scale, const float* __restrict__ bn_bias,
+                const bf16* __restrict__ G, float* __restrict__ acc, int T, int Hc, int Hp)
+{
+    __shared__ float Ws[49][64], Bs[49][64];
+    __shared__ float xs[11][SB_XC];
+    __shared__ int rowin[11];
+    const int o = threadIdx.x, b = blockIdx.y, hp0 = blockIdx.x * SB_PH;
+    {
+        const float w0[3] = {conv0_w[0], conv0_w[1], conv0_w[2]}, b0[3] = {conv0_b[0], conv0_b[1], conv0_b[2]};
+        for (int tap = 0; tap < 49; ++tap) {
+            float w = 0.f, bb = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const float k = conv1_w[(o * 3 + c) * 49 + tap]; w = fmaf(k, w0[c], w); bb = fmaf(k, b0[c], bb); }
+            Ws[tap][o] = w; Bs[tap][o] = bb;
+        }
+    }
+    const float sc = bn_scale[o], bi = bn_bias[o];
+    float dW[49], dB[49];
+#pragma unroll
+    for (int i = 0; i < 49; ++i) { dW[i] = 0.f; dB[i] = 0.f; }
+    const float* xb = x + (size_t)b * T * 64;
+    for (int hp = hp0; hp < hp0 + SB_PH && hp < Hp; ++hp) {
+        const int irow0 = 4 * hp - 5;
+        __syncthreads();
+        for (int i = o; i < 11 * SB_XC; i += 64) {
+            const int lr = i / SB_XC, lc = i - lr * SB_XC;
+            const int row = irow0 + lr, col = lc - 5;
+            xs[lr][lc] = (row >= 0 && row < T && col >= 0 && col < 64) ? xb[(size_t)row * 64 + col] : 0.f;
+        }
+        if (o < 11) rowin[o] = (irow0 + o >= 0 && irow0 + o < T) ? 1 : 0;
+        __syncthreads();
+        for (int wp = 0; wp < 16; ++wp) {
+            const float g = __bfloat162float(G[(((size_t)b * Hp + hp) * 16 + wp) * 64 + o]);
+            float best = -CUDART_INF_F; int bdy = 0, bdx = 0;
+            for (int dy = 0; dy < 3; ++dy) {
+                const int hc = 2 * hp - 1 + dy;
+                if (hc < 0 || hc >= Hc) continue;
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int wc = 2 * wp - 1 + dx;
+                    if (wc < 0 || wc >= 32) continue;
+                    float z = 0.f;
+                    for (int r = 0; r < 7; ++r) {
+                        if (!rowin[2 * dy + r]) continue;
+                        const float* xr = &xs[2 * dy + r][2 * wc - 3 + 5];
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) {
+                            const int ic = 2 * wc - 3 + q;
+                            if (ic >= 0 && ic < 64) z += fmaf(Ws[r * 7 + q][o], xr[q], Bs[r * 7 + q][o]);
+                        }
+                    }
+                    const float a = fmaf(z, sc, bi);
+                    if (a > best) { best = a; bdy = dy; bdx = dx; }
+                }
+            }
+            if (best > 0.f && g != 0.f) {
+                const float dz = g * sc;
+                const int wc = 2 * wp - 1 + bdx;
+#pragma unroll
+                for (int r = 0; r < 7; ++r) {
+                    if (!rowin[2 * bdy + r]) continue;
+                    const float* xr = &xs[2 * bdy + r][2 * wc - 3 + 5];
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) {
+                        const int ic = 2 * wc - 3 + q;
+                        if (ic >= 0 && ic < 64) { dW[r * 7 + q] = fmaf(dz, xr[q], dW[r * 7 + q]); dB[r * 7 + q] += dz; }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 49; ++i) {
+        if (dW[i] != 0.f) atomicAdd(acc + i * 64 + o, dW[i]);
+        if (dB[i] != 0.f) atomicAdd(acc + 49 * 64 + i * 64 + o, dB[i]);
+    }
+}
+
+// d(conv0.weight)[c] = sum_{o,tap} dWeff[o][tap] conv1[o][c][tap];  d(conv0.bias)[c] likewise with dBeff
+__global__ void __launch_bounds__(256)
+stem_bwd_finish_kernel(const float* __restrict__ acc, const float* __restrict__ conv1_w, float* __restrict__ g_w, float* __restrict__ g_b)
+{
+    __shared__ float red[6][256];
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = threadIdx.x; i < 49 * 64; i += 256) {
+        const int tap = i / 64, o = i % 64;
+        const float dw = acc[i], db = acc[49 * 64 + i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float k = conv1_w[(o * 3 + c) * 49 + tap];
+            s[c] = fmaf(dw, k, s[c]); s[3 + c] = fmaf(db, k, s[3 + c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) red[c][threadIdx.x] = s[c];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float t = 0.f;
+        for (int i = 0; i < 256; ++i) t += red[threadIdx.x][i];
+        if (threadIdx.x < 3) g_w[threadIdx.x] = t; else g_b[threadIdx.x - 3] = t;
+    }
+}
+
 static inline unsigned grid_for(int64_t n, int per_block = 256) { return (unsigned)std::min<int64_t>(ceil_div(n, per_block), 148 * 16); }
 
 }  // namespace
 
-int launch_repack_dgrad(const float* w_oihw, const float* scale, void* out, int dt, int Cout, int Cin, int R, int S,
+int launch_repack_dgrad(const float* w_oihw, const float* scale, void* out, int dt, int Cout, int Cout_pad, int Cin, int R, int S,
                         cudaStream_t stream)
 {
-    const int64_t total = (int64_t)Cout * Cin * R * S;
+    SEDT_REQUIRE(Cout_pad >= Cout, "repack_dgrad: Cout_pad=%d < Cout=%d", Cout_pad, Cout);
+    const int64_t total = (int64_t)Cout_pad * Cin * R * S;
     if (total == 0) return SEDT_OK;
-    if (dt == DT_F32) repack_dgrad_kernel<float><<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, (float*)out, Cout, Cin, R, S);
-    else repack_dgrad_kernel<bf16><<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, (bf16*)out, Cout, Cin, R, S);
+    if (dt == DT_F32) repack_dgrad_kernel<float><<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, (float*)out, Cout, Cout_pad, Cin, R, S);
+    else repack_dgrad_kernel<bf16><<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, (bf16*)out, Cout, Cout_pad, Cin, R, S);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_unpack_wgrad(const float* dw, const float* scale, float* grad, int Cout, int Cin, int RS, cudaStream_t stream)
+{
+    const int64_t total = (int64_t)Cout * Cin * RS;
+    if (total == 0) return SEDT_OK;
+    unpack_wgrad_kernel<<<grid_for(total), 256, 0, stream>>>(dw, scale, grad, Cout, Cin, RS);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_heads_bwd_prepare(const float* d_logits, const float* d_boxes, const float* d_at, const float* boxes, const float* at,
+                             void* dcls, void* dbox, void* dweak, int D_, int B, int Qall, int start, int C1, int C,
+                             cudaStream_t stream)
+{
+    const int64_t n = (int64_t)D_ * B * Qall * 256 + (dweak != nullptr ? (int64_t)B * 128 : 0);
+    if (n == 0) return SEDT_OK;
+    heads_bwd_prepare_kernel<<<grid_for(n), 256, 0, stream>>>(d_logits, d_boxes, d_at, boxes, at, (bf16*)dcls, (bf16*)dbox,
+                                                             (bf16*)dweak, D_, B, Qall, start, C1, C);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
@@ -350,6 +546,23 @@ int launch_layernorm_bwd(const float* x, const float* gamma, const void* g1, con
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows, 8), 148 * 4);
     ProfScope _prof(PROF_NORM, stream);
     layernorm_bwd_kernel<<<grid, 256, 0, stream>>>(x, gamma, (const bf16*)g1, (const bf16*)g2, g3, dres, dx, dgamma, dbeta, rows);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_stem_bwd(const float* x, const float* conv0_w, const float* conv0_b, const float* conv1_w, const float* bn_scale,
+                    const float* bn_bias, const void* G, float* scratch, float* g_conv0_w, float* g_conv0_b, int B, int T, int F,
+                    cudaStream_t stream)
+{
+    SEDT_REQUIRE(F == 64, "stem_bwd: F=%d must be 64", F);
+    if (B == 0) return SEDT_OK;
+    const int Hc = (T + 2 * 3 - 7) / 2 + 1, Hp = (Hc + 2 - 3) / 2 + 1;
+    SEDT_TRY(launch_fill_zero(scratch, (size_t)2 * 49 * 64 * 4, stream));
+    stem_bwd_kernel<<<dim3((unsigned)ceil_div(Hp, SB_PH), (unsigned)B), 64, 0, stream>>>(x, conv0_w, conv0_b, conv1_w, bn_scale, bn_bias,
+                                                                                      (const bf16*)G, scratch, T, Hc, Hp);
+    SEDT_COUNT_LAUNCH();
+    stem_bwd_finish_kernel<<<1, 256, 0, stream>>>(scratch, conv1_w, g_conv0_w, g_conv0_b);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;

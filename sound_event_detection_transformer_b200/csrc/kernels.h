@@ -80,8 +80,15 @@ int launch_cast(const float* in, void* out, int dt, int64_t n, cudaStream_t stre
 
 // ---- backward.cu : the non-GEMM kernels of the backward pass (bf16 tier)
 // dX = conv(dY, Wd):  Wd[ci][r'][s'][co] = scale[co] * W[co][ci][R-1-r'][S-1-s'] from the OIHW fp32 weights
-int launch_repack_dgrad(const float* w_oihw, const float* scale, void* out, int dt, int Cout, int Cin, int R, int S,
+// (the Cout axis, which the data-gradient GEMM reduces over, is zero-padded to Cout_pad)
+int launch_repack_dgrad(const float* w_oihw, const float* scale, void* out, int dt, int Cout, int Cout_pad, int Cin, int R, int S,
                         cudaStream_t stream);
+// grad[co][ci][r][s] = scale[co] * dw[co][(r,s)][ci]: gemm_wgrad.cu's result back in the reference's OIHW layout
+int launch_unpack_wgrad(const float* dw, const float* scale, float* grad, int Cout, int Cin, int RS, cudaStream_t stream);
+// gradients of pred_logits / pred_boxes / at -> zero-padded [rows, 128] bf16 GEMM operands (sigmoid backward included)
+int launch_heads_bwd_prepare(const float* d_logits, const float* d_boxes, const float* d_at, const float* boxes, const float* at,
+                             void* dcls, void* dbox, void* dweak, int D_, int B, int Qall, int start, int C1, int C,
+                             cudaStream_t stream);
 // zero insertion for stride-2 transposed convolutions: u[b,2ho,2wo,:] = dy[b,ho,wo,:] (bf16, C % 8 == 0)
 int launch_upsample2(const void* dy, void* u, int B, int H, int W, int Ho, int Wo, int C, cudaStream_t stream);
 // out = act > 0 ? g1 + g2 : 0 (bf16; g2 may be null; out may alias g1)
@@ -92,6 +99,11 @@ int launch_colsum(const void* in, int dt, int64_t ld, float* out, int64_t M, int
 // be null), dres an fp32 gradient added to dx (the residual branch); dgamma / dbeta accumulate atomically
 int launch_layernorm_bwd(const float* x, const float* gamma, const void* g1, const void* g2, const float* g3, const float* dres,
                          float* dx, float* dgamma, float* dbeta, int64_t rows, cudaStream_t stream);
+// gradients of conv0.weight[3] / conv0.bias[3] from G = d/d(stem output) (bf16 [B,Hp,16,64], ReLU mask applied);
+// scratch: 2*49*64 floats
+int launch_stem_bwd(const float* x, const float* conv0_w, const float* conv0_b, const float* conv1_w, const float* bn_scale,
+                    const float* bn_bias, const void* G, float* scratch, float* g_conv0_w, float* g_conv0_b, int B, int T, int F,
+                    cudaStream_t stream);
 // attention core backward (bf16, head_dim 32, Lq, Lk <= 128): recomputes P from Q, K and the masks
 int launch_attention_bwd(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
                          void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm, const float* amask,

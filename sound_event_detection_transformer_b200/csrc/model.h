@@ -80,7 +80,22 @@ public:
                 Arena& ws, const ForwardOut& out, cudaStream_t stream, bool dry);
     static void feature_shape(int T, int F, bool dilation, int* H, int* W);
 
+    // ---- training step (train.cu): bf16 tier, pre-norm, supervised model, dropout = 0
+    int64_t tape_bytes(int B, int T, int F, bool has_mask) const;
+    int64_t backward_workspace_bytes(int B, int T, int F) const;
+    int64_t grad_offset(int slot) const;       // element offset of a state_dict entry in the flat fp32 gradient buffer
+    int64_t grad_numel() const;
+    int forward_train(const float* x, const uint8_t* mask, int B, int T, int F, void* tape, size_t tape_bytes,
+                      const ForwardOut& out, cudaStream_t stream);
+    int backward(const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F, void* tape,
+                 size_t tape_bytes, void* workspace, size_t ws_bytes, const float* d_logits, const float* d_boxes,
+                 const float* d_at, float* grads, int train_backbone, cudaStream_t stream);
+
 private:
+    struct BlockTape; struct EncTape; struct DecTape; struct Tape; struct BwdBufs;
+    void tape_layout(int B, int T, int F, bool has_mask, Arena& a, Tape& tp) const;
+    void bwd_layout(int B, const Tape& tp, Arena& a, BwdBufs& bb) const;
+    int check_train_config() const;
     int add_slot(const std::string& name, int64_t numel);
     size_t reserve(size_t bytes);
     ConvLayer make_conv(const std::string& conv, const std::string& bn, int cin, int cout, int k, int stride, int dil,

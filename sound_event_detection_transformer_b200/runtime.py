@@ -65,6 +65,7 @@ class ForwardRuntime:
             _lib.check(self.lib.sedt_model_pack(self.handle, ptrs, self._aligned(self.packed), self.packed_bytes,
                                                 _lib.current_stream()))
         self._keep = keep
+        self._ptrs = ptrs
         self._stamp = stamp
         self._graphs.clear()          # graphs bake in the packed-weight pointers: re-capture after a repack
 
@@ -183,6 +184,66 @@ class ForwardRuntime:
         g["graph"].replay()
         self.graph_kernel_launches += g["nlaunch"]
         return g["res"]
+
+    # ---- training step ---------------------------------------------------------
+    def grad_layout(self):
+        """(total fp32 elements of the flat gradient buffer, {state_dict name: element offset})."""
+        if getattr(self, "_grad_layout", None) is None:
+            n = int(self.lib.sedt_grad_numel(self.handle))
+            offs = {name: int(self.lib.sedt_grad_offset(self.handle, i)) for i, name in enumerate(self.names)}
+            self._grad_layout = (n, offs)
+        return self._grad_layout
+
+    def forward_train(self, x: torch.Tensor, mask: Optional[torch.Tensor]):
+        """Forward in train mode: same outputs as forward(); the activations stay in a runtime-owned tape until
+        backward() (one forward/backward pair in flight per runtime)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 1
+        x = x.contiguous()
+        B, _, T, F = x.shape
+        dev = x.device
+        need = int(self.lib.sedt_train_tape_bytes(self.handle, B, T, F, int(mask is not None)))
+        if need < 0:
+            _lib.check(need)
+        tape = getattr(self, "_tape", None)
+        if tape is None or tape.numel() < need + 256 or tape.device != dev:
+            self._tape = None
+            self._tape = tape = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        m8 = None
+        if mask is not None:
+            m8 = mask.to(dev).contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(dev, torch.uint8).contiguous()
+        res = self._alloc_outputs(B, T, F, 0, dev)
+        outs = _lib.SedtOutputs(**{k: _lib.ptr(res.get(k)) or None for k, _ in _lib.SedtOutputs._fields_})
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.sedt_forward_train(self.handle, x.data_ptr(), _lib.ptr(m8) or None, B, T, F, self._aligned(tape),
+                                                   tape.numel() - 256, C.byref(outs), _lib.current_stream()))
+        return res, (x, m8, B, T, F)
+
+    def backward(self, ctx, d_logits, d_boxes, d_at, train_backbone: bool) -> torch.Tensor:
+        """Gradients of every trainable state_dict entry in one flat fp32 tensor (see grad_layout())."""
+        x, m8, B, T, F = ctx
+        dev = x.device
+        need = int(self.lib.sedt_backward_workspace_bytes(self.handle, B, T, F))
+        if need < 0:
+            _lib.check(need)
+        ws = getattr(self, "_bws", None)
+        if ws is None or ws.numel() < need + 256 or ws.device != dev:
+            self._bws = None
+            self._bws = ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        n, _ = self.grad_layout()
+        flat = torch.empty(n + 64, dtype=torch.float32, device=dev)
+        shift = ((-flat.data_ptr()) % 256) // 4
+        grads = flat[shift:shift + n]
+
+        def f32(t):
+            return None if t is None else t.detach().to(torch.float32).contiguous()
+        d_logits, d_boxes, d_at = f32(d_logits), f32(d_boxes), f32(d_at)
+        tape = self._tape
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.sedt_backward(self.handle, self._ptrs, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
+                                              self._aligned(tape), tape.numel() - 256, self._aligned(ws), ws.numel() - 256,
+                                              _lib.ptr(d_logits) or None, _lib.ptr(d_boxes) or None, _lib.ptr(d_at) or None,
+                                              grads.data_ptr(), int(train_backbone), _lib.current_stream()))
+        return grads
 
     def kernel_launches(self) -> int:
         """Kernels of this library executed so far on behalf of this process (eager + graph replays)."""

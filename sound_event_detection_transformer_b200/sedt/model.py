@@ -15,6 +15,35 @@ from .modules import MLP
 PRECISIONS = {"fp32": 0, "bf16": 1}
 
 
+class _TrainStep(torch.autograd.Function):
+    """forward = sedt_forward_train, backward = sedt_backward (hand-written kernels both ways); the trainable
+    parameters are inputs so that autograd hands their gradients to the optimizer as usual (engine.py:70-80)."""
+
+    @staticmethod
+    def forward(ctx, model, x, mask, names, *params):
+        rt = model.runtime()
+        res, tctx = rt.forward_train(x, mask)
+        ctx.model, ctx.tctx, ctx.names, ctx.shapes = model, tctx, names, [p.shape for p in params]
+        ctx.has_at = "at" in res
+        outs = (res["logits"], res["boxes"]) + ((res["at"],) if ctx.has_at else ())
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_logits, d_boxes, d_at=None):
+        model = ctx.model
+        rt = model._rt
+        train_backbone = any(n.startswith("backbone.") for n in ctx.names)
+        flat = rt.backward(ctx.tctx, d_logits, d_boxes, d_at, train_backbone)
+        _, offs = rt.grad_layout()
+        grads = []
+        for n, shp in zip(ctx.names, ctx.shapes):
+            k = 1
+            for v in shp:
+                k *= v
+            grads.append(flat[offs[n]:offs[n] + k].view(shp))
+        return (None, None, None, None, *grads)
+
+
 class SEDT(nn.Module):
     """Drop-in for sedt.sedt.SEDT.  Extra keyword `precision`: "bf16" (default: bf16 operands,
     fp32 accumulation on tcgen05 tensor cores) or "fp32" (CUDA-core tier held to 1e-4 parity)."""
@@ -84,12 +113,35 @@ class SEDT(nn.Module):
         self._rt.ensure_packed(tensors)
         return self._rt
 
+    def _wants_grad(self) -> bool:
+        return torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
+
     def _check_mode(self):
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "the B200 path currently implements the forward (eval / no_grad); the backward kernels for the "
-                "training step (SURVEY.md section 8, config 4) are not built yet. Call model.eval() or wrap in "
-                "torch.no_grad().")
+        """Training with gradients runs through the native backward (SEDT only, bf16 tier, pre-norm, dropout 0);
+        everything else that would need autograd raises instead of silently falling back."""
+        if not self._wants_grad():
+            return
+        why = None
+        if self._self_sup:
+            why = "SP-SEDT training (random query drop, feature loss) has no backward kernels yet"
+        elif self.precision != "bf16" or not self.use_tensor_cores:
+            why = "the backward kernels exist for the bf16 tcgen05 tier only"
+        elif not self.transformer.normalize_before:
+            why = "the backward kernels implement the pre-norm layers only"
+        elif float(self.transformer.dropout) != 0.0:
+            why = ("dropout is not implemented in the training kernels: build the model with args.dropout = 0 "
+                   f"(got {self.transformer.dropout})")
+        if why is not None:
+            raise NotImplementedError(why + ". Call model.eval() / torch.no_grad() for inference.")
+
+    def _forward_train(self, x, mask):
+        named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+        names = tuple(n for n, _ in named)
+        outs = _TrainStep.apply(self, x, mask, names, *[p for _, p in named])
+        res = {"logits": outs[0], "boxes": outs[1]}
+        if self.dec_at:
+            res["at"] = outs[2]
+        return res
 
     def _device(self):
         return self.query_embed.weight.device
@@ -117,7 +169,10 @@ class SEDT(nn.Module):
         (center, width), `at` [B,C] under dec_at, and aux_outputs for the earlier decoder layers."""
         self._check_mode()
         x, mask = self._prepare(samples)
-        res = self.runtime().forward(x, mask, use_graph=self.use_cuda_graph)
+        if self._wants_grad():
+            res = self._forward_train(x, mask)
+        else:
+            res = self.runtime().forward(x, mask, use_graph=self.use_cuda_graph)
         out = {"pred_logits": res["logits"][-1], "pred_boxes": res["boxes"][-1]}
         if self.dec_at:
             out["at"] = res["at"].squeeze()              # sedt.py:92 squeezes: [C] when B == 1
