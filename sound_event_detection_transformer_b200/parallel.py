@@ -70,3 +70,13 @@ def gather_shards(local: torch.Tensor, sizes: Sequence[int]) -> List[torch.Tenso
     out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
     dist.gather(buf, out, dst=0)
     return [o[:s] for o, s in zip(out, sizes)] if rank == 0 else None
+
+
+def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
+    """The training step's one exchange: sum-all-reduce of the flat gradient bucket written by
+    sedt_backward, divided by the world size (what DistributedDataParallel does bucket by bucket,
+    train_spsedt.py:157-158).  In place; a no-op for a single process."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(dist.get_world_size())
+    return flat

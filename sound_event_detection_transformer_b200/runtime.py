@@ -39,10 +39,17 @@ class ForwardRuntime:
             pass
 
     # ---- weights -------------------------------------------------------------
-    def ensure_packed(self, tensors: Dict[str, torch.Tensor]) -> None:
-        """tensors: reference state_dict name -> live parameter/buffer (CUDA, fp32)."""
+    def ensure_packed(self, tensors: Dict[str, torch.Tensor], use_graph: bool = False) -> None:
+        """tensors: reference state_dict name -> live parameter/buffer (CUDA, fp32).  use_graph (training loop: the
+        optimizer rewrites the same tensors in place every step) replays the ~400 small packing kernels as one
+        CUDA graph keyed by the parameter addresses."""
         stamp = tuple((tensors[n].data_ptr(), tensors[n]._version) for n in self.names)
         if stamp == self._stamp and self.packed is not None:
+            return
+        pkey = tuple(p for p, _ in stamp)
+        if use_graph and self.packed is not None and getattr(self, "_pack_graph_key", None) == pkey:
+            self._pack_graph.replay()
+            self._stamp = stamp
             return
         dev = None
         ptrs = (C.c_void_p * len(self.names))()
@@ -68,6 +75,16 @@ class ForwardRuntime:
         self._ptrs = ptrs
         self._stamp = stamp
         self._graphs.clear()          # graphs bake in the packed-weight pointers: re-capture after a repack
+        self._train_graphs = {}
+        self._pack_graph_key = None
+        if use_graph and not keep:
+            with torch.cuda.device(dev):
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    _lib.check(self.lib.sedt_model_pack(self.handle, ptrs, self._aligned(self.packed), self.packed_bytes,
+                                                        _lib.current_stream()))
+            self._pack_graph, self._pack_graph_key = g, pkey
 
     @staticmethod
     def _aligned(buf: torch.Tensor) -> int:
@@ -194,13 +211,16 @@ class ForwardRuntime:
             self._grad_layout = (n, offs)
         return self._grad_layout
 
-    def forward_train(self, x: torch.Tensor, mask: Optional[torch.Tensor]):
+    def forward_train(self, x: torch.Tensor, mask: Optional[torch.Tensor], use_graph: bool = False):
         """Forward in train mode: same outputs as forward(); the activations stay in a runtime-owned tape until
-        backward() (one forward/backward pair in flight per runtime)."""
+        backward() (one forward/backward pair in flight per runtime).  use_graph replays the launch sequence as a
+        CUDA graph per input shape (static input / output buffers, overwritten by the next step)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 1
         x = x.contiguous()
         B, _, T, F = x.shape
         dev = x.device
+        if use_graph:
+            return self._forward_train_graph(x, mask)
         need = int(self.lib.sedt_train_tape_bytes(self.handle, B, T, F, int(mask is not None)))
         if need < 0:
             _lib.check(need)
@@ -218,8 +238,94 @@ class ForwardRuntime:
                                                    tape.numel() - 256, C.byref(outs), _lib.current_stream()))
         return res, (x, m8, B, T, F)
 
+    def _train_graph_state(self, B, T, F, has_mask, dev):
+        key = (B, T, F, has_mask, dev.index)
+        g = getattr(self, "_train_graphs", {}).get(key)
+        if g is None:
+            if not hasattr(self, "_train_graphs"):
+                self._train_graphs = {}
+            need = int(self.lib.sedt_train_tape_bytes(self.handle, B, T, F, int(has_mask)))
+            if need < 0:
+                _lib.check(need)
+            self._tape = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+            g = {"x": torch.empty(B, 1, T, F, dtype=torch.float32, device=dev),
+                 "mask": torch.empty(B, T, F, dtype=torch.uint8, device=dev) if has_mask else None,
+                 "res": self._alloc_outputs(B, T, F, 0, dev), "fwd": None, "bwd": None}
+            self._train_graphs[key] = g
+        return g
+
+    def _forward_train_graph(self, x, mask):
+        B, _, T, F = x.shape
+        dev = x.device
+        g = self._train_graph_state(B, T, F, mask is not None, dev)
+        g["x"].copy_(x, non_blocking=True)
+        if mask is not None:
+            g["mask"].copy_(mask.view(torch.uint8) if mask.dtype == torch.bool else mask, non_blocking=True)
+        if g["fwd"] is None:
+            res, tape = g["res"], self._tape
+            outs = _lib.SedtOutputs(**{k: _lib.ptr(res.get(k)) or None for k, _ in _lib.SedtOutputs._fields_})
+
+            def launch():
+                _lib.check(self.lib.sedt_forward_train(self.handle, g["x"].data_ptr(), _lib.ptr(g["mask"]) or None, B, T, F,
+                                                       self._aligned(tape), tape.numel() - 256, C.byref(outs), _lib.current_stream()))
+            with torch.cuda.device(dev):
+                launch()                                  # lazy one-time setup must not be captured
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                n0 = self.lib.sedt_launch_count()
+                with torch.cuda.graph(graph):
+                    launch()
+                g["fwd_launches"] = int(self.lib.sedt_launch_count() - n0)
+            g["fwd"] = graph
+        g["fwd"].replay()
+        self.graph_kernel_launches += g["fwd_launches"]
+        return g["res"], (g["x"], g["mask"], B, T, F, g)
+
+    def _backward_graph(self, ctx, d_logits, d_boxes, d_at, train_backbone):
+        x, m8, B, T, F, g = ctx
+        dev = x.device
+        if g["bwd"] is None or g.get("bwd_tb") != bool(train_backbone):
+            need = int(self.lib.sedt_backward_workspace_bytes(self.handle, B, T, F))
+            if need < 0:
+                _lib.check(need)
+            n, _ = self.grad_layout()
+            res = g["res"]
+            g["ws"] = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+            g["flat"] = torch.zeros(n + 64, dtype=torch.float32, device=dev)
+            g["dl"], g["db"] = torch.zeros_like(res["logits"]), torch.zeros_like(res["boxes"])
+            g["da"] = torch.zeros_like(res["at"]) if "at" in res else None
+            shift = ((-g["flat"].data_ptr()) % 256) // 4
+            g["grads"] = g["flat"][shift:shift + n]
+            tape, ws = self._tape, g["ws"]
+
+            def launch():
+                _lib.check(self.lib.sedt_backward(self.handle, self._ptrs, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
+                                                  self._aligned(tape), tape.numel() - 256, self._aligned(ws), ws.numel() - 256,
+                                                  g["dl"].data_ptr(), g["db"].data_ptr(), _lib.ptr(g["da"]) or None,
+                                                  g["grads"].data_ptr(), int(train_backbone), _lib.current_stream()))
+            with torch.cuda.device(dev):
+                launch()
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                n0 = self.lib.sedt_launch_count()
+                with torch.cuda.graph(graph):
+                    launch()
+                g["bwd_launches"] = int(self.lib.sedt_launch_count() - n0)
+            g["bwd"], g["bwd_tb"] = graph, bool(train_backbone)
+        for dst, src in ((g["dl"], d_logits), (g["db"], d_boxes), (g["da"], d_at)):
+            if dst is not None:
+                if src is None:
+                    dst.zero_()
+                else:
+                    dst.copy_(src, non_blocking=True)
+        g["bwd"].replay()
+        self.graph_kernel_launches += g["bwd_launches"]
+        return g["grads"]
+
     def backward(self, ctx, d_logits, d_boxes, d_at, train_backbone: bool) -> torch.Tensor:
         """Gradients of every trainable state_dict entry in one flat fp32 tensor (see grad_layout())."""
+        if len(ctx) == 6:
+            return self._backward_graph(ctx, d_logits, d_boxes, d_at, train_backbone)
         x, m8, B, T, F = ctx
         dev = x.device
         need = int(self.lib.sedt_backward_workspace_bytes(self.handle, B, T, F))

@@ -109,12 +109,86 @@ class SetCriterion(nn.Module):
             gt.index_put_((torch.cat(rows).to(dev), torch.cat(cols).to(dev)), torch.cat(vals).to(dev), accumulate=True)
         return {"loss_weak": F.binary_cross_entropy(pred, gt.clamp(0, 1))}
 
+    # -- batched path: no per-clip work, no host round trip between the matcher and the losses --------------
+    def _batched_ok(self, tg, fine_tune, normalize) -> bool:
+        return (not fine_tune and not normalize and "feature" not in self.losses and hasattr(self.matcher, "pack_targets")
+                and not any("ratio" in t for t in tg))
+
+    def _pack(self, tg, Q, dev):
+        pk = self.matcher.pack_targets(tg, dev)
+        n = [min(Q, k) for k in pk["sizes"]]
+        total = sum(n)
+        nt = torch.tensor(n, dtype=torch.int64)
+        bi = torch.repeat_interleave(torch.arange(len(n)), nt, output_size=total)
+        starts = torch.cumsum(nt, 0) - nt
+        pos = torch.arange(total) - starts[bi]
+        pk.update(n=n, total=total, bi=bi.to(dev, non_blocking=True), pos=pos.to(dev, non_blocking=True),
+                  off64=pk["offsets"].to(torch.int64))
+        return pk
+
+    def _layer_losses_batched(self, out, full_logits, tg, pk, num_boxes, log: bool):
+        """Same losses as _layer_losses (sedt/sedt.py:188-261) from the matcher's device-resident index matrices.
+        full_logits: pred_logits of the whole batch (the cardinality metric is not restricted to strong_mask)."""
+        logits, boxes = out["pred_logits"], out["pred_boxes"]
+        dev = logits.device
+        rows, cols, _, status = self.matcher.match(logits, boxes, tg, packed=pk, check=False)
+        bi, pos = pk["bi"], pk["pos"]
+        si, ci = rows[bi, pos], cols[bi, pos]
+        gidx = pk["off64"][bi] + ci
+        res = {}
+        if "labels" in self.losses:
+            matched = pk["labels"][gidx]
+            cls = torch.full(logits.shape[:2], self.num_classes, dtype=torch.int64, device=dev)
+            cls[bi, si] = matched
+            ce = F.cross_entropy(logits.transpose(1, 2), cls, self.empty_weight, reduction="none")
+            res["loss_ce"] = ce.sum() / num_boxes
+            if log:
+                if pk["total"] == 0:
+                    res["class_error"] = torch.zeros([], device=dev)
+                else:
+                    res["class_error"] = 100 - (logits[bi, si].argmax(-1) == matched).float().mean() * 100.0
+        if "cardinality" in self.losses:
+            with torch.no_grad():
+                n_pred = (full_logits.argmax(-1) != full_logits.shape[-1] - 1).sum(1).float()
+                res["cardinality_error"] = F.l1_loss(n_pred, pk["n_tgt_all"])
+        if "boxes" in self.losses:
+            l1, giou = paired_l1_giou(boxes[bi, si], pk["boxes"][gidx])
+            res["loss_bbox"] = l1.sum() / num_boxes
+            res["loss_giou"] = (1 - giou).sum() / num_boxes
+        return res, (rows, cols, status)
+
     # -- reference entry point ---------------------------------------------------
     def forward(self, outputs, targets, weak_mask=None, strong_mask=None, fine_tune=False, normalize=False, fl=False):
         if fl:
             raise NotImplementedError("focal-loss branch (semi-supervised only) is out of scope (SURVEY.md section 2, #9)")
         losses = {}
         indices = None
+        if strong_mask is not None and self._batched_ok(targets[strong_mask], fine_tune, normalize):
+            tg = targets[strong_mask]
+            top = {k: v[strong_mask] for k, v in outputs.items() if k != "aux_outputs"}
+            dev = top["pred_logits"].device
+            pk = self._pack(tg, top["pred_logits"].shape[1], dev)
+            num_boxes = torch.as_tensor([float(pk["total"])], dtype=torch.float, device=dev)
+            pk["n_tgt_all"] = torch.tensor([len(v["labels"]) for v in targets], dtype=torch.float32).to(dev, non_blocking=True)
+            part, (rows, cols, status) = self._layer_losses_batched(top, outputs["pred_logits"], tg, pk, num_boxes, log=True)
+            losses.update(part)
+            stats = [status]
+            if "weak" in self.losses:
+                losses.update(self._weak_loss(outputs, targets, strong_mask, weak_mask))
+            for i, aux in enumerate(outputs.get("aux_outputs", [])):
+                sub = {k: v[strong_mask] for k, v in aux.items()}
+                part, (_, _, st) = self._layer_losses_batched(sub, aux["pred_logits"], tg, pk, num_boxes, log=False)
+                losses.update({f"{k}_{i}": v for k, v in part.items()})
+                stats.append(st)
+            # one read-back for the whole step: matcher status of every layer + the top layer's index matrices
+            packed = torch.cat([torch.stack(stats).flatten().to(torch.int64), rows.flatten(), cols.flatten()]).cpu()
+            for st in packed[:len(stats)].tolist():
+                self.matcher.raise_on_status(int(st))
+            B, Q = rows.shape
+            r = packed[len(stats):len(stats) + B * Q].view(B, Q)
+            c = packed[len(stats) + B * Q:].view(B, Q)
+            indices = [(r[i, :k], c[i, :k]) for i, k in enumerate(pk["n"])]
+            return losses, indices
         if strong_mask is not None:
             top = {k: v[strong_mask] for k, v in outputs.items() if k != "aux_outputs"}
             indices, coef = self.matcher(top, targets[strong_mask], fine_tune=fine_tune, normalize=normalize, fl=fl)

@@ -52,23 +52,12 @@ class HungarianMatcher(nn.Module):
             coef = list(torch.ones(sum(counts), dtype=torch.float32).split(counts))
         return idx, coef
 
-    @torch.no_grad()
-    def match(self, pred_logits: torch.Tensor, pred_boxes: torch.Tensor, targets: Sequence[dict],
-              return_cost: bool = False):
-        """Raw batched call: returns rows [B,Q] int64, cols [B,Q] int64 (padded with -1) on the device and
-        the per-clip pair counts as a Python list (known on the host: min(Q, K_i))."""
-        lib = _lib.load()
-        if not pred_logits.is_cuda:
-            raise RuntimeError("HungarianMatcher needs CUDA tensors (there is no CPU path)")
-        dev = pred_logits.device
-        B, Q, C1 = pred_logits.shape
-        assert len(targets) == B
+    @staticmethod
+    def pack_targets(targets: Sequence[dict], dev) -> dict:
+        """Concatenate the per-clip target lists once (labels int64 [sumK], boxes fp32 [sumK,2], offsets int32 [B+1]
+        on the device); SetCriterion reuses one pack for the matcher calls of all decoder layers."""
         sizes = [int(len(v["boxes"])) for v in targets]
-        kmax = max(sizes) if sizes else 0
-        logits = pred_logits.detach().to(torch.float32).contiguous()
-        boxes = pred_boxes.detach().to(torch.float32).contiguous()
         if sum(sizes) > 0:
-            # matcher.py:69 slices labels to the number of boxes; skip the per-clip slice when they already agree
             labs = [v["labels"] if v["labels"].shape[0] == k else v["labels"][:k] for v, k in zip(targets, sizes)]
             tgt_ids = torch.cat(labs).reshape(-1).to(dev, torch.int64).contiguous()
             tgt_box = torch.cat([v["boxes"] for v in targets]).reshape(-1, 2).to(dev, torch.float32).contiguous()
@@ -79,6 +68,44 @@ class HungarianMatcher(nn.Module):
         for k in sizes:
             off.append(off[-1] + k)
         offsets = torch.tensor(off, dtype=torch.int32).to(dev, non_blocking=True)
+        return {"sizes": sizes, "labels": tgt_ids, "boxes": tgt_box, "offsets": offsets}
+
+    @torch.no_grad()
+    def match(self, pred_logits: torch.Tensor, pred_boxes: torch.Tensor, targets: Sequence[dict],
+              return_cost: bool = False, packed: dict = None, check: bool = True):
+        """Raw batched call: returns rows [B,Q] int64, cols [B,Q] int64 on the device (every clip's pairs first,
+        sorted by query, then -1 padding) and the per-clip pair counts as a Python list (known on the host:
+        min(Q, K_i)).  packed: a pack_targets() result to reuse; check=False skips the status read-back (no
+        sync; the status tensor is returned as a fourth value instead)."""
+        lib = _lib.load()
+        if not pred_logits.is_cuda:
+            raise RuntimeError("HungarianMatcher needs CUDA tensors (there is no CPU path)")
+        dev = pred_logits.device
+        B, Q, C1 = pred_logits.shape
+        assert len(targets) == B
+        logits = pred_logits.detach().to(torch.float32).contiguous()
+        boxes = pred_boxes.detach().to(torch.float32).contiguous()
+        if packed is not None:
+            sizes, tgt_ids, tgt_box, offsets = packed["sizes"], packed["labels"], packed["boxes"], packed["offsets"]
+            kmax = max(sizes) if sizes else 0
+        else:
+            sizes = [int(len(v["boxes"])) for v in targets]
+            kmax = max(sizes) if sizes else 0
+        if packed is not None:
+            pass
+        elif sum(sizes) > 0:
+            # matcher.py:69 slices labels to the number of boxes; skip the per-clip slice when they already agree
+            labs = [v["labels"] if v["labels"].shape[0] == k else v["labels"][:k] for v, k in zip(targets, sizes)]
+            tgt_ids = torch.cat(labs).reshape(-1).to(dev, torch.int64).contiguous()
+            tgt_box = torch.cat([v["boxes"] for v in targets]).reshape(-1, 2).to(dev, torch.float32).contiguous()
+        else:
+            tgt_ids = torch.zeros(1, dtype=torch.int64, device=dev)
+            tgt_box = torch.zeros(1, 2, dtype=torch.float32, device=dev)
+        if packed is None:
+            off = [0]
+            for k in sizes:
+                off.append(off[-1] + k)
+            offsets = torch.tensor(off, dtype=torch.int32).to(dev, non_blocking=True)
         rows = torch.empty(B, Q, dtype=torch.int64, device=dev)
         cols = torch.empty(B, Q, dtype=torch.int64, device=dev)
         counts = torch.empty(B, dtype=torch.int32, device=dev)
@@ -89,16 +116,21 @@ class HungarianMatcher(nn.Module):
                                         offsets.data_ptr(), B, Q, C1, kmax, float(self.cost_class), float(self.cost_bbox),
                                         float(self.cost_giou), _lib.ptr(cost) or None, max(kmax, 1), rows.data_ptr(),
                                         cols.data_ptr(), counts.data_ptr(), status.data_ptr(), _lib.current_stream()))
-        if not self.device_indices:
-            st = int(status.item())
-            if st == -4:
-                raise ValueError("matrix contains invalid numeric entries")      # scipy's message (matcher.py:95)
-            if st != 0:
-                raise ValueError("cost matrix is infeasible")
         n = [min(Q, k) for k in sizes]
+        if not check:
+            return rows, cols, n, status
+        if not self.device_indices:
+            self.raise_on_status(int(status.item()))
         if return_cost:
             return rows, cols, n, cost
         return rows, cols, n
+
+    @staticmethod
+    def raise_on_status(st: int):
+        if st == -4:
+            raise ValueError("matrix contains invalid numeric entries")      # scipy's message (matcher.py:95)
+        if st != 0:
+            raise ValueError("cost matrix is infeasible")
 
 
 def lsap_batched(cost: torch.Tensor, sizes: Sequence[int]):

@@ -21,8 +21,8 @@ class _TrainStep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, mask, names, *params):
-        rt = model.runtime()
-        res, tctx = rt.forward_train(x, mask)
+        rt = model.runtime(use_graph=model.use_cuda_graph)
+        res, tctx = rt.forward_train(x, mask, use_graph=model.use_cuda_graph)
         ctx.model, ctx.tctx, ctx.names, ctx.shapes = model, tctx, names, [p.shape for p in params]
         ctx.has_at = "at" in res
         outs = (res["logits"], res["boxes"]) + ((res["at"],) if ctx.has_at else ())
@@ -34,6 +34,9 @@ class _TrainStep(torch.autograd.Function):
         rt = model._rt
         train_backbone = any(n.startswith("backbone.") for n in ctx.names)
         flat = rt.backward(ctx.tctx, d_logits, d_boxes, d_at, train_backbone)
+        if model.grad_allreduce:
+            from ..parallel import allreduce_mean_
+            allreduce_mean_(flat)                 # one NCCL all-reduce of the whole gradient bucket
         _, offs = rt.grad_layout()
         grads = []
         for n, shp in zip(ctx.names, ctx.shapes):
@@ -77,6 +80,9 @@ class SEDT(nn.Module):
         # replay the forward as one CUDA graph per input shape (outputs then live in runtime-owned buffers that
         # the next call with the same shape overwrites)
         self.use_cuda_graph = False
+        # data-parallel training: average the flat gradient bucket over the ranks inside backward (the model is then
+        # NOT wrapped in DistributedDataParallel; one all-reduce instead of DDP's per-bucket hooks)
+        self.grad_allreduce = False
         self._rt: Optional[ForwardRuntime] = None
         self._self_sup = False
         self._feature_recon = False
@@ -105,12 +111,12 @@ class SEDT(nn.Module):
         self._rt = None
         return self
 
-    def runtime(self) -> ForwardRuntime:
+    def runtime(self, use_graph: bool = False) -> ForwardRuntime:
         if self._rt is None:
             self._rt = ForwardRuntime(self._native_config())
         tensors = dict(self.named_parameters())
         tensors.update(dict(self.named_buffers()))
-        self._rt.ensure_packed(tensors)
+        self._rt.ensure_packed(tensors, use_graph=use_graph)
         return self._rt
 
     def _wants_grad(self) -> bool:

@@ -151,3 +151,23 @@ def synth_matcher_case(B: int, Q: int, C: int, kmin: int = 0, kmax: int = 10, se
         targets.append({"labels": torch.randint(0, C, (k,), generator=g),
                         "boxes": torch.rand(k, 2, generator=g) * scale})
     return {"pred_logits": logits, "pred_boxes": boxes}, targets
+
+
+def synth_criterion_case(B: int, Q: int, C: int, D: int, kmin: int = 0, kmax: int = 10, seed: int = 7):
+    """Model-shaped outputs of all D decoder layers (top + D-1 aux) and config-3 style targets for SetCriterion."""
+    g = torch.Generator().manual_seed(7000 + seed)
+    scale = torch.tensor([1.0, 0.5])
+
+    def layer():
+        return {"pred_logits": torch.randn(B, Q, C + 1, generator=g),
+                "pred_boxes": (torch.rand(B, Q, 2, generator=g) * 0.9 + 0.05) * scale}
+    outputs = layer()
+    outputs["at"] = torch.sigmoid(torch.randn(B, C, generator=g))
+    outputs["aux_outputs"] = [layer() for _ in range(D - 1)]
+    sizes = torch.randint(kmin, kmax + 1, (B,), generator=g)
+    targets = []
+    for k in sizes.tolist():
+        targets.append({"labels": torch.randint(0, C, (k,), generator=g),
+                        "boxes": (torch.rand(k, 2, generator=g) * 0.9 + 0.05) * scale,
+                        "orig_size": torch.tensor(10.0)})
+    return outputs, targets

@@ -138,9 +138,40 @@ def run_matcher(tag, B, Q, C, kmin, kmax, seed, chunk=32, normalize=False):
     print(f"matcher_{tag}: {B} clips, {int(np.sum(counts))} pairs")
 
 
+def run_criterion(tag, args, B, seed, kmin=0, kmax=10):
+    """Reference SetCriterion (sedt/sedt.py:134-352) built directly (build_model returns None for it
+    without CUDA) on seeded model-shaped outputs: every loss value and the gradient of the weighted sum."""
+    from sedt.sedt import SetCriterion
+    weight_dict = {"loss_ce": args.ce_loss_coef, "loss_bbox": args.bbox_loss_coef, "loss_giou": args.giou_loss_coef,
+                   "loss_weak": args.weak_loss_coef}
+    for i in range(args.dec_layers - 1):
+        weight_dict.update({k + f"_{i}": v for k, v in list(weight_dict.items()) if "_" in k and not k[-1].isdigit()})
+    crit = SetCriterion(args.num_classes, matcher=build_matcher(args), weight_dict=weight_dict, eos_coef=args.eos_coef,
+                        losses=["labels", "boxes", "cardinality", "weak"])
+    outputs, targets = synth.synth_criterion_case(B, args.num_queries, args.num_classes, args.dec_layers, kmin, kmax, seed)
+    leaves = [outputs["pred_logits"], outputs["pred_boxes"], outputs["at"]]
+    for a in outputs["aux_outputs"]:
+        leaves += [a["pred_logits"], a["pred_boxes"]]
+    for t in leaves:
+        t.requires_grad_(True)
+    losses, indices = crit(outputs, np.array(targets, dtype=object), None, slice(B))
+    total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)
+    total.backward()
+    fx = {"loss_names": np.array(sorted(losses)), "loss_values": np.array([float(losses[k]) for k in sorted(losses)], np.float64),
+          "total": np.float64(float(total)), "meta": np.asarray([B, kmin, kmax, seed], np.int64)}
+    for i, t in enumerate(leaves):
+        fx[f"grad_{i}"] = t.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, f"criterion_{tag}.npz"), **fx)
+    print(f"criterion_{tag}: total {float(total):.5f}, {len(losses)} entries")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-criterion" in sys.argv:
+        run_criterion("c2", spec.config_args("c2"), 48, seed=1)
+        run_criterion("c1_edges", spec.config_args("c1"), 16, seed=2, kmin=8, kmax=14)
+        sys.exit(0)
     # config-1 shape (URBAN-SED: T=500, E=3, Q=10) and config-2 shape (DCASE: T=496, E=6, Q=20), batch 2
     run_sedt("c1_b2", spec.config_args("c1"), synth.synth_clips(2, 500, 64, seed=1), seed=11)
     run_sedt("c2_b2", spec.config_args("c2"), synth.synth_clips(2, 496, 64, seed=2), seed=12)
@@ -163,3 +194,5 @@ if __name__ == "__main__":
     run_matcher("c3_edges", 64, 20, 10, 18, 28, seed=4)
     run_matcher("urban_q10", 64, 10, 10, 0, 12, seed=5)
     run_matcher("c3_normalize", 32, 20, 10, 0, 10, seed=6, normalize=True)
+    run_criterion("c2", spec.config_args("c2"), 48, seed=1)
+    run_criterion("c1_edges", spec.config_args("c1"), 16, seed=2, kmin=8, kmax=14)

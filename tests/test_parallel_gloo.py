@@ -57,3 +57,37 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    parallel.init_from_env("gloo")
+    # the flat gradient bucket of the training step: each rank holds the gradient of its own clip shard
+    flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    view = flat[10:20].view(2, 5)                       # a parameter's .grad is a view into the bucket
+    parallel.allreduce_mean_(flat)
+    if rank == 0:
+        q.put((flat.tolist(), view.flatten().tolist()))
+    torch.distributed.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_mean_gloo():
+    """The training step's only collective: the bucket is averaged in place, so parameter views see the result."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    flat, view = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert flat == [1.5 * i for i in range(1000)]
+    assert view == [1.5 * i for i in range(10, 20)]
+
+
+def test_allreduce_mean_single_process_is_identity():
+    t = torch.ones(8)
+    assert parallel.allreduce_mean_(t) is t and torch.equal(t, torch.ones(8))

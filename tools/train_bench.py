@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Config 4: the SEDT E=6 training step (forward + 3 matcher calls + set loss + backward + gradient all-reduce +
+clip + AdamW), batch 64 per GPU, dropout 0.  Prints step time, clips/s and a per-phase breakdown.
+
+    python tools/train_bench.py [--batch 64] [--steps 10] [--profile]
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/train_bench.py
+"""
+import argparse, os, sys, json, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
+import torch
+from sound_event_detection_transformer_b200 import spec, synth, parallel, _lib, flops
+from sound_event_detection_transformer_b200.sedt import build_model
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    o = ap.parse_args()
+    rank, world, local = parallel.env_ranks()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    parallel.init_from_env("nccl", dev)
+    args = spec.config_args("c2")
+    args.dropout = 0.0
+    sd = synth.synth_state_dict(args, 12)
+    model, criterion, _ = build_model(args)
+    model.load_state_dict(sd)
+    model = model.to(dev).train()
+    criterion = criterion.to(dev)
+    model.grad_allreduce = world > 1
+    model.use_cuda_graph = not o.no_graph
+    B = o.batch
+    x = synth.synth_clips(B, 496, 64, seed=200 + rank).to(dev)
+    _, targets = synth.synth_matcher_case(B, args.num_queries, args.num_classes, 0, 10, seed=5 + rank)
+    for t in targets:
+        t["labels"] = t["labels"].to(dev); t["boxes"] = t["boxes"].to(dev)
+        t["orig_size"] = torch.tensor(10.0, device=dev)
+    import numpy as np
+    targets_arr = np.array(targets, dtype=object)
+    params = [p for p in model.parameters() if p.requires_grad]
+    named = dict(model.named_parameters())
+    groups = [{"params": [p for n, p in named.items() if "backbone" not in n and p.requires_grad]},
+              {"params": [p for n, p in named.items() if "backbone" in n and p.requires_grad], "lr": 1e-5}]
+    opt = torch.optim.AdamW(groups, lr=1e-4, weight_decay=1e-4)          # train_sedt.py:234-240,269-270
+    wd = criterion.weight_dict
+    lib = _lib.load()
+
+    def step(timers=None):
+        def mark(name):
+            if timers is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); timers.append((name, e))
+        mark("start")
+        out = model(x)
+        mark("forward")
+        losses, _ = criterion(out, targets_arr, None, slice(B))
+        loss = sum(losses[k] * wd[k] for k in losses if k in wd)
+        mark("matcher+loss")
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        mark("backward(+allreduce)")
+        torch.nn.utils.clip_grad_norm_(params, 0.1)                      # engine.py:76-78
+        opt.step()
+        mark("clip+adamw")
+        return loss
+
+    for _ in range(o.warmup):
+        step()
+    torch.cuda.synchronize(); parallel.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.sedt_launch_count()
+    e0.record()
+    for _ in range(o.steps):
+        loss = step()
+    e1.record(); torch.cuda.synchronize(); parallel.barrier()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev) / o.steps
+    launches = (lib.sedt_launch_count() - l0) / o.steps
+    timers = []
+    step(timers); torch.cuda.synchronize()
+    phases = {timers[i][0]: round(timers[i - 1][1].elapsed_time(timers[i][1]), 3) for i in range(1, len(timers))}
+    per_class = None
+    if o.profile:
+        ms_cls = (C.c_double * len(_lib.KERNEL_CLASSES))(); n_cls = (C.c_longlong * len(_lib.KERNEL_CLASSES))()
+        model.use_cuda_graph = False
+        step(); torch.cuda.synchronize()
+        lib.sedt_profile_enable(1)
+        step(); torch.cuda.synchronize()
+        _lib.check(lib.sedt_profile_read(ms_cls, n_cls)); lib.sedt_profile_enable(0)
+        per_class = {n: {"ms": round(ms_cls[i], 3), "launches": int(n_cls[i])} for i, n in enumerate(_lib.KERNEL_CLASSES) if n_cls[i]}
+    if rank == 0:
+        fl = flops.forward_flops_per_clip(args, 496, 64)["total"]
+        step_flops = 3 * fl - 0.99e9            # fwd + dgrad + wgrad minus the frozen conv1 + layer1 weight gradients
+        print(json.dumps({"metric": "clips/sec SEDT E=6 training step (fwd + matcher x3 + set loss + bwd + allreduce + clip + AdamW)",
+                          "value": world * B / ms * 1e3, "unit": "clips/s", "n_gpus": world, "ms_per_step": ms,
+                          "batch_per_gpu": B, "loss": float(loss.detach()), "kernel_launches_per_step": launches, "phases_ms": phases,
+                          "achieved_tflops": B * step_flops / ms / 1e9, "per_class": per_class, "dropout": 0.0}))
+
+
+if __name__ == "__main__":
+    main()
