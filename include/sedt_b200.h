@@ -176,10 +176,11 @@ SEDT_API int sedt_op_colsum(const void* in, int dtype, int64_t ld, float* out, i
  * forward's y / y+pos / fp32 outputs (NULL = none), dres is added to dx. */
 SEDT_API int sedt_op_layernorm_bwd(const float* x, const float* gamma, const void* g1, const void* g2, const float* g3,
                                    const float* dres, float* dx, float* dgamma, float* dbeta, int64_t rows, void* stream);
-/* backward of the attention core of nn.MultiheadAttention (softmax(QK^T * scale + masks) V), bf16, head_dim 32 */
+/* backward of the attention core of nn.MultiheadAttention (softmax(QK^T * scale + masks) V), bf16, head_dim 32;
+ * engine 0 = CUDA-core kernel, 1 = tcgen05 kernel */
 SEDT_API int sedt_op_attention_bwd(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
                                    void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm,
-                                   const float* amask, int B, int nheads, int Lq, int Lk, float scale, void* stream);
+                                   const float* amask, int B, int nheads, int Lq, int Lk, float scale, int engine, void* stream);
 SEDT_API int sedt_op_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int k,
                                 int stride, int dil, int pad, void* stream);
 SEDT_API int sedt_op_conv_tc_supported(const sedt_conv_desc* d);

@@ -69,7 +69,7 @@ SIGNATURES = {
     "sedt_op_relu_mask": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "sedt_op_colsum": (_i, [_vp, _i, _i64, _vp, _i64, _i, _vp]),
     "sedt_op_layernorm_bwd": (_i, [_vp] * 9 + [_i64, _vp]),
-    "sedt_op_attention_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "sedt_op_attention_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     "sedt_op_conv_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "sedt_op_repack_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sedt_op_cast": (_i, [_vp, _vp, _i, _i64, _vp]),

@@ -241,10 +241,17 @@ int sedt_op_layernorm_bwd(const float* x, const float* gamma, const void* g1, co
 
 int sedt_op_attention_bwd(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
                           void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm, const float* amask,
-                          int B, int nheads, int Lq, int Lk, float scale, void* stream)
+                          int B, int nheads, int Lq, int Lk, float scale, int engine, void* stream)
 {
-    return launch_attention_bwd(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, kpm, amask, B, nheads, Lq, Lk,
-                                scale, (cudaStream_t)stream);
+    if (engine == 0)
+        return launch_attention_bwd(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, kpm, amask, B, nheads, Lq, Lk,
+                                    scale, (cudaStream_t)stream);
+    if (!attention_bwd_tc_supported(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, Lq, Lk)) {
+        set_error("op_attention_bwd: shape / alignment not supported by the tcgen05 kernel");
+        return SEDT_ERR_UNSUPPORTED;
+    }
+    return launch_attention_bwd_tc(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, kpm, amask, B, nheads, Lq, Lk,
+                                   scale, (cudaStream_t)stream);
 }
 
 int sedt_op_conv_tc_supported(const sedt_conv_desc* d) { return d != nullptr && conv_tc_supported(to_gemm(d)) ? 1 : 0; }

@@ -109,6 +109,13 @@ int launch_attention_bwd(const void* Q, int ldq, const void* K, int ldk, const v
                          void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm, const float* amask,
                          int B, int nheads, int Lq, int Lk, float scale, cudaStream_t stream);
 
+// attention_bwd_tc.cu: the same on tcgen05 / TMEM (production path; the SIMT kernel above is the plain reference)
+bool attention_bwd_tc_supported(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
+                                const void* dQ, int lddq, const void* dK, int lddk, const void* dV, int lddv, int Lq, int Lk);
+int launch_attention_bwd_tc(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
+                            void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm, const float* amask,
+                            int B, int nheads, int Lq, int Lk, float scale, cudaStream_t stream);
+
 // ---- transformer.cu
 // LayerNorm over D=256, eps 1e-5.  Any of y / ypos / y32 may be null.
 //   y    = LN(x)                      (dtype dt)

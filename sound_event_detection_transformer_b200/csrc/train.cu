@@ -14,6 +14,7 @@
 #include "model.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace sedt {
 
@@ -401,6 +402,16 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
         SEDT_TRY(dgrad_lin(Wp(weak_.w_slot), ncls, 128, d, bb.dweak, 128, B, dst, Qall * d, 0, dst, DT_F32, Qall * d));
     }
 
+    // attention core backward: tcgen05 kernel (SEDT_ATT_BWD_SIMT=1 selects the CUDA-core one)
+    static const bool att_simt = [] { const char* e = getenv("SEDT_ATT_BWD_SIMT"); return e != nullptr && e[0] == '1'; }();
+    auto attn_bwd = [&](const void* Qp, int ldq, const void* Kp, int ldk, const void* Vp, int ldv, const void* dOp, int ldo, void* dQp,
+                        int lddq, void* dKp, int lddk, void* dVp, int lddv, const uint8_t* kpm, const float* am, int Bn, int nh, int Lq,
+                        int Lk, float sc, cudaStream_t st) -> int {
+        if (!att_simt && attention_bwd_tc_supported(Qp, ldq, Kp, ldk, Vp, ldv, dOp, ldo, dQp, lddq, dKp, lddk, dVp, lddv, Lq, Lk))
+            return launch_attention_bwd_tc(Qp, ldq, Kp, ldk, Vp, ldv, dOp, ldo, dQp, lddq, dKp, lddk, dVp, lddv, kpm, am, Bn, nh, Lq, Lk, sc, st);
+        return launch_attention_bwd(Qp, ldq, Kp, ldk, Vp, ldv, dOp, ldo, dQp, lddq, dKp, lddk, dVp, lddv, kpm, am, Bn, nh, Lq, Lk, sc, st);
+    };
+
     // ================= decoder (transformer.py:263-284), last layer first ===============================
     // self-attention + its LayerNorm, shared by encoder and decoder layers.
     //   in : gx = d(loss)/d(x_mid) fp32 (x_mid = x_in + out_proj(attn))      out: gout = d(loss)/d(x_in) fp32
@@ -410,7 +421,7 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
         SEDT_TRY(to16(gx, bb.g16, R * d));
         SEDT_TRY(lin_param_grads(A.out_proj, 0, d, ao, d, bb.g16, d, R));
         SEDT_TRY(dgrad_lin(Wp(A.out_proj.w_slot), d, d, d, bb.g16, d, R, nullptr, 0, 0, bb.dao, dt, d));
-        SEDT_TRY(launch_attention_bwd(qk, 2 * d, (const char*)qk + d * es, 2 * d, v, d, bb.dao, d, bb.dqk, 2 * d,
+        SEDT_TRY(attn_bwd(qk, 2 * d, (const char*)qk + d * es, 2 * d, v, d, bb.dao, d, bb.dqk, 2 * d,
                                       (char*)bb.dqk + d * es, 2 * d, bb.dv, d, kpm, nullptr, B, cfg_.nheads, L, L, scale, s));
         SEDT_TRY(lin_param_grads(A.in_proj, 0, 2 * d, nap, d, bb.dqk, 2 * d, R));
         SEDT_TRY(lin_param_grads(A.in_proj, 2 * d, d, na, d, bb.dv, d, R));
@@ -446,7 +457,7 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
         SEDT_TRY(to16(gcur, bb.g16, qrows * d));
         SEDT_TRY(lin_param_grads(e.cross_attn.out_proj, 0, d, t.ao2, d, bb.g16, d, qrows));
         SEDT_TRY(dgrad_lin(Wp(e.cross_attn.out_proj.w_slot), d, d, d, bb.g16, d, qrows, nullptr, 0, 0, bb.dao, dt, d));
-        SEDT_TRY(launch_attention_bwd(t.qb, d, (const char*)tp.ck + (size_t)l * d * es, Dn * d, (const char*)tp.cv + (size_t)l * d * es,
+        SEDT_TRY(attn_bwd(t.qb, d, (const char*)tp.ck + (size_t)l * d * es, Dn * d, (const char*)tp.cv + (size_t)l * d * es,
                                       Dn * d, bb.dao, d, bb.dq, d, (char*)bb.dck + (size_t)l * d * es, Dn * d,
                                       (char*)bb.dcv + (size_t)l * d * es, Dn * d, tp.mask_ds, nullptr, B, cfg_.nheads, Qall, S, scale, s));
         SEDT_TRY(lin_param_grads(e.cross_attn.in_proj, 0, d, t.dap2, d, bb.dq, d, qrows));

@@ -201,7 +201,7 @@ def layernorm_bwd(x, gamma, g1=None, g2=None, g3=None, dres=None):
     return dx, dg, db
 
 
-def attention_bwd(q, k, v, do, nheads, kpm=None, amask=None, scale=None):
+def attention_bwd(q, k, v, do, nheads, kpm=None, amask=None, scale=None, engine=1):
     """q, do [B, Lq, E]; k, v [B, Lk, E] bf16 -> dq, dk, dv."""
     lib = _lib.load()
     B, Lq, E = q.shape
@@ -211,5 +211,5 @@ def attention_bwd(q, k, v, do, nheads, kpm=None, amask=None, scale=None):
     k8 = kpm.to(torch.uint8).contiguous() if kpm is not None else None
     _lib.check(lib.sedt_op_attention_bwd(q.data_ptr(), E, k.data_ptr(), E, v.data_ptr(), E, do.data_ptr(), E, dq.data_ptr(), E,
                                          dk.data_ptr(), E, dv.data_ptr(), E, _lib.ptr(k8) or None, _lib.ptr(amask) or None, B,
-                                         nheads, Lq, Lk, scale, _lib.current_stream()))
+                                         nheads, Lq, Lk, scale, engine, _lib.current_stream()))
     return dq, dk, dv

@@ -115,9 +115,10 @@ def test_layernorm_backward(rows):
     assert rel_err(dx1, x.grad) < 1e-5
 
 
+@pytest.mark.parametrize("engine", [0, 1])
 @pytest.mark.parametrize("case", [(5, 124, 124, False, False), (4, 21, 124, True, False), (3, 21, 21, False, True),
-                                  (2, 128, 128, True, False), (3, 11, 128, False, False)])
-def test_attention_backward(case):
+                                  (2, 128, 128, True, False), (3, 11, 128, False, False), (2, 70, 50, True, True)])
+def test_attention_backward(case, engine):
     B, Lq, Lk, use_kpm, use_amask = case
     E, nh = 256, 8
     g = torch.Generator().manual_seed(Lq * 7 + Lk)
@@ -147,6 +148,6 @@ def test_attention_backward(case):
         s = s.masked_fill(kpm[:, None, None, :], float("-inf"))
     o = (torch.softmax(s, -1) @ heads(vf, Lk)).transpose(1, 2).reshape(B, Lq, E)
     o.backward(do.float())
-    dq, dk, dv = gpu_ops.attention_bwd(q, k, v, do, nh, kpm, amask)
+    dq, dk, dv = gpu_ops.attention_bwd(q, k, v, do, nh, kpm, amask, engine=engine)
     torch.cuda.synchronize()
     assert rel_err(dq, qf.grad) < 6e-3 and rel_err(dk, kf.grad) < 6e-3 and rel_err(dv, vf.grad) < 6e-3
