@@ -175,10 +175,24 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--mode", default="eval", choices=["eval", "train"],
+                    help="eval: the headline metric (configs[1]); train: the config-4 training step (batch 64 per GPU by default)")
     opts = ap.parse_args()
     opts.warmup = max(opts.warmup, 3)
     if opts.impl == "reference":
         return run_reference(opts)
+    if opts.mode == "train":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_bench
+        import torch.distributed as dist
+        opts.batch = 64 if opts.batch == 256 else opts.batch
+        opts.profile = False
+        res = train_bench.run(opts)
+        if res is not None:
+            emit(res)
+        if dist.is_initialized():
+            dist.destroy_process_group()
+        return
 
     import torch
     import torch.distributed as dist

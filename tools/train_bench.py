@@ -21,6 +21,15 @@ def main():
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     o = ap.parse_args()
+    res = run(o)
+    if res is not None:
+        print(json.dumps(res))
+    if torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+def run(o):
+    """o: namespace with batch, steps, warmup, profile, no_graph.  Returns the result dict on rank 0, None elsewhere."""
     rank, world, local = parallel.env_ranks()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -73,6 +82,7 @@ def main():
     torch.cuda.synchronize(); parallel.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.sedt_launch_count()
+    kl0 = model.runtime().kernel_launches()
     e0.record()
     for _ in range(o.steps):
         loss = step()
@@ -91,13 +101,19 @@ def main():
         step(); torch.cuda.synchronize()
         _lib.check(lib.sedt_profile_read(ms_cls, n_cls)); lib.sedt_profile_enable(0)
         per_class = {n: {"ms": round(ms_cls[i], 3), "launches": int(n_cls[i])} for i, n in enumerate(_lib.KERNEL_CLASSES) if n_cls[i]}
-    if rank == 0:
-        fl = flops.forward_flops_per_clip(args, 496, 64)["total"]
-        step_flops = 3 * fl - 0.99e9            # fwd + dgrad + wgrad minus the frozen conv1 + layer1 weight gradients
-        print(json.dumps({"metric": "clips/sec SEDT E=6 training step (fwd + matcher x3 + set loss + bwd + allreduce + clip + AdamW)",
-                          "value": world * B / ms * 1e3, "unit": "clips/s", "n_gpus": world, "ms_per_step": ms,
-                          "batch_per_gpu": B, "loss": float(loss.detach()), "kernel_launches_per_step": launches, "phases_ms": phases,
-                          "achieved_tflops": B * step_flops / ms / 1e9, "per_class": per_class, "dropout": 0.0}))
+    if rank != 0:
+        return None
+    fl = flops.forward_flops_per_clip(args, 496, 64)["total"]
+    step_flops = 3 * fl - 0.99e9            # fwd + dgrad + wgrad minus the frozen conv1 + layer1 weight gradients
+    return {"metric": "clips/sec SEDT E=6 training step (fwd + matcher x3 + set loss + bwd + allreduce + clip + AdamW)",
+            "value": world * B / ms * 1e3, "unit": "clips/s", "n_gpus": world, "steps": o.steps, "warmup": o.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "SEDT E=6, num_queries=20, dec_at, aux_loss, [B,1,496,64] clips, 0..10 events per clip, dropout 0",
+                       "clips_per_gpu_per_step": B, "cuda_graph": not o.no_graph,
+                       "optimizer": "torch AdamW (2 groups) + clip_grad_norm_ 0.1 (stock PyTorch, SURVEY 8f.1)"},
+            "loss": float(loss.detach()), "gpu_launches": int(model.runtime().kernel_launches() - kl0),
+            "kernel_launches_eager_per_step": launches, "phases_ms": phases,
+            "achieved_tflops_per_gpu": B * step_flops / ms / 1e9, "per_class": per_class}
 
 
 if __name__ == "__main__":
