@@ -41,6 +41,31 @@ __global__ void repack_dgrad_kernel(const float* __restrict__ w, const float* __
     }
 }
 
+// Same re-layout through a 32 x 32 shared-memory tile: reads run along Cin (stride R*S floats), writes along Cout.
+// grid (ceil(Cin/32), ceil(Cout_pad/32), R*S), block (32, 8)
+template <typename T>
+__global__ void repack_dgrad_tiled_kernel(const float* __restrict__ w, const float* __restrict__ scale, T* __restrict__ out, int Cout,
+                                          int Cout_pad, int Cin, int RS)
+{
+    __shared__ float tile[32][33];
+    const int tap = blockIdx.z, src_tap = RS - 1 - tap;          // 180-degree rotation = reversed tap order
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int co = co0 + j, ci = ci0 + threadIdx.x;
+        float v = 0.f;
+        if (co < Cout && ci < Cin) {
+            v = w[((int64_t)co * Cin + ci) * RS + src_tap];
+            if (scale != nullptr) v *= scale[co];
+        }
+        tile[j][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int ci = ci0 + j, co = co0 + threadIdx.x;
+        if (ci < Cin && co < Cout_pad) out[((int64_t)ci * RS + tap) * Cout_pad + co] = from_f32<T>(tile[threadIdx.x][j]);
+    }
+}
+
 // grad[co][ci][r][s] = scale[co] * dw[co][(r,s)][ci]   (weight gradient back in the reference's OIHW layout)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, const float* __restrict__ scale, float* __restrict__ grad, int Cout,
                                     int Cin, int RS)
@@ -476,7 +501,11 @@ int launch_repack_dgrad(const float* w_oihw, const float* scale, void* out, int 
     SEDT_REQUIRE(Cout_pad >= Cout, "repack_dgrad: Cout_pad=%d < Cout=%d", Cout_pad, Cout);
     const int64_t total = (int64_t)Cout_pad * Cin * R * S;
     if (total == 0) return SEDT_OK;
-    if (dt == DT_F32) repack_dgrad_kernel<float><<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, (float*)out, Cout, Cout_pad, Cin, R, S);
+    if (R == S) {          // rotating both axes of a square filter reverses the flattened tap index
+        dim3 grid((unsigned)ceil_div(Cin, 32), (unsigned)ceil_div(Cout_pad, 32), (unsigned)(R * S)), block(32, 8);
+        if (dt == DT_F32) repack_dgrad_tiled_kernel<float><<<grid, block, 0, stream>>>(w_oihw, scale, (float*)out, Cout, Cout_pad, Cin, R * S);
+        else repack_dgrad_tiled_kernel<bf16><<<grid, block, 0, stream>>>(w_oihw, scale, (bf16*)out, Cout, Cout_pad, Cin, R * S);
+    } else if (dt == DT_F32) repack_dgrad_kernel<float><<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, (float*)out, Cout, Cout_pad, Cin, R, S);
     else repack_dgrad_kernel<bf16><<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, (bf16*)out, Cout, Cout_pad, Cin, R, S);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());

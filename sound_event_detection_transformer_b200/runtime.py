@@ -66,7 +66,8 @@ class ForwardRuntime:
                 raise RuntimeError(f"parameter {n} has {t.numel()} elements, expected {self.numels[i]}")
             dev = t.device
             ptrs[i] = t.data_ptr()
-        if self.packed is None or self.packed.device != dev:
+        realloc = self.packed is None or self.packed.device != dev
+        if realloc:
             self.packed = torch.empty(self.packed_bytes + 256, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(self.lib.sedt_model_pack(self.handle, ptrs, self._aligned(self.packed), self.packed_bytes,
@@ -74,10 +75,13 @@ class ForwardRuntime:
         self._keep = keep
         self._ptrs = ptrs
         self._stamp = stamp
-        self._graphs.clear()          # graphs bake in the packed-weight pointers: re-capture after a repack
-        self._train_graphs = {}
-        self._pack_graph_key = None
-        if use_graph and not keep:
+        # graphs bake in the packed-buffer and parameter addresses (not the values): re-capture only when those move
+        if realloc or keep or getattr(self, "_ptr_key", None) != pkey:
+            self._graphs.clear()
+            self._train_graphs = {}
+            self._pack_graph_key = None
+        self._ptr_key = pkey
+        if use_graph and not keep and self._pack_graph_key != pkey:
             with torch.cuda.device(dev):
                 torch.cuda.synchronize(dev)
                 g = torch.cuda.CUDAGraph()

@@ -97,16 +97,18 @@ class SetCriterion(nn.Module):
         pred = outputs["at"][labeled]
         dev = pred.device
         gt = torch.zeros(pred.shape, device=dev)
-        rows, cols, vals = [], [], []
-        for i in range(pred.shape[0]):
-            lab = targets[i]["labels"]
-            if len(lab) == 0:
-                continue
-            rows.append(torch.full((len(lab),), i, dtype=torch.int64))
-            cols.append(torch.as_tensor(lab, dtype=torch.int64).cpu())
-            vals.append(targets[i]["ratio"].float().cpu() if "ratio" in targets[i] else torch.ones(len(lab)))
-        if rows:
-            gt.index_put_((torch.cat(rows).to(dev), torch.cat(cols).to(dev)), torch.cat(vals).to(dev), accumulate=True)
+        # multi-hot clip labels (sedt/sedt.py:169-174), one index_put for the whole batch
+        tg = targets[:pred.shape[0]] if not isinstance(targets, (list, tuple)) else list(targets)[:pred.shape[0]]
+        sizes = [int(len(t["labels"])) for t in tg]
+        if sum(sizes) > 0:
+            cols = torch.cat([torch.as_tensor(t["labels"], dtype=torch.int64).reshape(-1) for t in tg]).to(dev)
+            rows = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes), output_size=sum(sizes)).to(dev)
+            if any("ratio" in t for t in tg):
+                vals = torch.cat([t["ratio"].float().reshape(-1).cpu() if "ratio" in t else torch.ones(k)
+                                  for t, k in zip(tg, sizes)]).to(dev)
+            else:
+                vals = torch.ones(sum(sizes), device=dev)
+            gt.index_put_((rows, cols), vals, accumulate=True)
         return {"loss_weak": F.binary_cross_entropy(pred, gt.clamp(0, 1))}
 
     # -- batched path: no per-clip work, no host round trip between the matcher and the losses --------------
