@@ -187,6 +187,7 @@ def main():
         import torch.distributed as dist
         opts.batch = 64 if opts.batch == 256 else opts.batch
         opts.profile = False
+        opts.dropout = 0.1
         res = train_bench.run(opts)
         if res is not None:
             emit(res)

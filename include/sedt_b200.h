@@ -121,16 +121,20 @@ SEDT_API int sedt_forward(sedt_model* m, const float* x, const uint8_t* mask, in
  * layout, at grads + sedt_grad_offset(slot) (one flat buffer of sedt_grad_numel floats = the data-parallel
  * all-reduce bucket; frozen entries - conv1, layer1, FrozenBN buffers - stay zero).  `weights` is the
  * array given to sedt_model_pack; train_backbone = 0 stops at input_proj (lr_backbone = 0,
- * sedt/backbone.py:135-141). */
+ * sedt/backbone.py:135-141).  dropout = args.dropout (transformer.py: attention weights, after out_proj, FFN hidden,
+ * after linear2): masks are counter-based (Philox keyed by `seed`, the dropout site and a per-tape step counter that
+ * sedt_forward_train advances), so the backward pass regenerates exactly the forward's masks; pass the same
+ * dropout to both calls. */
 SEDT_API int64_t sedt_train_tape_bytes(sedt_model* m, int B, int T, int F, int has_mask);
 SEDT_API int64_t sedt_backward_workspace_bytes(sedt_model* m, int B, int T, int F);
 SEDT_API int64_t sedt_grad_numel(const sedt_model* m);
 SEDT_API int64_t sedt_grad_offset(const sedt_model* m, int slot);
 SEDT_API int sedt_forward_train(sedt_model* m, const float* x, const uint8_t* mask, int B, int T, int F, void* tape,
-                                int64_t tape_bytes, const sedt_outputs* out, void* stream);
+                                int64_t tape_bytes, const sedt_outputs* out, float dropout, uint64_t seed, void* stream);
 SEDT_API int sedt_backward(sedt_model* m, const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F,
                            void* tape, int64_t tape_bytes, void* workspace, int64_t workspace_bytes, const float* d_logits,
-                           const float* d_boxes, const float* d_at, float* grads, int train_backbone, void* stream);
+                           const float* d_boxes, const float* d_at, float* grads, int train_backbone, float dropout,
+                           void* stream);
 
 /* ---- HungarianMatcher.forward default path (sedt/matcher.py:41-97; utilities/box_ops.py:9-56)
  *   logits [B, Q, C1] fp32, boxes [B, Q, 2] fp32 (center, width)
@@ -181,6 +185,12 @@ SEDT_API int sedt_op_layernorm_bwd(const float* x, const float* gamma, const voi
 SEDT_API int sedt_op_attention_bwd(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
                                    void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm,
                                    const float* amask, int B, int nheads, int Lq, int Lk, float scale, int engine, void* stream);
+/* keep flags (1 = kept) of elements [0, n) of dropout site `site` at training step `step`: exactly the masks the
+ * training kernels draw (sites: encoder layer l -> 8l + {0 attention weights, 1 after out_proj, 2 FFN hidden, 3 after
+ * linear2}; decoder layer l -> 1024 + 8l + {0 self-attn weights, 1 after its out_proj, 2 cross-attn weights, 3 after its
+ * out_proj, 4 FFN hidden, 5 after linear2}; element index: row-major [B*L, C] for activations,
+ * ((clip*heads + head)*128 + query)*128 + key for attention weights).  Test hook. */
+SEDT_API int sedt_op_dropout_mask(uint8_t* out, int64_t n, uint64_t seed, uint64_t step, uint32_t site, float p, void* stream);
 SEDT_API int sedt_op_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int k,
                                 int stride, int dil, int pad, void* stream);
 SEDT_API int sedt_op_conv_tc_supported(const sedt_conv_desc* d);

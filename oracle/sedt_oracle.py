@@ -102,12 +102,22 @@ def position_sine(mask: Tensor, num_pos_feats: int = 256, temperature: float = 1
 # --------------------------------------------------------------------------
 # transformer
 # --------------------------------------------------------------------------
+# Train-mode dropout points of the pre-norm layers (transformer.py:192-204, :263-284; functional.py:6650).  None = eval.
+# When set: callable(site: str, t: Tensor) -> Tensor applied at "<layer prefix>{attn|drop1|hidden|drop2}" (encoder) and
+# "<layer prefix>{self_attn|drop1|cross_attn|drop2|hidden|drop3}" (decoder); tests inject the kernels' own masks.
+DROPOUT = None
+
+
+def _drop(site: str, t: Tensor) -> Tensor:
+    return t if DROPOUT is None else DROPOUT(site, t)
+
+
 def layer_norm(x: Tensor, sd: SD, name: str) -> Tensor:
     return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], 1e-5)
 
 
 def mha(query: Tensor, key: Tensor, value: Tensor, sd: SD, name: str, nheads: int,
-        attn_mask: Optional[Tensor] = None, key_padding_mask: Optional[Tensor] = None) -> Tensor:
+        attn_mask: Optional[Tensor] = None, key_padding_mask: Optional[Tensor] = None, drop_site: Optional[str] = None) -> Tensor:
     """torch/nn/functional.py:5833-5867 (packed in-proj split into three
     linears because q is k but k is not v) and :6630-6659 (need_weights=True
     eager path: q*sqrt(1/hd), baddbmm/bmm, softmax, bmm, out-proj).
@@ -137,6 +147,8 @@ def mha(query: Tensor, key: Tensor, value: Tensor, sd: SD, name: str, nheads: in
     else:
         attn = torch.bmm(q_scaled, k.transpose(-2, -1))
     attn = F.softmax(attn, dim=-1)
+    if drop_site is not None:
+        attn = _drop(drop_site, attn)
     out = torch.bmm(attn, v)
     out = out.transpose(0, 1).contiguous().view(L * B, E)
     out = F.linear(out, sd[name + ".out_proj.weight"], sd[name + ".out_proj.bias"])
@@ -144,7 +156,7 @@ def mha(query: Tensor, key: Tensor, value: Tensor, sd: SD, name: str, nheads: in
 
 
 def ffn(x: Tensor, sd: SD, p: str) -> Tensor:
-    return F.linear(F.relu(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
+    return F.linear(_drop(p + "hidden", F.relu(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"]))),
                     sd[p + "linear2.weight"], sd[p + "linear2.bias"])
 
 
@@ -154,9 +166,9 @@ def encoder_layer(src: Tensor, sd: SD, p: str, nheads: int, pos: Tensor, kpm: Op
     if pre_norm:
         src2 = layer_norm(src, sd, p + "norm1")
         q = k = src2 + pos
-        src = src + mha(q, k, src2, sd, p + "self_attn", nheads, key_padding_mask=kpm)
+        src = src + _drop(p + "drop1", mha(q, k, src2, sd, p + "self_attn", nheads, key_padding_mask=kpm, drop_site=p + "attn"))
         src2 = layer_norm(src, sd, p + "norm2")
-        return src + ffn(src2, sd, p)
+        return src + _drop(p + "drop2", ffn(src2, sd, p))
     q = k = src + pos
     src = layer_norm(src + mha(q, k, src, sd, p + "self_attn", nheads, key_padding_mask=kpm), sd, p + "norm1")
     return layer_norm(src + ffn(src, sd, p), sd, p + "norm2")
@@ -168,11 +180,12 @@ def decoder_layer(tgt: Tensor, memory: Tensor, sd: SD, p: str, nheads: int, pos:
     if pre_norm:
         t2 = layer_norm(tgt, sd, p + "norm1")
         q = k = t2 + query_pos
-        tgt = tgt + mha(q, k, t2, sd, p + "self_attn", nheads, attn_mask=tgt_mask)
+        tgt = tgt + _drop(p + "drop1", mha(q, k, t2, sd, p + "self_attn", nheads, attn_mask=tgt_mask, drop_site=p + "self_attn"))
         t2 = layer_norm(tgt, sd, p + "norm2")
-        tgt = tgt + mha(t2 + query_pos, memory + pos, memory, sd, p + "multihead_attn", nheads, key_padding_mask=kpm)
+        tgt = tgt + _drop(p + "drop2", mha(t2 + query_pos, memory + pos, memory, sd, p + "multihead_attn", nheads,
+                                           key_padding_mask=kpm, drop_site=p + "cross_attn"))
         t2 = layer_norm(tgt, sd, p + "norm3")
-        return tgt + ffn(t2, sd, p)
+        return tgt + _drop(p + "drop3", ffn(t2, sd, p))
     q = k = tgt + query_pos
     tgt = layer_norm(tgt + mha(q, k, tgt, sd, p + "self_attn", nheads, attn_mask=tgt_mask), sd, p + "norm1")
     tgt = layer_norm(tgt + mha(tgt + query_pos, memory + pos, memory, sd, p + "multihead_attn", nheads,

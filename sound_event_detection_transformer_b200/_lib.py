@@ -58,8 +58,8 @@ SIGNATURES = {
     "sedt_backward_workspace_bytes": (_i64, [_vp, _i, _i, _i]),
     "sedt_grad_numel": (_i64, [_vp]),
     "sedt_grad_offset": (_i64, [_vp, _i]),
-    "sedt_forward_train": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i64, C.POINTER(SedtOutputs), _vp]),
-    "sedt_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp]),
+    "sedt_forward_train": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i64, C.POINTER(SedtOutputs), _f, C.c_uint64, _vp]),
+    "sedt_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i, _f, _vp]),
     "sedt_matcher": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sedt_lsap": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "sedt_op_conv": (_i, [C.POINTER(SedtConvDesc), _i, _vp]),
@@ -70,6 +70,7 @@ SIGNATURES = {
     "sedt_op_colsum": (_i, [_vp, _i, _i64, _vp, _i64, _i, _vp]),
     "sedt_op_layernorm_bwd": (_i, [_vp] * 9 + [_i64, _vp]),
     "sedt_op_attention_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    "sedt_op_dropout_mask": (_i, [_vp, _i64, C.c_uint64, C.c_uint64, C.c_uint32, _f, _vp]),
     "sedt_op_conv_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "sedt_op_repack_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sedt_op_cast": (_i, [_vp, _vp, _i, _i64, _vp]),

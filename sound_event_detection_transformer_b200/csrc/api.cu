@@ -137,26 +137,26 @@ int64_t sedt_grad_offset(const sedt_model* m, int slot)
 }
 
 int sedt_forward_train(sedt_model* m, const float* x, const uint8_t* mask, int B, int T, int F, void* tape, int64_t tape_bytes,
-                       const sedt_outputs* out, void* stream)
+                       const sedt_outputs* out, float dropout, uint64_t seed, void* stream)
 {
     SEDT_REQUIRE(m != nullptr && x != nullptr && out != nullptr && tape != nullptr, "forward_train: null argument");
     SEDT_REQUIRE(out->hs != nullptr && out->logits != nullptr && out->boxes != nullptr, "forward_train: hs/logits/boxes outputs are required");
     SEDT_REQUIRE(!m->impl->cfg().dec_at || out->at != nullptr, "forward_train: dec_at model needs the `at` output");
     SEDT_REQUIRE(((uintptr_t)tape & 255) == 0, "forward_train: tape must be 256-byte aligned");
     ForwardOut o{out->hs, out->logits, out->boxes, out->at, out->memory, nullptr, nullptr, nullptr};
-    return m->impl->forward_train(x, mask, B, T, F, tape, (size_t)tape_bytes, o, (cudaStream_t)stream);
+    return m->impl->forward_train(x, mask, B, T, F, tape, (size_t)tape_bytes, o, dropout, (unsigned long long)seed, (cudaStream_t)stream);
 }
 
 int sedt_backward(sedt_model* m, const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F, void* tape,
                   int64_t tape_bytes, void* workspace, int64_t workspace_bytes, const float* d_logits, const float* d_boxes,
-                  const float* d_at, float* grads, int train_backbone, void* stream)
+                  const float* d_at, float* grads, int train_backbone, float dropout, void* stream)
 {
     SEDT_REQUIRE(m != nullptr && weights != nullptr && x != nullptr && tape != nullptr && workspace != nullptr && grads != nullptr,
                  "backward: null argument");
     SEDT_REQUIRE(((uintptr_t)tape & 255) == 0 && ((uintptr_t)workspace & 255) == 0 && ((uintptr_t)grads & 255) == 0,
                  "backward: tape, workspace and grads must be 256-byte aligned");
     return m->impl->backward(weights, x, mask, B, T, F, tape, (size_t)tape_bytes, workspace, (size_t)workspace_bytes, d_logits,
-                             d_boxes, d_at, grads, train_backbone, (cudaStream_t)stream);
+                             d_boxes, d_at, grads, train_backbone, dropout, (cudaStream_t)stream);
 }
 
 int sedt_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
@@ -251,7 +251,13 @@ int sedt_op_attention_bwd(const void* Q, int ldq, const void* K, int ldk, const 
         return SEDT_ERR_UNSUPPORTED;
     }
     return launch_attention_bwd_tc(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, kpm, amask, B, nheads, Lq, Lk,
-                                   scale, (cudaStream_t)stream);
+                                   scale, nullptr, (cudaStream_t)stream);
+}
+
+int sedt_op_dropout_mask(uint8_t* out, int64_t n, uint64_t seed, uint64_t step, uint32_t site, float p, void* stream)
+{
+    SEDT_REQUIRE(out != nullptr || n == 0, "op_dropout_mask: null output");
+    return launch_dropout_mask(out, n, (unsigned long long)seed, (unsigned long long)step, site, p, (cudaStream_t)stream);
 }
 
 int sedt_op_conv_tc_supported(const sedt_conv_desc* d) { return d != nullptr && conv_tc_supported(to_gemm(d)) ? 1 : 0; }

@@ -12,6 +12,7 @@
 // and as MN-major operands with N = 64 (reduction over the rows).
 // Replaces autograd's backward of torch/nn/functional.py:6630-6659 (baddbmm, softmax, bmm).
 #include "tc_common.cuh"
+#include "dropout.cuh"
 #include <math_constants.h>
 
 namespace sedt {
@@ -48,12 +49,14 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo_bytes) 
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-template <bool HAS_AMASK>
+// DROP: the forward dropped the attention weights (P_drop = P o keep / (1-p) fed the P V product), so
+// dP_eff = dP o keep / (1-p), dS = P o (dP_eff - rowsum(P o dP_eff)), dV = P_drop^T dO.
+template <bool HAS_AMASK, bool DROP>
 __global__ void __launch_bounds__(AB_THREADS)
 attention_bwd_tc_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, int ldk, const bf16* __restrict__ V, int ldv,
                         const bf16* __restrict__ dO, int ldo, bf16* __restrict__ dQ, int lddq, bf16* __restrict__ dK, int lddk,
                         bf16* __restrict__ dV, int lddv, const uint8_t* __restrict__ kpm, const float* __restrict__ amask, int Lq,
-                        int Lk, float scale)
+                        int Lk, float scale, DropSite drop)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -143,19 +146,35 @@ attention_bwd_tc_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restr
     }
     const float mc = m * cs;
     float l = 0.f, pd = 0.f;
+    unsigned long long d_seed = 0ull, d_step = 0ull;
+    if (DROP) { d_seed = drop.state[0]; d_step = drop.state[1]; }
+    const unsigned long long d_row = ((unsigned long long)(blockIdx.y * gridDim.x + blockIdx.x) * 128ull + (unsigned long long)t) * 32ull;
+    // keep / (1-p) factors of keys c*32 + 4*g .. +3 of this row (same counters as the forward kernel)
+    auto keep4 = [&](int c, int g, float (&k)[4]) {
+        const uint4 r = drop_draw4(drop, d_seed, d_step, d_row + (unsigned long long)(c * 8 + g));
+        k[0] = r.x < drop.thresh ? drop.inv_keep : 0.f; k[1] = r.y < drop.thresh ? drop.inv_keep : 0.f;
+        k[2] = r.z < drop.thresh ? drop.inv_keep : 0.f; k[3] = r.w < drop.thresh ? drop.inv_keep : 0.f;
+    };
 #pragma unroll 1
     for (int c = 0; c < nkc; ++c) {
         uint32_t acc[32], dp[32];
         tmem_ld32_nowait(lane_addr + C_S + c * 32, acc);
         tmem_ld32_nowait(lane_addr + C_DP + c * 32, dp);
         tmem_ld_wait();
+        float kq[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             float e;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(score(__uint_as_float(acc[j]), c * 32 + j), cs, -mc)));
             e *= s_mask[c * 32 + j];
             l += e;
-            pd = fmaf(e, __uint_as_float(dp[j]), pd);
+            float dpj = __uint_as_float(dp[j]);
+            if (DROP) {
+                float k4[4];
+                if ((j & 3) == 0) { keep4(c, j >> 2, k4); kq[0] = k4[0]; kq[1] = k4[1]; kq[2] = k4[2]; kq[3] = k4[3]; }
+                dpj *= kq[j & 3];
+            }
+            pd = fmaf(e, dpj, pd);
         }
     }
     const float inv = (row_ok && l > 0.f) ? 1.f / l : 0.f;       // rows beyond Lq contribute nothing
@@ -168,14 +187,20 @@ attention_bwd_tc_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restr
             tmem_ld32_nowait(lane_addr + C_S + c * 32, acc);
             tmem_ld32_nowait(lane_addr + C_DP + c * 32, dp);
             tmem_ld_wait();
+            float kq3[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 float e0, e1;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(score(__uint_as_float(acc[j]), c * 32 + j), cs, -mc)));
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(score(__uint_as_float(acc[j + 1]), c * 32 + j + 1), cs, -mc)));
                 const float p0 = e0 * s_mask[c * 32 + j] * inv, p1 = e1 * s_mask[c * 32 + j + 1] * inv;
-                pk[j >> 1] = pack2(p0, p1);
-                dk[j >> 1] = pack2(p0 * (__uint_as_float(dp[j]) - delta), p1 * (__uint_as_float(dp[j + 1]) - delta));
+                float k0 = 1.f, k1 = 1.f;
+                if (DROP) {
+                    if ((j & 3) == 0) keep4(c, j >> 2, kq3);
+                    k0 = kq3[j & 3]; k1 = kq3[(j & 3) + 1];
+                }
+                pk[j >> 1] = pack2(p0 * k0, p1 * k1);
+                dk[j >> 1] = pack2(p0 * (__uint_as_float(dp[j]) * k0 - delta), p1 * (__uint_as_float(dp[j + 1]) * k1 - delta));
             }
         } else {
 #pragma unroll
@@ -270,27 +295,38 @@ bool attention_bwd_tc_supported(const void* Q, int ldq, const void* K, int ldk, 
     return true;
 }
 
-int launch_attention_bwd_tc(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
-                            void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm, const float* amask,
-                            int B, int nheads, int Lq, int Lk, float scale, cudaStream_t stream)
+template <bool AM, bool DR>
+static int launch_ab_variant(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
+                             void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm, const float* amask,
+                             int B, int nheads, int Lq, int Lk, float scale, const DropSite& drop, cudaStream_t stream)
 {
-    if (B == 0) return SEDT_OK;
     static bool attr_set = false;
     if (!attr_set) {
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_TC));
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_TC));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<AM, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_TC));
         attr_set = true;
     }
     dim3 grid((unsigned)nheads, (unsigned)B), block(AB_THREADS);
     ProfScope _prof(PROF_ATTENTION, stream);
-#define SEDT_AB_ARGS (const bf16*)Q, ldq, (const bf16*)K, ldk, (const bf16*)V, ldv, (const bf16*)dO, ldo, (bf16*)dQ, lddq, (bf16*)dK, \
-                     lddk, (bf16*)dV, lddv, kpm, amask, Lq, Lk, scale
-    if (amask != nullptr) attention_bwd_tc_kernel<true><<<grid, block, AB_SMEM_TC, stream>>>(SEDT_AB_ARGS);
-    else attention_bwd_tc_kernel<false><<<grid, block, AB_SMEM_TC, stream>>>(SEDT_AB_ARGS);
-#undef SEDT_AB_ARGS
+    attention_bwd_tc_kernel<AM, DR><<<grid, block, AB_SMEM_TC, stream>>>(
+        (const bf16*)Q, ldq, (const bf16*)K, ldk, (const bf16*)V, ldv, (const bf16*)dO, ldo, (bf16*)dQ, lddq, (bf16*)dK, lddk,
+        (bf16*)dV, lddv, kpm, amask, Lq, Lk, scale, drop);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
+}
+
+int launch_attention_bwd_tc(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
+                            void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm, const float* amask,
+                            int B, int nheads, int Lq, int Lk, float scale, const DropSite* drop, cudaStream_t stream)
+{
+    if (B == 0) return SEDT_OK;
+#define SEDT_AB_CALL(AM, DR, D) launch_ab_variant<AM, DR>(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, kpm, amask, B, \
+                                                         nheads, Lq, Lk, scale, D, stream)
+    if (drop != nullptr && drop->state != nullptr)
+        return amask != nullptr ? SEDT_AB_CALL(true, true, *drop) : SEDT_AB_CALL(false, true, *drop);
+    const DropSite none = make_drop_site(nullptr, 0, 0.f);
+    return amask != nullptr ? SEDT_AB_CALL(true, false, none) : SEDT_AB_CALL(false, false, none);
+#undef SEDT_AB_CALL
 }
 
 }  // namespace sedt

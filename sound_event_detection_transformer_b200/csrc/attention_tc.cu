@@ -14,6 +14,7 @@
 // Replaces the need_weights=True eager path of nn.MultiheadAttention
 // (torch/nn/functional.py:6630-6659: q*sqrt(1/hd), baddbmm, softmax, bmm).
 #include "tc_common.cuh"
+#include "dropout.cuh"
 #include <math_constants.h>
 
 namespace sedt {
@@ -42,11 +43,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-template <bool HAS_AMASK>
+// DROP (training forward): the attention weights are dropped (nn.MultiheadAttention dropout, functional.py:6650):
+// O = sum_j (p_j * keep_j / (1 - p)) v_j with p_j normalised over ALL valid keys.
+template <bool HAS_AMASK, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ K, int ldk,
                     const __nv_bfloat16* __restrict__ V, int ldv, __nv_bfloat16* __restrict__ O, int ldo,
-                    const uint8_t* __restrict__ kpm, const float* __restrict__ amask, int Lq, int Lk, float scale)
+                    const uint8_t* __restrict__ kpm, const float* __restrict__ amask, int Lq, int Lk, float scale, DropSite drop)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS)
@@ -147,6 +150,9 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
     }
     const float mc = m * cs;
     float l = 0.f;
+    unsigned long long d_seed = 0ull, d_step = 0ull;
+    if (DROP) { d_seed = drop.state[0]; d_step = drop.state[1]; }
+    const unsigned long long d_row = ((unsigned long long)(blockIdx.y * gridDim.x + blockIdx.x) * 128ull + (unsigned long long)t) * 32ull;
 #pragma unroll 1
     for (int c = 0; c < (row_warp ? nkc : 0); ++c) {
         uint32_t acc[32];
@@ -166,6 +172,13 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(sv, cs, -mc)));
                 pv[q] = e * vmv[q];
                 l += pv[q];
+            }
+            if (DROP) {
+                const uint4 r = drop_draw4(drop, d_seed, d_step, d_row + (unsigned long long)(c * 8 + j4));
+                pv[0] = r.x < drop.thresh ? pv[0] * drop.inv_keep : 0.f;
+                pv[1] = r.y < drop.thresh ? pv[1] * drop.inv_keep : 0.f;
+                pv[2] = r.z < drop.thresh ? pv[2] * drop.inv_keep : 0.f;
+                pv[3] = r.w < drop.thresh ? pv[3] * drop.inv_keep : 0.f;
             }
             packed[j4 * 2] = pack2(pv[0], pv[1]);
             packed[j4 * 2 + 1] = pack2(pv[2], pv[3]);
@@ -230,29 +243,43 @@ bool attention_tc_supported(const void* Q, int ldq, const void* K, int ldk, cons
     return true;
 }
 
-int launch_attention_tc(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo,
-                        const uint8_t* kpm, const float* amask, int B, int nheads, int Lq, int Lk, float scale,
-                        cudaStream_t stream)
+template <bool AM, bool DR>
+static int launch_att_variant(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo,
+                              const uint8_t* kpm, const float* amask, int B, int nheads, int Lq, int Lk, float scale,
+                              const DropSite& drop, cudaStream_t stream)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<AM, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         attr_set = true;
     }
     dim3 grid((unsigned)nheads, (unsigned)B), block(ATT_THREADS);
     ProfScope _prof(PROF_ATTENTION, stream);
-    if (amask != nullptr)
-        attention_tc_kernel<true><<<grid, block, ATT_SMEM, stream>>>((const __nv_bfloat16*)Q, ldq, (const __nv_bfloat16*)K, ldk,
-                                                                     (const __nv_bfloat16*)V, ldv, (__nv_bfloat16*)O, ldo, kpm,
-                                                                     amask, Lq, Lk, scale);
-    else
-        attention_tc_kernel<false><<<grid, block, ATT_SMEM, stream>>>((const __nv_bfloat16*)Q, ldq, (const __nv_bfloat16*)K, ldk,
-                                                                      (const __nv_bfloat16*)V, ldv, (__nv_bfloat16*)O, ldo, kpm,
-                                                                      amask, Lq, Lk, scale);
+    attention_tc_kernel<AM, DR><<<grid, block, ATT_SMEM, stream>>>((const __nv_bfloat16*)Q, ldq, (const __nv_bfloat16*)K, ldk,
+                                                                  (const __nv_bfloat16*)V, ldv, (__nv_bfloat16*)O, ldo, kpm, amask,
+                                                                  Lq, Lk, scale, drop);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
+}
+
+int launch_attention_tc(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo,
+                        const uint8_t* kpm, const float* amask, int B, int nheads, int Lq, int Lk, float scale,
+                        cudaStream_t stream)
+{
+    const DropSite none = make_drop_site(nullptr, 0, 0.f);
+    if (amask != nullptr) return launch_att_variant<true, false>(Q, ldq, K, ldk, V, ldv, O, ldo, kpm, amask, B, nheads, Lq, Lk, scale, none, stream);
+    return launch_att_variant<false, false>(Q, ldq, K, ldk, V, ldv, O, ldo, kpm, amask, B, nheads, Lq, Lk, scale, none, stream);
+}
+
+// training forward with dropout on the attention weights
+int launch_attention_tc_drop(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo,
+                             const uint8_t* kpm, const float* amask, int B, int nheads, int Lq, int Lk, float scale,
+                             const DropSite& drop, cudaStream_t stream)
+{
+    SEDT_REQUIRE(drop.state != nullptr, "attention_tc_drop: RNG state missing");
+    if (amask != nullptr) return launch_att_variant<true, true>(Q, ldq, K, ldk, V, ldv, O, ldo, kpm, amask, B, nheads, Lq, Lk, scale, drop, stream);
+    return launch_att_variant<false, true>(Q, ldq, K, ldk, V, ldv, O, ldo, kpm, amask, B, nheads, Lq, Lk, scale, drop, stream);
 }
 
 }  // namespace sedt

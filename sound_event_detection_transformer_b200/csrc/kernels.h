@@ -114,7 +114,22 @@ bool attention_bwd_tc_supported(const void* Q, int ldq, const void* K, int ldk, 
                                 const void* dQ, int lddq, const void* dK, int lddk, const void* dV, int lddv, int Lq, int Lk);
 int launch_attention_bwd_tc(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
                             void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm, const float* amask,
-                            int B, int nheads, int Lq, int Lk, float scale, cudaStream_t stream);
+                            int B, int nheads, int Lq, int Lk, float scale, const struct DropSite* drop, cudaStream_t stream);
+
+// ---- dropout.cu / dropout.cuh : counter-based (Philox) dropout of the training step; state = {seed, step} on the device
+struct DropSite;
+int launch_fill_value(float* p, float v, int n, cudaStream_t stream);
+int launch_dropout_mask(unsigned char* out, int64_t n, unsigned long long seed, unsigned long long step, uint32_t site, float p,
+                        cudaStream_t stream);
+int launch_rng_init(unsigned long long* state, unsigned long long seed, cudaStream_t stream);
+int launch_rng_step(unsigned long long* state, cudaStream_t stream);
+int launch_dropout_add(const float* y, const float* resid, float* out, int64_t n, const DropSite& d, cudaStream_t stream);
+int launch_dropout_bf16(void* h, int64_t n, const DropSite& d, cudaStream_t stream);
+int launch_cast_dropout(const float* g, void* out16, int64_t n, const DropSite& d, cudaStream_t stream);
+// attention_tc.cu: training forward with dropout on the attention weights
+int launch_attention_tc_drop(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo,
+                             const uint8_t* kpm, const float* amask, int B, int nheads, int Lq, int Lk, float scale,
+                             const DropSite& drop, cudaStream_t stream);
 
 // ---- transformer.cu
 // LayerNorm over D=256, eps 1e-5.  Any of y / ypos / y32 may be null.

@@ -86,10 +86,10 @@ public:
     int64_t grad_offset(int slot) const;       // element offset of a state_dict entry in the flat fp32 gradient buffer
     int64_t grad_numel() const;
     int forward_train(const float* x, const uint8_t* mask, int B, int T, int F, void* tape, size_t tape_bytes,
-                      const ForwardOut& out, cudaStream_t stream);
+                      const ForwardOut& out, float dropout, unsigned long long seed, cudaStream_t stream);
     int backward(const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F, void* tape,
                  size_t tape_bytes, void* workspace, size_t ws_bytes, const float* d_logits, const float* d_boxes,
-                 const float* d_at, float* grads, int train_backbone, cudaStream_t stream);
+                 const float* d_at, float* grads, int train_backbone, float dropout, cudaStream_t stream);
 
 private:
     struct BlockTape; struct EncTape; struct DecTape; struct Tape; struct BwdBufs;
@@ -142,6 +142,8 @@ private:
     // encoder memory is projected by two GEMMs instead of 2*D
     size_t off_ck_w, off_ck_b, off_cv_w, off_cv_b;
     int qall_;
+    const void* rng_tape_ = nullptr;          // tape whose dropout RNG state {seed, step} has been initialised
+    unsigned long long rng_seed_ = 0;
 };
 
 }  // namespace sedt

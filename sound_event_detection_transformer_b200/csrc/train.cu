@@ -12,6 +12,7 @@
 // Gradients are written in the reference's parameter layout into ONE flat fp32 buffer (offset of a
 // state_dict entry = Model::grad_offset(slot)), which is also the bucket a data-parallel run all-reduces.
 #include "model.h"
+#include "dropout.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -29,6 +30,8 @@ struct Model::DecTape {
 };
 struct Model::Tape {
     int H0, W0, H, W, S;
+    unsigned long long* rng;    // {seed, step} of the dropout masks
+    float* tmp32;               // GEMM output before dropout + residual add
     void* stem_out;
     std::vector<BlockTape> blk;
     uint8_t* mask_ds; float* pos; int64_t pos_rows;
@@ -44,6 +47,7 @@ struct Model::Tape {
 struct Model::BwdBufs {
     void* wd;            // re-laid-out weights of the layer being differentiated (bf16)
     float* dw;           // weight gradient of a conv layer in the GEMM layout, before the OIHW permute
+    float* vscale;       // [dim_feedforward] = 1 / (1 - dropout)
     // heads
     void *dcls, *dbox, *dweak, *dh2, *dh1, *hh2b; float* dhs32;
     // transformer (sized for max(rows, qrows))
@@ -61,6 +65,7 @@ void Model::tape_layout(int B, int T, int F, bool has_mask, Arena& a, Tape& tp) 
     const size_t es = 2;
     tp.H0 = conv_out_dim(conv_out_dim(T, 7, 2, 3, 1), 3, 2, 1, 1);
     tp.W0 = conv_out_dim(conv_out_dim(F, 7, 2, 3, 1), 3, 2, 1, 1);
+    tp.rng = (unsigned long long*)a.alloc(256);
     tp.stem_out = a.alloc((size_t)B * tp.H0 * tp.W0 * 64 * es);
     int h = tp.H0, w = tp.W0;
     tp.blk.clear();
@@ -121,6 +126,7 @@ void Model::tape_layout(int B, int T, int F, bool has_mask, Arena& a, Tape& tp) 
     tp.cls_raw = (float*)a.alloc((size_t)hrows * C1 * 4);
     tp.box_raw = (float*)a.alloc((size_t)hrows * 2 * 4);
     tp.weak_raw = cfg_.dec_at ? (float*)a.alloc((size_t)B * ncls * 4) : nullptr;
+    tp.tmp32 = (float*)a.alloc((size_t)std::max(rows, qrows) * d * 4);
     tp.boxes = (float*)a.alloc((size_t)Dn * B * cfg_.num_queries * 2 * 4);
     tp.at = cfg_.dec_at ? (float*)a.alloc((size_t)B * ncls * 4) : nullptr;
 }
@@ -143,9 +149,16 @@ int64_t Model::tape_bytes(int B, int T, int F, bool has_mask) const
     return (int64_t)a.peak + 256;
 }
 
+// dropout sites: encoder layer l -> 8*l + {0 attention weights, 1 after out_proj, 2 FFN hidden, 3 after linear2};
+// decoder layer l -> 1024 + 8*l + {0 self-attention weights, 1 after its out_proj, 2 cross-attention weights, 3 after its
+// out_proj, 4 FFN hidden, 5 after linear2}   (transformer.py:160-175, :220-240)
+static inline uint32_t enc_site(int l, int k) { return (uint32_t)(8 * l + k); }
+static inline uint32_t dec_site(int l, int k) { return (uint32_t)(1024 + 8 * l + k); }
+
 int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int F, void* tape, size_t tape_bytes_,
-                         const ForwardOut& out, cudaStream_t s)
+                         const ForwardOut& out, float dropout, unsigned long long seed, cudaStream_t s)
 {
+    SEDT_REQUIRE(dropout >= 0.f && dropout < 1.f, "forward_train: dropout=%f", dropout);
     SEDT_TRY(check_train_config());
     SEDT_REQUIRE(packed_ != nullptr, "forward_train: sedt_model_pack has not been called");
     SEDT_REQUIRE(F == 64, "stem: the fused stem kernel needs 64 mel bins, got F=%d", F);
@@ -160,6 +173,31 @@ int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int 
         return launch_layernorm(xin, P_(n.off_g), P_(n.off_b), pos, pos_rows, y, ypos, y32, dt, rows, s);
     };
     const float scale = (float)std::sqrt(1.0 / (double)(d / cfg_.nheads));
+    const bool drop = dropout > 0.f;
+    if (drop) {
+        // the {seed, step} pair lives in the tape: initialised once per tape (outside any graph capture, which only
+        // records the per-step increment), so that every replayed step draws fresh masks
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        SEDT_CHECK_CUDA(cudaStreamIsCapturing(s, &cap));
+        if (cap == cudaStreamCaptureStatusNone && (rng_tape_ != tape || rng_seed_ != seed)) {
+            SEDT_TRY(launch_rng_init(tp.rng, seed, s));
+            rng_tape_ = tape; rng_seed_ = seed;
+        }
+        SEDT_REQUIRE(rng_tape_ == tape, "forward_train: dropout RNG state of this tape was not initialised before graph capture");
+        SEDT_TRY(launch_rng_step(tp.rng, s));
+    }
+    auto site = [&](uint32_t id) { return make_drop_site(tp.rng, id, dropout); };
+    // y = resid + dropout(x W^T + b)
+    auto linear_drop_add = [&](const Linear& L, const void* in, int lda, int64_t R, const float* resid, float* y, uint32_t id) -> int {
+        if (!drop) return linear(L, 0, L.out, in, dt, lda, R, resid, y, DT_F32, L.out, 0, s, false);
+        SEDT_TRY(linear(L, 0, L.out, in, dt, lda, R, nullptr, tp.tmp32, DT_F32, L.out, 0, s, false));
+        return launch_dropout_add(tp.tmp32, resid, y, R * L.out, site(id), s);
+    };
+    auto attention = [&](const void* Qp, int ldq, const void* Kp, int ldk, const void* Vp, int ldv, void* Op, const uint8_t* kpm,
+                         int Lq, int Lk, uint32_t id) -> int {
+        if (!drop) return launch_attention(Qp, ldq, Kp, ldk, Vp, ldv, Op, d, dt, kpm, nullptr, B, cfg_.nheads, Lq, Lk, scale, s);
+        return launch_attention_tc_drop(Qp, ldq, Kp, ldk, Vp, ldv, Op, d, kpm, nullptr, B, cfg_.nheads, Lq, Lk, scale, site(id), s);
+    };
 
     // ---- backbone
     SEDT_TRY(launch_stem_tc(x, packed_ + off_stem_wtc, P_(off_stem_bias), tp.stem_out, B, T, F, s));
@@ -195,12 +233,12 @@ int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int 
         SEDT_TRY(LN(e.n1, t.x_in, tp.pos, tp.pos_rows, t.na, t.nap, nullptr, rows));
         SEDT_TRY(linear(e.attn.in_proj, 2 * d, d, t.na, dt, d, rows, nullptr, t.v, dt, d, 0, s, false));
         SEDT_TRY(linear(e.attn.in_proj, 0, 2 * d, t.nap, dt, d, rows, nullptr, t.qk, dt, 2 * d, 0, s, false));
-        SEDT_TRY(launch_attention(t.qk, 2 * d, (const char*)t.qk + d * es, 2 * d, t.v, d, t.ao, d, dt, tp.mask_ds, nullptr, B,
-                                  cfg_.nheads, S, S, scale, s));
-        SEDT_TRY(linear(e.attn.out_proj, 0, d, t.ao, dt, d, rows, t.x_in, t.x_mid, DT_F32, d, 0, s, false));
+        SEDT_TRY(attention(t.qk, 2 * d, (const char*)t.qk + d * es, 2 * d, t.v, d, t.ao, tp.mask_ds, S, S, enc_site((int)l, 0)));
+        SEDT_TRY(linear_drop_add(e.attn.out_proj, t.ao, d, rows, t.x_in, t.x_mid, enc_site((int)l, 1)));
         SEDT_TRY(LN(e.n2, t.x_mid, nullptr, 1, t.n2, nullptr, nullptr, rows));
         SEDT_TRY(linear(e.lin1, 0, ff, t.n2, dt, d, rows, nullptr, t.h, dt, ff, 1, s, false));
-        SEDT_TRY(linear(e.lin2, 0, d, t.h, dt, ff, rows, t.x_mid, t.x_out, DT_F32, d, 0, s, false));
+        if (drop) SEDT_TRY(launch_dropout_bf16(t.h, rows * ff, site(enc_site((int)l, 2)), s));
+        SEDT_TRY(linear_drop_add(e.lin2, t.h, ff, rows, t.x_mid, t.x_out, enc_site((int)l, 3)));
     }
     const float* xe = enc_.empty() ? tp.x0 : tp.enc.back().x_out;
     SEDT_TRY(LN(enc_norm_, xe, tp.pos, tp.pos_rows, tp.mem, tp.mempos, out.memory, rows));
@@ -228,17 +266,17 @@ int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int 
         SEDT_TRY(LN(e.n1, t.t_in, qpos, Qall, t.da, t.dap, nullptr, qrows));
         SEDT_TRY(linear(e.self_attn.in_proj, 2 * d, d, t.da, dt, d, qrows, nullptr, t.v, dt, d, 0, s, false));
         SEDT_TRY(linear(e.self_attn.in_proj, 0, 2 * d, t.dap, dt, d, qrows, nullptr, t.qk, dt, 2 * d, 0, s, false));
-        SEDT_TRY(launch_attention(t.qk, 2 * d, (const char*)t.qk + d * es, 2 * d, t.v, d, t.ao1, d, dt, nullptr, nullptr, B,
-                                  cfg_.nheads, Qall, Qall, scale, s));
-        SEDT_TRY(linear(e.self_attn.out_proj, 0, d, t.ao1, dt, d, qrows, t.t_in, t.t_mid1, DT_F32, d, 0, s, false));
+        SEDT_TRY(attention(t.qk, 2 * d, (const char*)t.qk + d * es, 2 * d, t.v, d, t.ao1, nullptr, Qall, Qall, dec_site(l, 0)));
+        SEDT_TRY(linear_drop_add(e.self_attn.out_proj, t.ao1, d, qrows, t.t_in, t.t_mid1, dec_site(l, 1)));
         SEDT_TRY(LN(e.n2, t.t_mid1, qpos, Qall, nullptr, t.dap2, nullptr, qrows));
         SEDT_TRY(linear(e.cross_attn.in_proj, 0, d, t.dap2, dt, d, qrows, nullptr, t.qb, dt, d, 0, s, false));
-        SEDT_TRY(launch_attention(t.qb, d, (const char*)tp.ck + (size_t)l * d * es, Dn * d, (const char*)tp.cv + (size_t)l * d * es,
-                                  Dn * d, t.ao2, d, dt, tp.mask_ds, nullptr, B, cfg_.nheads, Qall, S, scale, s));
-        SEDT_TRY(linear(e.cross_attn.out_proj, 0, d, t.ao2, dt, d, qrows, t.t_mid1, t.t_mid2, DT_F32, d, 0, s, false));
+        SEDT_TRY(attention(t.qb, d, (const char*)tp.ck + (size_t)l * d * es, Dn * d, (const char*)tp.cv + (size_t)l * d * es, Dn * d,
+                           t.ao2, tp.mask_ds, Qall, S, dec_site(l, 2)));
+        SEDT_TRY(linear_drop_add(e.cross_attn.out_proj, t.ao2, d, qrows, t.t_mid1, t.t_mid2, dec_site(l, 3)));
         SEDT_TRY(LN(e.n3, t.t_mid2, nullptr, 1, t.da3, nullptr, nullptr, qrows));
         SEDT_TRY(linear(e.lin1, 0, ff, t.da3, dt, d, qrows, nullptr, t.h, dt, ff, 1, s, false));
-        SEDT_TRY(linear(e.lin2, 0, d, t.h, dt, ff, qrows, t.t_mid2, t.t_out, DT_F32, d, 0, s, false));
+        if (drop) SEDT_TRY(launch_dropout_bf16(t.h, qrows * ff, site(dec_site(l, 4)), s));
+        SEDT_TRY(linear_drop_add(e.lin2, t.h, ff, qrows, t.t_mid2, t.t_out, dec_site(l, 5)));
         SEDT_TRY(LN(dec_norm_, t.t_out, nullptr, 1, (char*)tp.hs_t + (size_t)l * qrows * d * es, nullptr,
                     out.hs + (size_t)l * qrows * d, qrows));
     }
@@ -306,6 +344,7 @@ void Model::bwd_layout(int B, const Tape& tp, Arena& a, BwdBufs& bb) const
     dwmax = std::max(dwmax, (size_t)2048 * d);
     bb.wd = a.alloc(wmax * es);
     bb.dw = (float*)a.alloc(dwmax * 4);
+    bb.vscale = (float*)a.alloc((size_t)ff * 4);
     const int64_t rows = (int64_t)B * tp.S, qrows = (int64_t)B * qall_, hrows = (int64_t)dec_.size() * qrows;
     bb.dcls = a.alloc((size_t)hrows * 128 * es); bb.dbox = a.alloc((size_t)hrows * 128 * es);
     bb.dweak = a.alloc((size_t)std::max(B, 1) * 128 * es);
@@ -323,9 +362,10 @@ void Model::bwd_layout(int B, const Tape& tp, Arena& a, BwdBufs& bb) const
 
 int Model::backward(const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F, void* tape, size_t tape_bytes_,
                     void* workspace, size_t ws_bytes, const float* d_logits, const float* d_boxes, const float* d_at,
-                    float* grads, int train_backbone, cudaStream_t s)
+                    float* grads, int train_backbone, float dropout, cudaStream_t s)
 {
     SEDT_TRY(check_train_config());
+    SEDT_REQUIRE(dropout >= 0.f && dropout < 1.f, "backward: dropout=%f", dropout);
     SEDT_REQUIRE(packed_ != nullptr, "backward: sedt_model_pack has not been called");
     SEDT_TRY(tc_init());
     Arena ta(tape, tape_bytes_);
@@ -347,13 +387,22 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     auto P_ = [&](size_t off) { return (const float*)(packed_ + off); };
 
     SEDT_TRY(launch_fill_zero(grads, (size_t)grad_numel() * 4, s));
+    const bool drop = dropout > 0.f;
+    SEDT_REQUIRE(!drop || rng_tape_ == tape, "backward: forward_train with dropout has not run on this tape");
+    auto site = [&](uint32_t id) { return make_drop_site(tp.rng, id, dropout); };
+    if (drop) SEDT_TRY(launch_fill_value(bb.vscale, 1.f / (1.f - dropout), ff, s));
+    // bf16 copy of a gradient that enters a GEMM whose forward output went through dropout site `id`
+    auto to16_drop = [&](const float* src, void* dst, int64_t n, uint32_t id) -> int {
+        if (!drop) return launch_cast(src, dst, dt, n, s);
+        return launch_cast_dropout(src, dst, n, site(id), s);
+    };
 
     // dx[M, in_f] = dy[M, out_pad] * W[out_f, in_f]  (+ residual, or masked by `aux` when relu_mode == 2)
     auto dgrad_lin = [&](const float* W, int out_f, int out_pad, int in_f, const void* dy, int ldy, int64_t M, const void* aux,
-                         int ld_aux, int relu_mode, void* dx, int dx_dt, int lddx) -> int {
+                         int ld_aux, int relu_mode, void* dx, int dx_dt, int lddx, const float* oscale = nullptr) -> int {
         SEDT_TRY(launch_repack_dgrad(W, nullptr, bb.wd, dt, out_f, out_pad, in_f, 1, 1, s));
         ConvGemm g;
-        g.in = dy; g.w = bb.wd; g.residual = aux; g.out = dx;
+        g.in = dy; g.w = bb.wd; g.residual = aux; g.out = dx; g.scale = oscale;
         g.in_dt = dt; g.out_dt = dx_dt;
         g.B = (int)M; g.H = g.W = g.Ho = g.Wo = 1; g.Cin = out_pad; g.lda = ldy;
         g.Cout = in_f; g.ldc = lddx; g.ld_res = ld_aux; g.relu = relu_mode;
@@ -406,9 +455,12 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     static const bool att_simt = [] { const char* e = getenv("SEDT_ATT_BWD_SIMT"); return e != nullptr && e[0] == '1'; }();
     auto attn_bwd = [&](const void* Qp, int ldq, const void* Kp, int ldk, const void* Vp, int ldv, const void* dOp, int ldo, void* dQp,
                         int lddq, void* dKp, int lddk, void* dVp, int lddv, const uint8_t* kpm, const float* am, int Bn, int nh, int Lq,
-                        int Lk, float sc, cudaStream_t st) -> int {
-        if (!att_simt && attention_bwd_tc_supported(Qp, ldq, Kp, ldk, Vp, ldv, dOp, ldo, dQp, lddq, dKp, lddk, dVp, lddv, Lq, Lk))
-            return launch_attention_bwd_tc(Qp, ldq, Kp, ldk, Vp, ldv, dOp, ldo, dQp, lddq, dKp, lddk, dVp, lddv, kpm, am, Bn, nh, Lq, Lk, sc, st);
+                        int Lk, float sc, uint32_t site_p, cudaStream_t st) -> int {
+        const DropSite ds = site(site_p);
+        if ((!att_simt || drop) && attention_bwd_tc_supported(Qp, ldq, Kp, ldk, Vp, ldv, dOp, ldo, dQp, lddq, dKp, lddk, dVp, lddv, Lq, Lk))
+            return launch_attention_bwd_tc(Qp, ldq, Kp, ldk, Vp, ldv, dOp, ldo, dQp, lddq, dKp, lddk, dVp, lddv, kpm, am, Bn, nh, Lq, Lk, sc,
+                                           drop ? &ds : nullptr, st);
+        SEDT_REQUIRE(!drop, "backward: attention dropout needs the tcgen05 kernel");
         return launch_attention_bwd(Qp, ldq, Kp, ldk, Vp, ldv, dOp, ldo, dQp, lddq, dKp, lddk, dVp, lddv, kpm, am, Bn, nh, Lq, Lk, sc, st);
     };
 
@@ -417,12 +469,12 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     //   in : gx = d(loss)/d(x_mid) fp32 (x_mid = x_in + out_proj(attn))      out: gout = d(loss)/d(x_in) fp32
     auto self_attn_bwd = [&](const Mha& A, const Norm& n1, const float* x_in, const void* na, const void* nap, const void* qk,
                              const void* v, const void* ao, const uint8_t* kpm, int L, int64_t R, const float* gx, float* gout,
-                             float* dqpos_acc) -> int {
-        SEDT_TRY(to16(gx, bb.g16, R * d));
+                             float* dqpos_acc, uint32_t site_p, uint32_t site_o) -> int {
+        SEDT_TRY(to16_drop(gx, bb.g16, R * d, site_o));
         SEDT_TRY(lin_param_grads(A.out_proj, 0, d, ao, d, bb.g16, d, R));
         SEDT_TRY(dgrad_lin(Wp(A.out_proj.w_slot), d, d, d, bb.g16, d, R, nullptr, 0, 0, bb.dao, dt, d));
         SEDT_TRY(attn_bwd(qk, 2 * d, (const char*)qk + d * es, 2 * d, v, d, bb.dao, d, bb.dqk, 2 * d,
-                                      (char*)bb.dqk + d * es, 2 * d, bb.dv, d, kpm, nullptr, B, cfg_.nheads, L, L, scale, s));
+                          (char*)bb.dqk + d * es, 2 * d, bb.dv, d, kpm, nullptr, B, cfg_.nheads, L, L, scale, site_p, s));
         SEDT_TRY(lin_param_grads(A.in_proj, 0, 2 * d, nap, d, bb.dqk, 2 * d, R));
         SEDT_TRY(lin_param_grads(A.in_proj, 2 * d, d, na, d, bb.dv, d, R));
         SEDT_TRY(dgrad_lin(Wp(A.in_proj.w_slot), 2 * d, 2 * d, d, bb.dqk, 2 * d, R, nullptr, 0, 0, bb.dn_b, dt, d));     // d(LN + pos)
@@ -432,10 +484,12 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     };
     // FFN + its LayerNorm:  in: gy = d/d(x_out) fp32, x_out = x_mid + lin2(relu(lin1(LN(x_mid))))   out: gout = d/d(x_mid)
     auto ffn_bwd = [&](const Linear& lin1, const Linear& lin2, const Norm& nn, const float* x_mid, const void* n_out, const void* h,
-                       int64_t R, const float* gy, float* gout) -> int {
-        SEDT_TRY(to16(gy, bb.g16, R * d));
+                       int64_t R, const float* gy, float* gout, uint32_t site_h, uint32_t site_o) -> int {
+        SEDT_TRY(to16_drop(gy, bb.g16, R * d, site_o));
         SEDT_TRY(lin_param_grads(lin2, 0, d, h, ff, bb.g16, d, R));
-        SEDT_TRY(dgrad_lin(Wp(lin2.w_slot), d, d, ff, bb.g16, d, R, h, ff, 2, bb.dh, dt, ff));
+        // h is stored after dropout: h > 0 is the ReLU AND the keep mask; the 1/(1-p) factor rides on the GEMM's output scale
+        (void)site_h;
+        SEDT_TRY(dgrad_lin(Wp(lin2.w_slot), d, d, ff, bb.g16, d, R, h, ff, 2, bb.dh, dt, ff, drop ? bb.vscale : nullptr));
         SEDT_TRY(lin_param_grads(lin1, 0, ff, n_out, d, bb.dh, ff, R));
         SEDT_TRY(dgrad_lin(Wp(lin1.w_slot), ff, ff, d, bb.dh, ff, R, nullptr, 0, 0, bb.dn_a, dt, d));
         return launch_layernorm_bwd(x_mid, P_(nn.off_g), bb.dn_a, nullptr, nullptr, gy, gout, Gp(nn.w_slot), Gp(nn.b_slot), R, s);
@@ -451,15 +505,16 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
         SEDT_TRY(launch_layernorm_bwd(t.t_out, P_(dec_norm_.off_g), nullptr, nullptr, bb.dhs32 + (size_t)l * qrows * d,
                                       l == Dn - 1 ? nullptr : gcur, gnext, Gp(dec_norm_.w_slot), Gp(dec_norm_.b_slot), qrows, s));
         std::swap(gcur, gnext);
-        SEDT_TRY(ffn_bwd(e.lin1, e.lin2, e.n3, t.t_mid2, t.da3, t.h, qrows, gcur, gnext));
+        SEDT_TRY(ffn_bwd(e.lin1, e.lin2, e.n3, t.t_mid2, t.da3, t.h, qrows, gcur, gnext, dec_site(l, 4), dec_site(l, 5)));
         std::swap(gcur, gnext);
         // cross attention: t_mid2 = t_mid1 + out_proj(attn(q = Wq(LN2(t_mid1) + qpos), K_l, V_l))
-        SEDT_TRY(to16(gcur, bb.g16, qrows * d));
+        SEDT_TRY(to16_drop(gcur, bb.g16, qrows * d, dec_site(l, 3)));
         SEDT_TRY(lin_param_grads(e.cross_attn.out_proj, 0, d, t.ao2, d, bb.g16, d, qrows));
         SEDT_TRY(dgrad_lin(Wp(e.cross_attn.out_proj.w_slot), d, d, d, bb.g16, d, qrows, nullptr, 0, 0, bb.dao, dt, d));
         SEDT_TRY(attn_bwd(t.qb, d, (const char*)tp.ck + (size_t)l * d * es, Dn * d, (const char*)tp.cv + (size_t)l * d * es,
                                       Dn * d, bb.dao, d, bb.dq, d, (char*)bb.dck + (size_t)l * d * es, Dn * d,
-                                      (char*)bb.dcv + (size_t)l * d * es, Dn * d, tp.mask_ds, nullptr, B, cfg_.nheads, Qall, S, scale, s));
+                                      (char*)bb.dcv + (size_t)l * d * es, Dn * d, tp.mask_ds, nullptr, B, cfg_.nheads, Qall, S, scale,
+                                      dec_site(l, 2), s));
         SEDT_TRY(lin_param_grads(e.cross_attn.in_proj, 0, d, t.dap2, d, bb.dq, d, qrows));
         SEDT_TRY(dgrad_lin(Wp(e.cross_attn.in_proj.w_slot), d, d, d, bb.dq, d, qrows, nullptr, 0, 0, bb.dn_b, dt, d));
         SEDT_TRY(launch_colsum(bb.dn_b, dt, (int64_t)Qall * d, dqpos, B, Qall * d, s));
@@ -470,7 +525,8 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
         SEDT_TRY(lin_param_grads(e.cross_attn.in_proj, d, d, tp.mempos, d, (const char*)bb.dck + (size_t)l * d * es, Dn * d, rows));
         SEDT_TRY(lin_param_grads(e.cross_attn.in_proj, 2 * d, d, tp.mem, d, (const char*)bb.dcv + (size_t)l * d * es, Dn * d, rows));
         // self attention
-        SEDT_TRY(self_attn_bwd(e.self_attn, e.n1, t.t_in, t.da, t.dap, t.qk, t.v, t.ao1, nullptr, Qall, qrows, gcur, gnext, dqpos));
+        SEDT_TRY(self_attn_bwd(e.self_attn, e.n1, t.t_in, t.da, t.dap, t.qk, t.v, t.ao1, nullptr, Qall, qrows, gcur, gnext, dqpos,
+                               dec_site(l, 0), dec_site(l, 1)));
         std::swap(gcur, gnext);
     }
     // memory: d(mem + pos) = sum_l dK_l Wk_l, d(mem) = sum_l dV_l Wv_l  -> encoder.norm backward
@@ -495,9 +551,10 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     for (int l = (int)enc_.size() - 1; l >= 0; --l) {
         const EncLayer& e = enc_[l];
         const EncTape& t = tp.enc[l];
-        SEDT_TRY(ffn_bwd(e.lin1, e.lin2, e.n2, t.x_mid, t.n2, t.h, rows, gcur, gnext));
+        SEDT_TRY(ffn_bwd(e.lin1, e.lin2, e.n2, t.x_mid, t.n2, t.h, rows, gcur, gnext, enc_site(l, 2), enc_site(l, 3)));
         std::swap(gcur, gnext);
-        SEDT_TRY(self_attn_bwd(e.attn, e.n1, t.x_in, t.na, t.nap, t.qk, t.v, t.ao, tp.mask_ds, S, rows, gcur, gnext, nullptr));
+        SEDT_TRY(self_attn_bwd(e.attn, e.n1, t.x_in, t.na, t.nap, t.qk, t.v, t.ao, tp.mask_ds, S, rows, gcur, gnext, nullptr,
+                               enc_site(l, 0), enc_site(l, 1)));
         std::swap(gcur, gnext);
     }
 

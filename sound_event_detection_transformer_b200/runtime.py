@@ -215,7 +215,7 @@ class ForwardRuntime:
             self._grad_layout = (n, offs)
         return self._grad_layout
 
-    def forward_train(self, x: torch.Tensor, mask: Optional[torch.Tensor], use_graph: bool = False):
+    def forward_train(self, x: torch.Tensor, mask: Optional[torch.Tensor], use_graph: bool = False, dropout: float = 0.0):
         """Forward in train mode: same outputs as forward(); the activations stay in a runtime-owned tape until
         backward() (one forward/backward pair in flight per runtime).  use_graph replays the launch sequence as a
         CUDA graph per input shape (static input / output buffers, overwritten by the next step)."""
@@ -223,6 +223,9 @@ class ForwardRuntime:
         x = x.contiguous()
         B, _, T, F = x.shape
         dev = x.device
+        self._dropout = float(dropout)
+        if getattr(self, "_seed", None) is None:
+            self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF        # fixed per runtime: graphs bake it in
         if use_graph:
             return self._forward_train_graph(x, mask)
         need = int(self.lib.sedt_train_tape_bytes(self.handle, B, T, F, int(mask is not None)))
@@ -239,11 +242,12 @@ class ForwardRuntime:
         outs = _lib.SedtOutputs(**{k: _lib.ptr(res.get(k)) or None for k, _ in _lib.SedtOutputs._fields_})
         with torch.cuda.device(dev):
             _lib.check(self.lib.sedt_forward_train(self.handle, x.data_ptr(), _lib.ptr(m8) or None, B, T, F, self._aligned(tape),
-                                                   tape.numel() - 256, C.byref(outs), _lib.current_stream()))
+                                                   tape.numel() - 256, C.byref(outs), self._dropout, self._seed,
+                                                   _lib.current_stream()))
         return res, (x, m8, B, T, F)
 
     def _train_graph_state(self, B, T, F, has_mask, dev):
-        key = (B, T, F, has_mask, dev.index)
+        key = (B, T, F, has_mask, dev.index, self._dropout)
         g = getattr(self, "_train_graphs", {}).get(key)
         if g is None:
             if not hasattr(self, "_train_graphs"):
@@ -271,7 +275,8 @@ class ForwardRuntime:
 
             def launch():
                 _lib.check(self.lib.sedt_forward_train(self.handle, g["x"].data_ptr(), _lib.ptr(g["mask"]) or None, B, T, F,
-                                                       self._aligned(tape), tape.numel() - 256, C.byref(outs), _lib.current_stream()))
+                                                       self._aligned(tape), tape.numel() - 256, C.byref(outs), self._dropout,
+                                                       self._seed, _lib.current_stream()))
             with torch.cuda.device(dev):
                 launch()                                  # lazy one-time setup must not be captured
                 torch.cuda.synchronize(dev)
@@ -306,7 +311,7 @@ class ForwardRuntime:
                 _lib.check(self.lib.sedt_backward(self.handle, self._ptrs, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
                                                   self._aligned(tape), tape.numel() - 256, self._aligned(ws), ws.numel() - 256,
                                                   g["dl"].data_ptr(), g["db"].data_ptr(), _lib.ptr(g["da"]) or None,
-                                                  g["grads"].data_ptr(), int(train_backbone), _lib.current_stream()))
+                                                  g["grads"].data_ptr(), int(train_backbone), self._dropout, _lib.current_stream()))
             with torch.cuda.device(dev):
                 launch()
                 torch.cuda.synchronize(dev)
@@ -352,7 +357,7 @@ class ForwardRuntime:
             _lib.check(self.lib.sedt_backward(self.handle, self._ptrs, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
                                               self._aligned(tape), tape.numel() - 256, self._aligned(ws), ws.numel() - 256,
                                               _lib.ptr(d_logits) or None, _lib.ptr(d_boxes) or None, _lib.ptr(d_at) or None,
-                                              grads.data_ptr(), int(train_backbone), _lib.current_stream()))
+                                              grads.data_ptr(), int(train_backbone), self._dropout, _lib.current_stream()))
         return grads
 
     def kernel_launches(self) -> int:

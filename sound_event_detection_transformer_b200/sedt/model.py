@@ -22,7 +22,7 @@ class _TrainStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x, mask, names, *params):
         rt = model.runtime(use_graph=model.use_cuda_graph)
-        res, tctx = rt.forward_train(x, mask, use_graph=model.use_cuda_graph)
+        res, tctx = rt.forward_train(x, mask, use_graph=model.use_cuda_graph, dropout=float(model.transformer.dropout))
         ctx.model, ctx.tctx, ctx.names, ctx.shapes = model, tctx, names, [p.shape for p in params]
         ctx.has_at = "at" in res
         outs = (res["logits"], res["boxes"]) + ((res["at"],) if ctx.has_at else ())
@@ -123,7 +123,7 @@ class SEDT(nn.Module):
         return torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
 
     def _check_mode(self):
-        """Training with gradients runs through the native backward (SEDT only, bf16 tier, pre-norm, dropout 0);
+        """Training with gradients runs through the native backward (SEDT only, bf16 tier, pre-norm);
         everything else that would need autograd raises instead of silently falling back."""
         if not self._wants_grad():
             return
@@ -134,9 +134,8 @@ class SEDT(nn.Module):
             why = "the backward kernels exist for the bf16 tcgen05 tier only"
         elif not self.transformer.normalize_before:
             why = "the backward kernels implement the pre-norm layers only"
-        elif float(self.transformer.dropout) != 0.0:
-            why = ("dropout is not implemented in the training kernels: build the model with args.dropout = 0 "
-                   f"(got {self.transformer.dropout})")
+        elif not 0.0 <= float(self.transformer.dropout) < 1.0:
+            why = f"dropout must be in [0, 1), got {self.transformer.dropout}"
         if why is not None:
             raise NotImplementedError(why + ". Call model.eval() / torch.no_grad() for inference.")
 

@@ -124,8 +124,96 @@ def test_training_step_frozen_backbone_and_repeatable():
 def test_training_mode_requirements():
     args = spec.config_args("c1")
     args.precision = "bf16"
-    model, _, _ = build_model(args)                      # default dropout 0.1
+    args.pre_norm = False
+    model, _, _ = build_model(args)
     model.load_state_dict(synth.synth_state_dict(args, 3))
     model.cuda().train()
-    with pytest.raises(NotImplementedError, match="dropout"):
+    with pytest.raises(NotImplementedError, match="pre-norm"):
         model(synth.synth_clips(1, 128, 64).cuda())
+
+
+# ---- dropout ---------------------------------------------------------------------------------------------------
+def _mask_provider(args, B, S, seed, step, p):
+    """oracle.DROPOUT hook that applies exactly the masks the training kernels draw (sedt_op_dropout_mask)."""
+    import ctypes as C
+    import re
+    from sound_event_detection_transformer_b200 import _lib
+    lib = _lib.load()
+    H = args.nheads
+
+    def flags(site, n):
+        out = torch.empty(n, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.sedt_op_dropout_mask(out.data_ptr(), n, C.c_uint64(seed), C.c_uint64(step), site, p, _lib.current_stream()))
+        return out.cpu().float()
+
+    enc_k = {"attn": 0, "drop1": 1, "hidden": 2, "drop2": 3}
+    dec_k = {"self_attn": 0, "drop1": 1, "cross_attn": 2, "drop2": 3, "hidden": 4, "drop3": 5}
+
+    def hook(site, t):
+        m = re.match(r"transformer\.(encoder|decoder)\.layers\.(\d+)\.(\w+)$", site)
+        kind, layer, what = m.group(1), int(m.group(2)), m.group(3)
+        sid = 8 * layer + enc_k[what] if kind == "encoder" else 1024 + 8 * layer + dec_k[what]
+        if what in ("attn", "self_attn", "cross_attn"):          # [B*H, L, Lk] <- ((b*H + h)*128 + i)*128 + j
+            BH, L, Lk = t.shape
+            keep = flags(sid, BH * 128 * 128).view(BH, 128, 128)[:, :L, :Lk]
+        else:                                                     # sequence-first [L, B, C] <- row-major [B*L, C]
+            L, Bn, Cc = t.shape
+            keep = flags(sid, Bn * L * Cc).view(Bn, L, Cc).permute(1, 0, 2)
+        return t * keep / (1.0 - p)
+    return hook
+
+
+def test_training_step_with_dropout_matches_reference_with_the_same_masks():
+    """dropout 0.1 (the reference's default): the fp32 oracle is given the kernels' own Philox masks at every dropout
+    site, so outputs and gradients must agree as in the dropout-free test."""
+    args = spec.config_args("c1")
+    args.enc_layers, args.dec_layers = 2, 2
+    B, T, p = 2, 200, 0.1
+    sd, model, clips, R = _setup(args, 23, B, T)
+    model.transformer.dropout = p
+    torch.manual_seed(1234)
+    out = model(clips.cuda())
+    Rc = {k: v.cuda() for k, v in R.items()}
+    _loss(out, Rc).backward()
+    torch.cuda.synchronize()
+    rt = model._rt
+    named = {n: pp for n, pp in model.named_parameters() if pp.requires_grad}
+    S = out["pred_logits"].shape[0]
+    sedt_oracle.DROPOUT = _mask_provider(args, B, S, rt._seed, 1, p)        # first step on a fresh tape: step counter = 1
+    try:
+        ref_grads, ref = _reference_grads(sd, args, clips, R, list(named))
+    finally:
+        sedt_oracle.DROPOUT = None
+    for k in ("pred_logits", "pred_boxes", "at"):
+        assert ((out[k].detach().cpu() - ref[k]).norm() / ref[k].norm()).item() < 3e-2, k
+    bad = []
+    for n, pp in named.items():
+        g, r = pp.grad.detach().float().cpu().flatten(), ref_grads[n].flatten()
+        if r.norm() == 0 and g.norm() == 0:
+            continue
+        rel = ((g - r).norm() / r.norm().clamp_min(1e-20)).item()
+        cos = (torch.dot(g, r) / (g.norm() * r.norm()).clamp_min(1e-30)).item()
+        if rel > 0.16 or cos < 0.985:
+            bad.append((n, round(rel, 4), round(cos, 5)))
+    assert not bad, f"{len(bad)} gradients off: {bad[:12]}"
+    # and the masks are really there: the dropout-free oracle must NOT match
+    ref0 = sedt_oracle.sedt_forward(sd, args, clips)
+    assert ((out["pred_logits"].detach().cpu() - ref0["pred_logits"]).norm() / ref0["pred_logits"].norm()).item() > 5e-2
+
+
+def test_dropout_masks_change_every_step_and_eval_is_unaffected():
+    args = spec.config_args("c1")
+    args.enc_layers, args.dec_layers = 1, 1
+    sd, model, clips, R = _setup(args, 24, 2, 160)
+    model.transformer.dropout = 0.1
+    x = clips.cuda()
+    for graph in (False, True):
+        model.use_cuda_graph = graph
+        a = model(x)["pred_logits"].detach().clone()
+        b = model(x)["pred_logits"].detach().clone()
+        assert (a - b).abs().max() > 1e-3, graph                         # fresh masks each step (also under graph replay)
+    model.eval()
+    with torch.no_grad():
+        e1 = model(x)["pred_logits"].clone()
+        e2 = model(x)["pred_logits"].clone()
+    assert torch.equal(e1, e2)

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1)
     o = ap.parse_args()
     res = run(o)
     if res is not None:
@@ -35,7 +36,7 @@ def run(o):
     torch.cuda.set_device(dev)
     parallel.init_from_env("nccl", dev)
     args = spec.config_args("c2")
-    args.dropout = 0.0
+    args.dropout = float(getattr(o, "dropout", 0.1))          # the reference's default (train_sedt.py:92)
     sd = synth.synth_state_dict(args, 12)
     model, criterion, _ = build_model(args)
     model.load_state_dict(sd)
@@ -108,7 +109,8 @@ def run(o):
     return {"metric": "clips/sec SEDT E=6 training step (fwd + matcher x3 + set loss + bwd + allreduce + clip + AdamW)",
             "value": world * B / ms * 1e3, "unit": "clips/s", "n_gpus": world, "steps": o.steps, "warmup": o.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "SEDT E=6, num_queries=20, dec_at, aux_loss, [B,1,496,64] clips, 0..10 events per clip, dropout 0",
+            "config": {"workload": "SEDT E=6, num_queries=20, dec_at, aux_loss, [B,1,496,64] clips, 0..10 events per clip",
+                       "dropout": args.dropout,
                        "clips_per_gpu_per_step": B, "cuda_graph": not o.no_graph,
                        "optimizer": "torch AdamW (2 groups) + clip_grad_norm_ 0.1 (stock PyTorch, SURVEY 8f.1)"},
             "loss": float(loss.detach()), "gpu_launches": int(model.runtime().kernel_launches() - kl0),
