@@ -153,6 +153,51 @@ SEDT_API int sedt_matcher(const float* logits, const float* boxes, const int64_t
 SEDT_API int sedt_lsap(const float* cost, int ld_cost, const int32_t* offsets, int B, int Q, int kmax,
               int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status, void* stream);
 
+/* ---- SetCriterion.forward, supervised default path (sedt/sedt.py:309-352 with fine_tune = normalize = fl = False and no
+ * mixup 'ratio'; losses labels / boxes / cardinality / weak): for every decoder layer l (aux_outputs 0..L-2, then the top
+ * layer) and clip b one warp runs the matcher (as sedt_matcher), loss_labels (:188-221), loss_boxes (:238-261),
+ * loss_cardinality (:223-236) AND their gradients; a second launch reduces the per-clip partials in a fixed order and
+ * evaluates loss_weak (:161-186) with its gradient.
+ *   logits [L, B, Q, C1], boxes [L, B, Q, 2] fp32; the first Bs clips are strong_mask (matched), all B count for cardinality
+ *   at [Bw, C1-1] or null; wl_labels / wl_offsets [Bw+1]: labels of the first Bw clips (targets[i]['labels'], :169-174)
+ *   tgt_labels / tgt_boxes / offsets [Bs+1]: as sedt_matcher, for the strong clips; n_tgt [B] = len(targets[b]['labels'])
+ *   num_boxes: sum of the Coef the matcher returns = sum_b min(Q, K_b) (sedt.py:323-324)
+ *   rows, cols [L, Bs, Q] int64 (-1 padded), status [1] zeroed by the caller, partials [L, B, 8] scratch
+ *   losses [L, 8]: loss_ce, loss_bbox, loss_giou, class_error, cardinality_error, loss_weak (row L-1 only), 0, 0
+ *   g_logits [L, B, Q, C1] = d loss_ce[l] / d logits; g_l1, g_giou [L, B, Q, 2] = d loss_bbox[l], d loss_giou[l] / d boxes;
+ *   g_at [Bw, C1-1] = d loss_weak / d at */
+SEDT_API int sedt_set_criterion(const float* logits, const float* boxes, const float* at, const int64_t* tgt_labels,
+                                const float* tgt_boxes, const int32_t* offsets, const float* n_tgt, const int64_t* wl_labels,
+                                const int32_t* wl_offsets, int L, int B, int Bs, int Bw, int Q, int C1, int kmax,
+                                float cost_class, float cost_bbox, float cost_giou, float eos_coef, float num_boxes,
+                                int64_t* rows, int64_t* cols, int32_t* status, float* partials, float* losses,
+                                float* g_logits, float* g_l1, float* g_giou, float* g_at, void* stream);
+
+/* ---- clip_grad_norm_ + AdamW: the optimizer half of the training step (engine.py:76-80; AdamW with two lr groups,
+ * train_sedt.py:234-240,269-270; torch/optim/adamw.py _single_tensor_adamw arithmetic, amsgrad = maximize = False).
+ * The caller keeps a device table of tensors and a device table of (tensor index, chunk index) pairs that splits
+ * every tensor into chunks of sedt_optim_chunk_elems() elements (one CTA each).
+ *   sedt_grad_norm:  norm_out[0] = || all grads ||_2 (fixed-order reduction; partials: nchunks floats of scratch)
+ *   sedt_clip_grads: grads *= min(1, max_norm / (norm[0] + 1e-6))        (torch.nn.utils.clip_grad_norm_)
+ *   sedt_adamw_step: one fused pass; when `norm` is non-null and max_norm > 0 the clip coefficient is applied to the
+ *                    gradients on the fly (the stored grads are left unscaled) -- no host synchronisation anywhere. */
+typedef struct sedt_optim_tensor {
+    float* param; float* grad; float* exp_avg; float* exp_avg_sq;
+    int64_t numel; int32_t group; int32_t reserved;
+} sedt_optim_tensor;
+/* per parameter group, computed in double on the host and rounded once (as torch does with Python scalars):
+ * decay = 1 - lr*weight_decay, w1 = 1 - beta1, w2 = 1 - beta2, bc2_sqrt = sqrt(1 - beta2^step),
+ * neg_step = -lr / (1 - beta1^step) */
+typedef struct sedt_adamw_group { float decay, w1, beta2, w2, bc2_sqrt, eps, neg_step, reserved; } sedt_adamw_group;
+SEDT_API int sedt_optim_chunk_elems(void);
+SEDT_API int sedt_grad_norm(const sedt_optim_tensor* tensors, const int32_t* chunks, int nchunks, float* partials,
+                            float* norm_out, void* stream);
+SEDT_API int sedt_clip_grads(const sedt_optim_tensor* tensors, const int32_t* chunks, int nchunks, const float* norm,
+                             float max_norm, void* stream);
+SEDT_API int sedt_adamw_step(const sedt_optim_tensor* tensors, const int32_t* chunks, int nchunks,
+                             const sedt_adamw_group* groups /* [host], 1..8 */, int ngroups, const float* norm, float max_norm,
+                             void* stream);
+
 /* ---- single operators, exported so the parity tests can pin each kernel against the oracle ---- */
 typedef struct sedt_conv_desc {
     const void* in; const void* w; const float* scale; const float* bias; const void* residual; void* out;

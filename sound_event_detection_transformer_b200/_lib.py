@@ -35,6 +35,15 @@ class SedtConvDesc(C.Structure):
                                          "ld_res", "R", "S", "stride", "dil", "pad", "relu")]
 
 
+class SedtOptimTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64), ("group", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SedtAdamWGroup(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("decay", "w1", "beta2", "w2", "bc2_sqrt", "eps", "neg_step", "reserved")]
+
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); must list every symbol include/sedt_b200.h declares
@@ -62,6 +71,11 @@ SIGNATURES = {
     "sedt_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i, _f, _vp]),
     "sedt_matcher": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sedt_lsap": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sedt_set_criterion": (_i, [_vp] * 9 + [_i] * 7 + [_f] * 5 + [_vp] * 10),
+    "sedt_optim_chunk_elems": (_i, []),
+    "sedt_grad_norm": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "sedt_clip_grads": (_i, [_vp, _vp, _i, _vp, _f, _vp]),
+    "sedt_adamw_step": (_i, [_vp, _vp, _i, C.POINTER(SedtAdamWGroup), _i, _vp, _f, _vp]),
     "sedt_op_conv": (_i, [C.POINTER(SedtConvDesc), _i, _vp]),
     "sedt_op_conv_tc_supported": (_i, [C.POINTER(SedtConvDesc)]),
     "sedt_op_repack_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -178,6 +178,37 @@ int sedt_lsap(const float* cost, int ld_cost, const int32_t* offsets, int B, int
                           rows, cols, counts, status, 1, (cudaStream_t)stream);
 }
 
+int sedt_set_criterion(const float* logits, const float* boxes, const float* at, const int64_t* tgt_labels, const float* tgt_boxes,
+                       const int32_t* offsets, const float* n_tgt, const int64_t* wl_labels, const int32_t* wl_offsets,
+                       int L, int B, int Bs, int Bw, int Q, int C1, int kmax, float cost_class, float cost_bbox, float cost_giou,
+                       float eos_coef, float num_boxes, int64_t* rows, int64_t* cols, int32_t* status, float* partials,
+                       float* losses, float* g_logits, float* g_l1, float* g_giou, float* g_at, void* stream)
+{
+    return launch_set_criterion(logits, boxes, at, tgt_labels, tgt_boxes, offsets, n_tgt, wl_labels, wl_offsets, L, B, Bs, Bw, Q, C1,
+                                kmax, cost_class, cost_bbox, cost_giou, eos_coef, num_boxes, rows, cols, status, partials, losses,
+                                g_logits, g_l1, g_giou, g_at, (cudaStream_t)stream);
+}
+
+int sedt_optim_chunk_elems(void) { return optim_chunk_elems(); }
+
+int sedt_grad_norm(const sedt_optim_tensor* tensors, const int32_t* chunks, int nchunks, float* partials, float* norm_out, void* stream)
+{
+    return launch_grad_norm(tensors, chunks, nchunks, partials, norm_out, (cudaStream_t)stream);
+}
+
+int sedt_clip_grads(const sedt_optim_tensor* tensors, const int32_t* chunks, int nchunks, const float* norm, float max_norm,
+                    void* stream)
+{
+    return launch_grad_scale(tensors, chunks, nchunks, norm, max_norm, (cudaStream_t)stream);
+}
+
+int sedt_adamw_step(const sedt_optim_tensor* tensors, const int32_t* chunks, int nchunks, const sedt_adamw_group* groups,
+                    int ngroups, const float* norm, float max_norm, void* stream)
+{
+    static_assert(sizeof(sedt_adamw_group) == 32 && sizeof(sedt_optim_tensor) == 48, "optimizer table layout");
+    return launch_adamw(tensors, chunks, nchunks, (const float*)groups, ngroups, norm, max_norm, (cudaStream_t)stream);
+}
+
 int sedt_op_conv(const sedt_conv_desc* d, int engine, void* stream)
 {
     SEDT_REQUIRE(d != nullptr, "op_conv: null descriptor");

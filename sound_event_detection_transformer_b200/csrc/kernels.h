@@ -175,4 +175,18 @@ int launch_matcher(const float* logits, const float* boxes, const int64_t* tgt_l
                    const float* cost_in, int ld_in, float* cost_out, int ld_out,
                    int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status, int solve, cudaStream_t stream);
 
+// matcher + loss_labels / loss_boxes / loss_cardinality / loss_weak and their gradients (sedt/sedt.py:309-352)
+int launch_set_criterion(const float* logits, const float* boxes, const float* at, const int64_t* tgt_labels, const float* tgt_boxes,
+                         const int32_t* offsets, const float* n_tgt, const int64_t* wl_labels, const int32_t* wl_offsets,
+                         int L, int B, int Bs, int Bw, int Q, int C1, int Kmax, float w_class, float w_bbox, float w_giou,
+                         float eos_coef, float num_boxes, int64_t* rows, int64_t* cols, int32_t* status, float* partials,
+                         float* losses, float* g_logits, float* g_l1, float* g_giou, float* g_at, cudaStream_t stream);
+
+// ---- optim.cu: clip_grad_norm_ + AdamW over a (tensor, chunk) table (engine.py:76-80)
+int optim_chunk_elems();
+int launch_grad_norm(const void* tensors, const int32_t* chunks, int nchunks, float* partials, float* norm_out, cudaStream_t stream);
+int launch_grad_scale(const void* tensors, const int32_t* chunks, int nchunks, const float* norm, float max_norm, cudaStream_t stream);
+int launch_adamw(const void* tensors, const int32_t* chunks, int nchunks, const float* groups_host, int ngroups,
+                 const float* norm, float max_norm, cudaStream_t stream);
+
 }  // namespace sedt

@@ -6,7 +6,7 @@ path, not part of it, and get fused kernels together with the training
 backward."""
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple  # noqa: F401
 
 import torch
 import torch.nn.functional as F
@@ -32,6 +32,89 @@ def paired_l1_giou(src: torch.Tensor, tgt: torch.Tensor) -> Tuple[torch.Tensor, 
     return l1, giou
 
 
+_LOSS_COL = {"loss_ce": 0, "loss_bbox": 1, "loss_giou": 2, "class_error": 3, "cardinality_error": 4, "loss_weak": 5}
+
+
+def _common_base(ts: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
+    """The [L, ...] tensor the per-layer outputs are select(0, l) views of (the native forward writes all decoder
+    layers into one buffer), or None."""
+    base = getattr(ts[0], "_base", None)
+    if base is None or base.dim() != ts[0].dim() + 1 or base.shape[0] != len(ts) or not base.is_contiguous():
+        return None
+    step = base.stride(0) * base.element_size()
+    for i, t in enumerate(ts):
+        if getattr(t, "_base", None) is not base or t.shape != base.shape[1:] or t.data_ptr() != base.data_ptr() + i * step \
+                or not t.is_contiguous():
+            return None
+    return base
+
+
+class _FusedSetLoss(torch.autograd.Function):
+    """sedt_set_criterion: matcher + losses + gradients of all decoder layers in two launches.  Outputs: one 0-dim
+    tensor per requested (layer, loss); backward scales the stored gradients by the incoming scalars."""
+
+    @staticmethod
+    def forward(ctx, logits, boxes, at, crit, pk, wanted):
+        from .. import _lib
+        lib = _lib.load()
+        L, B, Q, C1 = logits.shape
+        dev = logits.device
+        lg = logits.detach().to(torch.float32).contiguous()
+        bx = boxes.detach().to(torch.float32).contiguous()
+        Bs, Bw = pk["Bs"], (pk["Bw"] if at is not None else 0)
+        at2 = at.detach().to(torch.float32).reshape(-1, C1 - 1).contiguous() if at is not None else None
+        rows = torch.empty(L, Bs, Q, dtype=torch.int64, device=dev)
+        cols = torch.empty(L, Bs, Q, dtype=torch.int64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        partials = torch.empty(L, B, 8, dtype=torch.float32, device=dev)
+        vals = torch.empty(L, 8, dtype=torch.float32, device=dev)
+        g_logits, g_l1, g_giou = torch.empty_like(lg), torch.empty_like(bx), torch.empty_like(bx)
+        g_at = torch.zeros_like(at2) if at2 is not None else None
+        m = crit.matcher
+        with torch.cuda.device(dev):
+            _lib.check(lib.sedt_set_criterion(
+                lg.data_ptr(), bx.data_ptr(), _lib.ptr(at2) or None, pk["labels"].data_ptr(), pk["boxes"].data_ptr(),
+                pk["offsets"].data_ptr(), pk["n_tgt"].data_ptr(), pk["wl_labels"].data_ptr(), pk["wl_offsets"].data_ptr(),
+                L, B, Bs, Bw, Q, C1, pk["kmax"], float(m.cost_class), float(m.cost_bbox), float(m.cost_giou),
+                float(crit.eos_coef), float(pk["total"]), rows.data_ptr(), cols.data_ptr(), status.data_ptr(),
+                partials.data_ptr(), vals.data_ptr(), g_logits.data_ptr(), g_l1.data_ptr(), g_giou.data_ptr(),
+                _lib.ptr(g_at) or None, _lib.current_stream()))
+        ctx.g = (g_logits, g_l1, g_giou, g_at)
+        ctx.wanted, ctx.at_shape, ctx.L = wanted, (None if at is None else at.shape), L
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(rows, cols, status)
+        outs = tuple(vals[l, j] for l, j in wanted)
+        return (rows, cols, status) + outs
+
+    @staticmethod
+    def backward(ctx, _r, _c, _s, *gs):
+        g_logits, g_l1, g_giou, g_at = ctx.g
+        L = ctx.L
+        dev = g_logits.device
+        zero = None
+        coef = [[None] * 6 for _ in range(L)]
+        for (l, j), g in zip(ctx.wanted, gs):
+            coef[l][j] = g
+        if all(g is None for g in gs):
+            return None, None, None, None, None, None
+        zero = torch.zeros([], dtype=torch.float32, device=dev)
+        cm = torch.stack([coef[l][j] if coef[l][j] is not None else zero for l in range(L) for j in (0, 1, 2)]).view(L, 3, 1, 1, 1)
+        d_logits = g_logits * cm[:, 0]
+        d_boxes = g_l1 * cm[:, 1] + g_giou * cm[:, 2]
+        d_at = None
+        if g_at is not None and coef[L - 1][5] is not None:
+            d_at = g_at * coef[L - 1][5]
+            n = 1
+            for v in ctx.at_shape:
+                n *= v
+            if d_at.numel() != n:                     # weak loss over the first Bw clips only
+                full = torch.zeros(n // d_at.shape[1], d_at.shape[1], dtype=d_at.dtype, device=dev)
+                full[:d_at.shape[0]] = d_at
+                d_at = full
+            d_at = d_at.view(ctx.at_shape)
+        return d_logits, d_boxes, d_at, None, None, None
+
+
 class SetCriterion(nn.Module):
     def __init__(self, num_classes, matcher, weight_dict, eos_coef, losses):
         super().__init__()
@@ -40,6 +123,91 @@ class SetCriterion(nn.Module):
         empty_weight = torch.ones(num_classes + 1)
         empty_weight[-1] = eos_coef
         self.register_buffer("empty_weight", empty_weight)
+        # one fused matcher + loss + gradient kernel for the supervised default path (csrc/matcher.cu: set_criterion_kernel);
+        # False keeps the batched torch expressions below (same values; used by the parity tests as a cross-check)
+        self.fused = True
+
+    # -- fused path: sedt_set_criterion ------------------------------------------------------------------------------
+    def _fused_ok(self, outputs, targets, strong_mask, weak_mask, fine_tune, normalize) -> bool:
+        if not self.fused or fine_tune or normalize or not hasattr(self.matcher, "pack_targets"):
+            return False
+        if not set(self.losses) <= {"labels", "boxes", "cardinality", "weak"} or not {"labels", "boxes"} <= set(self.losses):
+            return False
+        for m in (strong_mask, weak_mask):
+            if m is not None and not (isinstance(m, slice) and m.step in (None, 1)):
+                return False
+        if strong_mask is None or strong_mask.start not in (None, 0) or strong_mask.stop is None:
+            return False
+        lg = outputs["pred_logits"]
+        if not lg.is_cuda or lg.dtype != torch.float32 or lg.dim() != 3:
+            return False
+        return not any("ratio" in t for t in targets)
+
+    def _pack_fused(self, targets, Bs, Bw, Q, dev) -> dict:
+        tg = list(targets)
+        pk = self.matcher.pack_targets(tg[:Bs], dev)
+        sizes = pk["sizes"]
+        pk["n"] = [min(Q, k) for k in sizes]
+        pk["total"] = sum(pk["n"])
+        pk["kmax"] = max(sizes) if sizes else 0
+        pk["Bs"], pk["Bw"] = Bs, Bw
+        nl = [int(len(t["labels"])) for t in tg]
+        pk["n_tgt"] = torch.tensor(nl, dtype=torch.float32).to(dev, non_blocking=True)
+        if Bw <= Bs and nl[:Bw] == sizes[:Bw]:
+            pk["wl_labels"], pk["wl_offsets"] = pk["labels"], pk["offsets"]        # same table: every label has a box
+        else:
+            labs = [torch.as_tensor(t["labels"]).reshape(-1) for t in tg[:Bw] if len(t["labels"])]
+            pk["wl_labels"] = (torch.cat(labs).to(dev, torch.int64) if labs else torch.zeros(1, dtype=torch.int64, device=dev))
+            off = [0]
+            for k in nl[:Bw]:
+                off.append(off[-1] + k)
+            pk["wl_offsets"] = torch.tensor(off, dtype=torch.int32).to(dev, non_blocking=True)
+        return pk
+
+    def _forward_fused(self, outputs, targets, strong_mask, weak_mask):
+        aux = outputs.get("aux_outputs", [])
+        lts = [a["pred_logits"] for a in aux] + [outputs["pred_logits"]]
+        bts = [a["pred_boxes"] for a in aux] + [outputs["pred_boxes"]]
+        logits = _common_base(lts)
+        boxes = _common_base(bts)
+        if logits is None or boxes is None:
+            logits, boxes = torch.stack(lts), torch.stack(bts)
+        L, B, Q, C1 = logits.shape
+        dev = logits.device
+        Bs = min(int(strong_mask.stop), B)
+        use_weak = "weak" in self.losses and "at" in outputs
+        Bw = min(int(weak_mask.stop if weak_mask is not None else strong_mask.stop), B) if use_weak else 0
+        pk = self._pack_fused(targets, Bs, Bw, Q, dev)
+        wanted = []
+        names = []
+        for l in range(L):
+            sfx = "" if l == L - 1 else f"_{l}"
+            keys = []
+            if "labels" in self.losses:
+                keys += ["loss_ce"] + (["class_error"] if l == L - 1 else [])
+            if "cardinality" in self.losses:
+                keys.append("cardinality_error")
+            if "boxes" in self.losses:
+                keys += ["loss_bbox", "loss_giou"]
+            if l == L - 1 and use_weak:
+                keys.append("loss_weak")
+            for k in keys:
+                wanted.append((l, _LOSS_COL[k]))
+                names.append(k + sfx)
+        at = outputs["at"] if use_weak else None
+        res = _FusedSetLoss.apply(logits, boxes, at, self, pk, tuple(wanted))
+        rows, cols, status = res[:3]
+        losses = dict(zip(names, res[3:]))
+        # reference key order: top layer first (sedt.py:329-351)
+        top = {k: v for k, v in losses.items() if not k[-1].isdigit()}
+        top.update({k: v for k, v in losses.items() if k[-1].isdigit()})
+        # one read-back for the whole step: matcher status + the top layer's index matrices
+        packed = torch.cat([status.to(torch.int64), rows[L - 1].flatten(), cols[L - 1].flatten()]).cpu()
+        self.matcher.raise_on_status(int(packed[0]))
+        r = packed[1:1 + Bs * Q].view(Bs, Q)
+        c = packed[1 + Bs * Q:].view(Bs, Q)
+        indices = [(r[i, :k], c[i, :k]) for i, k in enumerate(pk["n"])]
+        return top, indices
 
     # -- helpers ------------------------------------------------------------
     @staticmethod
@@ -64,8 +232,8 @@ class SetCriterion(nn.Module):
             ce = F.cross_entropy(logits.transpose(1, 2), cls, self.empty_weight, reduction="none")
             res["loss_ce"] = (ce * wq).sum() / num_boxes
             if log:
-                if matched.numel() == 0:
-                    res["class_error"] = torch.zeros([], device=dev)
+                if matched.numel() == 0:                 # utilities/utils.py:566-567: accuracy() is 0 without targets
+                    res["class_error"] = torch.full([], 100.0, device=dev)
                 else:
                     acc = (logits[bi, si].argmax(-1) == matched).float().mean() * 100.0
                     res["class_error"] = 100 - acc
@@ -146,7 +314,7 @@ class SetCriterion(nn.Module):
             res["loss_ce"] = ce.sum() / num_boxes
             if log:
                 if pk["total"] == 0:
-                    res["class_error"] = torch.zeros([], device=dev)
+                    res["class_error"] = torch.full([], 100.0, device=dev)
                 else:
                     res["class_error"] = 100 - (logits[bi, si].argmax(-1) == matched).float().mean() * 100.0
         if "cardinality" in self.losses:
@@ -163,6 +331,8 @@ class SetCriterion(nn.Module):
     def forward(self, outputs, targets, weak_mask=None, strong_mask=None, fine_tune=False, normalize=False, fl=False):
         if fl:
             raise NotImplementedError("focal-loss branch (semi-supervised only) is out of scope (SURVEY.md section 2, #9)")
+        if self._fused_ok(outputs, targets, strong_mask, weak_mask, fine_tune, normalize):
+            return self._forward_fused(outputs, targets, strong_mask, weak_mask)
         losses = {}
         indices = None
         if strong_mask is not None and self._batched_ok(targets[strong_mask], fine_tune, normalize):

@@ -13,13 +13,14 @@ from sound_event_detection_transformer_b200.sedt import build_model
 pytestmark = pytest.mark.gpu
 
 
-def _run(tag, cfg, batched):
+def _run(tag, cfg, path):
     fx = np.load(os.path.join(GOLDEN, f"criterion_{tag}.npz"))
     B, kmin, kmax, seed = [int(v) for v in fx["meta"]]
     args = spec.config_args(cfg)
     _, criterion, _ = build_model(args)
     criterion = criterion.cuda()
-    if not batched:
+    criterion.fused = path == "fused"                 # one sedt_set_criterion launch (default)
+    if path == "per_clip":                            # neither fused nor batched: the reference's per-clip structure
         criterion._batched_ok = lambda *a, **k: False
     outputs, targets = synth.synth_criterion_case(B, args.num_queries, args.num_classes, args.dec_layers, kmin, kmax, seed)
 
@@ -48,7 +49,40 @@ def _run(tag, cfg, batched):
                                      for (r, c), t in zip(indices, targets))
 
 
-@pytest.mark.parametrize("batched", [True, False])
+@pytest.mark.parametrize("path", ["fused", "batched", "per_clip"])
 @pytest.mark.parametrize("tag,cfg", [("c2", "c2"), ("c1_edges", "c1")])
-def test_set_criterion_matches_reference(tag, cfg, batched):
-    _run(tag, cfg, batched)
+def test_set_criterion_matches_reference(tag, cfg, path):
+    _run(tag, cfg, path)
+
+
+def test_fused_criterion_strong_and_weak_subsets():
+    """strong_mask = first 5 clips, weak labels on the first 8 (weakly labelled clips carry labels but no boxes), 12 clips in
+    the batch: the fused kernel against the per-clip torch path (which the golden test above ties to the reference)."""
+    args = spec.config_args("c1")
+    _, criterion, _ = build_model(args)
+    criterion = criterion.cuda()
+    B = 12
+    outputs, targets = synth.synth_criterion_case(B, args.num_queries, args.num_classes, args.dec_layers, 0, 6, 11)
+    for t in targets[5:8]:
+        t["boxes"] = t["boxes"][:0]
+    results = []
+    for path in ("fused", "per_clip"):
+        criterion.fused = path == "fused"
+        criterion._batched_ok = lambda *a, **k: False
+        outs = {"pred_logits": outputs["pred_logits"].cuda().requires_grad_(True),
+                "pred_boxes": outputs["pred_boxes"].cuda().requires_grad_(True), "at": outputs["at"].cuda().requires_grad_(True),
+                "aux_outputs": [{k: v.cuda().requires_grad_(True) for k, v in a.items()} for a in outputs["aux_outputs"]]}
+        tg = np.array([{k: v.cuda() for k, v in t.items()} for t in targets], dtype=object)
+        losses, indices = criterion(outs, tg, slice(5, 8), slice(5))
+        wd = criterion.weight_dict
+        sum(losses[k] * wd[k] for k in losses if k in wd).backward()
+        leaves = [outs["pred_logits"], outs["pred_boxes"], outs["at"]] + [v for a in outs["aux_outputs"] for v in a.values()]
+        results.append((losses, indices, [t.grad.clone() for t in leaves]))
+    (lf, idf, gf), (lp, idp, gp) = results
+    assert sorted(lf) == sorted(lp)
+    for k in lf:
+        assert abs(float(lf[k]) - float(lp[k])) <= 2e-5 * max(1.0, abs(float(lp[k]))), k
+    for (r1, c1), (r2, c2) in zip(idf, idp):
+        assert torch.equal(r1.cpu(), r2.cpu()) and torch.equal(c1.cpu(), c2.cpu())
+    for a, b in zip(gf, gp):
+        assert (a - b).abs().max() <= 1e-6 + 1e-4 * b.abs().max()
