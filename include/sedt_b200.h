@@ -148,6 +148,14 @@ SEDT_API int sedt_matcher(const float* logits, const float* boxes, const int64_t
                  float cost_class, float cost_bbox, float cost_giou,
                  float* cost_out, int ld_cost, int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status,
                  void* stream);
+/* The matcher's other branches (sedt/matcher.py:77-82, 99-106): fl != 0 replaces the softmax class cost by the focal
+ * cost on sigmoid probabilities (alpha_fl / gamma_fl = config.py:71-72); lmin / largmin [B, Q] (optional, together) receive
+ * each query's smallest location cost cost_bbox * L1 + cost_giou * (-GIoU) and the target attaining it (first minimum; -1
+ * when the clip has no target) -- the quantities HungarianMatcher's fine_tune relaxation thresholds with epsilon. */
+SEDT_API int sedt_matcher_ex(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
+                    const int32_t* offsets, int B, int Q, int C1, int kmax, float cost_class, float cost_bbox, float cost_giou,
+                    int fl, float alpha_fl, float gamma_fl, float* cost_out, int ld_cost, int64_t* rows, int64_t* cols,
+                    int32_t* counts, int32_t* status, float* lmin, int64_t* largmin, void* stream);
 /* Only the per-clip assignment (scipy.optimize.linear_sum_assignment, sedt/matcher.py:95) on caller
  * supplied fp32 cost blocks cost[B, Q, ld_cost]; clip b uses its first offsets[b+1]-offsets[b] columns. */
 SEDT_API int sedt_lsap(const float* cost, int ld_cost, const int32_t* offsets, int B, int Q, int kmax,

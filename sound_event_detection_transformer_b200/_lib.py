@@ -70,6 +70,7 @@ SIGNATURES = {
     "sedt_forward_train": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i64, C.POINTER(SedtOutputs), _f, C.c_uint64, _vp]),
     "sedt_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i, _f, _vp]),
     "sedt_matcher": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sedt_matcher_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sedt_lsap": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "sedt_set_criterion": (_i, [_vp] * 9 + [_i] * 7 + [_f] * 5 + [_vp] * 10),
     "sedt_optim_chunk_elems": (_i, []),

@@ -169,6 +169,18 @@ int sedt_matcher(const float* logits, const float* boxes, const int64_t* tgt_lab
                           nullptr, 0, cost_out, ld_cost, rows, cols, counts, status, 1, (cudaStream_t)stream);
 }
 
+int sedt_matcher_ex(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
+                    const int32_t* offsets, int B, int Q, int C1, int kmax, float cost_class, float cost_bbox, float cost_giou,
+                    int fl, float alpha_fl, float gamma_fl, float* cost_out, int ld_cost, int64_t* rows, int64_t* cols,
+                    int32_t* counts, int32_t* status, float* lmin, int64_t* largmin, void* stream)
+{
+    SEDT_REQUIRE(B == 0 || (logits && boxes && offsets && rows && cols && counts && status), "matcher: null argument");
+    SEDT_REQUIRE(cost_out == nullptr || ld_cost >= kmax, "matcher: ld_cost=%d < kmax=%d", ld_cost, kmax);
+    return launch_matcher(logits, boxes, tgt_labels, tgt_boxes, offsets, B, Q, C1, kmax, cost_class, cost_bbox, cost_giou,
+                          nullptr, 0, cost_out, ld_cost, rows, cols, counts, status, 1, (cudaStream_t)stream, fl, alpha_fl, gamma_fl,
+                          lmin, largmin);
+}
+
 int sedt_lsap(const float* cost, int ld_cost, const int32_t* offsets, int B, int Q, int kmax, int64_t* rows, int64_t* cols,
               int32_t* counts, int32_t* status, void* stream)
 {

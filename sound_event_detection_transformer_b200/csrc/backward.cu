@@ -381,31 +381,20 @@ attention_bwd_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict
 // ---- stem backward: gradients of conv0 (1 -> 3 channels, 1x1, bias), the only trainable parameters below layer2 ---------
 // Forward (sedt/backbone.py:102 + resnet conv1/bn1/relu/maxpool): z[o] = sum_taps Weff[o][tap] x[tap] + sum_{taps inside
 // the image} Beff[o][tap], Weff = sum_c conv1[o][c][tap] w0[c], Beff = sum_c conv1[o][c][tap] b0[c]; a = z * bn_scale + bn_bias;
-// out = maxpool3x3s2(relu(a)).  Given G = d/d(out): the kernel recomputes the (up to) nine a values of every pooling
-// window in fp32, routes G to the first maximum (if positive) and accumulates dWeff[o][tap] += dz * x[tap],
-// dBeff[o][tap] += dz (dz = G * bn_scale) in registers; thread = output channel o, CTA = (clip, 8 pooled rows).
-constexpr int SB_PH = 8;            // pooled rows per CTA
+// out = maxpool3x3s2(relu(a)).  Given G = d/d(out) and the window arg-max the training forward recorded (stem_tc_kernel<true>:
+// 0..8 = position, 9 = dead), the kernel routes G to that conv pixel and accumulates dWeff[o][tap] += dz * x[tap],
+// dBeff[o][tap] += dz (dz = G * bn_scale) in registers; thread = output channel o, CTA = (clip, SB_PH pooled rows).
+constexpr int SB_PH = 4;            // pooled rows per CTA
 constexpr int SB_XC = 64 + 10;      // padded input row
 
 __global__ void __launch_bounds__(64)
-stem_bwd_kernel(const float* __restrict__ x, const float* __restrict__ conv0_w, const float* __restrict__ conv0_b,
-                const float* __restrict__ conv1_w, const float* __restrict__ bn_scale, const float* __restrict__ bn_bias,
-                const bf16* __restrict__ G, float* __restrict__ acc, int T, int Hc, int Hp)
+stem_bwd_kernel(const float* __restrict__ x, const float* __restrict__ bn_scale, const bf16* __restrict__ G,
+                const uint8_t* __restrict__ amax, float* __restrict__ acc, int T, int Hc, int Hp)
 {
-    __shared__ float Ws[49][64], Bs[49][64];
     __shared__ float xs[11][SB_XC];
     __shared__ int rowin[11];
     const int o = threadIdx.x, b = blockIdx.y, hp0 = blockIdx.x * SB_PH;
-    {
-        const float w0[3] = {conv0_w[0], conv0_w[1], conv0_w[2]}, b0[3] = {conv0_b[0], conv0_b[1], conv0_b[2]};
-        for (int tap = 0; tap < 49; ++tap) {
-            float w = 0.f, bb = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { const float k = conv1_w[(o * 3 + c) * 49 + tap]; w = fmaf(k, w0[c], w); bb = fmaf(k, b0[c], bb); }
-            Ws[tap][o] = w; Bs[tap][o] = bb;
-        }
-    }
-    const float sc = bn_scale[o], bi = bn_bias[o];
+    const float sc = bn_scale[o];
     float dW[49], dB[49];
 #pragma unroll
     for (int i = 0; i < 49; ++i) { dW[i] = 0.f; dB[i] = 0.f; }
@@ -421,29 +410,11 @@ stem_bwd_kernel(const float* __restrict__ x, const float* __restrict__ conv0_w, 
         if (o < 11) rowin[o] = (irow0 + o >= 0 && irow0 + o < T) ? 1 : 0;
         __syncthreads();
         for (int wp = 0; wp < 16; ++wp) {
-            const float g = __bfloat162float(G[(((size_t)b * Hp + hp) * 16 + wp) * 64 + o]);
-            float best = -CUDART_INF_F; int bdy = 0, bdx = 0;
-            for (int dy = 0; dy < 3; ++dy) {
-                const int hc = 2 * hp - 1 + dy;
-                if (hc < 0 || hc >= Hc) continue;
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int wc = 2 * wp - 1 + dx;
-                    if (wc < 0 || wc >= 32) continue;
-                    float z = 0.f;
-                    for (int r = 0; r < 7; ++r) {
-                        if (!rowin[2 * dy + r]) continue;
-                        const float* xr = &xs[2 * dy + r][2 * wc - 3 + 5];
-#pragma unroll
-                        for (int q = 0; q < 7; ++q) {
-                            const int ic = 2 * wc - 3 + q;
-                            if (ic >= 0 && ic < 64) z += fmaf(Ws[r * 7 + q][o], xr[q], Bs[r * 7 + q][o]);
-                        }
-                    }
-                    const float a = fmaf(z, sc, bi);
-                    if (a > best) { best = a; bdy = dy; bdx = dx; }
-                }
-            }
-            if (best > 0.f && g != 0.f) {
+            const size_t e = (((size_t)b * Hp + hp) * 16 + wp) * 64 + o;
+            const float g = __bfloat162float(G[e]);
+            const int a = amax[e];
+            if (a < 9 && g != 0.f) {
+                const int bdy = a / 3, bdx = a - 3 * bdy;
                 const float dz = g * sc;
                 const int wc = 2 * wp - 1 + bdx;
 #pragma unroll
@@ -580,16 +551,16 @@ int launch_layernorm_bwd(const float* x, const float* gamma, const void* g1, con
     return SEDT_OK;
 }
 
-int launch_stem_bwd(const float* x, const float* conv0_w, const float* conv0_b, const float* conv1_w, const float* bn_scale,
-                    const float* bn_bias, const void* G, float* scratch, float* g_conv0_w, float* g_conv0_b, int B, int T, int F,
-                    cudaStream_t stream)
+int launch_stem_bwd(const float* x, const float* conv1_w, const float* bn_scale, const void* G, const uint8_t* amax,
+                    float* scratch, float* g_conv0_w, float* g_conv0_b, int B, int T, int F, cudaStream_t stream)
 {
     SEDT_REQUIRE(F == 64, "stem_bwd: F=%d must be 64", F);
+    SEDT_REQUIRE(amax != nullptr, "stem_bwd: needs the pooling arg-max recorded by the training forward");
     if (B == 0) return SEDT_OK;
     const int Hc = (T + 2 * 3 - 7) / 2 + 1, Hp = (Hc + 2 - 3) / 2 + 1;
     SEDT_TRY(launch_fill_zero(scratch, (size_t)2 * 49 * 64 * 4, stream));
-    stem_bwd_kernel<<<dim3((unsigned)ceil_div(Hp, SB_PH), (unsigned)B), 64, 0, stream>>>(x, conv0_w, conv0_b, conv1_w, bn_scale, bn_bias,
-                                                                                      (const bf16*)G, scratch, T, Hc, Hp);
+    stem_bwd_kernel<<<dim3((unsigned)ceil_div(Hp, SB_PH), (unsigned)B), 64, 0, stream>>>(x, bn_scale, (const bf16*)G, amax, scratch, T, Hc,
+                                                                                      Hp);
     SEDT_COUNT_LAUNCH();
     stem_bwd_finish_kernel<<<1, 256, 0, stream>>>(scratch, conv1_w, g_conv0_w, g_conv0_b);
     SEDT_COUNT_LAUNCH();

@@ -68,7 +68,9 @@ int launch_stem(const float* x, const StemWeights& w, void* out, int out_dt, int
 // stem_tc.cu: the same stem on tcgen05 (bf16 output).  wtc: 16 KiB pre-swizzled weight image, bn_scale folded in
 int launch_stem_tc_pack(const float* conv0_w, const float* conv0_b, const float* conv1_w, const float* bn_scale, void* wtc,
                         cudaStream_t stream);
-int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, void* out, int B, int T, int F, cudaStream_t stream);
+// amax (optional, training): [B, Hp, 16, 64] uint8 arg-max of every pooling window (0..8 = dr*3+dc, 9 = dead ReLU)
+int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, void* out, int B, int T, int F, cudaStream_t stream,
+                   uint8_t* amax = nullptr);
 
 // ---- pack.cu
 int launch_bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* bias,
@@ -99,11 +101,10 @@ int launch_colsum(const void* in, int dt, int64_t ld, float* out, int64_t M, int
 // be null), dres an fp32 gradient added to dx (the residual branch); dgamma / dbeta accumulate atomically
 int launch_layernorm_bwd(const float* x, const float* gamma, const void* g1, const void* g2, const float* g3, const float* dres,
                          float* dx, float* dgamma, float* dbeta, int64_t rows, cudaStream_t stream);
-// gradients of conv0.weight[3] / conv0.bias[3] from G = d/d(stem output) (bf16 [B,Hp,16,64], ReLU mask applied);
-// scratch: 2*49*64 floats
-int launch_stem_bwd(const float* x, const float* conv0_w, const float* conv0_b, const float* conv1_w, const float* bn_scale,
-                    const float* bn_bias, const void* G, float* scratch, float* g_conv0_w, float* g_conv0_b, int B, int T, int F,
-                    cudaStream_t stream);
+// gradients of conv0.weight[3] / conv0.bias[3] from G = d/d(stem output) (bf16 [B,Hp,16,64], ReLU mask applied) and the
+// pooling arg-max the training forward recorded (launch_stem_tc amax); scratch: 2*49*64 floats
+int launch_stem_bwd(const float* x, const float* conv1_w, const float* bn_scale, const void* G, const uint8_t* amax,
+                    float* scratch, float* g_conv0_w, float* g_conv0_b, int B, int T, int F, cudaStream_t stream);
 // attention core backward (bf16, head_dim 32, Lq, Lk <= 128): recomputes P from Q, K and the masks
 int launch_attention_bwd(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, const void* dO, int ldo,
                          void* dQ, int lddq, void* dK, int lddk, void* dV, int lddv, const uint8_t* kpm, const float* amask,
@@ -173,7 +174,8 @@ int prof_read(double* ms, long long* counts);   // model.cu
 int launch_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
                    const int32_t* offsets, int B, int Q, int C1, int Kmax, float w_class, float w_bbox, float w_giou,
                    const float* cost_in, int ld_in, float* cost_out, int ld_out,
-                   int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status, int solve, cudaStream_t stream);
+                   int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status, int solve, cudaStream_t stream,
+                   int fl = 0, float alpha_fl = 0.f, float gamma_fl = 0.f, float* lmin = nullptr, int64_t* largmin = nullptr);
 
 // matcher + loss_labels / loss_boxes / loss_cardinality / loss_weak and their gradients (sedt/sedt.py:309-352)
 int launch_set_criterion(const float* logits, const float* boxes, const float* at, const int64_t* tgt_labels, const float* tgt_boxes,

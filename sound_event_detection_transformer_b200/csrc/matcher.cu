@@ -196,12 +196,16 @@ __device__ int lsap_warp(const float* sc, int Q, int K, int lane, int64_t* rows_
 __device__ bool build_cost_block(const float* __restrict__ logits, const float* __restrict__ boxes,
                                  const int64_t* __restrict__ tgt_labels, const float* __restrict__ tgt_boxes,
                                  int Q, int C1, int K, float w_class, float w_bbox, float w_giou,
-                                 float* sc, float* sp, int lane)
+                                 float* sc, float* sp, int lane, int fl = 0, float alpha_fl = 0.f, float gamma_fl = 0.f)
 {
     bool bad = false;
-    // softmax over classes, one query row per lane (matcher.py:65)
+    // softmax over classes, one query row per lane (matcher.py:65); sigmoid under fl (focal class cost)
     for (int q = lane; q < Q; q += 32) {
         const float* lg = logits + (size_t)q * C1;
+        if (fl) {
+            for (int c = 0; c < C1; ++c) sp[q * C1 + c] = 1.f / (1.f + expf(-lg[c]));
+            continue;
+        }
         float m = -CUDART_INF_F;
         for (int c = 0; c < C1; ++c) m = fmaxf(m, lg[c]);
         float s = 0.f;
@@ -217,7 +221,15 @@ __device__ bool build_cost_block(const float* __restrict__ logits, const float* 
         // box_ops.py:9-14  (c,l) -> (c - l/2, 0, c + l/2, 1)
         const float s_p = cp - lp / 2.f, e_p = cp + lp / 2.f;
         const float s_t = ct - lt / 2.f, e_t = ct + lt / 2.f;
-        const float cost_class = -sp[q * C1 + (int)lab];                       // matcher.py:76
+        float cost_class = -sp[q * C1 + (int)lab];                             // matcher.py:76
+        if (fl) {                                                              // matcher.py:78-82
+            const float p = sp[q * C1 + (int)lab];
+            const float pg = gamma_fl == 1.f ? p : (gamma_fl == 2.f ? p * p : powf(p, gamma_fl));
+            const float qg = gamma_fl == 1.f ? 1.f - p : (gamma_fl == 2.f ? (1.f - p) * (1.f - p) : powf(1.f - p, gamma_fl));
+            const float neg = __fmul_rn(__fmul_rn(1.f - alpha_fl, pg), -logf(__fadd_rn(1.f - p, 1e-8f)));
+            const float pos = __fmul_rn(__fmul_rn(alpha_fl, qg), -logf(__fadd_rn(p, 1e-8f)));
+            cost_class = __fsub_rn(pos, neg);
+        }
         const float cost_bbox = __fadd_rn(fabsf(s_p - s_t), fabsf(e_p - e_t));   // matcher.py:85 (cdist p=1)
         // box_ops.py:29-42 with y-extent [0,1]
         const float area_p = e_p - s_p, area_t = e_t - s_t;
@@ -245,7 +257,8 @@ matcher_kernel(const float* __restrict__ logits, const float* __restrict__ boxes
                const float* __restrict__ cost_in, int ld_in,
                float* __restrict__ cost_out, int ld_out,
                int64_t* __restrict__ rows, int64_t* __restrict__ cols, int32_t* __restrict__ counts,
-               int32_t* __restrict__ status, int solve)
+               int32_t* __restrict__ status, int solve, int fl, float alpha_fl, float gamma_fl,
+               float* __restrict__ lmin, int64_t* __restrict__ largmin)
 {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -266,7 +279,29 @@ matcher_kernel(const float* __restrict__ logits, const float* __restrict__ boxes
         }
     } else {
         bad = build_cost_block(logits + (size_t)b * Q * C1, boxes + (size_t)b * Q * 2, tgt_labels + k0, tgt_boxes + (size_t)k0 * 2,
-                               Q, C1, K, w_class, w_bbox, w_giou, sc, sp, lane);
+                               Q, C1, K, w_class, w_bbox, w_giou, sc, sp, lane, fl, alpha_fl, gamma_fl);
+        if (lmin != nullptr) {
+            // fine_tune (matcher.py:99-106): per query the smallest location cost C_l = w_bbox * L1 + w_giou * (-GIoU) and its
+            // target (first minimum, as torch.min(-1))
+            for (int q = lane; q < Q; q += 32) {
+                const float cp = boxes[((size_t)b * Q + q) * 2], lp = boxes[((size_t)b * Q + q) * 2 + 1];
+                const float s_p = cp - lp / 2.f, e_p = cp + lp / 2.f;
+                float best = CUDART_INF_F; int bt = -1;
+                for (int t = 0; t < K; ++t) {
+                    const float ct = tgt_boxes[(size_t)(k0 + t) * 2], lt = tgt_boxes[(size_t)(k0 + t) * 2 + 1];
+                    const float s_t = ct - lt / 2.f, e_t = ct + lt / 2.f;
+                    const float cost_bbox = __fadd_rn(fabsf(s_p - s_t), fabsf(e_p - e_t));
+                    const float inter = fmaxf(fminf(e_p, e_t) - fmaxf(s_p, s_t), 0.f);
+                    const float uni = __fsub_rn(__fadd_rn(e_p - s_p, e_t - s_t), inter);
+                    const float enc = fmaxf(fmaxf(e_p, e_t) - fminf(s_p, s_t), 0.f);
+                    const float giou = __fsub_rn(__fdiv_rn(inter, uni), __fdiv_rn(__fsub_rn(enc, uni), enc));
+                    const float cl = __fadd_rn(__fmul_rn(w_bbox, cost_bbox), __fmul_rn(w_giou, -giou));
+                    if (cl < best || bt < 0) { best = cl; bt = t; }
+                }
+                lmin[(size_t)b * Q + q] = best;
+                largmin[(size_t)b * Q + q] = bt;
+            }
+        }
     }
     __syncwarp();
     if (cost_out != nullptr) {
@@ -485,9 +520,12 @@ set_criterion_finish_kernel(const float* __restrict__ partials, const float* __r
 int launch_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
                    const int32_t* offsets, int B, int Q, int C1, int Kmax, float w_class, float w_bbox, float w_giou,
                    const float* cost_in, int ld_in, float* cost_out, int ld_out,
-                   int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status, int solve, cudaStream_t stream)
+                   int64_t* rows, int64_t* cols, int32_t* counts, int32_t* status, int solve, cudaStream_t stream,
+                   int fl, float alpha_fl, float gamma_fl, float* lmin, int64_t* largmin)
 {
     if (B == 0) return SEDT_OK;
+    SEDT_REQUIRE((lmin == nullptr) == (largmin == nullptr), "matcher: lmin and largmin go together");
+    SEDT_REQUIRE(lmin == nullptr || cost_in == nullptr, "matcher: the location-cost minimum needs boxes, not a cost matrix");
     SEDT_REQUIRE(Q >= 1 && Kmax >= 0 && C1 >= 1, "matcher: bad sizes Q=%d Kmax=%d C1=%d", Q, Kmax, C1);
     const int nmax = Q > Kmax ? Q : Kmax;
     SEDT_REQUIRE(nmax <= 128, "matcher: max(Q, K)=%d exceeds the 128 supported by the warp solve", nmax);
@@ -502,7 +540,8 @@ int launch_matcher(const float* logits, const float* boxes, const int64_t* tgt_l
             SEDT_CHECK_CUDA(cudaFuncSetAttribute(matcher_kernel<CPL>,                                     \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         matcher_kernel<CPL><<<grid, block, smem, stream>>>(logits, boxes, tgt_labels, tgt_boxes, offsets, B, Q, C1, \
-            kpad, w_class, w_bbox, w_giou, cost_in, ld_in, cost_out, ld_out, rows, cols, counts, status, solve);  \
+            kpad, w_class, w_bbox, w_giou, cost_in, ld_in, cost_out, ld_out, rows, cols, counts, status, solve,   \
+            fl, alpha_fl, gamma_fl, lmin, largmin);                                                               \
     } while (0)
     if (nmax <= 32) SEDT_MATCHER_LAUNCH(1);
     else if (nmax <= 64) SEDT_MATCHER_LAUNCH(2);

@@ -37,9 +37,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// kArgmax (training forward): also records, per pooled element, which of the 9 window positions (dr * 3 + dc, first
+// maximum) supplied the value, or 9 when the window's maximum is <= 0 (dead ReLU: no gradient) -- the backward of
+// max-pool + ReLU (stem_bwd_kernel) then needs no recomputation of the convolution.
+template <bool kArgmax>
 __global__ void __launch_bounds__(128)
 stem_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wtc, const float* __restrict__ bias,
-               __nv_bfloat16* __restrict__ out, int T, int Hc, int Hp)
+               __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ amax, int T, int Hc, int Hp)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -159,6 +163,40 @@ stem_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wtc, con
         const int cg = i & 7, wp = (i >> 3) & 15, hl = i >> 7;
         const int hp = hp0 + hl;
         if (hp >= Hp) continue;
+        if constexpr (kArgmax) {
+            float best[8]; uint32_t arg[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { best[q] = 0.f; arg[q] = 9u; }
+#pragma unroll
+            for (int dr = 0; dr < 3; ++dr) {
+                const int hcc = 2 * hp - 1 + dr;
+                if (hcc < 0 || hcc >= Hc) continue;
+#pragma unroll
+                for (int dc = 0; dc < 3; ++dc) {
+                    const int wcc = 2 * wp - 1 + dc;
+                    if (wcc < 0 || wcc >= 32) continue;
+                    const int px = (2 * hl + dr) * 32 + wcc;
+                    const uint4 u = *reinterpret_cast<const uint4*>(smem + C_OFF + px * 128 + ((cg ^ (px & 7)) << 4));
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+                        if (f.x > best[2 * q]) { best[2 * q] = f.x; arg[2 * q] = (uint32_t)(dr * 3 + dc); }
+                        if (f.y > best[2 * q + 1]) { best[2 * q + 1] = f.y; arg[2 * q + 1] = (uint32_t)(dr * 3 + dc); }
+                    }
+                }
+            }
+            const size_t e = (((size_t)b * Hp + hp) * 16 + wp) * 64 + cg * 8;
+            uint4 o;
+            o.x = pack_bf16(best[0], best[1]); o.y = pack_bf16(best[2], best[3]);
+            o.z = pack_bf16(best[4], best[5]); o.w = pack_bf16(best[6], best[7]);
+            *reinterpret_cast<uint4*>(out + e) = o;
+            uint2 a;
+            a.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+            a.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+            *reinterpret_cast<uint2*>(amax + e) = a;
+            continue;
+        }
         __nv_bfloat162 m[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) m[q] = __floats2bfloat162_rn(0.f, 0.f);
@@ -225,7 +263,8 @@ int launch_stem_tc_pack(const float* conv0_w, const float* conv0_b, const float*
     return SEDT_OK;
 }
 
-int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, void* out, int B, int T, int F, cudaStream_t stream)
+int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, void* out, int B, int T, int F, cudaStream_t stream,
+                   uint8_t* amax)
 {
     SEDT_REQUIRE(F == 64, "stem: the fused stem kernel needs 64 mel bins (config.py n_mels), got F=%d", F);
     SEDT_REQUIRE(((uintptr_t)wtc & 15) == 0, "stem_tc: weight image must be 16-byte aligned");
@@ -233,12 +272,18 @@ int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, void* 
     const int Hc = (T - 1) / 2 + 1, Hp = (Hc - 1) / 2 + 1;
     static bool attr_set = false;
     if (!attr_set) {
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
         attr_set = true;
     }
     dim3 grid((unsigned)ceil_div(Hp, ST_PH), (unsigned)B), block(128);
     ProfScope _prof(PROF_STEM, stream);
-    stem_tc_kernel<<<grid, block, ST_SMEM, stream>>>(x, (const uint8_t*)wtc, bn_bias, (__nv_bfloat16*)out, T, Hc, Hp);
+    if (amax != nullptr) {
+        SEDT_REQUIRE(((uintptr_t)amax & 7) == 0, "stem_tc: arg-max buffer must be 8-byte aligned");
+        stem_tc_kernel<true><<<grid, block, ST_SMEM, stream>>>(x, (const uint8_t*)wtc, bn_bias, (__nv_bfloat16*)out, amax, T, Hc, Hp);
+    } else {
+        stem_tc_kernel<false><<<grid, block, ST_SMEM, stream>>>(x, (const uint8_t*)wtc, bn_bias, (__nv_bfloat16*)out, nullptr, T, Hc, Hp);
+    }
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;

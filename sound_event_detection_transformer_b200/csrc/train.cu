@@ -33,6 +33,7 @@ struct Model::Tape {
     unsigned long long* rng;    // {seed, step} of the dropout masks
     float* tmp32;               // GEMM output before dropout + residual add
     void* stem_out;
+    uint8_t* stem_amax;         // [B, H0, W0, 64] arg-max of the stem's pooling windows (9 = dead ReLU)
     std::vector<BlockTape> blk;
     uint8_t* mask_ds; float* pos; int64_t pos_rows;
     float* x0;
@@ -67,6 +68,7 @@ void Model::tape_layout(int B, int T, int F, bool has_mask, Arena& a, Tape& tp) 
     tp.W0 = conv_out_dim(conv_out_dim(F, 7, 2, 3, 1), 3, 2, 1, 1);
     tp.rng = (unsigned long long*)a.alloc(256);
     tp.stem_out = a.alloc((size_t)B * tp.H0 * tp.W0 * 64 * es);
+    tp.stem_amax = (uint8_t*)a.alloc((size_t)B * tp.H0 * tp.W0 * 64);
     int h = tp.H0, w = tp.W0;
     tp.blk.clear();
     for (const Block& b : blocks_) {
@@ -200,7 +202,7 @@ int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int 
     };
 
     // ---- backbone
-    SEDT_TRY(launch_stem_tc(x, packed_ + off_stem_wtc, P_(off_stem_bias), tp.stem_out, B, T, F, s));
+    SEDT_TRY(launch_stem_tc(x, packed_ + off_stem_wtc, P_(off_stem_bias), tp.stem_out, B, T, F, s, tp.stem_amax));
     const void* cur = tp.stem_out;
     for (size_t i = 0; i < blocks_.size(); ++i) {
         const Block& b = blocks_[i];
@@ -620,8 +622,7 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
         std::swap(G, Gn);
     }
     // G = d(loss)/d(stem output): conv0 is the only trainable parameter below (sedt/backbone.py:60,102)
-    return launch_stem_bwd(x, Wp(s_conv0_w), Wp(s_conv0_b), Wp(s_conv1_w), P_(off_stem_scale), P_(off_stem_bias), G, bb.dw,
-                           Gp(s_conv0_w), Gp(s_conv0_b), B, T, F, s);
+    return launch_stem_bwd(x, Wp(s_conv1_w), P_(off_stem_scale), G, tp.stem_amax, bb.dw, Gp(s_conv0_w), Gp(s_conv0_b), B, T, F, s);
 }
 
 }  // namespace sedt
