@@ -181,6 +181,19 @@ SEDT_API int sedt_set_criterion(const float* logits, const float* boxes, const f
                                 int64_t* rows, int64_t* cols, int32_t* status, float* partials, float* losses,
                                 float* g_logits, float* g_l1, float* g_giou, float* g_at, void* stream);
 
+/* ---- The consumer right after the eval forward (engine.py:277-291): PostProcess.forward (sedt/sedt.py:359-396) and
+ * BoxEncoder.decode_strong with del_overlap (utilities/BoxEncoder.py:179-226), one warp per clip.
+ *   logits [B, Q, C1], boxes [B, Q, 2] (center, width), target_sizes [B] seconds (ignored when is_semi)
+ *   audio_tags [B, C1-1] fp32 0/1 or null; at_m 1/2/3 = `fusion_strategy` (train_sedt.py:71); fuse_threshold = PostProcess's
+ *   `threshold` (0.5); score_threshold = decode_strong's threshold; min_duration = 0.2 s (BoxEncoder.py:205)
+ *   scores [B, Q], labels [B, Q] int64, boxes_se [B, Q, 2]: the PostProcess result
+ *   ev_class / ev_onset / ev_offset / ev_score [B, Q], ev_count [B]: decoded events per clip in the reference's order
+ *   (classes by first appearance among the kept queries, events of a class by onset); pass ev_count = null to skip decoding. */
+SEDT_API int sedt_decode_events(const float* logits, const float* boxes, const float* target_sizes, const float* audio_tags,
+                                int B, int Q, int C1, int at_m, float fuse_threshold, int is_semi, float score_threshold,
+                                float min_duration, float* scores, int64_t* labels, float* boxes_se, int32_t* ev_class,
+                                float* ev_onset, float* ev_offset, float* ev_score, int32_t* ev_count, void* stream);
+
 /* ---- clip_grad_norm_ + AdamW: the optimizer half of the training step (engine.py:76-80; AdamW with two lr groups,
  * train_sedt.py:234-240,269-270; torch/optim/adamw.py _single_tensor_adamw arithmetic, amsgrad = maximize = False).
  * The caller keeps a device table of tensors and a device table of (tensor index, chunk index) pairs that splits

@@ -201,6 +201,16 @@ int sedt_set_criterion(const float* logits, const float* boxes, const float* at,
                                 g_logits, g_l1, g_giou, g_at, (cudaStream_t)stream);
 }
 
+int sedt_decode_events(const float* logits, const float* boxes, const float* target_sizes, const float* audio_tags, int B, int Q,
+                       int C1, int at_m, float fuse_threshold, int is_semi, float score_threshold, float min_duration,
+                       float* scores, int64_t* labels, float* boxes_se, int32_t* ev_class, float* ev_onset, float* ev_offset,
+                       float* ev_score, int32_t* ev_count, void* stream)
+{
+    return launch_decode_events(logits, boxes, target_sizes, audio_tags, B, Q, C1, at_m, fuse_threshold, is_semi, score_threshold,
+                                min_duration, scores, labels, boxes_se, ev_class, ev_onset, ev_offset, ev_score, ev_count,
+                                (cudaStream_t)stream);
+}
+
 int sedt_optim_chunk_elems(void) { return optim_chunk_elems(); }
 
 int sedt_grad_norm(const sedt_optim_tensor* tensors, const int32_t* chunks, int nchunks, float* partials, float* norm_out, void* stream)

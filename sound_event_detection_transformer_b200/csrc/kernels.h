@@ -184,6 +184,12 @@ int launch_set_criterion(const float* logits, const float* boxes, const float* a
                          float eos_coef, float num_boxes, int64_t* rows, int64_t* cols, int32_t* status, float* partials,
                          float* losses, float* g_logits, float* g_l1, float* g_giou, float* g_at, cudaStream_t stream);
 
+// ---- decode.cu: PostProcess.forward + BoxEncoder.decode_strong (sedt/sedt.py:359-396, utilities/BoxEncoder.py:179-226)
+int launch_decode_events(const float* logits, const float* boxes, const float* sizes, const float* tags, int B, int Q, int C1,
+                         int at_m, float fuse_threshold, int is_semi, float score_threshold, float min_duration,
+                         float* out_scores, int64_t* out_labels, float* out_boxes, int32_t* ev_class, float* ev_onset,
+                         float* ev_offset, float* ev_score, int32_t* ev_count, cudaStream_t stream);
+
 // ---- optim.cu: clip_grad_norm_ + AdamW over a (tensor, chunk) table (engine.py:76-80)
 int optim_chunk_elems();
 int launch_grad_norm(const void* tensors, const int32_t* chunks, int nchunks, float* partials, float* norm_out, cudaStream_t stream);

@@ -49,6 +49,30 @@ def _common_base(ts: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
     return base
 
 
+ALPHA_FL, GAMMA_FL = 0.5, 1.0          # config.py:71-72
+
+
+def sigmoid_focal_loss(inputs, targets, weight=None, alpha=ALPHA_FL, gamma=GAMMA_FL):
+    """Per-query focal loss on the class logits (sedt/sedt.py:412-421; the semi-supervised recipe's `fl` branch)."""
+    prob = inputs.sigmoid()
+    ce = F.binary_cross_entropy_with_logits(inputs, targets, pos_weight=weight, reduction="none")
+    p_t = prob * targets + (1 - prob) * (1 - targets)
+    loss = ce * (1 - p_t) ** gamma
+    if alpha >= 0:
+        loss = (alpha * targets + (1 - alpha) * (1 - targets)) * loss
+    return loss.sum(2)
+
+
+def weak_focal_loss(prob, targets, alpha=ALPHA_FL, gamma=GAMMA_FL):
+    """Focal variant of the clip-level tagging loss (sedt/sedt.py:424-433)."""
+    ce = F.binary_cross_entropy(prob, targets, reduction="none")
+    p_t = prob * targets + (1 - prob) * (1 - targets)
+    loss = ce * (1 - p_t) ** gamma
+    if alpha >= 0:
+        loss = (alpha * targets + (1 - alpha) * (1 - targets)) * loss
+    return loss.sum(1).mean()
+
+
 class _FusedSetLoss(torch.autograd.Function):
     """sedt_set_criterion: matcher + losses + gradients of all decoder layers in two launches.  Outputs: one 0-dim
     tensor per requested (layer, loss); backward scales the stored gradients by the incoming scalars."""
@@ -216,7 +240,7 @@ class SetCriterion(nn.Module):
         src = torch.cat([src for src, _ in indices]).to(device)
         return batch, src
 
-    def _layer_losses(self, out, targets, indices, coef, num_boxes, strong_mask, log: bool):
+    def _layer_losses(self, out, targets, indices, coef, num_boxes, strong_mask, log: bool, fl: bool = False):
         res = {}
         dev = out["pred_logits"].device
         tg = targets[strong_mask]
@@ -229,7 +253,11 @@ class SetCriterion(nn.Module):
             wq = torch.ones(logits.shape[:2], dtype=torch.float32, device=dev)
             cls[bi, si] = matched
             wq[bi, si] = coef_cat
-            ce = F.cross_entropy(logits.transpose(1, 2), cls, self.empty_weight, reduction="none")
+            if fl:                                       # sedt.py:209-217: one-hot over C+1 columns, no-object included
+                onehot = F.one_hot(cls, logits.shape[2]).to(logits.dtype)
+                ce = sigmoid_focal_loss(logits, onehot, self.empty_weight)
+            else:
+                ce = F.cross_entropy(logits.transpose(1, 2), cls, self.empty_weight, reduction="none")
             res["loss_ce"] = (ce * wq).sum() / num_boxes
             if log:
                 if matched.numel() == 0:                 # utilities/utils.py:566-567: accuracy() is 0 without targets
@@ -258,7 +286,7 @@ class SetCriterion(nn.Module):
             res["loss_feature"] = F.mse_loss(src, tgt, reduction="none").sum() / num_boxes
         return res
 
-    def _weak_loss(self, outputs, targets, strong_mask, weak_mask):
+    def _weak_loss(self, outputs, targets, strong_mask, weak_mask, fl: bool = False):
         if "at" not in outputs:
             return {}
         labeled = slice(weak_mask.stop) if weak_mask is not None else slice(strong_mask.stop)
@@ -277,7 +305,8 @@ class SetCriterion(nn.Module):
             else:
                 vals = torch.ones(sum(sizes), device=dev)
             gt.index_put_((rows, cols), vals, accumulate=True)
-        return {"loss_weak": F.binary_cross_entropy(pred, gt.clamp(0, 1))}
+        gt = gt.clamp(0, 1)
+        return {"loss_weak": weak_focal_loss(pred, gt) if fl else F.binary_cross_entropy(pred, gt)}
 
     # -- batched path: no per-clip work, no host round trip between the matcher and the losses --------------
     def _batched_ok(self, tg, fine_tune, normalize) -> bool:
@@ -329,13 +358,11 @@ class SetCriterion(nn.Module):
 
     # -- reference entry point ---------------------------------------------------
     def forward(self, outputs, targets, weak_mask=None, strong_mask=None, fine_tune=False, normalize=False, fl=False):
-        if fl:
-            raise NotImplementedError("focal-loss branch (semi-supervised only) is out of scope (SURVEY.md section 2, #9)")
-        if self._fused_ok(outputs, targets, strong_mask, weak_mask, fine_tune, normalize):
+        if not fl and self._fused_ok(outputs, targets, strong_mask, weak_mask, fine_tune, normalize):
             return self._forward_fused(outputs, targets, strong_mask, weak_mask)
         losses = {}
         indices = None
-        if strong_mask is not None and self._batched_ok(targets[strong_mask], fine_tune, normalize):
+        if not fl and strong_mask is not None and self._batched_ok(targets[strong_mask], fine_tune, normalize):
             tg = targets[strong_mask]
             top = {k: v[strong_mask] for k, v in outputs.items() if k != "aux_outputs"}
             dev = top["pred_logits"].device
@@ -366,23 +393,84 @@ class SetCriterion(nn.Module):
             indices, coef = self.matcher(top, targets[strong_mask], fine_tune=fine_tune, normalize=normalize, fl=fl)
             num_boxes = torch.cat(coef).sum()
             num_boxes = torch.as_tensor([num_boxes], dtype=torch.float, device=outputs["pred_boxes"].device)
-            losses.update(self._layer_losses(outputs, targets, indices, coef, num_boxes, strong_mask, log=True))
+            losses.update(self._layer_losses(outputs, targets, indices, coef, num_boxes, strong_mask, log=True, fl=fl))
         if "weak" in self.losses:
-            losses.update(self._weak_loss(outputs, targets, strong_mask, weak_mask))
+            losses.update(self._weak_loss(outputs, targets, strong_mask, weak_mask, fl=fl))
         if "aux_outputs" in outputs and strong_mask is not None:
             for i, aux in enumerate(outputs["aux_outputs"]):
                 sub = {k: v[strong_mask] for k, v in aux.items()}
                 sub_idx, sub_coef = self.matcher(sub, targets[strong_mask], fl=fl)
-                part = self._layer_losses(aux, targets, sub_idx, sub_coef, num_boxes, strong_mask, log=False)
+                part = self._layer_losses(aux, targets, sub_idx, sub_coef, num_boxes, strong_mask, log=False, fl=fl)
                 losses.update({f"{k}_{i}": v for k, v in part.items()})
         return losses, indices
 
 
 class PostProcess(nn.Module):
-    """outputs -> per-clip {'scores','labels','boxes'} in seconds (sedt/sedt.py:359-396)."""
+    """outputs -> per-clip {'scores','labels','boxes'} in seconds (sedt/sedt.py:359-396).  On CUDA tensors the whole
+    batch is one sedt_decode_events launch (softmax, at_m fusion, arg-max, (c,l)->(s,e)); `decode_events` also runs
+    BoxEncoder.decode_strong (utilities/BoxEncoder.py:179-226) in the same launch."""
+
+    @staticmethod
+    def _run(outputs, target_sizes, audio_tags, at_m, is_semi, threshold, decode_threshold=None):
+        from .. import _lib
+        lib = _lib.load()
+        logits = outputs["pred_logits"].detach().to(torch.float32).contiguous()
+        boxes = outputs["pred_boxes"].detach().to(torch.float32).contiguous()
+        dev = logits.device
+        B, Q, C1 = logits.shape
+        sizes = None if is_semi else torch.as_tensor(target_sizes).to(dev, torch.float32).reshape(-1).contiguous()
+        if sizes is not None and sizes.numel() != B:
+            raise ValueError(f"target_sizes has {sizes.numel()} entries for a batch of {B}")
+        tags = None
+        if audio_tags is not None:
+            tags = audio_tags.to(dev, torch.float32).reshape(B, C1 - 1).contiguous()
+        scores = torch.empty(B, Q, dtype=torch.float32, device=dev)
+        labels = torch.empty(B, Q, dtype=torch.int64, device=dev)
+        se = torch.empty(B, Q, 2, dtype=torch.float32, device=dev)
+        ev = None
+        if decode_threshold is not None:
+            ev = {"cls": torch.empty(B, Q, dtype=torch.int32, device=dev), "onset": torch.empty(B, Q, device=dev),
+                  "offset": torch.empty(B, Q, device=dev), "score": torch.empty(B, Q, device=dev),
+                  "count": torch.zeros(B, dtype=torch.int32, device=dev)}
+        with torch.cuda.device(dev):
+            _lib.check(lib.sedt_decode_events(
+                logits.data_ptr(), boxes.data_ptr(), _lib.ptr(sizes) or None, _lib.ptr(tags) or None, B, Q, C1, int(at_m),
+                float(threshold), int(bool(is_semi)), float(decode_threshold if decode_threshold is not None else 0.0), 0.2,
+                scores.data_ptr(), labels.data_ptr(), se.data_ptr(),
+                *( [ev[k].data_ptr() for k in ("cls", "onset", "offset", "score", "count")] if ev else [None] * 5),
+                _lib.current_stream()))
+        return scores, labels, se, ev
 
     @torch.no_grad()
     def forward(self, outputs, target_sizes, audio_tags=None, at_m=2, is_semi=False, threshold=0.5):
+        if outputs["pred_logits"].is_cuda:
+            scores, labels, se, _ = self._run(outputs, target_sizes, audio_tags, at_m, is_semi, threshold)
+            return [{"scores": s, "labels": lb, "boxes": b} for s, lb, b in zip(scores, labels, se)]
+        return self._forward_torch(outputs, target_sizes, audio_tags, at_m, is_semi, threshold)
+
+    @torch.no_grad()
+    def decode_events(self, outputs, target_sizes, audio_tags=None, at_m=2, threshold=0.5, decode_threshold=0.5,
+                      class_names: Optional[Sequence[str]] = None):
+        """PostProcess + BoxEncoder.decode_strong(res, decode_threshold) for the whole batch (engine.py:277-291 without
+        the per-clip Python loop).  Returns one list per clip of [label, onset, offset, score] (label = class name if
+        class_names is given, else the class index), in the reference's order.  One launch, one device->host copy."""
+        if not outputs["pred_logits"].is_cuda:
+            raise RuntimeError("decode_events needs CUDA tensors (there is no CPU path)")
+        _, _, _, ev = self._run(outputs, target_sizes, audio_tags, at_m, False, threshold, decode_threshold)
+        B, Q = ev["cls"].shape
+        packed = torch.cat([ev["count"].to(torch.float64).reshape(B, 1), ev["cls"].to(torch.float64),
+                            ev["onset"].to(torch.float64), ev["offset"].to(torch.float64),
+                            ev["score"].to(torch.float64)], dim=1).cpu().numpy()
+        out = []
+        for row in packed:
+            n = int(row[0])
+            cls, on, off, sc = row[1:1 + Q], row[1 + Q:1 + 2 * Q], row[1 + 2 * Q:1 + 3 * Q], row[1 + 3 * Q:]
+            out.append([[class_names[int(cls[i])] if class_names is not None else int(cls[i]), float(on[i]), float(off[i]),
+                         float(sc[i])] for i in range(n)])
+        return out
+
+    @torch.no_grad()
+    def _forward_torch(self, outputs, target_sizes, audio_tags=None, at_m=2, is_semi=False, threshold=0.5):
         logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
         prob = F.softmax(logits, -1)
         nq = prob.shape[1]

@@ -1,7 +1,9 @@
 """HungarianMatcher with the reference's call contract (sedt/matcher.py:41-133)
 running on the GPU: one sedt_matcher launch builds every clip's cost block and
 solves it (one warp per clip), replacing the [B*Q, sum K] cross-batch matrix,
-the .cpu() copy and the serial scipy loop."""
+the .cpu() copy and the serial scipy loop.  All of the reference's branches are
+covered: the focal class cost (fl), the fine_tune relaxation, and the
+normalize / mixup-ratio coefficients."""
 from __future__ import annotations
 
 import ctypes as C
@@ -21,22 +23,28 @@ class HungarianMatcher(nn.Module):
         self.epsilon, self.alpha = epsilon, alpha
         assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0, "all costs cant be 0"
         self.device_indices = False      # True: keep index tensors on the GPU (skips the D2H copy + sync)
+        self.alpha_fl, self.gamma_fl = 0.5, 1.0      # config.py:71-72 (module constants in the reference)
 
     @torch.no_grad()
     def forward(self, outputs, targets: Sequence[dict], fine_tune=False, normalize=False, fl=False):
         """Returns (indices, Coef): indices[i] = (int64 rows ascending, int64 cols) with
         len = min(num_queries, K_i); Coef[i] fp32 (ones | 1/multiplicity | targets[i]['ratio'])."""
-        if fl or fine_tune:
-            raise NotImplementedError("the focal-loss class cost (fl) and the fine_tune relaxation "
-                                      "(sedt/matcher.py:77-82,99-121) are not on the B200 hot path yet (SURVEY 8f.3)")
-        rows, cols, counts = self.match(outputs["pred_logits"], outputs["pred_boxes"], targets)
+        if fine_tune:
+            rows, cols, counts, lmin, largmin = self.match(outputs["pred_logits"], outputs["pred_boxes"], targets, fl=fl,
+                                                           want_lmin=True)
+        else:
+            rows, cols, counts = self.match(outputs["pred_logits"], outputs["pred_boxes"], targets, fl=fl)
         # compact the padded [B,Q] index matrices once on the device, then one split on the host
         valid = rows >= 0
         flat_r, flat_c = rows[valid], cols[valid]
-        if not self.device_indices:
+        if not self.device_indices or fine_tune:
             flat_r, flat_c = flat_r.cpu(), flat_c.cpu()
         rs, cs = flat_r.split(counts), flat_c.split(counts)
         idx: List[Tuple[torch.Tensor, torch.Tensor]] = list(zip(rs, cs))
+        if fine_tune:
+            idx = self._relax(idx, lmin.cpu(), largmin.cpu(), rows.shape[1], [int(len(v["boxes"])) for v in targets])
+            rs, cs = [r for r, _ in idx], [c for _, c in idx]
+            counts = [len(r) for r in rs]
         coef: List[torch.Tensor] = []
         if normalize or any("ratio" in t for t in targets):
             for i, n in enumerate(counts):
@@ -51,6 +59,28 @@ class HungarianMatcher(nn.Module):
         else:
             coef = list(torch.ones(sum(counts), dtype=torch.float32).split(counts))
         return idx, coef
+
+    def _relax(self, idx1, lmin, largmin, num_queries, sizes):
+        """The fine_tune relaxation (sedt/matcher.py:99-121), statement for statement on the kernel's per-query location-cost
+        minimum / arg-min: Hungarian pairs survive only where the query's best location cost is below epsilon; other
+        queries below epsilon are attached to their nearest target, each kept with probability alpha * num_gt / num_queries
+        (torch.rand on the host generator, drawn per clip in the reference's order, so a seeded run reproduces it)."""
+        out = []
+        for b, (r, c) in enumerate(idx1):
+            if sizes[b] == 0:
+                raise IndexError("fine_tune matching needs at least one target per clip "
+                                 "(the reference's c[i].min(-1) fails on an empty target list, sedt/matcher.py:106)")
+            num_gt = len(c)
+            reserved = lmin[b] < self.epsilon
+            keep = reserved[r] == True                                   # noqa: E712
+            r, c = r[keep], c[keep]
+            reserved[r] = False
+            reserved_index = torch.where(reserved == True)[0]            # noqa: E712
+            random_del_index = torch.where(torch.rand(len(reserved_index)) > (self.alpha * num_gt / num_queries))[0]
+            reserved[reserved_index[random_del_index]] = False
+            out.append((torch.cat([r, torch.arange(num_queries)[reserved]], dim=-1),
+                        torch.cat([c, largmin[b][reserved]], dim=-1)))
+        return out
 
     @staticmethod
     def pack_targets(targets: Sequence[dict], dev) -> dict:
@@ -72,7 +102,7 @@ class HungarianMatcher(nn.Module):
 
     @torch.no_grad()
     def match(self, pred_logits: torch.Tensor, pred_boxes: torch.Tensor, targets: Sequence[dict],
-              return_cost: bool = False, packed: dict = None, check: bool = True):
+              return_cost: bool = False, packed: dict = None, check: bool = True, fl: bool = False, want_lmin: bool = False):
         """Raw batched call: returns rows [B,Q] int64, cols [B,Q] int64 on the device (every clip's pairs first,
         sorted by query, then -1 padding) and the per-clip pair counts as a Python list (known on the host:
         min(Q, K_i)).  packed: a pack_targets() result to reuse; check=False skips the status read-back (no
@@ -111,16 +141,22 @@ class HungarianMatcher(nn.Module):
         counts = torch.empty(B, dtype=torch.int32, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         cost = torch.full((B, Q, max(kmax, 1)), float("nan"), dtype=torch.float32, device=dev) if return_cost else None
+        lmin = torch.empty(B, Q, dtype=torch.float32, device=dev) if want_lmin else None
+        largmin = torch.empty(B, Q, dtype=torch.int64, device=dev) if want_lmin else None
         with torch.cuda.device(dev):
-            _lib.check(lib.sedt_matcher(logits.data_ptr(), boxes.data_ptr(), tgt_ids.data_ptr(), tgt_box.data_ptr(),
-                                        offsets.data_ptr(), B, Q, C1, kmax, float(self.cost_class), float(self.cost_bbox),
-                                        float(self.cost_giou), _lib.ptr(cost) or None, max(kmax, 1), rows.data_ptr(),
-                                        cols.data_ptr(), counts.data_ptr(), status.data_ptr(), _lib.current_stream()))
+            _lib.check(lib.sedt_matcher_ex(logits.data_ptr(), boxes.data_ptr(), tgt_ids.data_ptr(), tgt_box.data_ptr(),
+                                           offsets.data_ptr(), B, Q, C1, kmax, float(self.cost_class), float(self.cost_bbox),
+                                           float(self.cost_giou), int(bool(fl)), float(self.alpha_fl), float(self.gamma_fl),
+                                           _lib.ptr(cost) or None, max(kmax, 1), rows.data_ptr(), cols.data_ptr(),
+                                           counts.data_ptr(), status.data_ptr(), _lib.ptr(lmin) or None,
+                                           _lib.ptr(largmin) or None, _lib.current_stream()))
         n = [min(Q, k) for k in sizes]
         if not check:
             return rows, cols, n, status
-        if not self.device_indices:
+        if not self.device_indices or want_lmin:
             self.raise_on_status(int(status.item()))
+        if want_lmin:
+            return rows, cols, n, lmin, largmin
         if return_cost:
             return rows, cols, n, cost
         return rows, cols, n

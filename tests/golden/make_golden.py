@@ -138,7 +138,27 @@ def run_matcher(tag, B, Q, C, kmin, kmax, seed, chunk=32, normalize=False):
     print(f"matcher_{tag}: {B} clips, {int(np.sum(counts))} pairs")
 
 
-def run_criterion(tag, args, B, seed, kmin=0, kmax=10):
+def run_matcher_variant(tag, B, Q, C, kmin, kmax, seed, fine_tune=False, normalize=False, fl=False, epsilon=1.0, alpha=1.0,
+                        rng_seed=1234):
+    """The matcher's other branches (sedt/matcher.py:77-82 focal cost, :99-121 fine_tune relaxation, :123-133 coefficients).
+    fine_tune draws torch.rand per clip from the global CPU generator: it is seeded with rng_seed right before the call and
+    the test does the same."""
+    args = spec.default_args()
+    args.epsilon, args.alpha = epsilon, alpha
+    matcher = build_matcher(args)
+    outputs, targets = synth.synth_matcher_case(B, Q, C, kmin, kmax, seed)
+    torch.manual_seed(rng_seed)
+    idx, coef = matcher(outputs, targets, fine_tune=fine_tune, normalize=normalize, fl=fl)
+    np.savez_compressed(os.path.join(HERE, f"matcher_{tag}.npz"),
+                        rows=np.concatenate([r.numpy() for r, _ in idx]), cols=np.concatenate([c.numpy() for _, c in idx]),
+                        coef=np.concatenate([c.numpy() for c in coef]).astype(np.float32),
+                        counts=np.asarray([len(r) for r, _ in idx], np.int32),
+                        meta=np.asarray([B, Q, C, kmin, kmax, seed, int(fine_tune), int(normalize), int(fl), rng_seed], np.int64),
+                        fmeta=np.asarray([epsilon, alpha], np.float64))
+    print(f"matcher_{tag}: {B} clips, {sum(len(r) for r, _ in idx)} pairs")
+
+
+def run_criterion(tag, args, B, seed, kmin=0, kmax=10, fine_tune=False, normalize=False, fl=False, rng_seed=1234):
     """Reference SetCriterion (sedt/sedt.py:134-352) built directly (build_model returns None for it
     without CUDA) on seeded model-shaped outputs: every loss value and the gradient of the weighted sum."""
     from sedt.sedt import SetCriterion
@@ -154,11 +174,14 @@ def run_criterion(tag, args, B, seed, kmin=0, kmax=10):
         leaves += [a["pred_logits"], a["pred_boxes"]]
     for t in leaves:
         t.requires_grad_(True)
-    losses, indices = crit(outputs, np.array(targets, dtype=object), None, slice(B))
+    torch.manual_seed(rng_seed)
+    losses, indices = crit(outputs, np.array(targets, dtype=object), None, slice(B), fine_tune=fine_tune, normalize=normalize,
+                           fl=fl)
     total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)
     total.backward()
     fx = {"loss_names": np.array(sorted(losses)), "loss_values": np.array([float(losses[k]) for k in sorted(losses)], np.float64),
-          "total": np.float64(float(total)), "meta": np.asarray([B, kmin, kmax, seed], np.int64)}
+          "total": np.float64(float(total)), "meta": np.asarray([B, kmin, kmax, seed], np.int64),
+          "flags": np.asarray([int(fine_tune), int(normalize), int(fl), rng_seed], np.int64)}
     for i, t in enumerate(leaves):
         fx[f"grad_{i}"] = t.grad.numpy()
     np.savez_compressed(os.path.join(HERE, f"criterion_{tag}.npz"), **fx)
@@ -168,6 +191,13 @@ def run_criterion(tag, args, B, seed, kmin=0, kmax=10):
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-variants" in sys.argv:
+        run_matcher_variant("v_fl", 64, 20, 10, 0, 10, seed=21, fl=True)
+        run_matcher_variant("v_finetune", 64, 20, 10, 1, 10, seed=22, fine_tune=True, normalize=True, epsilon=1.0, alpha=1.0)
+        run_matcher_variant("v_finetune_q10", 32, 10, 10, 1, 6, seed=23, fine_tune=True, epsilon=0.5, alpha=2.0, fl=True)
+        run_criterion("v_fl", spec.config_args("c1"), 12, seed=24, fl=True)
+        run_criterion("v_finetune", spec.config_args("c1"), 12, seed=25, kmin=1, kmax=6, fine_tune=True, normalize=True)
+        sys.exit(0)
     if "--only-criterion" in sys.argv:
         run_criterion("c2", spec.config_args("c2"), 48, seed=1)
         run_criterion("c1_edges", spec.config_args("c1"), 16, seed=2, kmin=8, kmax=14)

@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 def _run(tag, cfg, path):
     fx = np.load(os.path.join(GOLDEN, f"criterion_{tag}.npz"))
     B, kmin, kmax, seed = [int(v) for v in fx["meta"]]
+    fine_tune, normalize, fl, rng_seed = [int(v) for v in fx["flags"]] if "flags" in fx else (0, 0, 0, 0)
     args = spec.config_args(cfg)
     _, criterion, _ = build_model(args)
     criterion = criterion.cuda()
@@ -33,7 +34,9 @@ def _run(tag, cfg, path):
         leaves += [a["pred_logits"], a["pred_boxes"]]
     for t in targets:
         t["labels"], t["boxes"] = t["labels"].cuda(), t["boxes"].cuda()
-    losses, indices = criterion(outputs, np.array(targets, dtype=object), None, slice(B))
+    torch.manual_seed(rng_seed)
+    losses, indices = criterion(outputs, np.array(targets, dtype=object), None, slice(B), fine_tune=bool(fine_tune),
+                                normalize=bool(normalize), fl=bool(fl))
     wd = criterion.weight_dict
     total = sum(losses[k] * wd[k] for k in losses if k in wd)
     total.backward()
@@ -45,14 +48,21 @@ def _run(tag, cfg, path):
     for i, t in enumerate(leaves):
         ref = torch.from_numpy(fx[f"grad_{i}"])
         assert (t.grad.cpu() - ref).abs().max() <= 1e-6 + 1e-4 * ref.abs().max(), i
-    assert len(indices) == B and all(len(r) == len(c) == min(args.num_queries, len(t["boxes"]))
-                                     for (r, c), t in zip(indices, targets))
+    assert len(indices) == B
+    if not fine_tune:
+        assert all(len(r) == len(c) == min(args.num_queries, len(t["boxes"])) for (r, c), t in zip(indices, targets))
 
 
 @pytest.mark.parametrize("path", ["fused", "batched", "per_clip"])
 @pytest.mark.parametrize("tag,cfg", [("c2", "c2"), ("c1_edges", "c1")])
 def test_set_criterion_matches_reference(tag, cfg, path):
     _run(tag, cfg, path)
+
+
+@pytest.mark.parametrize("tag", ["v_fl", "v_finetune"])
+def test_set_criterion_variants_match_reference(tag):
+    """focal losses (fl) and the fine_tune + normalize recipe (train_sedt.py:298-310) against the reference's SetCriterion."""
+    _run(tag, "c1", "fused")          # these flags route around the fused kernel by themselves
 
 
 def test_fused_criterion_strong_and_weak_subsets():

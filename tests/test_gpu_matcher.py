@@ -39,6 +39,31 @@ def test_matcher_matches_reference_golden(tag, normalize):
         assert cf.dtype == torch.float32 and np.allclose(cf.numpy(), ocf)
 
 
+@pytest.mark.parametrize("tag", ["v_fl", "v_finetune", "v_finetune_q10"])
+def test_matcher_variants_match_reference_golden(tag):
+    """fl (focal class cost), fine_tune (relaxation with the host generator seeded like the reference run) and
+    normalize, bit-exact against the reference's own outputs (sedt/matcher.py:77-82,99-133)."""
+    fx = np.load(os.path.join(GOLDEN, f"matcher_{tag}.npz"))
+    B, Q, C, kmin, kmax, seed, fine_tune, normalize, fl, rng_seed = [int(v) for v in fx["meta"]]
+    args = spec.default_args()
+    args.epsilon, args.alpha = [float(v) for v in fx["fmeta"]]
+    outputs, targets = synth.synth_matcher_case(B, Q, C, kmin, kmax, seed)
+    matcher = build_matcher(args)
+    torch.manual_seed(rng_seed)
+    idx, coef = matcher(*_to_cuda(outputs, targets), fine_tune=bool(fine_tune), normalize=bool(normalize), fl=bool(fl))
+    assert np.array_equal(np.asarray([len(r) for r, _ in idx], np.int32), fx["counts"])
+    assert np.array_equal(torch.cat([r for r, _ in idx]).numpy(), fx["rows"])
+    assert np.array_equal(torch.cat([c for _, c in idx]).numpy(), fx["cols"])
+    assert np.allclose(torch.cat(coef).numpy(), fx["coef"])
+
+
+def test_fine_tune_without_targets_raises_like_the_reference():
+    outputs, targets = synth.synth_matcher_case(4, 20, 10, 0, 0, seed=1)
+    matcher = build_matcher(spec.default_args())
+    with pytest.raises(IndexError):
+        matcher(*_to_cuda(outputs, targets), fine_tune=True)
+
+
 def test_matcher_cost_matrix_matches_oracle():
     outputs, targets = synth.synth_matcher_case(97, 20, 10, 0, 12, seed=11)
     matcher = build_matcher(spec.default_args())

@@ -109,3 +109,22 @@ def test_matcher_oracle_matches_reference(tag, normalize, solver):
     for (r, c), cf, t in zip(idx, coef, targets):
         assert len(r) == min(Q, len(t["boxes"])) and cf.shape == c.shape
         assert np.all(np.diff(r) > 0)
+
+
+@pytest.mark.parametrize("tag", ["v_fl", "v_finetune", "v_finetune_q10"])
+def test_matcher_oracle_variants_match_reference(tag):
+    """focal class cost, fine_tune relaxation (seeded torch.rand, per clip, reference order) and normalize coefficients
+    against indices / Coef produced by the reference's own HungarianMatcher (make_golden.py: run_matcher_variant)."""
+    fx = np.load(os.path.join(GOLDEN, f"matcher_{tag}.npz"))
+    B, Q, C, kmin, kmax, seed, fine_tune, normalize, fl, rng_seed = [int(v) for v in fx["meta"]]
+    epsilon, alpha = [float(v) for v in fx["fmeta"]]
+    outputs, targets = synth.synth_matcher_case(B, Q, C, kmin, kmax, seed)
+    torch.manual_seed(rng_seed)
+    idx, coef = matcher_oracle.hungarian_matcher(
+        {k: v.numpy() for k, v in outputs.items()}, [{k: v.numpy() for k, v in t.items()} for t in targets],
+        normalize=bool(normalize), fl=bool(fl), fine_tune=bool(fine_tune), epsilon=epsilon, alpha=alpha,
+        rand=lambda n: torch.rand(n).numpy())
+    assert np.array_equal(np.asarray([len(r) for r, _ in idx], np.int32), fx["counts"])
+    assert np.array_equal(np.concatenate([r for r, _ in idx]), fx["rows"])
+    assert np.array_equal(np.concatenate([c for _, c in idx]), fx["cols"])
+    assert np.allclose(np.concatenate(coef), fx["coef"])
