@@ -67,6 +67,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc<128>(tmem_slot);
+    pdl_wait();            // Q, K, V come from the preceding projection kernels
 
     // ---- stage Q, K (row t) and V^T (column t) ----------------------------------------------
     {
@@ -104,6 +105,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfl
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();         // TMEM is owned: a successor scheduled next to this CTA cannot starve it
     const uint32_t tmem_base = *tmem_slot;
 
     // ---- S = Q K^T -----------------------------------------------------------------------------
@@ -255,9 +257,9 @@ static int launch_att_variant(const void* Q, int ldq, const void* K, int ldk, co
     }
     dim3 grid((unsigned)nheads, (unsigned)B), block(ATT_THREADS);
     ProfScope _prof(PROF_ATTENTION, stream);
-    attention_tc_kernel<AM, DR><<<grid, block, ATT_SMEM, stream>>>((const __nv_bfloat16*)Q, ldq, (const __nv_bfloat16*)K, ldk,
-                                                                  (const __nv_bfloat16*)V, ldv, (__nv_bfloat16*)O, ldo, kpm, amask,
-                                                                  Lq, Lk, scale, drop);
+    SEDT_CHECK_CUDA(launch_pdl(attention_tc_kernel<AM, DR>, grid, block, ATT_SMEM, stream, 1, (const __nv_bfloat16*)Q, ldq,
+                               (const __nv_bfloat16*)K, ldk, (const __nv_bfloat16*)V, ldv, (__nv_bfloat16*)O, ldo, kpm, amask, Lq, Lk,
+                               scale, drop));
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;

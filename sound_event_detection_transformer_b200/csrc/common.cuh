@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 
 namespace sedt {
 
@@ -66,6 +67,40 @@ struct ProfScope {
     ProfScope(int cls, cudaStream_t st) : s(st), on(g_prof_on) { if (on) prof_begin(cls, s); }
     ~ProfScope() { if (on) prof_end(s); }
 };
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------
+// A kernel launched through launch_pdl() may start while its predecessor on the stream is still draining: its
+// prologue (barrier init, TMEM allocation, tensor-map prefetch, launch latency itself) overlaps the predecessor's
+// tail.  Contract: such a kernel executes pdl_wait() before it touches any global memory another kernel produces or
+// reads (the wait returns once the predecessor grid has completed and its writes are visible; every kernel in the
+// chain waits the same way, so completion is transitive), and pdl_trigger() at its top so that ITS successor may be
+// scheduled early.  Both are no-ops when the kernel was launched without the attribute.  Opt-in with SEDT_PDL=1 (measured slower, see
+// pdl_enabled()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                              Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = (unsigned)n;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 
 // ---- device-side conversions -------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);

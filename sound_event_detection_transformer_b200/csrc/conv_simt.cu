@@ -39,6 +39,8 @@ conv_simt_kernel(const TA* __restrict__ in, const TA* __restrict__ w, const floa
 {
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int64_t M = (int64_t)g.B * g.Ho * g.Wo;
@@ -129,16 +131,16 @@ int launch_conv_simt(const ConvGemm& c, cudaStream_t stream)
     dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(c.Cout, BN)), block(NT);
     ProfScope _prof(PROF_GEMM_SIMT, stream);
     if (c.in_dt == DT_F32 && c.out_dt == DT_F32) {
-        conv_simt_kernel<float, float><<<grid, block, 0, stream>>>(
-            (const float*)c.in, (const float*)c.w, c.scale, c.bias, (const float*)c.residual, (float*)c.out, g);
+        SEDT_CHECK_CUDA(launch_pdl(conv_simt_kernel<float, float>, grid, block, 0, stream, 1,
+                                   (const float*)c.in, (const float*)c.w, c.scale, c.bias, (const float*)c.residual, (float*)c.out, g));
     } else if (c.in_dt == DT_BF16 && c.out_dt == DT_BF16) {
-        conv_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, stream>>>(
-            (const __nv_bfloat16*)c.in, (const __nv_bfloat16*)c.w, c.scale, c.bias,
-            (const __nv_bfloat16*)c.residual, (__nv_bfloat16*)c.out, g);
+        SEDT_CHECK_CUDA(launch_pdl(conv_simt_kernel<__nv_bfloat16, __nv_bfloat16>, grid, block, 0, stream, 1,
+                                   (const __nv_bfloat16*)c.in, (const __nv_bfloat16*)c.w, c.scale, c.bias,
+                                   (const __nv_bfloat16*)c.residual, (__nv_bfloat16*)c.out, g));
     } else if (c.in_dt == DT_BF16 && c.out_dt == DT_F32) {
-        conv_simt_kernel<__nv_bfloat16, float><<<grid, block, 0, stream>>>(
-            (const __nv_bfloat16*)c.in, (const __nv_bfloat16*)c.w, c.scale, c.bias,
-            (const float*)c.residual, (float*)c.out, g);
+        SEDT_CHECK_CUDA(launch_pdl(conv_simt_kernel<__nv_bfloat16, float>, grid, block, 0, stream, 1,
+                                   (const __nv_bfloat16*)c.in, (const __nv_bfloat16*)c.w, c.scale, c.bias,
+                                   (const float*)c.residual, (float*)c.out, g));
     } else {
         SEDT_REQUIRE(false, "conv_simt: unsupported dtype combination in=%d out=%d", c.in_dt, c.out_dt);
     }

@@ -75,6 +75,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // PDL: the successor may be scheduled from here on (this CTA owns its TMEM columns already, so a co-resident
+    // successor CTA can never starve it); everything above overlapped the predecessor's tail, whose outputs are our operands
+    pdl_trigger();
+    pdl_wait();
     const uint32_t tmem_base = *tmem_slot;
     const int first_item = (int)blockIdx.x, item_stride = (int)gridDim.x;
 
@@ -238,8 +242,8 @@ int launch_v2(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr,
     const int total = pr.tiles_m * pr.tiles_nc;
     const int grid = std::min(total, num_sms());
     ProfScope _prof(PROF_GEMM_TC, stream);
-    kern<<<grid, NUM_THREADS2, L::TOTAL, stream>>>(pr.map_a[0], pr.map_a[1], pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p,
-                                                   pr.tiles_nc, total);
+    SEDT_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(NUM_THREADS2), L::TOTAL, stream, 1, pr.map_a[0], pr.map_a[1],
+                               pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p, pr.tiles_nc, total));
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;

@@ -111,6 +111,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
+    // PDL: the successor may be scheduled from here on (this CTA owns its TMEM columns already, so a co-resident
+    // successor CTA can never starve it); everything above overlapped the predecessor's tail, whose outputs are our operands
+    pdl_trigger();
+    pdl_wait();
     const uint32_t tmem_base = *tmem_slot;
 
     const int first_item = (int)(blockIdx.x >> 1), item_stride = (int)(gridDim.x >> 1);
@@ -276,15 +280,9 @@ int launch_v3(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr,
     }
     const int total = ((pr.tiles_m + 1) / 2) * pr.tiles_nc;
     const int grid = std::min(total * 2, num_sms()) & ~1;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
     ProfScope _prof(PROF_GEMM_TC, stream);
-    SEDT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pr.map_a[0], pr.map_a[1], pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p,
-                                       pr.tiles_nc, total));
+    SEDT_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(T3_THREADS), L::TOTAL, stream, 2, pr.map_a[0], pr.map_a[1], pr.map_a[2],
+                               pr.map_a[3], pr.map_b, mo, mr, pr.p, pr.tiles_nc, total));
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;

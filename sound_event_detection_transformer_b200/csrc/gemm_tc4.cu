@@ -70,6 +70,10 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // PDL: the successor may be scheduled from here on (this CTA owns its TMEM columns already, so a co-resident
+    // successor CTA can never starve it); everything above overlapped the predecessor's tail, whose outputs are our operands
+    pdl_trigger();
+    pdl_wait();
     const uint32_t tmem_base = *tmem_slot;
     // schedule: this CTA owns ONE N tile (its weights stay in shared memory) and walks over M tiles
     const int n_tile = (int)blockIdx.x % tiles_nc;
@@ -240,8 +244,8 @@ int launch_v4(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr,
     const int per_n = std::max(1, std::min(num_sms() / pr.tiles_nc, pr.tiles_m));
     const int grid = per_n * pr.tiles_nc;
     ProfScope _prof(PROF_GEMM_TC, stream);
-    kern<<<grid, NUM_THREADS4, L::TOTAL, stream>>>(pr.map_a[0], pr.map_a[1], pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p,
-                                                   pr.tiles_nc, pr.tiles_m);
+    SEDT_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(NUM_THREADS4), L::TOTAL, stream, 1, pr.map_a[0], pr.map_a[1],
+                               pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p, pr.tiles_nc, pr.tiles_m));
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;

@@ -13,6 +13,14 @@ namespace sedt {
 static thread_local char g_err[1024] = "";
 unsigned long long g_launch_count = 0;
 
+bool pdl_enabled()
+{
+    // off by default: measured on B200 inside the CUDA graph, 4.85 ms (off) vs 5.00 ms (on) per 256-clip forward and no
+    // change for the training step -- graph replay already hides the launch latency and the early CTAs only add contention
+    static const bool on = [] { const char* e = getenv("SEDT_PDL"); return e != nullptr && atoi(e) != 0; }();
+    return on;
+}
+
 void set_error(const char* fmt, ...)
 {
     va_list ap;

@@ -58,6 +58,7 @@ stem_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wtc, con
     const int cr0 = 2 * hp0 - 1;                 // first conv row of this CTA
     const int row0 = 2 * cr0 - 3;                // first input row held in xs
 
+    pdl_wait();            // the output buffer may still be read by the previous kernel (workspace reuse across steps)
     if (t == 0) {
         mbar_init(bar_w, 1); mbar_init(bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -77,6 +78,7 @@ stem_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wtc, con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();         // TMEM is owned: a successor scheduled next to this CTA cannot starve it
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
 
@@ -280,9 +282,11 @@ int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, void* 
     ProfScope _prof(PROF_STEM, stream);
     if (amax != nullptr) {
         SEDT_REQUIRE(((uintptr_t)amax & 7) == 0, "stem_tc: arg-max buffer must be 8-byte aligned");
-        stem_tc_kernel<true><<<grid, block, ST_SMEM, stream>>>(x, (const uint8_t*)wtc, bn_bias, (__nv_bfloat16*)out, amax, T, Hc, Hp);
+        SEDT_CHECK_CUDA(launch_pdl(stem_tc_kernel<true>, grid, block, ST_SMEM, stream, 1, x, (const uint8_t*)wtc, bn_bias,
+                                   (__nv_bfloat16*)out, amax, T, Hc, Hp));
     } else {
-        stem_tc_kernel<false><<<grid, block, ST_SMEM, stream>>>(x, (const uint8_t*)wtc, bn_bias, (__nv_bfloat16*)out, nullptr, T, Hc, Hp);
+        SEDT_CHECK_CUDA(launch_pdl(stem_tc_kernel<false>, grid, block, ST_SMEM, stream, 1, x, (const uint8_t*)wtc, bn_bias,
+                                   (__nv_bfloat16*)out, (uint8_t*)nullptr, T, Hc, Hp));
     }
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());

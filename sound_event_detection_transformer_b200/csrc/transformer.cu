@@ -38,6 +38,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                  const float* __restrict__ pos, int64_t pos_rows, T* __restrict__ y, T* __restrict__ ypos,
                  float* __restrict__ y32, int64_t rows)
 {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -289,8 +291,8 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, cons
     if (rows == 0) return SEDT_OK;
     dim3 grid((unsigned)ceil_div(rows, 8)), block(256);
     ProfScope _prof(PROF_NORM, stream);
-    if (dt == DT_F32) layernorm_kernel<float, true><<<grid, block, 0, stream>>>(x, gamma, beta, pos, pos_rows, (float*)y, (float*)ypos, y32, rows);
-    else layernorm_kernel<__nv_bfloat16, true><<<grid, block, 0, stream>>>(x, gamma, beta, pos, pos_rows, (__nv_bfloat16*)y, (__nv_bfloat16*)ypos, y32, rows);
+    if (dt == DT_F32) SEDT_CHECK_CUDA(launch_pdl(layernorm_kernel<float, true>, grid, block, 0, stream, 1, x, gamma, beta, pos, pos_rows, (float*)y, (float*)ypos, y32, rows));
+    else SEDT_CHECK_CUDA(launch_pdl(layernorm_kernel<__nv_bfloat16, true>, grid, block, 0, stream, 1, x, gamma, beta, pos, pos_rows, (__nv_bfloat16*)y, (__nv_bfloat16*)ypos, y32, rows));
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
@@ -302,8 +304,8 @@ int launch_cast_addpos(const float* x, const float* pos, int64_t pos_rows, void*
     if (rows == 0) return SEDT_OK;
     dim3 grid((unsigned)ceil_div(rows, 8)), block(256);
     ProfScope _prof(PROF_NORM, stream);
-    if (dt == DT_F32) layernorm_kernel<float, false><<<grid, block, 0, stream>>>(x, nullptr, nullptr, pos, pos_rows, (float*)y, (float*)ypos, nullptr, rows);
-    else layernorm_kernel<__nv_bfloat16, false><<<grid, block, 0, stream>>>(x, nullptr, nullptr, pos, pos_rows, (__nv_bfloat16*)y, (__nv_bfloat16*)ypos, nullptr, rows);
+    if (dt == DT_F32) SEDT_CHECK_CUDA(launch_pdl(layernorm_kernel<float, false>, grid, block, 0, stream, 1, x, (const float*)nullptr, (const float*)nullptr, pos, pos_rows, (float*)y, (float*)ypos, (float*)nullptr, rows));
+    else SEDT_CHECK_CUDA(launch_pdl(layernorm_kernel<__nv_bfloat16, false>, grid, block, 0, stream, 1, x, (const float*)nullptr, (const float*)nullptr, pos, pos_rows, (__nv_bfloat16*)y, (__nv_bfloat16*)ypos, (float*)nullptr, rows));
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;

@@ -443,10 +443,10 @@ class PostProcess(nn.Module):
 
     @torch.no_grad()
     def forward(self, outputs, target_sizes, audio_tags=None, at_m=2, is_semi=False, threshold=0.5):
-        if outputs["pred_logits"].is_cuda:
-            scores, labels, se, _ = self._run(outputs, target_sizes, audio_tags, at_m, is_semi, threshold)
-            return [{"scores": s, "labels": lb, "boxes": b} for s, lb, b in zip(scores, labels, se)]
-        return self._forward_torch(outputs, target_sizes, audio_tags, at_m, is_semi, threshold)
+        if not outputs["pred_logits"].is_cuda:
+            raise RuntimeError("PostProcess needs CUDA tensors (there is no CPU path)")
+        scores, labels, se, _ = self._run(outputs, target_sizes, audio_tags, at_m, is_semi, threshold)
+        return [{"scores": s, "labels": lb, "boxes": b} for s, lb, b in zip(scores, labels, se)]
 
     @torch.no_grad()
     def decode_events(self, outputs, target_sizes, audio_tags=None, at_m=2, threshold=0.5, decode_threshold=0.5,
@@ -468,29 +468,3 @@ class PostProcess(nn.Module):
             out.append([[class_names[int(cls[i])] if class_names is not None else int(cls[i]), float(on[i]), float(off[i]),
                          float(sc[i])] for i in range(n)])
         return out
-
-    @torch.no_grad()
-    def _forward_torch(self, outputs, target_sizes, audio_tags=None, at_m=2, is_semi=False, threshold=0.5):
-        logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
-        prob = F.softmax(logits, -1)
-        nq = prob.shape[1]
-        if audio_tags is not None:
-            ev = prob[..., :-1]                                   # view: writes go through to prob
-            best = ev.argmax(1, keepdim=True)                     # per (clip, class): the strongest query
-            tags = audio_tags.to(prob.device)
-            if at_m in (2, 3):
-                top = ev.gather(1, best)
-                lift = top < threshold
-                if at_m == 3:
-                    lift = lift & tags.bool().unsqueeze(1)
-                ev.scatter_(1, best, torch.where(lift, torch.full_like(top, threshold), top))
-            if at_m in (1, 2):
-                ev.mul_(tags.unsqueeze(1).expand(-1, nq, -1).to(ev.dtype))
-        scores, labels = prob[..., :-1].max(-1)
-        if not is_semi:
-            c, l = boxes.unbind(-1)
-            se = torch.stack([c - l / 2, c + l / 2], dim=-1)
-            se = se * target_sizes.to(se.device).unsqueeze(-1)[:, None, :]
-        else:
-            se = boxes
-        return [{"scores": s, "labels": lb, "boxes": b} for s, lb, b in zip(scores, labels, se)]
