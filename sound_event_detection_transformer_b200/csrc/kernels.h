@@ -157,6 +157,11 @@ int launch_mask_downsample(const uint8_t* mask, uint8_t* out, int B, int T, int 
 int launch_pos_table(const uint8_t* mask_ds, float* pos, int nb, int H, int W, cudaStream_t stream);
 int launch_fill_zero(void* p, size_t bytes, cudaStream_t stream);
 // slice decoder slots and apply sigmoid: see model.cu
+// class_embed / last bbox_embed layer (+ sigmoid) / weak_class_embed (+ sigmoid) in one pass over the decoder states:
+// hs [D*B*Qall, 256] fp32, h2 = second box-MLP hidden layer [D*B*Qall, 256] fp32, fp32 weights [out, 256]
+int launch_heads_out(const float* hs, const float* h2, const float* wc, const float* bc, const float* wb, const float* bb,
+                     const float* ww, const float* bw, float* logits, float* boxes, float* at, int D_, int B, int Qall, int start,
+                     int C1, int C, cudaStream_t stream);
 int launch_heads_finalize(const float* cls_raw, const float* box_raw, const float* weak_raw, float* logits, float* boxes,
                           float* at, int D, int B, int Qall, int start, int C1, int C, cudaStream_t stream);
 // [N, HW, C] -> [N, C] mean (SP-SEDT avgpool), fp32 out

@@ -653,16 +653,25 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
     float* h2 = (float*)ws.alloc((size_t)hrows * d * 4);
     float* box_raw = (float*)ws.alloc((size_t)hrows * 2 * 4);
     float* weak_raw = cfg_.dec_at ? (float*)ws.alloc((size_t)B * ncls * 4) : nullptr;
-    SEDT_TRY(linear(class_embed_, 0, C1, out.hs, DT_F32, d, hrows, nullptr, cls_raw, DT_F32, C1, 0, s, dry));
+    static const bool heads_simt = [] { const char* e = getenv("SEDT_HEADS_SIMT"); return e != nullptr && e[0] == '1'; }();
     SEDT_TRY(linear(bbox0_, 0, d, hs_t, dt, d, hrows, nullptr, h1, dt, d, 1, s, dry));
     SEDT_TRY(linear(bbox1_, 0, d, h1, dt, d, hrows, nullptr, h2, DT_F32, d, 1, s, dry));
-    SEDT_TRY(linear(bbox2_, 0, 2, h2, DT_F32, d, hrows, nullptr, box_raw, DT_F32, 2, 0, s, dry));
-    if (cfg_.dec_at)     // slot 0 of the last layer: rows at stride Qall*d (sedt.py:92)
-        SEDT_TRY(linear(weak_, 0, ncls, out.hs + (size_t)(Dn - 1) * qrows * d, DT_F32, Qall * d, B, nullptr, weak_raw,
-                        DT_F32, ncls, 0, s, dry));
-    if (!dry)
-        SEDT_TRY(launch_heads_finalize(cls_raw, box_raw, weak_raw, out.logits, out.boxes, cfg_.dec_at ? out.at : nullptr,
-                                       Dn, B, Qall, start, C1, ncls, s));
+    if (!heads_simt) {
+        auto Pf = [&](size_t off) { return (const float*)(packed_ + off); };
+        if (!dry)
+            SEDT_TRY(launch_heads_out(out.hs, h2, Pf(class_embed_.off_w), Pf(class_embed_.off_b), Pf(bbox2_.off_w), Pf(bbox2_.off_b),
+                                      cfg_.dec_at ? Pf(weak_.off_w) : nullptr, cfg_.dec_at ? Pf(weak_.off_b) : nullptr, out.logits,
+                                      out.boxes, cfg_.dec_at ? out.at : nullptr, Dn, B, Qall, start, C1, ncls, s));
+    } else {
+        SEDT_TRY(linear(class_embed_, 0, C1, out.hs, DT_F32, d, hrows, nullptr, cls_raw, DT_F32, C1, 0, s, dry));
+        SEDT_TRY(linear(bbox2_, 0, 2, h2, DT_F32, d, hrows, nullptr, box_raw, DT_F32, 2, 0, s, dry));
+        if (cfg_.dec_at)     // slot 0 of the last layer: rows at stride Qall*d (sedt.py:92)
+            SEDT_TRY(linear(weak_, 0, ncls, out.hs + (size_t)(Dn - 1) * qrows * d, DT_F32, Qall * d, B, nullptr, weak_raw,
+                            DT_F32, ncls, 0, s, dry));
+        if (!dry)
+            SEDT_TRY(launch_heads_finalize(cls_raw, box_raw, weak_raw, out.logits, out.boxes, cfg_.dec_at ? out.at : nullptr,
+                                           Dn, B, Qall, start, C1, ncls, s));
+    }
     if (cfg_.self_sup && cfg_.feature_recon && out.pred_feature != nullptr) {
         SEDT_TRY(linear(falign0_, 0, d, hs_t, dt, d, hrows, nullptr, h1, dt, d, 1, s, dry));
         SEDT_TRY(linear(falign1_, 0, 2048, h1, dt, d, hrows, nullptr, out.pred_feature, DT_F32, 2048, 0, s, dry));

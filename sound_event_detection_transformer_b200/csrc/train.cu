@@ -286,15 +286,11 @@ int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int 
     // ---- heads
     const int64_t hrows = (int64_t)Dn * qrows;
     const int ncls = cfg_.num_classes, C1 = ncls + 1, start = cfg_.dec_at ? 1 : 0;
-    SEDT_TRY(linear(class_embed_, 0, C1, out.hs, DT_F32, d, hrows, nullptr, tp.cls_raw, DT_F32, C1, 0, s, false));
     SEDT_TRY(linear(bbox0_, 0, d, tp.hs_t, dt, d, hrows, nullptr, tp.hh1, dt, d, 1, s, false));
     SEDT_TRY(linear(bbox1_, 0, d, tp.hh1, dt, d, hrows, nullptr, tp.hh2, DT_F32, d, 1, s, false));
-    SEDT_TRY(linear(bbox2_, 0, 2, tp.hh2, DT_F32, d, hrows, nullptr, tp.box_raw, DT_F32, 2, 0, s, false));
-    if (cfg_.dec_at)
-        SEDT_TRY(linear(weak_, 0, ncls, out.hs + (size_t)(Dn - 1) * qrows * d, DT_F32, Qall * d, B, nullptr, tp.weak_raw, DT_F32,
-                        ncls, 0, s, false));
-    SEDT_TRY(launch_heads_finalize(tp.cls_raw, tp.box_raw, tp.weak_raw, out.logits, out.boxes, cfg_.dec_at ? out.at : nullptr, Dn, B,
-                                   Qall, start, C1, ncls, s));
+    SEDT_TRY(launch_heads_out(out.hs, tp.hh2, P_(class_embed_.off_w), P_(class_embed_.off_b), P_(bbox2_.off_w), P_(bbox2_.off_b),
+                              cfg_.dec_at ? P_(weak_.off_w) : nullptr, cfg_.dec_at ? P_(weak_.off_b) : nullptr, out.logits, out.boxes,
+                              cfg_.dec_at ? out.at : nullptr, Dn, B, Qall, start, C1, ncls, s));
     // sigmoid outputs for the backward pass (the caller's tensors may be modified by then)
     SEDT_CHECK_CUDA(cudaMemcpyAsync(tp.boxes, out.boxes, (size_t)Dn * B * cfg_.num_queries * 2 * 4, cudaMemcpyDeviceToDevice, s));
     if (cfg_.dec_at) SEDT_CHECK_CUDA(cudaMemcpyAsync(tp.at, out.at, (size_t)B * ncls * 4, cudaMemcpyDeviceToDevice, s));

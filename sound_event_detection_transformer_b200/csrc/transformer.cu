@@ -243,6 +243,84 @@ __global__ void heads_finalize_kernel(const float* __restrict__ cls_raw, const f
     }
 }
 
+// The three output projections in one pass (sedt/sedt.py:89-95): class_embed on the event slots, the last bbox_embed layer
+// + sigmoid, weak_class_embed + sigmoid on slot 0 of the last decoder layer.  One warp per decoder-state row; the 13..23
+// weight rows live in shared memory; replaces three 64x64-tile CUDA-core GEMMs (29 + 28 + 22 us at B = 256) and the
+// slice / sigmoid pass that followed them.
+// four output features at a time: independent shuffle chains instead of one serial reduction per output
+__device__ __forceinline__ void dot4(const float (&x)[8], const float* w, int n, int lane, float (&out)[4])
+{
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < n) {
+            const float4 w0 = *reinterpret_cast<const float4*>(w + j * D + lane * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(w + j * D + lane * 8 + 4);
+            a[j] = fmaf(x[0], w0.x, fmaf(x[1], w0.y, fmaf(x[2], w0.z, fmaf(x[3], w0.w,
+                   fmaf(x[4], w1.x, fmaf(x[5], w1.y, fmaf(x[6], w1.z, x[7] * w1.w)))))));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = a[j];
+}
+
+__device__ __forceinline__ float pick4(const float (&a)[4], int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : (i == 2 ? a[2] : a[3])); }
+
+__global__ void __launch_bounds__(256)
+heads_out_kernel(const float* __restrict__ hs, const float* __restrict__ h2, const float* __restrict__ wc, const float* __restrict__ bc,
+                 const float* __restrict__ wb, const float* __restrict__ bb, const float* __restrict__ ww, const float* __restrict__ bw,
+                 float* __restrict__ logits, float* __restrict__ boxes, float* __restrict__ at, int D_, int B, int Qall, int start,
+                 int C1, int C)
+{
+    extern __shared__ float hsm[];
+    float* s_wc = hsm;                       // [C1][256]
+    float* s_wb = s_wc + C1 * D;             // [2][256]
+    float* s_ww = s_wb + 2 * D;              // [C][256] (dec_at only)
+    pdl_trigger();
+    for (int i = threadIdx.x; i < C1 * D; i += blockDim.x) s_wc[i] = wc[i];
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) s_wb[i] = wb[i];
+    if (at != nullptr) for (int i = threadIdx.x; i < C * D; i += blockDim.x) s_ww[i] = ww[i];
+    pdl_wait();
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const int Q = Qall - start;
+    const int64_t rows = (int64_t)D_ * B * Qall;
+    for (int64_t r = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * warps) {
+        const int q = (int)(r % Qall);
+        const int64_t lb = r / Qall;                         // l * B + b
+        const bool is_at = at != nullptr && q == 0 && lb >= (int64_t)(D_ - 1) * B;
+        if (q < start && !is_at) continue;
+        float x[8];
+        load8(hs + r * D + lane * 8, x);
+        if (q >= start) {
+            const int64_t o = lb * Q + (q - start);
+            for (int c0 = 0; c0 < C1; c0 += 4) {
+                float a[4];
+                dot4(x, s_wc + c0 * D, C1 - c0, lane, a);
+                if (lane < 4 && c0 + lane < C1) logits[o * C1 + c0 + lane] = pick4(a, lane) + bc[c0 + lane];
+            }
+            float y[8];
+            load8(h2 + r * D + lane * 8, y);
+            float a[4];
+            dot4(y, s_wb, 2, lane, a);
+            if (lane < 2) boxes[o * 2 + lane] = sigmoidf(pick4(a, lane) + bb[lane]);
+        }
+        if (is_at) {
+            const int64_t b = lb - (int64_t)(D_ - 1) * B;
+            for (int c0 = 0; c0 < C; c0 += 4) {
+                float a[4];
+                dot4(x, s_ww + c0 * D, C - c0, lane, a);
+                if (lane < 4 && c0 + lane < C) at[b * C + c0 + lane] = sigmoidf(pick4(a, lane) + bw[c0 + lane]);
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void avgpool_kernel(const T* __restrict__ x, float* __restrict__ out, int HW, int C)
 {
@@ -362,6 +440,25 @@ int launch_pos_table(const uint8_t* mask_ds, float* pos, int nb, int H, int W, c
     dim3 grid((unsigned)(H * W), (unsigned)nb), block(D);
     ProfScope _prof(PROF_OTHER, stream);
     pos_table_kernel<<<grid, block, 0, stream>>>(mask_ds, pos, H, W);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_heads_out(const float* hs, const float* h2, const float* wc, const float* bc, const float* wb, const float* bb,
+                     const float* ww, const float* bw, float* logits, float* boxes, float* at, int D_, int B, int Qall, int start,
+                     int C1, int C, cudaStream_t stream)
+{
+    const int64_t rows = (int64_t)D_ * B * Qall;
+    if (rows == 0) return SEDT_OK;
+    const size_t smem = (size_t)(C1 + 2 + (at != nullptr ? C : 0)) * D * sizeof(float);
+    SEDT_REQUIRE(smem <= 200 * 1024, "heads: %d classes do not fit shared memory", C1);
+    if (smem > 48 * 1024)
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(heads_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows, 8 * 4), 148 * 4);
+    ProfScope _prof(PROF_OTHER, stream);
+    SEDT_CHECK_CUDA(launch_pdl(heads_out_kernel, dim3(grid), dim3(256), smem, stream, 1, hs, h2, wc, bc, wb, bb, ww, bw, logits, boxes,
+                               at, D_, B, Qall, start, C1, C));
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
