@@ -66,6 +66,43 @@ __global__ void repack_dgrad_tiled_kernel(const float* __restrict__ w, const flo
     }
 }
 
+// All data-gradient weight re-layouts of one backward pass in one launch (square filters: R == S); a CTA is one 32 x 32
+// tile of one job, found through the tile prefix.  Jobs travel in the kernel parameters.
+__global__ void __launch_bounds__(256)
+repack_dgrad_batched_kernel(const __grid_constant__ DgradJobs jobs)
+{
+    __shared__ float tile[32][33];
+    int lo = 0, hi = jobs.n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs.j[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const DgradJob& J = jobs.j[lo];
+    const int Cout = J.Cout, Cout_pad = J.Cout_pad, Cin = J.Cin, RS = J.RS;
+    const int tx = (Cin + 31) / 32, ty = (Cout_pad + 31) / 32;
+    int t = (int)blockIdx.x - J.tile0;
+    const int bx = t % tx; t /= tx;
+    const int by = t % ty;
+    const int tap = t / ty, src_tap = RS - 1 - tap;
+    const int ci0 = bx * 32, co0 = by * 32;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    for (int j = ly; j < 32; j += 8) {
+        const int co = co0 + j, ci = ci0 + lx;
+        float v = 0.f;
+        if (co < Cout && ci < Cin) {
+            v = J.w[((int64_t)co * Cin + ci) * RS + src_tap];
+            if (J.scale != nullptr) v *= J.scale[co];
+        }
+        tile[j][lx] = v;
+    }
+    __syncthreads();
+    bf16* out = (bf16*)J.out;
+    for (int j = ly; j < 32; j += 8) {
+        const int ci = ci0 + j, co = co0 + lx;
+        if (ci < Cin && co < Cout_pad) out[((int64_t)ci * RS + tap) * Cout_pad + co] = __float2bfloat16_rn(tile[lx][j]);
+    }
+}
+
 // grad[co][ci][r][s] = scale[co] * dw[co][(r,s)][ci]   (weight gradient back in the reference's OIHW layout)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, const float* __restrict__ scale, float* __restrict__ grad, int Cout,
                                     int Cin, int RS)
@@ -479,6 +516,25 @@ int launch_repack_dgrad(const float* w_oihw, const float* scale, void* out, int 
     } else if (dt == DT_F32) repack_dgrad_kernel<float><<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, (float*)out, Cout, Cout_pad, Cin, R, S);
     else repack_dgrad_kernel<bf16><<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, (bf16*)out, Cout, Cout_pad, Cin, R, S);
     SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_repack_dgrad_batched(const DgradJob* jobs, int n, cudaStream_t stream)
+{
+    for (int j0 = 0; j0 < n; j0 += kDgradMaxJobs) {
+        DgradJobs P;
+        P.n = std::min(kDgradMaxJobs, n - j0);
+        int tiles = 0;
+        for (int j = 0; j < P.n; ++j) {
+            P.j[j] = jobs[j0 + j];
+            P.j[j].tile0 = tiles;
+            tiles += (int)(ceil_div(P.j[j].Cin, 32) * ceil_div(P.j[j].Cout_pad, 32) * P.j[j].RS);
+        }
+        if (tiles == 0) continue;
+        repack_dgrad_batched_kernel<<<(unsigned)tiles, 256, 0, stream>>>(P);
+        SEDT_COUNT_LAUNCH();
+    }
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
 }

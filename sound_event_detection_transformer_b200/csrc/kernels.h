@@ -175,6 +175,35 @@ int launch_blockdiag_mask(float* m, int Q, int qpp, cudaStream_t stream);
 
 int prof_read(double* ms, long long* counts);   // model.cu
 
+// every data-gradient weight re-layout (launch_repack_dgrad with R == S, bf16 output) of a backward pass in one launch
+struct DgradJob { const float* w; const float* scale; void* out; int32_t Cout, Cout_pad, Cin, RS, tile0, pad_; };
+constexpr int kDgradMaxJobs = 256;
+struct DgradJobs { DgradJob j[kDgradMaxJobs]; int32_t n; };
+int launch_repack_dgrad_batched(const DgradJob* jobs, int n, cudaStream_t stream);
+
+// ---- pack.cu: all casts / repacks / BN folds of one pack call batched into one launch (jobs in the kernel parameters)
+enum : int { PACK_CAST = 0, PACK_REPACK = 1, PACK_BNFOLD = 2 };
+struct PackJob {
+    const float* src; void* dst; float* dst2; const float* bn_w; const float* bn_mean; const float* bn_var;
+    int32_t kind, dt, a, b, c, chunk0;
+};
+constexpr int kPackMaxJobs = 400;                       // 400 * 72 B = 28.8 KB of kernel parameters (limit 32 KB)
+struct PackJobs { PackJob j[kPackMaxJobs]; int32_t n; };
+class PackBatch {
+public:
+    explicit PackBatch(cudaStream_t s) : stream_(s) { cur_.n = 0; }
+    int cast(const float* in, void* out, int dt, int64_t n);
+    // out[o][tap][c] = w[o][c][tap] * (bn_w ? bn_w[o] * rsqrt(bn_var[o] + 1e-5) : 1)
+    int repack_conv(const float* w_oihw, const float* bn_w, const float* bn_var, void* out, int dt, int Cout, int Cin, int RS);
+    int bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* bias, int n);
+    int flush();
+private:
+    int add(const PackJob& job, int64_t elems);
+    PackJobs cur_;
+    int chunks_ = 0;
+    cudaStream_t stream_;
+};
+
 // ---- matcher.cu
 int launch_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
                    const int32_t* offsets, int B, int Q, int C1, int Kmax, float w_class, float w_bbox, float w_giou,

@@ -233,21 +233,34 @@ int Model::pack(const void* const* weights, void* packed, size_t bytes, cudaStre
     auto P = [&](size_t off) { return (void*)(packed_ + off); };
     const int dt = act_dt();
 
+    // everything below is recorded into one batched launch (pack.cu: pack_jobs_kernel); SEDT_PACK_BATCH=0 keeps the
+    // one-launch-per-tensor path
+    static const bool batched = [] { const char* e = getenv("SEDT_PACK_BATCH"); return e == nullptr || atoi(e) != 0; }();
+    PackBatch pb(s);
+    auto do_cast = [&](const float* in, void* out, int odt, int64_t n) -> int {
+        return batched ? pb.cast(in, out, odt, n) : launch_cast(in, out, odt, n, s);
+    };
+    auto do_bn_fold = [&](int bn_slot, float* scale, float* bias, int n) -> int {
+        return batched ? pb.bn_fold(W(bn_slot), W(bn_slot + 1), W(bn_slot + 2), W(bn_slot + 3), scale, bias, n)
+                       : launch_bn_fold(W(bn_slot), W(bn_slot + 1), W(bn_slot + 2), W(bn_slot + 3), scale, bias, n, s);
+    };
     auto pack_conv = [&](const ConvLayer& L) -> int {
-        SEDT_TRY(launch_bn_fold(W(L.bn_slot), W(L.bn_slot + 1), W(L.bn_slot + 2), W(L.bn_slot + 3),
-                                (float*)P(L.off_scale), (float*)P(L.off_bias), L.cout, s));
+        SEDT_TRY(do_bn_fold(L.bn_slot, (float*)P(L.off_scale), (float*)P(L.off_bias), L.cout));
         // bf16 tier: the FrozenBN scale is folded into the weights before rounding (one rounding instead of
         // two, and the epilogue only adds the bias); the fp32 tier keeps x*scale+bias like the reference
+        if (batched)
+            return pb.repack_conv(W(L.w_slot), fold_scale() ? W(L.bn_slot) : nullptr, fold_scale() ? W(L.bn_slot + 3) : nullptr,
+                                  P(L.off_w), dt, L.cout, L.cin, L.k * L.k);
         return launch_repack_conv(W(L.w_slot), fold_scale() ? (const float*)P(L.off_scale) : nullptr, P(L.off_w), dt, L.cout,
                                   L.cin, L.k, L.k, s);
     };
     auto pack_linear = [&](const Linear& L) -> int {
-        SEDT_TRY(launch_cast(W(L.w_slot), P(L.off_w), L.f32_only ? DT_F32 : dt, (int64_t)L.in * L.out, s));
-        return launch_cast(W(L.b_slot), P(L.off_b), DT_F32, L.out, s);
+        SEDT_TRY(do_cast(W(L.w_slot), P(L.off_w), L.f32_only ? DT_F32 : dt, (int64_t)L.in * L.out));
+        return do_cast(W(L.b_slot), P(L.off_b), DT_F32, L.out);
     };
     auto pack_norm = [&](const Norm& n) -> int {
-        SEDT_TRY(launch_cast(W(n.w_slot), P(n.off_g), DT_F32, cfg_.hidden_dim, s));
-        return launch_cast(W(n.b_slot), P(n.off_b), DT_F32, cfg_.hidden_dim, s);
+        SEDT_TRY(do_cast(W(n.w_slot), P(n.off_g), DT_F32, cfg_.hidden_dim));
+        return do_cast(W(n.b_slot), P(n.off_b), DT_F32, cfg_.hidden_dim);
     };
     for (auto& e : enc_) {
         SEDT_TRY(pack_linear(e.attn.in_proj)); SEDT_TRY(pack_linear(e.attn.out_proj));
@@ -267,14 +280,15 @@ int Model::pack(const void* const* weights, void* packed, size_t bytes, cudaStre
         const size_t es = dtype_size(dt);
         const float* w = W(dec_[l].cross_attn.in_proj.w_slot);
         const float* b = W(dec_[l].cross_attn.in_proj.b_slot);
-        SEDT_TRY(launch_cast(w + (size_t)d * d, (char*)P(off_ck_w) + l * d * d * es, dt, (int64_t)d * d, s));
-        SEDT_TRY(launch_cast(w + (size_t)2 * d * d, (char*)P(off_cv_w) + l * d * d * es, dt, (int64_t)d * d, s));
-        SEDT_TRY(launch_cast(b + d, (float*)P(off_ck_b) + l * d, DT_F32, d, s));
-        SEDT_TRY(launch_cast(b + 2 * d, (float*)P(off_cv_b) + l * d, DT_F32, d, s));
+        SEDT_TRY(do_cast(w + (size_t)d * d, (char*)P(off_ck_w) + l * d * d * es, dt, (int64_t)d * d));
+        SEDT_TRY(do_cast(w + (size_t)2 * d * d, (char*)P(off_cv_w) + l * d * d * es, dt, (int64_t)d * d));
+        SEDT_TRY(do_cast(b + d, (float*)P(off_ck_b) + l * d, DT_F32, d));
+        SEDT_TRY(do_cast(b + 2 * d, (float*)P(off_cv_b) + l * d, DT_F32, d));
     }
     SEDT_TRY(pack_linear(class_embed_)); SEDT_TRY(pack_linear(bbox0_)); SEDT_TRY(pack_linear(bbox1_));
     SEDT_TRY(pack_linear(bbox2_)); SEDT_TRY(pack_linear(input_proj_));
     SEDT_TRY(launch_stem_pack(W(s_conv0_w), W(s_conv0_b), W(s_conv1_w), (float*)P(off_weff), (float*)P(off_sat), s));
+    // the stem's scale / bias feed the stem_tc_pack launch right below: folded by their own launch, not by the batch
     SEDT_TRY(launch_bn_fold(W(s_bn1), W(s_bn1 + 1), W(s_bn1 + 2), W(s_bn1 + 3), (float*)P(off_stem_scale),
                             (float*)P(off_stem_bias), 64, s));
     if (cfg_.precision == 1)
@@ -283,13 +297,13 @@ int Model::pack(const void* const* weights, void* packed, size_t bytes, cudaStre
         SEDT_TRY(pack_conv(b.c1)); SEDT_TRY(pack_conv(b.c2)); SEDT_TRY(pack_conv(b.c3));
         if (b.has_ds) SEDT_TRY(pack_conv(b.ds));
     }
-    SEDT_TRY(launch_cast(W(s_query_embed), P(off_query_embed), DT_F32, (int64_t)qall_ * cfg_.hidden_dim, s));
+    SEDT_TRY(do_cast(W(s_query_embed), P(off_query_embed), DT_F32, (int64_t)qall_ * cfg_.hidden_dim));
     if (cfg_.dec_at) SEDT_TRY(pack_linear(weak_));
     if (cfg_.self_sup) {
         SEDT_TRY(pack_linear(patch2query_));
         if (cfg_.feature_recon) { SEDT_TRY(pack_linear(falign0_)); SEDT_TRY(pack_linear(falign1_)); }
     }
-    return SEDT_OK;
+    return pb.flush();
 }
 
 // ---- launch helpers -------------------------------------------------------------------

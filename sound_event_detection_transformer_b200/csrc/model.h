@@ -142,6 +142,10 @@ private:
     // encoder memory is projected by two GEMMs instead of 2*D
     size_t off_ck_w, off_ck_b, off_cv_w, off_cv_b;
     int qall_;
+    // data-gradient weight re-layouts of one backward pass, recorded by the first call and replayed as one batched launch
+    // by the following ones while the weight / workspace addresses stay put (train.cu: Model::backward)
+    struct DgradPlan { std::vector<DgradJob> jobs; unsigned long long key = 0; bool ready = false; };
+    DgradPlan dgrad_plan_;
     const void* rng_tape_ = nullptr;          // tape whose dropout RNG state {seed, step} has been initialised
     unsigned long long rng_seed_ = 0;
 };

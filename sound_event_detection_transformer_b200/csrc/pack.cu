@@ -45,6 +45,54 @@ __global__ void fill_zero_kernel(uint4* __restrict__ p, size_t n16, unsigned cha
     if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = 0;
 }
 
+// ---- batched packing: every cast / repack / BN fold of one sedt_model_pack call in one launch ---------------------
+// The training loop re-packs after every optimizer step; as ~260 separate launches that costs ~0.7 ms of launch
+// latency per step for ~0.05 ms of memory traffic.  Jobs travel in the kernel parameters (no table in memory, so the
+// launch is safe to capture in a CUDA graph); CTA -> job through the chunk prefix.
+constexpr int kPackChunk = 4096;           // elements per CTA
+
+__device__ __forceinline__ void pack_store(void* dst, int dt, int64_t i, float v)
+{
+    if (dt == DT_F32) ((float*)dst)[i] = v;
+    else ((__nv_bfloat16*)dst)[i] = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(256)
+pack_jobs_kernel(const __grid_constant__ PackJobs jobs)
+{
+    // job of this CTA: last j with chunk0[j] <= blockIdx.x
+    int lo = 0, hi = jobs.n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs.j[mid].chunk0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const PackJob& J = jobs.j[lo];
+    const int64_t beg = (int64_t)((int)blockIdx.x - J.chunk0) * kPackChunk;
+    if (J.kind == PACK_CAST) {
+        const int64_t n = J.a;
+        for (int64_t i = beg + threadIdx.x; i < beg + kPackChunk && i < n; i += 256) pack_store(J.dst, J.dt, i, J.src[i]);
+    } else if (J.kind == PACK_REPACK) {
+        // out[o][tap][c] = w[o][c][tap] (* FrozenBN scale of channel o, folded before rounding)
+        const int Cin = J.b, RS = J.c;
+        const int64_t n = (int64_t)J.a * Cin * RS;
+        for (int64_t i = beg + threadIdx.x; i < beg + kPackChunk && i < n; i += 256) {
+            const int c = (int)(i % Cin);
+            const int tap = (int)((i / Cin) % RS);
+            const int o = (int)(i / ((int64_t)Cin * RS));
+            float v = J.src[((int64_t)o * Cin + c) * RS + tap];
+            if (J.bn_w != nullptr) v *= J.bn_w[o] * rsqrtf(J.bn_var[o] + 1e-5f);
+            pack_store(J.dst, J.dt, i, v);
+        }
+    } else {      // PACK_BNFOLD: scale -> dst, bias -> dst2 (sedt/backbone.py:43-53)
+        const int64_t n = J.a;
+        for (int64_t i = beg + threadIdx.x; i < beg + kPackChunk && i < n; i += 256) {
+            const float sc = J.bn_w[i] * rsqrtf(J.bn_var[i] + 1e-5f);
+            ((float*)J.dst)[i] = sc;
+            J.dst2[i] = J.src[i] - J.bn_mean[i] * sc;
+        }
+    }
+}
+
 static inline unsigned grid_for(int64_t n, int block = 256)
 {
     int64_t g = ceil_div(n, block);
@@ -52,6 +100,46 @@ static inline unsigned grid_for(int64_t n, int block = 256)
 }
 
 }  // namespace
+
+int PackBatch::add(const PackJob& job, int64_t elems)
+{
+    if (elems <= 0) return SEDT_OK;
+    if (cur_.n == kPackMaxJobs) SEDT_TRY(flush());
+    PackJob j = job;
+    j.chunk0 = chunks_;
+    cur_.j[cur_.n++] = j;
+    chunks_ += (int)ceil_div(elems, kPackChunk);
+    return SEDT_OK;
+}
+
+int PackBatch::flush()
+{
+    if (cur_.n == 0) return SEDT_OK;
+    pack_jobs_kernel<<<(unsigned)chunks_, 256, 0, stream_>>>(cur_);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    cur_.n = 0; chunks_ = 0;
+    return SEDT_OK;
+}
+
+int PackBatch::cast(const float* in, void* out, int dt, int64_t n)
+{
+    PackJob j{}; j.kind = PACK_CAST; j.src = in; j.dst = out; j.dt = dt; j.a = (int)n;
+    return add(j, n);
+}
+
+int PackBatch::repack_conv(const float* w_oihw, const float* bn_w, const float* bn_var, void* out, int dt, int Cout, int Cin, int RS)
+{
+    PackJob j{}; j.kind = PACK_REPACK; j.src = w_oihw; j.bn_w = bn_w; j.bn_var = bn_var; j.dst = out; j.dt = dt;
+    j.a = Cout; j.b = Cin; j.c = RS;
+    return add(j, (int64_t)Cout * Cin * RS);
+}
+
+int PackBatch::bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* bias, int n)
+{
+    PackJob j{}; j.kind = PACK_BNFOLD; j.bn_w = w; j.src = b; j.bn_mean = mean; j.bn_var = var; j.dst = scale; j.dst2 = bias; j.a = n;
+    return add(j, n);
+}
 
 int launch_bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* bias,
                    int n, cudaStream_t stream)

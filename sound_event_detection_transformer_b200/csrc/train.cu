@@ -46,7 +46,9 @@ struct Model::Tape {
 };
 
 struct Model::BwdBufs {
-    void* wd;            // re-laid-out weights of the layer being differentiated (bf16)
+    void* wd;            // re-laid-out weights of the layer being differentiated (bf16): scratch for the unplanned sites
+    char* wd_all;        // one slot per data-gradient site of the pass (filled by the batched re-layout)
+    size_t wd_all_bytes;
     float* dw;           // weight gradient of a conv layer in the GEMM layout, before the OIHW permute
     float* vscale;       // [dim_feedforward] = 1 / (1 - dropout)
     // heads
@@ -341,6 +343,13 @@ void Model::bwd_layout(int B, const Tape& tp, Arena& a, BwdBufs& bb) const
     wmax = std::max(wmax, (size_t)2048 * d);
     dwmax = std::max(dwmax, (size_t)2048 * d);
     bb.wd = a.alloc(wmax * es);
+    // every parameter appears in at most one data-gradient GEMM; padded head matrices and 256-byte slot alignment are
+    // covered by the slack
+    bb.wd_all_bytes = ((size_t)grad_numel() + (size_t)4 * 1024 * 1024) * es;
+    for (const Block& b : blocks_)            // frozen layers carry no gradient slot but their data gradient still flows
+        for (const ConvLayer* L : {&b.c1, &b.c2, &b.c3, b.has_ds ? &b.ds : nullptr})
+            if (L != nullptr) bb.wd_all_bytes += (size_t)L->k * L->k * L->cin * L->cout * es + 256;
+    bb.wd_all = (char*)a.alloc(bb.wd_all_bytes);
     bb.dw = (float*)a.alloc(dwmax * 4);
     bb.vscale = (float*)a.alloc((size_t)ff * 4);
     const int64_t rows = (int64_t)B * tp.S, qrows = (int64_t)B * qall_, hrows = (int64_t)dec_.size() * qrows;
@@ -385,6 +394,44 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     auto P_ = [&](size_t off) { return (const float*)(packed_ + off); };
 
     SEDT_TRY(launch_fill_zero(grads, (size_t)grad_numel() * 4, s));
+
+    // ---- data-gradient weights: wd[ci][r'][s'][co] = scale[co] * w[co][ci][R-1-r'][S-1-s'] for every layer.  The first pass
+    // over given weight / workspace addresses re-lays them out site by site and records the job list; later passes (the
+    // CUDA-graph capture included) run the whole list as ONE launch up front (SEDT_DGRAD_BATCH=0: always site by site).
+    static const bool dgrad_batch = [] { const char* e = getenv("SEDT_DGRAD_BATCH"); return e == nullptr || atoi(e) != 0; }();
+    unsigned long long plan_key = 1469598103934665603ull;
+    {
+        auto mix = [&](unsigned long long v) { plan_key = (plan_key ^ v) * 1099511628211ull; };
+        for (size_t i = 0; i < slots_.size(); ++i) mix((unsigned long long)(uintptr_t)weights[i]);
+        mix((unsigned long long)(uintptr_t)bb.wd_all); mix((unsigned long long)(uintptr_t)packed_); mix((unsigned long long)train_backbone);
+    }
+    const bool use_plan = dgrad_batch && dgrad_plan_.ready && dgrad_plan_.key == plan_key;
+    if (!use_plan) { dgrad_plan_.jobs.clear(); dgrad_plan_.ready = false; }
+    else SEDT_TRY(launch_repack_dgrad_batched(dgrad_plan_.jobs.data(), (int)dgrad_plan_.jobs.size(), s));
+    size_t wd_site = 0, wd_bump = 0;
+    auto dgrad_weights = [&](const float* W, const float* scale, int Cout, int Cout_pad, int Cin, int k, const void** out) -> int {
+        const size_t bytes = align_up((size_t)Cout_pad * Cin * k * k * 2, 256);
+        SEDT_REQUIRE(wd_bump + bytes <= bb.wd_all_bytes, "backward: data-gradient weight region too small");
+        void* dst = bb.wd_all + wd_bump;
+        wd_bump += bytes;
+        *out = dst;
+        if (use_plan) {
+            SEDT_REQUIRE(wd_site < dgrad_plan_.jobs.size(), "backward: data-gradient plan is out of step");
+            const DgradJob& J = dgrad_plan_.jobs[wd_site++];
+            SEDT_REQUIRE(J.w == W && J.out == dst && J.Cout == Cout && J.Cout_pad == Cout_pad && J.Cin == Cin && J.RS == k * k,
+                         "backward: data-gradient plan does not match this pass");
+            return SEDT_OK;
+        }
+        DgradJob J{};
+        J.w = W; J.scale = scale; J.out = dst; J.Cout = Cout; J.Cout_pad = Cout_pad; J.Cin = Cin; J.RS = k * k;
+        dgrad_plan_.jobs.push_back(J);
+        return launch_repack_dgrad(W, scale, dst, DT_BF16, Cout, Cout_pad, Cin, k, k, s);
+    };
+    auto finish_plan = [&]() -> int {
+        if (use_plan) SEDT_REQUIRE(wd_site == dgrad_plan_.jobs.size(), "backward: data-gradient plan has unused entries");
+        else if (dgrad_batch) { dgrad_plan_.key = plan_key; dgrad_plan_.ready = true; }
+        return SEDT_OK;
+    };
     const bool drop = dropout > 0.f;
     SEDT_REQUIRE(!drop || rng_tape_ == tape, "backward: forward_train with dropout has not run on this tape");
     auto site = [&](uint32_t id) { return make_drop_site(tp.rng, id, dropout); };
@@ -397,10 +444,13 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
 
     // dx[M, in_f] = dy[M, out_pad] * W[out_f, in_f]  (+ residual, or masked by `aux` when relu_mode == 2)
     auto dgrad_lin = [&](const float* W, int out_f, int out_pad, int in_f, const void* dy, int ldy, int64_t M, const void* aux,
-                         int ld_aux, int relu_mode, void* dx, int dx_dt, int lddx, const float* oscale = nullptr) -> int {
-        SEDT_TRY(launch_repack_dgrad(W, nullptr, bb.wd, dt, out_f, out_pad, in_f, 1, 1, s));
+                         int ld_aux, int relu_mode, void* dx, int dx_dt, int lddx, const float* oscale = nullptr,
+                         bool scratch_weights = false) -> int {
+        const void* wd = bb.wd;
+        if (scratch_weights) SEDT_TRY(launch_repack_dgrad(W, nullptr, bb.wd, dt, out_f, out_pad, in_f, 1, 1, s));   // W is itself a scratch
+        else SEDT_TRY(dgrad_weights(W, nullptr, out_f, out_pad, in_f, 1, &wd));
         ConvGemm g;
-        g.in = dy; g.w = bb.wd; g.residual = aux; g.out = dx; g.scale = oscale;
+        g.in = dy; g.w = wd; g.residual = aux; g.out = dx; g.scale = oscale;
         g.in_dt = dt; g.out_dt = dx_dt;
         g.B = (int)M; g.H = g.W = g.Ho = g.Wo = 1; g.Cin = out_pad; g.lda = ldy;
         g.Cout = in_f; g.ldc = lddx; g.ld_res = ld_aux; g.relu = relu_mode;
@@ -534,11 +584,11 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
         for (int l = 0; l < Dn; ++l)
             SEDT_CHECK_CUDA(cudaMemcpyAsync(wcat + (size_t)l * d * d, Wp(dec_[l].cross_attn.in_proj.w_slot) + (size_t)d * d,
                                             (size_t)d * d * 4, cudaMemcpyDeviceToDevice, s));
-        SEDT_TRY(dgrad_lin(wcat, Dn * d, Dn * d, d, bb.dck, Dn * d, rows, nullptr, 0, 0, bb.dn_b, dt, d));
+        SEDT_TRY(dgrad_lin(wcat, Dn * d, Dn * d, d, bb.dck, Dn * d, rows, nullptr, 0, 0, bb.dn_b, dt, d, nullptr, true));
         for (int l = 0; l < Dn; ++l)
             SEDT_CHECK_CUDA(cudaMemcpyAsync(wcat + (size_t)l * d * d, Wp(dec_[l].cross_attn.in_proj.w_slot) + (size_t)2 * d * d,
                                             (size_t)d * d * 4, cudaMemcpyDeviceToDevice, s));
-        SEDT_TRY(dgrad_lin(wcat, Dn * d, Dn * d, d, bb.dcv, Dn * d, rows, nullptr, 0, 0, bb.dn_a, dt, d));
+        SEDT_TRY(dgrad_lin(wcat, Dn * d, Dn * d, d, bb.dcv, Dn * d, rows, nullptr, 0, 0, bb.dn_a, dt, d, nullptr, true));
     }
     const float* xe = enc_.empty() ? tp.x0 : tp.enc.back().x_out;
     SEDT_TRY(launch_layernorm_bwd(xe, P_(enc_norm_.off_g), bb.dn_a, bb.dn_b, nullptr, nullptr, bb.gA, Gp(enc_norm_.w_slot),
@@ -560,7 +610,7 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     const void* feat = tp.blk.back().out;
     SEDT_TRY(to16(gcur, bb.g16, rows * d));
     SEDT_TRY(lin_param_grads(input_proj_, 0, d, feat, 2048, bb.g16, d, rows));
-    if (!train_backbone) return SEDT_OK;
+    if (!train_backbone) return finish_plan();
     // gradient w.r.t. the layer4 output, already masked by its ReLU
     SEDT_TRY(dgrad_lin(Wp(input_proj_.w_slot), d, d, 2048, bb.g16, d, rows, feat, 2048, 2, bb.G0, dt, 2048));
 
@@ -569,11 +619,12 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     void* Gn = bb.G1;
     auto conv_dgrad = [&](const ConvLayer& L, const void* dy, int Hin, int Win, int Ho, int Wo, const void* aux, int relu_mode,
                           void* dx) -> int {
-        SEDT_TRY(launch_repack_dgrad(Wp(L.w_slot), P_(L.off_scale), bb.wd, dt, L.cout, L.cout, L.cin, L.k, L.k, s));
+        const void* wd = nullptr;
+        SEDT_TRY(dgrad_weights(Wp(L.w_slot), P_(L.off_scale), L.cout, L.cout, L.cin, L.k, &wd));
         const void* gin = dy;
         if (L.stride == 2) { SEDT_TRY(launch_upsample2(dy, bb.up, B, Hin, Win, Ho, Wo, L.cout, s)); gin = bb.up; }
         ConvGemm g;
-        g.in = gin; g.w = bb.wd; g.residual = aux; g.out = dx;
+        g.in = gin; g.w = wd; g.residual = aux; g.out = dx;
         g.in_dt = g.out_dt = dt;
         g.B = B; g.H = Hin; g.W = Win; g.Ho = Hin; g.Wo = Win; g.Cin = L.cout; g.lda = L.cout;
         g.Cout = L.cin; g.ldc = L.cin; g.ld_res = L.cin;
@@ -618,7 +669,8 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
         std::swap(G, Gn);
     }
     // G = d(loss)/d(stem output): conv0 is the only trainable parameter below (sedt/backbone.py:60,102)
-    return launch_stem_bwd(x, Wp(s_conv1_w), P_(off_stem_scale), G, tp.stem_amax, bb.dw, Gp(s_conv0_w), Gp(s_conv0_b), B, T, F, s);
+    SEDT_TRY(launch_stem_bwd(x, Wp(s_conv1_w), P_(off_stem_scale), G, tp.stem_amax, bb.dw, Gp(s_conv0_w), Gp(s_conv0_b), B, T, F, s));
+    return finish_plan();
 }
 
 }  // namespace sedt
