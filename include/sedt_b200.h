@@ -270,7 +270,7 @@ SEDT_API int sedt_op_stem(const float* x, const float* conv0_w, const float* con
 /* the same stem on tcgen05 tensor cores (bf16 output only) */
 SEDT_API int sedt_op_stem_tc(const float* x, const float* conv0_w, const float* conv0_b, const float* conv1_w,
                     const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var,
-                    void* scratch /* >= 32 KiB */, void* out, int B, int T, int F, void* stream);
+                    void* scratch /* >= 64 KiB */, void* out, int B, int T, int F, void* stream);
 SEDT_API int sedt_op_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int64_t pos_rows,
                       void* y, void* ypos, float* y32, int dtype, int64_t rows, void* stream);
 SEDT_API int sedt_op_attention(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo,

@@ -349,10 +349,13 @@ int sedt_op_stem_tc(const float* x, const float* conv0_w, const float* conv0_b, 
     uint8_t* wtc = (uint8_t*)scratch;                 // 16 KiB
     float* scale = (float*)(wtc + 16384);
     float* bias = scale + 64;
+    float* weff = bias + 64;                          // 49 x 64
+    float* sat = weff + 49 * 64;                      // 8 x 8 x 64
     cudaStream_t s = (cudaStream_t)stream;
     SEDT_TRY(launch_bn_fold(bn_w, bn_b, bn_mean, bn_var, scale, bias, 64, s));
+    SEDT_TRY(launch_stem_pack(conv0_w, conv0_b, conv1_w, weff, sat, s));
     SEDT_TRY(launch_stem_tc_pack(conv0_w, conv0_b, conv1_w, scale, wtc, s));
-    return launch_stem_tc(x, wtc, bias, out, B, T, F, s);
+    return launch_stem_tc(x, wtc, bias, scale, sat, out, B, T, F, s);
 }
 
 int sedt_op_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int64_t pos_rows, void* y,

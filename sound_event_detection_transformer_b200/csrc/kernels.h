@@ -69,8 +69,9 @@ int launch_stem(const float* x, const StemWeights& w, void* out, int out_dt, int
 int launch_stem_tc_pack(const float* conv0_w, const float* conv0_b, const float* conv1_w, const float* bn_scale, void* wtc,
                         cudaStream_t stream);
 // amax (optional, training): [B, Hp, 16, 64] uint8 arg-max of every pooling window (0..8 = dr*3+dc, 9 = dead ReLU)
-int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, void* out, int B, int T, int F, cudaStream_t stream,
-                   uint8_t* amax = nullptr);
+// sat: the 8x8x64 summed-area table of the conv0-bias taps (launch_stem_pack), bn_scale / bn_bias: folded FrozenBN
+int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, const float* bn_scale, const float* sat, void* out, int B,
+                   int T, int F, cudaStream_t stream, uint8_t* amax = nullptr);
 
 // ---- pack.cu
 int launch_bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* bias,

@@ -439,8 +439,7 @@ int Model::backbone(const float* x, int N, int T, int F, Arena& ws, void** feat,
         const int n0 = c * chunk, nc = std::min(chunk, N - n0);
         if (!dry) {
             if (cfg_.precision == 1 && cfg_.use_tensor_cores)
-                SEDT_TRY(launch_stem_tc(x + (size_t)n0 * T * F, packed_ + off_stem_wtc, (const float*)(packed_ + off_stem_bias),
-                                        fb.pong, nc, T, F, s));
+                SEDT_TRY(launch_stem_tc(x + (size_t)n0 * T * F, packed_ + off_stem_wtc, sw.bias, sw.scale, sw.sat, fb.pong, nc, T, F, s));
             else
                 SEDT_TRY(launch_stem(x + (size_t)n0 * T * F, sw, fb.pong, dt, nc, T, F, s));
         }

@@ -1,16 +1,19 @@
 // Backbone stem on tcgen05 (bf16 tier): conv0 (1x1, bias) + conv1 (7x7 s2 p3) + FrozenBN + ReLU +
 // maxpool (3x3 s2 p1) in one kernel.  Reference: sedt/backbone.py:97-111, torchvision resnet.py:266-272.
 //
-// conv0 folded into conv1 turns the stem into a 2-input-channel 7x7 convolution: channel 0 is the
-// log-mel value, channel 1 is an indicator that is 1 inside the clip and 0 in conv1's zero padding
-// (conv0's bias only reaches taps that land inside the clip).  As a GEMM that is K = 2 x 49, padded
-// to 2 x 64: the A tile [128 conv pixels x 128] is built in shared memory by the CTA's threads
-// (im2col of a staged fp32 patch, written directly in the 128B-swizzled K-major layout), B
-// [64 channels x 128] is a pre-swizzled 16 KiB image produced at pack time (BN scale folded in) and
-// fetched with one bulk copy.  D lives in TMEM; the epilogue adds the BN bias, applies ReLU and
-// parks the conv tile in shared memory as bf16, from where the 3x3/s2 max-pool is taken.
+// conv0 folded into conv1 is a 1-input-channel 7x7 convolution (weights Weff = sum_c conv1[:, c] * w0[c]) plus a bias term
+// that only counts the taps landing INSIDE the clip (conv1's zero padding comes after conv0's bias).  As a GEMM the
+// convolution is K = 49, padded to 64: the A tile [128 conv pixels x 64] is built in shared memory by the CTA's threads
+// (im2col of a staged fp32 patch, written directly in the 128B-swizzled K-major layout), B [64 channels x 64] is a
+// pre-swizzled 8 KiB image produced at pack time (BN scale folded in) and fetched with one bulk copy.  The inside-the-clip
+// bias depends only on the pixel's border class (row class x {col 0, col 1, col 31, interior}); it is evaluated in fp32
+// from the 8x8 summed-area table of the bias taps (stem_pack_kernel) into a small shared-memory table per CTA and added
+// in the epilogue together with the BN bias.  (The first version carried it as a second, inside-indicator input channel:
+// K = 2 x 64, twice the im2col work and MMA time.)  D lives in TMEM; the epilogue applies ReLU and parks the conv tile in
+// shared memory as bf16, from where the 3x3/s2 max-pool is taken.
 //
-// One CTA = 4 pooled rows of one clip = 9 conv rows = 3 M-tiles of 4 conv rows.
+// One CTA = 4 pooled rows of one clip = 9 conv rows = 2 M-tiles of 4 conv rows + 1 M-tile of which only the first row
+// (32 pixels, one warp) is built and kept.  ~70 KiB of shared memory: three CTAs per SM.
 #include "tc_common.cuh"
 
 namespace sedt {
@@ -19,16 +22,20 @@ namespace {
 using namespace tc;
 
 constexpr int ST_PH = 4;                    // pooled rows per CTA
-constexpr int ST_TILES = 3;                 // 12 conv rows are computed, 9 are used
+constexpr int ST_CR = 2 * ST_PH + 1;        // 9 conv rows
+constexpr int ST_TILES = 3;
 constexpr int ST_XR = 2 * (4 * ST_TILES) + 5;   // 29 input rows
 constexpr int ST_XC = 72;
-constexpr int A_OFF = 0;                    // 2 chunks x [128 px][64 k] bf16 = 32 KiB
-constexpr int B_OFF = 32768;                // 2 chunks x [64 ch][64 k] bf16 = 16 KiB
-constexpr int C_OFF = 49152;                // [12 conv rows][32 px][64 ch] bf16 = 48 KiB
-constexpr int X_OFF = 98304;                // [29][72] fp32
-constexpr int BIAS_OFF = X_OFF + ST_XR * ST_XC * 4;
-constexpr int STBAR_OFF = ((BIAS_OFF + 256 + 15) / 16) * 16;
+constexpr int ST_NCLS = 5;                  // bias tables: interior rows + up to 4 border rows per CTA
+constexpr int A_OFF = 0;                    // [128 px][64 k] bf16 = 16 KiB
+constexpr int B_OFF = 16384;                // [64 ch][64 k] bf16 = 8 KiB
+constexpr int C_OFF = 24576;                // [9 conv rows][32 px][64 ch] bf16 = 36 KiB
+constexpr int X_OFF = C_OFF + ST_CR * 32 * 128;                 // [29][72] fp32
+constexpr int TAB_OFF = X_OFF + ST_XR * ST_XC * 4;              // [ST_NCLS][4 col classes][64] fp32 bias tables
+constexpr int ROWCLS_OFF = TAB_OFF + ST_NCLS * 4 * 64 * 4;      // [12] int: bias table of each local conv row
+constexpr int STBAR_OFF = ((ROWCLS_OFF + 64 + 15) / 16) * 16;
 constexpr int ST_SMEM = STBAR_OFF + 64 + 1024;
+static_assert(ST_SMEM * 3 <= 232448, "three stem CTAs per SM");
 
 __device__ __forceinline__ uint32_t swz128(int row, int piece) { return (uint32_t)(row * 128 + ((piece ^ (row & 7)) << 4)); }
 
@@ -43,12 +50,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <bool kArgmax>
 __global__ void __launch_bounds__(128)
 stem_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wtc, const float* __restrict__ bias,
+               const float* __restrict__ scale, const float* __restrict__ sat,
                __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ amax, int T, int Hc, int Hp)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* xs = (float*)(smem + X_OFF);
-    float* sbias = (float*)(smem + BIAS_OFF);
+    float* tab = (float*)(smem + TAB_OFF);
+    int* rowcls = (int*)(smem + ROWCLS_OFF);
     uint64_t* bar_w = (uint64_t*)(smem + STBAR_OFF);
     uint64_t* bar_mma = bar_w + 1;
     uint32_t* tmem_slot = (uint32_t*)(bar_mma + 1);
@@ -62,19 +71,67 @@ stem_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wtc, con
     if (t == 0) {
         mbar_init(bar_w, 1); mbar_init(bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar_w, 16384);
+        mbar_expect_tx(bar_w, 8192);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(smem + B_OFF)), "l"(wtc), "r"(16384), "r"(smem_u32(bar_w)) : "memory");
+                     ::"r"(smem_u32(smem + B_OFF)), "l"(wtc), "r"(8192), "r"(smem_u32(bar_w)) : "memory");
     }
     if (warp == 0) tmem_alloc<64>(tmem_slot);
 
+    // ---- stage the 29 x 64 input patch (columns -3..68 in xs, zero outside the clip): all loads of a thread are issued
+    // before the first store (ncu: 35 % of the stall samples sat on a load-then-store loop here) ----
     const float* xb = x + (size_t)b * T * 64;
-    for (int i = t; i < ST_XR * ST_XC; i += 128) {
-        const int ri = i / ST_XC, ci = i - ri * ST_XC;
-        const int row = row0 + ri, col = ci - 3;
-        xs[i] = (row >= 0 && row < T && col >= 0 && col < 64) ? __ldg(xb + (size_t)row * 64 + col) : 0.f;
+    {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = t + k * 128, ri = i >> 4, c4 = i & 15;
+            const int row = row0 + ri;
+            v[k] = (i < ST_XR * 16 && row >= 0 && row < T) ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * 64) + c4)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int i = t; i < ST_XR * 8; i += 128) {            // the 3 + 5 padding columns of every row
+            const int ri = i >> 3, k = i & 7;
+            xs[ri * ST_XC + (k < 3 ? k : 64 + k)] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = t + k * 128, ri = i >> 4, c4 = i & 15;
+            if (i < ST_XR * 16) {
+                float* d = xs + ri * ST_XC + 3 + c4 * 4;
+                d[0] = v[k].x; d[1] = v[k].y; d[2] = v[k].z; d[3] = v[k].w;
+            }
+        }
     }
-    if (t < 64) sbias[t] = bias[t];
+    // ---- bias tables: table 0 = rows whose 7 tap rows all lie inside the clip; border rows get their own ----
+    // valid tap rows of conv row hc: [max(0, 3 - 2 hc), min(6, T + 2 - 2 hc)]; tap columns of conv column wc likewise
+    // with 64 mel bins: wc = 0 -> [3, 6], wc = 1 -> [1, 6], wc = 31 -> [0, 4], else [0, 6]
+    int ncls = 1;
+    int cls_rlo[ST_NCLS], cls_rhi[ST_NCLS];
+    cls_rlo[0] = 0; cls_rhi[0] = 6;
+#pragma unroll 1
+    for (int lr = 0; lr < ST_CR; ++lr) {
+        const int hc = cr0 + lr;
+        int cls = 0;
+        if (hc >= 0 && hc < Hc) {
+            const int rlo = max(0, 3 - 2 * hc), rhi = min(6, T + 2 - 2 * hc);
+            if (rlo != 0 || rhi != 6) {
+                cls = -1;
+                for (int k = 1; k < ncls; ++k) if (cls_rlo[k] == rlo && cls_rhi[k] == rhi) cls = k;
+                if (cls < 0 && ncls < ST_NCLS) { cls = ncls; cls_rlo[ncls] = rlo; cls_rhi[ncls] = rhi; ++ncls; }
+                if (cls < 0) cls = 0;            // cannot happen: at most 2 top + 2 bottom border rows exist
+            }
+        }
+        if (t == 0) rowcls[lr] = cls;
+    }
+    for (int i = t; i < ncls * 4 * 64; i += 128) {
+        const int ch = i & 63, cc = (i >> 6) & 3, k = i >> 8;
+        const int rlo = cls_rlo[k], rhi = cls_rhi[k];
+        const int slo = cc == 1 ? 3 : (cc == 2 ? 1 : 0), shi = cc == 3 ? 4 : 6;
+        // inclusive summed-area table with a zero border: S[r + 1][s + 1]
+        const float bsum = __ldg(sat + ((rhi + 1) * 8 + (shi + 1)) * 64 + ch) - __ldg(sat + (rlo * 8 + (shi + 1)) * 64 + ch)
+                         - __ldg(sat + ((rhi + 1) * 8 + slo) * 64 + ch) + __ldg(sat + (rlo * 8 + slo) * 64 + ch);
+        tab[i] = fmaf(bsum, __ldg(scale + ch), __ldg(bias + ch));
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -83,37 +140,32 @@ stem_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wtc, con
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
 
     const int wc = t & 31;
+    const int cc = wc == 0 ? 1 : (wc == 1 ? 2 : (wc == 31 ? 3 : 0));
 #pragma unroll 1
     for (int tile = 0; tile < ST_TILES; ++tile) {
         const int lr = tile * 4 + (t >> 5);      // local conv row of this thread's pixel
-        const int hc = cr0 + lr;
-        // ---- im2col row of pixel (hc, wc): chunk 0 = log-mel taps, chunk 1 = inside indicator ----
-        {
-            uint32_t av[32], iv[32];
+        const bool active = lr < ST_CR;          // the last tile only carries conv row 8 (warp 0)
+        // ---- im2col row of pixel (cr0 + lr, wc): 49 log-mel taps, zero padded to 64 ----
+        if (active) {
+            uint32_t av[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { av[i] = 0u; iv[i] = 0u; }
-            float prev = 0.f; float pin = 0.f;
+            for (int i = 0; i < 32; ++i) av[i] = 0u;
+            float prev = 0.f;
 #pragma unroll
             for (int r = 0; r < 7; ++r) {
                 const float* xr = xs + (2 * lr + r) * ST_XC + 2 * wc;
-                const int irow = 2 * hc - 3 + r;
-                const bool rin = irow >= 0 && irow < T;
 #pragma unroll
-                for (int s = 0; s < 7; ++s) {
-                    const int k = r * 7 + s;
-                    const int icol = 2 * wc - 3 + s;
-                    const float v = xr[s];
-                    const float ind = (rin && icol >= 0 && icol < 64) ? 1.f : 0.f;
-                    if (k & 1) { av[k >> 1] = pack_bf16(prev, v); iv[k >> 1] = pack_bf16(pin, ind); }
-                    else { prev = v; pin = ind; }
+                for (int s_ = 0; s_ < 7; ++s_) {
+                    const int k = r * 7 + s_;
+                    const float v = xr[s_];
+                    if (k & 1) av[k >> 1] = pack_bf16(prev, v);
+                    else prev = v;
                 }
             }
-            av[24] = pack_bf16(prev, 0.f); iv[24] = pack_bf16(pin, 0.f);      // k = 48 is the last tap
+            av[24] = pack_bf16(prev, 0.f);       // k = 48 is the last tap
 #pragma unroll
-            for (int pc = 0; pc < 8; ++pc) {
+            for (int pc = 0; pc < 8; ++pc)
                 *reinterpret_cast<uint4*>(smem + A_OFF + swz128(t, pc)) = make_uint4(av[4 * pc], av[4 * pc + 1], av[4 * pc + 2], av[4 * pc + 3]);
-                *reinterpret_cast<uint4*>(smem + A_OFF + 16384 + swz128(t, pc)) = make_uint4(iv[4 * pc], iv[4 * pc + 1], iv[4 * pc + 2], iv[4 * pc + 3]);
-            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
@@ -124,19 +176,18 @@ stem_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wtc, con
             constexpr uint32_t idesc = make_idesc(128, 64);
             const uint32_t sa = smem_u32(smem + A_OFF), sb = smem_u32(smem + B_OFF);
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base, make_smem_desc(sa + c * 16384 + k * 32), make_smem_desc(sb + c * 8192 + k * 32), idesc,
-                              (c > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, k > 0 ? 1u : 0u);
             umma_commit(bar_mma);
         }
         mbar_wait(bar_mma, tile & 1);
         tc_fence_after();
-        // ---- epilogue: + BN bias, ReLU, bf16, park the conv pixel (64 channels = 128 bytes) ----
-        {
+        // ---- epilogue: + (BN bias + inside-the-clip conv0 bias of this pixel's border class), ReLU, bf16, park the
+        // conv pixel (64 channels = 128 bytes) ----
+        if (active) {
             const int px = lr * 32 + wc;
             uint8_t* crow = smem + C_OFF + px * 128;
+            const float* pb = tab + (rowcls[lr] * 4 + cc) * 64;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t acc[32];
@@ -147,8 +198,8 @@ stem_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wtc, con
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int ch = half * 32 + j8 * 8 + 2 * q;
-                        const float a = fmaxf(__uint_as_float(acc[j8 * 8 + 2 * q]) + sbias[ch], 0.f);
-                        const float c = fmaxf(__uint_as_float(acc[j8 * 8 + 2 * q + 1]) + sbias[ch + 1], 0.f);
+                        const float a = fmaxf(__uint_as_float(acc[j8 * 8 + 2 * q]) + pb[ch], 0.f);
+                        const float c = fmaxf(__uint_as_float(acc[j8 * 8 + 2 * q + 1]) + pb[ch + 1], 0.f);
                         w[q] = pack_bf16(a, c);
                     }
                     *reinterpret_cast<uint4*>(crow + (((half * 4 + j8) ^ (px & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -265,9 +316,11 @@ int launch_stem_tc_pack(const float* conv0_w, const float* conv0_b, const float*
     return SEDT_OK;
 }
 
-int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, void* out, int B, int T, int F, cudaStream_t stream,
-                   uint8_t* amax)
+int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, const float* bn_scale, const float* sat, void* out, int B,
+                   int T, int F, cudaStream_t stream, uint8_t* amax)
 {
+    SEDT_REQUIRE(bn_scale != nullptr && sat != nullptr, "stem_tc: needs the BN scale and the bias summed-area table");
+    SEDT_REQUIRE(T >= 1, "stem_tc: T=%d", T);
     SEDT_REQUIRE(F == 64, "stem: the fused stem kernel needs 64 mel bins (config.py n_mels), got F=%d", F);
     SEDT_REQUIRE(((uintptr_t)wtc & 15) == 0, "stem_tc: weight image must be 16-byte aligned");
     if (B == 0) return SEDT_OK;
@@ -282,10 +335,10 @@ int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, void* 
     ProfScope _prof(PROF_STEM, stream);
     if (amax != nullptr) {
         SEDT_REQUIRE(((uintptr_t)amax & 7) == 0, "stem_tc: arg-max buffer must be 8-byte aligned");
-        SEDT_CHECK_CUDA(launch_pdl(stem_tc_kernel<true>, grid, block, ST_SMEM, stream, 1, x, (const uint8_t*)wtc, bn_bias,
+        SEDT_CHECK_CUDA(launch_pdl(stem_tc_kernel<true>, grid, block, ST_SMEM, stream, 1, x, (const uint8_t*)wtc, bn_bias, bn_scale, sat,
                                    (__nv_bfloat16*)out, amax, T, Hc, Hp));
     } else {
-        SEDT_CHECK_CUDA(launch_pdl(stem_tc_kernel<false>, grid, block, ST_SMEM, stream, 1, x, (const uint8_t*)wtc, bn_bias,
+        SEDT_CHECK_CUDA(launch_pdl(stem_tc_kernel<false>, grid, block, ST_SMEM, stream, 1, x, (const uint8_t*)wtc, bn_bias, bn_scale, sat,
                                    (__nv_bfloat16*)out, (uint8_t*)nullptr, T, Hc, Hp));
     }
     SEDT_COUNT_LAUNCH();

@@ -204,7 +204,8 @@ int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int 
     };
 
     // ---- backbone
-    SEDT_TRY(launch_stem_tc(x, packed_ + off_stem_wtc, P_(off_stem_bias), tp.stem_out, B, T, F, s, tp.stem_amax));
+    SEDT_TRY(launch_stem_tc(x, packed_ + off_stem_wtc, P_(off_stem_bias), P_(off_stem_scale), P_(off_sat), tp.stem_out, B, T, F, s,
+                            tp.stem_amax));
     const void* cur = tp.stem_out;
     for (size_t i = 0; i < blocks_.size(); ++i) {
         const Block& b = blocks_[i];
