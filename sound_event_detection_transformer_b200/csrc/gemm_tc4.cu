@@ -17,21 +17,29 @@ using namespace tc;
 
 constexpr int NUM_THREADS4 = 352;
 
-template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO, int MAX_KB>
+// HALO (3x3, stride 1, dilation 1, 64 input channels, 8- or 16-pixel-wide tiles): instead of nine [128 px x 64 ch] boxes per
+// tile - which re-read nearly the same pixels nine times from L2 (ncu: these launches sat at 20 % tensor pipe, 13 % DRAM,
+// i.e. on the L2 -> SM path) - the producer loads three boxes of bh + 2 rows, one per horizontal tap shift.  The three
+// vertical taps of a shift are the same shared-memory image read at row offsets 0, bw, 2 bw pixels: whole 1024-byte swizzle
+// atoms, so the UMMA descriptor just starts further down.  A traffic per tile: 3 x (bh + 2) / bh boxes instead of 9.
+constexpr int HALO_SLOT_BYTES = 20480;                                      // (bh + 2) * bw pixels * 128 B <= 160 pixels
+
+template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO, int MAX_KB, int HALO = 0>
 struct Smem4 {
+    static constexpr int A_SLOT = HALO ? HALO_SLOT_BYTES : A_STAGE_BYTES;
     static constexpr int B_KB_BYTES = BLOCK_N * BLOCK_K * 2;                // one 64-wide k block of the weight tile
     static constexpr int CHUNK_COLS = 128 / (int)sizeof(TO);
     static constexpr int NCHUNK = BLOCK_N / CHUNK_COLS;
     static constexpr int CHUNK_BYTES = BLOCK_M * 128;
     static constexpr int OUT_BYTES = NCHUNK * CHUNK_BYTES;
-    static constexpr int B_OFFSET = STAGES * A_STAGE_BYTES;                 // A ring first, then the resident weights
+    static constexpr int B_OFFSET = STAGES * A_SLOT;                        // A ring first, then the resident weights
     static constexpr int OUT_OFFSET = B_OFFSET + MAX_KB * B_KB_BYTES;
     static constexpr int BAR_OFFSET = OUT_OFFSET + OUT_BUFS * OUT_BYTES;
     static constexpr int NBARS = 2 * STAGES + 4 + 2 * OUT_BUFS + 1;
     static constexpr int TOTAL = BAR_OFFSET + NBARS * 8 + 16 + 1024;
 };
 
-template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO, int MAX_KB>
+template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO, int MAX_KB, int HALO = 0>
 __global__ void __launch_bounds__(NUM_THREADS4, 1)
 conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                 const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
@@ -39,7 +47,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ TcParams p,
                 const int tiles_nc, const int total_tiles)
 {
-    using L = Smem4<BLOCK_N, STAGES, OUT_BUFS, TO, MAX_KB>;
+    using L = Smem4<BLOCK_N, STAGES, OUT_BUFS, TO, MAX_KB, HALO>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // keep the pointer derived from the __shared__ symbol so that staging traffic compiles to LDS/STS
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -101,6 +109,18 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             for (int t = first_item; t < total_tiles; t += item_stride) {
                 int w0, h0, n0, col0;
                 tile_coords(t, w0, h0, n0, col0);
+                if constexpr (HALO) {
+                    // map_a3: the same activation with a (64 ch, bw, bh + 2, 1) box; rows above / below the clip and the
+                    // columns left / right of it are zero-filled by TMA = the convolution's zero padding
+                    const uint32_t halo_bytes = (uint32_t)((p.bh + 2) * p.bw * 128);
+                    for (int dwi = 0; dwi < 3; ++dwi) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], halo_bytes);
+                        tma_load_4d(&map_a3, smem + stage * L::A_SLOT, &full_bar[stage], 0, w0 + dwi - 1, h0 - 1, n0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    continue;
+                }
                 for (int tap = 0; tap < p.ntaps; ++tap) {
                     const int mi = p.tap_map[tap];
                     const CUtensorMap* ma = mi == 0 ? &map_a0 : (mi == 1 ? &map_a1 : (mi == 2 ? &map_a2 : &map_a3));
@@ -108,7 +128,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                     for (int c0 = 0; c0 < p.Cin; c0 += BLOCK_K) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES);
-                        tma_load_4d(ma, smem + stage * A_STAGE_BYTES, &full_bar[stage], c0, cw, ch, n0);
+                        tma_load_4d(ma, smem + stage * L::A_SLOT, &full_bar[stage], c0, cw, ch, n0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -126,10 +146,30 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                 mbar_wait(&acc_empty[as], ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+                if constexpr (HALO) {
+                    for (int dwi = 0; dwi < 3; ++dwi) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t base = smem_u32(smem + stage * L::A_SLOT);
+#pragma unroll
+                        for (int dhi = 0; dhi < 3; ++dhi) {
+                            const uint32_t sa = base + (uint32_t)(dhi * p.bw * 128);       // tap (dhi, dwi): rows shifted by dhi
+                            const uint32_t sb = smem_u32(sB + (dhi * 3 + dwi) * L::B_KB_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma_bf16(tmem_d, make_smem_desc(sa + k * UMMA_K * 2), make_smem_desc(sb + k * UMMA_K * 2), idesc,
+                                          (dwi > 0 || dhi > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(&acc_full[as]);
+                    continue;
+                }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * A_STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + stage * L::A_SLOT);
                     const uint32_t sb = smem_u32(sB + kb * L::B_KB_BYTES);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -229,12 +269,12 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     }
 }
 
-template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO, int MAX_KB>
+template <int BLOCK_N, int STAGES, int OUT_BUFS, typename TO, int MAX_KB, int HALO = 0>
 int launch_v4(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr, cudaStream_t stream)
 {
-    using L = Smem4<BLOCK_N, STAGES, OUT_BUFS, TO, MAX_KB>;
+    using L = Smem4<BLOCK_N, STAGES, OUT_BUFS, TO, MAX_KB, HALO>;
     static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-    auto kern = conv_tc4_kernel<BLOCK_N, STAGES, OUT_BUFS, TO, MAX_KB>;
+    auto kern = conv_tc4_kernel<BLOCK_N, STAGES, OUT_BUFS, TO, MAX_KB, HALO>;
     static bool attr_set = false;
     if (!attr_set) {
         SEDT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -273,7 +313,20 @@ int launch_conv_tc_ws(const ConvGemm& g, cudaStream_t stream)
     SEDT_TRY(encode_out_map(&mo, g.out, g.ldc, f32, g, pr.p));
     if (g.residual != nullptr) SEDT_TRY(encode_out_map(&mr, g.residual, g.ld_res, f32, g, pr.p));
     else mr = mo;
-    if (block_n == 64) return launch_v4<64, 6, 2, __nv_bfloat16, 9>(pr, mo, mr, stream);
+    if (block_n == 64) {
+        static const bool halo_on = [] { const char* e = getenv("SEDT_HALO"); return e == nullptr || atoi(e) != 0; }();
+        const TcParams& q = pr.p;
+        if (halo_on && g.R == 3 && g.S == 3 && g.stride == 1 && g.dil == 1 && g.pad == 1 && g.Cin == 64 && q.bn == 1 &&
+            (q.bw == 8 || q.bw == 16) && q.bw * q.bh == BLOCK_M) {
+            // the halo box: same tensor as map_a[0], (bh + 2) rows per box
+            const uint64_t dims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+            const uint64_t strides[3] = {(uint64_t)g.lda * 2, (uint64_t)g.W * g.lda * 2, (uint64_t)g.H * g.W * g.lda * 2};
+            const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)q.bw, (uint32_t)(q.bh + 2), 1u};
+            SEDT_TRY(encode_map(&pr.map_a[3], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, g.in, 4, dims, strides, box));
+            return launch_v4<64, 5, 2, __nv_bfloat16, 9, 1>(pr, mo, mr, stream);
+        }
+        return launch_v4<64, 6, 2, __nv_bfloat16, 9>(pr, mo, mr, stream);
+    }
     return f32 ? launch_v4<128, 6, 1, float, 4>(pr, mo, mr, stream) : launch_v4<128, 6, 2, __nv_bfloat16, 4>(pr, mo, mr, stream);
 }
 
