@@ -194,6 +194,15 @@ SEDT_API int sedt_decode_events(const float* logits, const float* boxes, const f
                                 float min_duration, float* scores, int64_t* labels, float* boxes_se, int32_t* ev_class,
                                 float* ev_onset, float* ev_offset, float* ev_score, int32_t* ev_count, void* stream);
 
+/* get_pseudo_labels (engine.py:300-348): teacher outputs -> pseudo targets for the unlabelled clips.  PostProcess with
+ * at_m = 1 and is_semi (audio_tags [B, C1-1] fp32 0/1 = at >= classwise_threshold, or null), keep queries with
+ * score >= class_threshold[label] and width > min_width (= 0.2 / clip seconds), then (del_overlap) greedy same-class overlap
+ * suppression in descending score order.  labels / scores [B, Q], boxes_out [B, Q, 2] (center, width): the first counts[b]
+ * entries are the kept queries in the reference's order. */
+SEDT_API int sedt_pseudo_labels(const float* logits, const float* boxes, const float* audio_tags, const float* class_threshold,
+                                int B, int Q, int C1, float min_width, int del_overlap, int64_t* labels, float* boxes_out,
+                                float* scores, int32_t* counts, void* stream);
+
 /* ---- clip_grad_norm_ + AdamW: the optimizer half of the training step (engine.py:76-80; AdamW with two lr groups,
  * train_sedt.py:234-240,269-270; torch/optim/adamw.py _single_tensor_adamw arithmetic, amsgrad = maximize = False).
  * The caller keeps a device table of tensors and a device table of (tensor index, chunk index) pairs that splits

@@ -43,3 +43,36 @@ def decode_strong(result: dict, class_names: Sequence[str], threshold: float = 0
         for r in arr:
             out.append([name, r[1], r[2], r[0]])
     return out
+
+
+def pseudo_labels(logits: np.ndarray, boxes: np.ndarray, at, class_thr: np.ndarray, clip_seconds: float,
+                  del_overlap: bool = True):
+    """numpy fp32 restatement of engine.get_pseudo_labels (engine.py:300-348) for one batch: PostProcess with at_m = 1 and
+    is_semi (sedt/sedt.py:359-396), class-wise threshold + minimum width, greedy same-class overlap suppression in
+    descending score order.  Returns per clip (labels int64 [n], boxes fp32 [n, 2] (center, width)).  Pinned against the
+    reference's own function by tests/golden/make_golden.py (fixture `pseudo_*.npz`)."""
+    f32 = np.float32
+    logits = np.asarray(logits, f32); boxes = np.asarray(boxes, f32); class_thr = np.asarray(class_thr, f32)
+    x = logits - logits.max(-1, keepdims=True)
+    e = np.exp(x, dtype=f32)
+    prob = (e / e.sum(-1, keepdims=True, dtype=f32)).astype(f32)
+    ev = prob[..., :-1]
+    if at is not None:
+        tags = (np.asarray(at, f32) >= class_thr).astype(f32)
+        ev = ev * tags[:, None, :]
+    out = []
+    min_w = f32(0.2 / clip_seconds)
+    for b in range(logits.shape[0]):
+        scores = ev[b].max(-1); labels = ev[b].argmax(-1)
+        keep0 = (scores >= class_thr[labels]) & (boxes[b, :, 1] > min_w)
+        lab, bx, sc = labels[keep0], boxes[b][keep0], scores[keep0]
+        if not del_overlap:
+            out.append((lab.astype(np.int64), bx)); continue
+        order = list(np.argsort(-sc, kind="stable"))
+        xs = bx[:, 0] - bx[:, 1] / f32(2); ys = bx[:, 0] + bx[:, 1] / f32(2)
+        keep = []
+        while order:
+            k = order[0]; keep.append(k)
+            order = [j for j in order[1:] if max(f32(0), min(ys[j], ys[k]) - max(xs[j], xs[k])) == 0 or lab[j] != lab[k]]
+        out.append((lab[keep].astype(np.int64), bx[keep]))
+    return out

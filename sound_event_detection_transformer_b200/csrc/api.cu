@@ -211,6 +211,14 @@ int sedt_decode_events(const float* logits, const float* boxes, const float* tar
                                 (cudaStream_t)stream);
 }
 
+int sedt_pseudo_labels(const float* logits, const float* boxes, const float* audio_tags, const float* class_threshold, int B, int Q,
+                       int C1, float min_width, int del_overlap, int64_t* labels, float* boxes_out, float* scores,
+                       int32_t* counts, void* stream)
+{
+    return launch_pseudo_labels(logits, boxes, audio_tags, class_threshold, B, Q, C1, min_width, del_overlap, labels, boxes_out,
+                                scores, counts, (cudaStream_t)stream);
+}
+
 int sedt_optim_chunk_elems(void) { return optim_chunk_elems(); }
 
 int sedt_grad_norm(const sedt_optim_tensor* tensors, const int32_t* chunks, int nchunks, float* partials, float* norm_out, void* stream)

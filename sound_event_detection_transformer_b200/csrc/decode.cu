@@ -120,7 +120,103 @@ decode_events_kernel(const float* __restrict__ logits, const float* __restrict__
     ev_count[b] = n_out;
 }
 
+// get_pseudo_labels (engine.py:300-348, the teacher's targets for the unlabelled clips in train_ss_sedt.py): PostProcess with
+// at_m = 1 and is_semi (boxes stay (center, width)), class-wise score thresholds, minimum width, then a greedy same-class
+// overlap suppression in descending score order.  One warp per clip; the greedy pass is sequential on lane 0.
+__global__ void __launch_bounds__(kDecWarps * 32)
+pseudo_labels_kernel(const float* __restrict__ logits, const float* __restrict__ boxes, const float* __restrict__ tags,
+                     const float* __restrict__ class_thr, int B, int Q, int C1, float min_width, int del_overlap,
+                     int64_t* __restrict__ out_labels, float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                     int32_t* __restrict__ out_count)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kDecWarps + warp;
+    if (b >= B) return;
+    const int C = C1 - 1;
+    const int per_warp = Q * C1 + 5 * Q;
+    float* prob = smem + warp * per_warp;
+    float* sc = prob + Q * C1;
+    float* xs = sc + Q;                            // onset  = c - l / 2
+    float* ys = xs + Q;                            // offset = c + l / 2
+    int* lab = reinterpret_cast<int*>(ys + Q);
+    int* ord = lab + Q;
+    const float* lg = logits + (size_t)b * Q * C1;
+    for (int q = lane; q < Q; q += 32) {
+        float m = -CUDART_INF_F;
+        for (int c = 0; c < C1; ++c) m = fmaxf(m, lg[q * C1 + c]);
+        float s = 0.f;
+        for (int c = 0; c < C1; ++c) { const float e = expf(lg[q * C1 + c] - m); prob[q * C1 + c] = e; s += e; }
+        for (int c = 0; c < C1; ++c) prob[q * C1 + c] = prob[q * C1 + c] / s;
+    }
+    __syncwarp();
+    for (int q = lane; q < Q; q += 32) {
+        int best = 0; float bv = -CUDART_INF_F;
+        for (int c = 0; c < C; ++c) {
+            const float v = tags != nullptr ? prob[q * C1 + c] * tags[(size_t)b * C + c] : prob[q * C1 + c];   // at_m = 1
+            if (v > bv) { bv = v; best = c; }
+        }
+        const float cx = boxes[((size_t)b * Q + q) * 2], w = boxes[((size_t)b * Q + q) * 2 + 1];
+        const bool keep = bv >= class_thr[best] && w > min_width;
+        sc[q] = bv; lab[q] = keep ? best : -1;
+        xs[q] = cx - w / 2.f; ys[q] = cx + w / 2.f;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    int n = 0;
+    for (int q = 0; q < Q; ++q) if (lab[q] >= 0) ord[n++] = q;
+    int n_out = 0;
+    auto emit = [&](int q) {
+        out_labels[(size_t)b * Q + n_out] = lab[q];
+        out_boxes[((size_t)b * Q + n_out) * 2] = boxes[((size_t)b * Q + q) * 2];
+        out_boxes[((size_t)b * Q + n_out) * 2 + 1] = boxes[((size_t)b * Q + q) * 2 + 1];
+        out_scores[(size_t)b * Q + n_out] = sc[q];
+        ++n_out;
+    };
+    if (!del_overlap) {
+        for (int i = 0; i < n; ++i) emit(ord[i]);
+    } else {
+        for (int i = 1; i < n; ++i) {              // descending score (stable)
+            const int v = ord[i];
+            int j = i - 1;
+            while (j >= 0 && sc[ord[j]] < sc[v]) { ord[j + 1] = ord[j]; --j; }
+            ord[j + 1] = v;
+        }
+        while (n > 0) {
+            const int k = ord[0];
+            emit(k);
+            int m = 0;
+            for (int i = 1; i < n; ++i) {
+                const int j = ord[i];
+                const float overlap = fmaxf(fminf(ys[j], ys[k]) - fmaxf(xs[j], xs[k]), 0.f);
+                if (overlap == 0.f || lab[j] != lab[k]) ord[m++] = j;
+            }
+            n = m;
+        }
+    }
+    out_count[b] = n_out;
+}
+
 }  // namespace
+
+int launch_pseudo_labels(const float* logits, const float* boxes, const float* tags, const float* class_thr, int B, int Q, int C1,
+                         float min_width, int del_overlap, int64_t* out_labels, float* out_boxes, float* out_scores,
+                         int32_t* out_count, cudaStream_t stream)
+{
+    if (B == 0) return SEDT_OK;
+    SEDT_REQUIRE(logits && boxes && class_thr && out_labels && out_boxes && out_scores && out_count, "pseudo_labels: null argument");
+    SEDT_REQUIRE(Q >= 1 && C1 >= 2, "pseudo_labels: bad sizes Q=%d C1=%d", Q, C1);
+    const size_t smem = (size_t)kDecWarps * (Q * C1 + 5 * Q) * sizeof(float);
+    SEDT_REQUIRE(smem <= 200 * 1024, "pseudo_labels: Q=%d x C1=%d does not fit shared memory", Q, C1);
+    if (smem > 48 * 1024)
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(pseudo_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope _prof(PROF_OTHER, stream);
+    pseudo_labels_kernel<<<(unsigned)ceil_div(B, kDecWarps), kDecWarps * 32, smem, stream>>>(
+        logits, boxes, tags, class_thr, B, Q, C1, min_width, del_overlap, out_labels, out_boxes, out_scores, out_count);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
 
 int launch_decode_events(const float* logits, const float* boxes, const float* sizes, const float* tags, int B, int Q, int C1,
                          int at_m, float fuse_threshold, int is_semi, float score_threshold, float min_duration,

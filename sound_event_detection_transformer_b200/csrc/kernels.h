@@ -225,6 +225,10 @@ int launch_decode_events(const float* logits, const float* boxes, const float* s
                          float* out_scores, int64_t* out_labels, float* out_boxes, int32_t* ev_class, float* ev_onset,
                          float* ev_offset, float* ev_score, int32_t* ev_count, cudaStream_t stream);
 
+int launch_pseudo_labels(const float* logits, const float* boxes, const float* tags, const float* class_thr, int B, int Q, int C1,
+                         float min_width, int del_overlap, int64_t* out_labels, float* out_boxes, float* out_scores,
+                         int32_t* out_count, cudaStream_t stream);
+
 // ---- optim.cu: clip_grad_norm_ + AdamW over a (tensor, chunk) table (engine.py:76-80)
 int optim_chunk_elems();
 int launch_grad_norm(const void* tensors, const int32_t* chunks, int nchunks, float* partials, float* norm_out, cudaStream_t stream);

@@ -468,3 +468,35 @@ class PostProcess(nn.Module):
             out.append([[class_names[int(cls[i])] if class_names is not None else int(cls[i]), float(on[i]), float(off[i]),
                          float(sc[i])] for i in range(n)])
         return out
+
+    @torch.no_grad()
+    def pseudo_labels(self, tea_outputs, target_sizes, classwise_threshold, del_overlap: bool = True):
+        """engine.get_pseudo_labels (engine.py:300-348) for the whole batch in one launch: returns per clip
+        {'labels': int64 [n], 'boxes': fp32 [n, 2] (center, width), 'scores': fp32 [n]} on the device, kept queries in the
+        reference's order (descending score after the same-class overlap suppression)."""
+        from .. import _lib
+        lib = _lib.load()
+        logits = tea_outputs["pred_logits"]
+        if not logits.is_cuda:
+            raise RuntimeError("pseudo_labels needs CUDA tensors (there is no CPU path)")
+        logits = logits.detach().to(torch.float32).contiguous()
+        boxes = tea_outputs["pred_boxes"].detach().to(torch.float32).contiguous()
+        dev = logits.device
+        B, Q, C1 = logits.shape
+        thr = torch.as_tensor(classwise_threshold).to(dev, torch.float32).reshape(-1).contiguous()
+        if thr.numel() != C1 - 1:
+            raise ValueError(f"classwise_threshold has {thr.numel()} entries for {C1 - 1} classes")
+        tags = None
+        if "at" in tea_outputs:
+            tags = (tea_outputs["at"].reshape(B, C1 - 1) >= thr).to(torch.float32).contiguous()
+        min_width = 0.2 / float(torch.as_tensor(target_sizes).reshape(-1)[0])
+        labels = torch.empty(B, Q, dtype=torch.int64, device=dev)
+        out_boxes = torch.empty(B, Q, 2, dtype=torch.float32, device=dev)
+        scores = torch.empty(B, Q, dtype=torch.float32, device=dev)
+        counts = torch.zeros(B, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sedt_pseudo_labels(logits.data_ptr(), boxes.data_ptr(), _lib.ptr(tags) or None, thr.data_ptr(), B, Q, C1,
+                                              float(min_width), int(bool(del_overlap)), labels.data_ptr(), out_boxes.data_ptr(),
+                                              scores.data_ptr(), counts.data_ptr(), _lib.current_stream()))
+        n = counts.tolist()
+        return [{"labels": labels[i, :k], "boxes": out_boxes[i, :k], "scores": scores[i, :k]} for i, k in enumerate(n)]

@@ -171,3 +171,15 @@ def synth_criterion_case(B: int, Q: int, C: int, D: int, kmin: int = 0, kmax: in
                         "boxes": (torch.rand(k, 2, generator=g) * 0.9 + 0.05) * scale,
                         "orig_size": torch.tensor(10.0)})
     return outputs, targets
+
+
+def synth_teacher_case(B: int, Q: int, C: int, seed: int):
+    """Teacher-shaped outputs for the pseudo-label path (same generator as tests/golden/make_golden.py)."""
+    g = torch.Generator().manual_seed(9000 + seed)
+    logits = torch.randn(B, Q, C + 1, generator=g)
+    hot = torch.randint(0, 4, (B, Q), generator=g)
+    logits.scatter_add_(2, hot.unsqueeze(-1), ((torch.rand(B, Q, generator=g) > 0.4).float() * 6.0).unsqueeze(-1))
+    boxes = torch.stack([torch.rand(B, Q, generator=g), torch.rand(B, Q, generator=g) * 0.3], -1)
+    boxes[:, ::5, 1] *= 0.05
+    at = torch.rand(B, C, generator=g)
+    return logits, boxes, at

@@ -158,6 +158,43 @@ def run_matcher_variant(tag, B, Q, C, kmin, kmax, seed, fine_tune=False, normali
     print(f"matcher_{tag}: {B} clips, {sum(len(r) for r, _ in idx)} pairs")
 
 
+def synth_teacher_case(B, Q, C, seed):
+    """Teacher-shaped outputs for the pseudo-label path: a few confident queries per clip, clustered intervals."""
+    g = torch.Generator().manual_seed(9000 + seed)
+    logits = torch.randn(B, Q, C + 1, generator=g)
+    hot = torch.randint(0, 4, (B, Q), generator=g)
+    logits.scatter_add_(2, hot.unsqueeze(-1), ((torch.rand(B, Q, generator=g) > 0.4).float() * 6.0).unsqueeze(-1))
+    boxes = torch.stack([torch.rand(B, Q, generator=g), torch.rand(B, Q, generator=g) * 0.3], -1)
+    boxes[:, ::5, 1] *= 0.05
+    at = torch.rand(B, C, generator=g)
+    return logits, boxes, at
+
+
+def run_pseudo_labels(tag, B, Q, C, seed, del_overlap=True):
+    """engine.get_pseudo_labels (engine.py:300-348) of the reference on seeded teacher outputs.  engine.py imports the data /
+    metric stack (librosa, sed_eval, psds_eval), absent here and never used by this function: stubbed like dcase_util."""
+    for name in ("librosa", "soundfile", "sed_eval", "psds_eval", "sed_eval.sound_event", "sed_eval.util", "librosa.display",
+                 "librosa.feature"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["psds_eval"].PSDSEval = object
+    sys.modules["psds_eval"].plot_psd_roc = None
+    import collections
+    import engine
+    logits, boxes, at = synth_teacher_case(B, Q, C, seed)
+    thr = torch.linspace(0.45, 0.7, C)
+    sizes = torch.full((B,), 10.0)
+    targets = [dict() for _ in range(B)]
+    counter = collections.Counter()
+    out = engine.get_pseudo_labels({"pred_logits": logits, "pred_boxes": boxes, "at": at}, {"bbox": PostProcess()}, sizes, targets,
+                                   counter, del_overlap=del_overlap, classwise_threshold=thr)
+    np.savez_compressed(os.path.join(HERE, f"pseudo_{tag}.npz"),
+                        labels=np.concatenate([t["labels"].numpy() for t in out]).astype(np.int64),
+                        boxes=np.concatenate([t["boxes"].numpy().reshape(-1, 2) for t in out]).astype(np.float32),
+                        counts=np.asarray([len(t["labels"]) for t in out], np.int32),
+                        meta=np.asarray([B, Q, C, seed, int(del_overlap)], np.int64), thr=thr.numpy())
+    print(f"pseudo_{tag}: {B} clips, {sum(len(t['labels']) for t in out)} pseudo events")
+
+
 def run_criterion(tag, args, B, seed, kmin=0, kmax=10, fine_tune=False, normalize=False, fl=False, rng_seed=1234):
     """Reference SetCriterion (sedt/sedt.py:134-352) built directly (build_model returns None for it
     without CUDA) on seeded model-shaped outputs: every loss value and the gradient of the weighted sum."""
@@ -191,6 +228,10 @@ def run_criterion(tag, args, B, seed, kmin=0, kmax=10, fine_tune=False, normaliz
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-pseudo" in sys.argv:
+        run_pseudo_labels("q20", 48, 20, 10, seed=31)
+        run_pseudo_labels("q10_keepall", 16, 10, 10, seed=32, del_overlap=False)
+        sys.exit(0)
     if "--only-variants" in sys.argv:
         run_matcher_variant("v_fl", 64, 20, 10, 0, 10, seed=21, fl=True)
         run_matcher_variant("v_finetune", 64, 20, 10, 1, 10, seed=22, fine_tune=True, normalize=True, epsilon=1.0, alpha=1.0)

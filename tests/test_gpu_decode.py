@@ -91,3 +91,32 @@ def test_decode_events_match_reference_golden(tag):
                 assert abs(e[1] - g[1]) < 1e-5 and abs(e[2] - g[2]) < 1e-5 and abs(e[3] - g[3]) < 1e-5
             total += len(ev)
     assert total > 0
+
+
+@pytest.mark.parametrize("tag", ["q20", "q10_keepall"])
+def test_pseudo_labels_match_reference_golden(tag):
+    """PostProcess.pseudo_labels (csrc/decode.cu: pseudo_labels_kernel) against engine.get_pseudo_labels of the reference
+    (engine.py:300-348; fixture made by tests/golden/make_golden.py: run_pseudo_labels): labels and boxes identical."""
+    from sound_event_detection_transformer_b200 import synth
+    fx = np.load(os.path.join(GOLDEN, f"pseudo_{tag}.npz"))
+    B, Q, C, seed, del_overlap = [int(v) for v in fx["meta"]]
+    logits, boxes, at = synth.synth_teacher_case(B, Q, C, seed)
+    out = PostProcess().pseudo_labels({"pred_logits": logits.cuda(), "pred_boxes": boxes.cuda(), "at": at.cuda()},
+                                      torch.full((B,), 10.0), torch.from_numpy(fx["thr"]), del_overlap=bool(del_overlap))
+    assert np.array_equal(np.asarray([len(t["labels"]) for t in out], np.int32), fx["counts"])
+    assert np.array_equal(torch.cat([t["labels"] for t in out]).cpu().numpy(), fx["labels"])
+    assert np.array_equal(torch.cat([t["boxes"] for t in out]).cpu().numpy(), fx["boxes"])
+    assert fx["counts"].sum() > 0
+
+
+def test_pseudo_labels_match_oracle_large():
+    from sound_event_detection_transformer_b200 import synth
+    logits, boxes, at = synth.synth_teacher_case(96, 40, 6, 77)
+    thr = np.linspace(0.4, 0.6, 6).astype(np.float32)
+    want = decode_oracle.pseudo_labels(logits.numpy(), boxes.numpy(), at.numpy(), thr, 10.0, True)
+    got = PostProcess().pseudo_labels({"pred_logits": logits.cuda(), "pred_boxes": boxes.cuda(), "at": at.cuda()},
+                                      torch.full((96,), 10.0), torch.from_numpy(thr))
+    suppressed = 0
+    for (wl, wb), g in zip(want, got):
+        assert np.array_equal(g["labels"].cpu().numpy(), wl) and np.array_equal(g["boxes"].cpu().numpy(), wb)
+    assert sum(len(wl) for wl, _ in want) > 0

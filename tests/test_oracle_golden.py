@@ -128,3 +128,15 @@ def test_matcher_oracle_variants_match_reference(tag):
     assert np.array_equal(np.concatenate([r for r, _ in idx]), fx["rows"])
     assert np.array_equal(np.concatenate([c for _, c in idx]), fx["cols"])
     assert np.allclose(np.concatenate(coef), fx["coef"])
+
+
+@pytest.mark.parametrize("tag", ["q20", "q10_keepall"])
+def test_pseudo_label_oracle_matches_reference(tag):
+    """oracle/decode_oracle.pseudo_labels against engine.get_pseudo_labels of the reference (fixture pseudo_*.npz)."""
+    fx = np.load(os.path.join(GOLDEN, f"pseudo_{tag}.npz"))
+    B, Q, C, seed, del_overlap = [int(v) for v in fx["meta"]]
+    logits, boxes, at = synth.synth_teacher_case(B, Q, C, seed)
+    out = decode_oracle.pseudo_labels(logits.numpy(), boxes.numpy(), at.numpy(), fx["thr"], 10.0, bool(del_overlap))
+    assert np.array_equal(np.asarray([len(l) for l, _ in out], np.int32), fx["counts"])
+    assert np.array_equal(np.concatenate([l for l, _ in out]), fx["labels"])
+    assert np.array_equal(np.concatenate([b.reshape(-1, 2) for _, b in out]), fx["boxes"])
