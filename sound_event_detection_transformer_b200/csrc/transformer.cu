@@ -295,8 +295,9 @@ heads_out_kernel(const float* __restrict__ hs, const float* __restrict__ h2, con
         const int64_t lb = r / Qall;                         // l * B + b
         const bool is_at = at != nullptr && q == 0 && lb >= (int64_t)(D_ - 1) * B;
         if (q < start && !is_at) continue;
-        float x[8];
+        float x[8], y[8];
         load8(hs + r * D + lane * 8, x);
+        if (q >= start) load8(h2 + r * D + lane * 8, y);          // both rows in flight before the first reduction
         if (q >= start) {
             const int64_t o = lb * Q + (q - start);
             for (int c0 = 0; c0 < C1; c0 += 4) {
@@ -304,8 +305,6 @@ heads_out_kernel(const float* __restrict__ hs, const float* __restrict__ h2, con
                 dot4(x, s_wc + c0 * D, C1 - c0, lane, a);
                 if (lane < 4 && c0 + lane < C1) logits[o * C1 + c0 + lane] = pick4(a, lane) + bc[c0 + lane];
             }
-            float y[8];
-            load8(h2 + r * D + lane * 8, y);
             float a[4];
             dot4(y, s_wb, 2, lane, a);
             if (lane < 2) boxes[o * 2 + lane] = sigmoidf(pick4(a, lane) + bb[lane]);
@@ -455,7 +454,7 @@ int launch_heads_out(const float* hs, const float* h2, const float* wc, const fl
     SEDT_REQUIRE(smem <= 200 * 1024, "heads: %d classes do not fit shared memory", C1);
     if (smem > 48 * 1024)
         SEDT_CHECK_CUDA(cudaFuncSetAttribute(heads_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows, 8 * 4), 148 * 4);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows, 8), 148 * 8);
     ProfScope _prof(PROF_OTHER, stream);
     SEDT_CHECK_CUDA(launch_pdl(heads_out_kernel, dim3(grid), dim3(256), smem, stream, 1, hs, h2, wc, bc, wb, bb, ww, bw, logits, boxes,
                                at, D_, B, Qall, start, C1, C));
