@@ -26,6 +26,7 @@ constexpr int WG_THREADS = 192;
 constexpr int WG_BOX_BYTES = BLOCK_M * BLOCK_K * 2;          // one [128 pixels][64 channels] box = 16 KiB
 
 struct WgParams {
+    const float* row_scale;      // optional per-output-channel factor applied in the epilogue
     float* dw;
     int ldw;                     // R*S*Cin
     int Cin;
@@ -136,6 +137,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_const
         const int quad = warp & 3;
         const int r = quad * 32 + lane;
         float* drow = p.dw + (size_t)(co0 + r) * p.ldw + (size_t)tap * p.Cin + ci0;
+        const float rs = p.row_scale != nullptr ? p.row_scale[co0 + r] : 1.f;
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         if (nkb > 0) {
@@ -146,8 +148,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_const
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     atomicAdd(reinterpret_cast<float4*>(drow + c * 32 + j),
-                              make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
-                                          __uint_as_float(acc[j + 3])));
+                              make_float4(__uint_as_float(acc[j]) * rs, __uint_as_float(acc[j + 1]) * rs, __uint_as_float(acc[j + 2]) * rs,
+                                          __uint_as_float(acc[j + 3]) * rs));
             }
         }
     }
@@ -215,7 +217,7 @@ int launch_conv_wgrad_tc(const WgradGemm& g, cudaStream_t stream)
 
     WgParams p;
     memset(&p, 0, sizeof(p));
-    p.dw = g.dw; p.ldw = g.R * g.S * g.Cin; p.Cin = g.Cin;
+    p.dw = g.dw; p.row_scale = g.row_scale; p.ldw = g.R * g.S * g.Cin; p.Cin = g.Cin;
     p.bw = pr.p.bw; p.bh = pr.p.bh; p.bn = pr.p.bn; p.tiles_w = pr.p.tiles_w; p.tiles_h = pr.p.tiles_h; p.tiles_m = pr.tiles_m;
     p.ntaps = g.R * g.S; p.cin_tiles = g.Cin / block_n;
     memcpy(p.tap_map, pr.p.tap_map, sizeof(p.tap_map));

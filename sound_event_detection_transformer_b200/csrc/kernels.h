@@ -47,6 +47,7 @@ struct WgradGemm {
     const void* x = nullptr;       // forward input, NHWC bf16, pixel stride lda
     const void* dy = nullptr;      // gradient of the forward output, NHWC bf16, pixel stride ldy
     float* dw = nullptr;           // fp32 [Cout][R*S*Cin], accumulated atomically (caller zeroes)
+    const float* row_scale = nullptr;   // optional [Cout]: every contribution to row co is multiplied by row_scale[co] (folded BN scale)
     int B = 0, H = 1, W = 1, Cin = 0, lda = 0;
     int Ho = 1, Wo = 1, Cout = 0, ldy = 0;
     int R = 1, S = 1, stride = 1, dil = 1, pad = 0;

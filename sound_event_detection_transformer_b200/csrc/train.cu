@@ -635,13 +635,17 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     };
     auto conv_wgrad = [&](const ConvLayer& L, const void* x, int Hin, int Win, int Ho, int Wo, const void* dy) -> int {
         const size_t n = (size_t)L.cout * L.k * L.k * L.cin;
-        SEDT_TRY(launch_fill_zero(bb.dw, n * 4, s));
+        // 1x1: the GEMM layout [co][ci] IS the reference's OIHW layout, so the kernel accumulates straight into the (already
+        // zeroed) gradient slot with the folded BN scale applied per row; 3x3 goes through the scratch + tap permutation
+        const bool direct = L.k == 1;
+        if (!direct) SEDT_TRY(launch_fill_zero(bb.dw, n * 4, s));
         WgradGemm g;
-        g.x = x; g.dy = dy; g.dw = bb.dw;
+        g.x = x; g.dy = dy; g.dw = direct ? Gp(L.w_slot) : bb.dw; g.row_scale = direct ? P_(L.off_scale) : nullptr;
         g.B = B; g.H = Hin; g.W = Win; g.Cin = L.cin; g.lda = L.cin; g.Ho = Ho; g.Wo = Wo; g.Cout = L.cout; g.ldy = L.cout;
         g.R = g.S = L.k; g.stride = L.stride; g.dil = L.dil; g.pad = L.pad;
         SEDT_REQUIRE(conv_wgrad_tc_supported(g), "backward: conv weight gradient %dx%d k%d not supported", L.cout, L.cin, L.k);
         SEDT_TRY(launch_conv_wgrad_tc(g, s));
+        if (direct) return SEDT_OK;
         return launch_unpack_wgrad(bb.dw, P_(L.off_scale), Gp(L.w_slot), L.cout, L.cin, L.k * L.k, s);
     };
     const size_t first_trainable = 3;                 // layer1 (blocks 0-2) is frozen (sedt/backbone.py:60-62)
