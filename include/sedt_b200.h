@@ -269,6 +269,10 @@ SEDT_API int sedt_op_dropout_mask(uint8_t* out, int64_t n, uint64_t seed, uint64
 SEDT_API int sedt_op_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int k,
                                 int stride, int dil, int pad, void* stream);
 SEDT_API int sedt_op_conv_tc_supported(const sedt_conv_desc* d);
+/* Fused transformer FFN of the eval forward (sedt/transformer.py:202-203): out[M,256] fp32 = residual + relu(x W1^T + b1) W2^T + b2,
+ * x [M,256] bf16, W1 [ff,256] / W2 [256,ff] bf16 (nn.Linear layout), ff % 256 == 0; the [M,ff] hidden activation never leaves the SM. */
+SEDT_API int sedt_op_ffn(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual,
+                         float* out, int64_t M, int ff, void* stream);
 /* OIHW fp32 -> O(HW)I in `dtype` */
 SEDT_API int sedt_op_repack_conv(const float* w_oihw, void* out, int dtype, int Cout, int Cin, int R, int S, void* stream);
 SEDT_API int sedt_op_cast(const float* in, void* out, int dtype, int64_t n, void* stream);

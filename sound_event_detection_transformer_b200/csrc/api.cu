@@ -219,6 +219,14 @@ int sedt_pseudo_labels(const float* logits, const float* boxes, const float* aud
                                 scores, counts, (cudaStream_t)stream);
 }
 
+int sedt_op_ffn(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual, float* out,
+                int64_t M, int ff, void* stream)
+{
+    SEDT_REQUIRE(x && w1 && b1 && w2 && b2 && residual && out, "op_ffn: null argument");
+    if (!ffn_fused_supported(256, ff, M, x, w1, w2, residual, out, 256, 256)) { set_error("op_ffn: unsupported shape"); return SEDT_ERR_UNSUPPORTED; }
+    return launch_ffn_fused(x, w1, b1, w2, b2, residual, 256, out, 256, M, ff, (cudaStream_t)stream);
+}
+
 int sedt_optim_chunk_elems(void) { return optim_chunk_elems(); }
 
 int sedt_grad_norm(const sedt_optim_tensor* tensors, const int32_t* chunks, int nchunks, float* partials, float* norm_out, void* stream)

@@ -1,0 +1,576 @@
+// Fused transformer FFN (eval): out = residual + linear2(relu(linear1(x)))   (sedt/transformer.py:202-203, forward_pre)
+//
+//   x [M, 256] bf16 (LayerNorm output), W1 [ff, 256], W2 [256, ff] bf16 (K-major as packed), fp32 biases, fp32 residual / out.
+//
+// The unfused path writes the [M, ff] hidden activation to HBM (130 MB per encoder layer at B = 256: linear1 is bound by that
+// write, linear2 by reading it back).  Here a CTA keeps a 128-row tile of x resident and walks over the hidden dimension in
+// chunks of 128: GEMM1 (x W1_j^T, K = 256) accumulates a 128 x 128 tile in TMEM, the epilogue warps add the bias, apply ReLU,
+// round to bf16 and park the tile in shared memory in the swizzled K-major layout, where it is the A operand of GEMM2
+// (h_j W2_j^T, K = 128) accumulating the 128 x 256 output tile in TMEM over all chunks.  Software-pipelined by one chunk
+// (GEMM1_{j+1} is issued before GEMM2_j) so the tensor core has work while chunk j goes through the epilogue.
+//
+// The weights (2 MB per layer) stream through every CTA once per tile; from L2 alone that is the bound (measured: 112 us per
+// encoder layer against 100 us for the two separate GEMMs).  CL = 2: two CTAs of a cluster walk the weight sequence in
+// lockstep on different row tiles, each loads half of every weight box and multicasts it to both, and a ring slot is
+// recycled only when BOTH MMA warps have consumed it (commit multicast to both CTAs' empty barriers).
+//
+// TMEM: Y 256 columns + 2 x 128 (hidden accumulator, double buffered) = 512.  Shared memory: x 64 KiB, hidden 2 x 32 KiB,
+// weight ring 6 x 16 KiB ([128 rows x 64 k] boxes of W1 / W2).  Warps: 0 TMA producer, 1 MMA issuer, 2..9 epilogue.
+#include "tc_common.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+namespace sedt {
+namespace {
+
+using namespace tc;
+
+constexpr int FF_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int FF_SLOTS = 6;
+constexpr int FF_SLOT_BYTES = 16384;
+constexpr int FX_OFF = 0;                       // 4 k-blocks of [128 rows][64 k]
+constexpr int FH_OFF = 65536;                   // 2 buffers x 2 k-blocks
+constexpr int FW_OFF = 131072;                  // weight ring
+constexpr int FBAR_OFF = FW_OFF + FF_SLOTS * FF_SLOT_BYTES;
+constexpr int FF_NBARS = 2 * FF_SLOTS + 2 + 4 + 4 + 2;
+constexpr int FF_SMEM = FBAR_OFF + FF_NBARS * 8 + 16 + 1024;
+static_assert(FF_SMEM <= 232448, "shared memory budget exceeded");
+
+struct FfnParams {
+    const float* b1; const float* b2; const float* residual; float* out;
+    int ld_res, ldo, M, nch, tiles_m;
+};
+
+template <int CL>
+__global__ void __launch_bounds__(FF_THREADS, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+                 const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ FfnParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* slot_full = (uint64_t*)(smem + FBAR_OFF);
+    uint64_t* slot_empty = slot_full + FF_SLOTS;
+    uint64_t* x_full = slot_empty + FF_SLOTS;
+    uint64_t* x_empty = x_full + 1;
+    uint64_t* hacc_full = x_empty + 1;          // [2] MMA -> epilogue: hidden accumulator ready
+    uint64_t* hacc_empty = hacc_full + 2;       // [2] epilogue -> MMA: accumulator drained
+    uint64_t* hsm_full = hacc_empty + 2;        // [2] epilogue -> MMA: bf16 hidden tile parked in smem
+    uint64_t* hsm_empty = hsm_full + 2;         // [2] MMA -> epilogue: GEMM2 has read the tile
+    uint64_t* y_full = hsm_empty + 2;
+    uint64_t* y_empty = y_full + 1;
+    uint32_t* tmem_slot = (uint32_t*)(y_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nch = p.nch, half_uses = nch >> 1;
+    // tile schedule: CTA cr of cluster c takes tiles CL * (c + i * nclusters) + cr, i = 0 .. iters - 1 (the same number of
+    // iterations in both CTAs of a cluster; a tile index past the end loads zeros and stores nothing)
+    const int cr = CL == 2 ? (int)cluster_ctarank() : 0;
+    const int ncl = (int)gridDim.x / CL, cl = (int)blockIdx.x / CL;
+    const int items = (p.tiles_m + CL - 1) / CL;
+    const int iters = cl < items ? (items - cl + ncl - 1) / ncl : 0;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_w2);
+        for (int s = 0; s < FF_SLOTS; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], CL); }
+        mbar_init(x_full, 1); mbar_init(x_empty, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&hacc_full[b], 1); mbar_init(&hacc_empty[b], 8);
+            mbar_init(&hsm_full[b], 8); mbar_init(&hsm_empty[b], 1);
+        }
+        mbar_init(y_full, 1); mbar_init(y_empty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();     // the peer's barriers exist before anything is multicast to them
+    tc_fence_after();
+    pdl_trigger();
+    pdl_wait();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t TM_Y = 0, TM_H = 256;
+
+    if (warp == 0) {
+        // ===== TMA producer: x tile, then the weight boxes in exactly the order the MMA warp consumes them =====
+        if (lane == 0) {
+            int slot = 0; uint32_t sphase = 0;
+            auto next_slot = [&](const CUtensorMap* m, int c0, int c1) {
+                mbar_wait(&slot_empty[slot], sphase ^ 1);
+                mbar_expect_tx(&slot_full[slot], FF_SLOT_BYTES);
+                if constexpr (CL == 2)      // my 64 rows of the box, delivered to both CTAs (maps carry 64-row boxes)
+                    tma_load_2d_mcast(m, smem + FW_OFF + slot * FF_SLOT_BYTES + cr * (FF_SLOT_BYTES / 2), &slot_full[slot], c0, c1 + cr * 64,
+                                      (uint16_t)3);
+                else
+                    tma_load_2d(m, smem + FW_OFF + slot * FF_SLOT_BYTES, &slot_full[slot], c0, c1);
+                if (++slot == FF_SLOTS) { slot = 0; sphase ^= 1; }
+            };
+            for (int ti = 0; ti < iters; ++ti) {
+                const int t = CL * (cl + ti * ncl) + cr;
+                mbar_wait(x_empty, (ti & 1) ^ 1);
+                mbar_expect_tx(x_full, 4 * FF_SLOT_BYTES);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_x, smem + FX_OFF + kb * FF_SLOT_BYTES, x_full, kb * 64, t * 128);
+                for (int s = 0; s <= nch; ++s) {
+                    if (s < nch)
+                        for (int kb = 0; kb < 4; ++kb) next_slot(&map_w1, kb * 64, s * 128);
+                    if (s >= 1) {
+                        const int j = s - 1;
+                        for (int kb = 0; kb < 2; ++kb)
+                            for (int nh = 0; nh < 2; ++nh) next_slot(&map_w2, j * 128 + kb * 64, nh * 128);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 128);
+            int slot = 0; uint32_t sphase = 0;
+            auto release_slot = [&](uint64_t* bar) {
+                if constexpr (CL == 2) umma_commit_mcast(bar, (uint16_t)3); else umma_commit(bar);
+            };
+            for (int ti = 0; ti < iters; ++ti) {
+                mbar_wait(x_full, ti & 1);
+                tc_fence_after();
+                for (int s = 0; s <= nch; ++s) {
+                    if (s < nch) {
+                        // GEMM1_s: hidden accumulator (s & 1) = x W1_s^T
+                        const int b = s & 1;
+                        const uint32_t u = (uint32_t)(ti * half_uses + (s >> 1));
+                        mbar_wait(&hacc_empty[b], (u & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + TM_H + (uint32_t)(b * 128);
+                        for (int kb = 0; kb < 4; ++kb) {
+                            mbar_wait(&slot_full[slot], sphase);
+                            tc_fence_after();
+                            const uint32_t sa = smem_u32(smem + FX_OFF + kb * FF_SLOT_BYTES);
+                            const uint32_t sb = smem_u32(smem + FW_OFF + slot * FF_SLOT_BYTES);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            release_slot(&slot_empty[slot]);
+                            if (++slot == FF_SLOTS) { slot = 0; sphase ^= 1; }
+                        }
+                        umma_commit(&hacc_full[b]);
+                        if (s == nch - 1) umma_commit(x_empty);          // the x tile may be replaced
+                    }
+                    if (s >= 1) {
+                        // GEMM2_j: Y += h_j W2_j^T
+                        const int j = s - 1, b = j & 1;
+                        const uint32_t u = (uint32_t)(ti * half_uses + (j >> 1));
+                        if (j == 0) { mbar_wait(y_empty, (ti & 1) ^ 1); }
+                        mbar_wait(&hsm_full[b], u & 1);
+                        tc_fence_after();
+                        for (int kb = 0; kb < 2; ++kb) {
+                            const uint32_t sa = smem_u32(smem + FH_OFF + (b * 2 + kb) * FF_SLOT_BYTES);
+                            for (int nh = 0; nh < 2; ++nh) {
+                                mbar_wait(&slot_full[slot], sphase);
+                                tc_fence_after();
+                                const uint32_t sb = smem_u32(smem + FW_OFF + slot * FF_SLOT_BYTES);
+                                const uint32_t d = tmem_base + TM_Y + (uint32_t)(nh * 128);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16(d, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc,
+                                              (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
+                                release_slot(&slot_empty[slot]);
+                                if (++slot == FF_SLOTS) { slot = 0; sphase ^= 1; }
+                            }
+                        }
+                        umma_commit(&hsm_empty[b]);
+                        if (j == nch - 1) umma_commit(y_full);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..9: warp & 3 = TMEM lane quadrant, (warp - 2) >> 2 = column half =====
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int r = quad * 32 + lane;
+        const int sw = r & 7;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        for (int ti = 0; ti < iters; ++ti) {
+            const int t = CL * (cl + ti * ncl) + cr;
+            for (int j = 0; j < nch; ++j) {
+                const int b = j & 1;
+                const uint32_t u = (uint32_t)(ti * half_uses + (j >> 1));
+                mbar_wait(&hacc_full[b], u & 1);
+                tc_fence_after();
+                uint32_t a0[32], a1[32];
+                const uint32_t ta = lane_base + TM_H + (uint32_t)(b * 128 + half * 64);
+                tmem_ld32_nowait(ta, a0);
+                tmem_ld32_nowait(ta + 32, a1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hacc_empty[b]);               // accumulator drained
+                // bias + ReLU + bf16
+                const float* bias = p.b1 + j * 128 + half * 64;
+                uint32_t w[32];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float2 bb = __ldg(reinterpret_cast<const float2*>(bias) + q);
+                    const float v0 = fmaxf(__uint_as_float(a0[2 * q]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(a0[2 * q + 1]) + bb.y, 0.f);
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                    w[q] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + 32) + q);
+                    const float v0 = fmaxf(__uint_as_float(a1[2 * q]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(a1[2 * q + 1]) + bb.y, 0.f);
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                    w[16 + q] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                // park in the A-operand layout of GEMM2: k-block = half, row r, 16-byte piece XOR (r & 7)
+                mbar_wait(&hsm_empty[b], (u & 1) ^ 1);
+                uint8_t* row = smem + FH_OFF + (b * 2 + half) * FF_SLOT_BYTES + r * 128;
+#pragma unroll
+                for (int pc = 0; pc < 8; ++pc)
+                    *reinterpret_cast<uint4*>(row + ((pc ^ sw) << 4)) = make_uint4(w[4 * pc], w[4 * pc + 1], w[4 * pc + 2], w[4 * pc + 3]);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hsm_full[b]);
+            }
+            // ---- output tile: Y + b2 + residual -> fp32 global (32 contiguous floats per thread and slab) ----
+            mbar_wait(y_full, ti & 1);
+            tc_fence_after();
+            const int64_t m = (int64_t)t * 128 + r;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t acc[32];
+                const int col = half * 128 + c * 32;
+                tmem_ld32(lane_base + TM_Y + (uint32_t)col, acc);
+                if (m < p.M) {
+                    const float4* res = reinterpret_cast<const float4*>(p.residual + m * p.ld_res + col);
+                    float4* dst = reinterpret_cast<float4*>(p.out + m * p.ldo + col);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + q);
+                        const float4 rr = res[q];
+                        dst[q] = make_float4(__uint_as_float(acc[4 * q]) + bb.x + rr.x, __uint_as_float(acc[4 * q + 1]) + bb.y + rr.y,
+                                             __uint_as_float(acc[4 * q + 2]) + bb.z + rr.z, __uint_as_float(acc[4 * q + 3]) + bb.w + rr.w);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(y_empty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();     // no CTA leaves while its peer may still multicast into it
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+
+// ---- variant TS: the bf16 hidden tile stays in TENSOR MEMORY ------------------------------------------------------------
+// Measured on the variant above: 113 us per encoder layer whatever the weight traffic (the 2-CTA multicast changed nothing):
+// the 6-slot weight ring (96 KB in flight) cannot cover TMA latency x consumption rate (8 boxes per ~1 us chunk), and the
+// rest of shared memory is taken by the hidden double buffer.  Here the epilogue packs relu(acc + b1) to bf16 IN PLACE in the
+// accumulator's TMEM columns (tcgen05.st) and GEMM2 reads its A operand from TMEM (tcgen05.mma with [a_tmem]), which frees
+// 64 KiB of shared memory: the ring grows to 9 slots and b1 is staged in shared memory.  Two epilogue groups of eight warps
+// take alternate chunks, so two chunks are in the epilogue at once.
+//
+// Status: bit-for-bit the same result as the SS variants (tests/test_gpu_ffn.py), 108 us per encoder layer against 97 us for
+// the two GEMMs it replaces, so it is OFF by default (SEDT_FFN_FUSED=1 turns it on).  Timing breakdown with parts of the kernel
+// disabled (B200, M = 31744, ff = 2048): skeleton without MMAs and without the output pass 40 us (520 MB of weights through
+// TMA = 13 TB/s, the L2 -> SM limit), + MMAs 75 us (the N = 128 SS-mode MMAs of GEMM1 already saturate the shared-memory
+// read bandwidth, so the TMA writes do not overlap them), + output pass 111 us: the register -> global fp32 output with the
+// residual read (128 B per thread at a 1 KB stride, exposed at every tile boundary) costs 35 us and is the first thing to
+// replace by a TMA-staged store through the x region; then N = 256 MMAs for GEMM2 and the 2-CTA weight multicast.
+constexpr int TS_THREADS = 576;              // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue (two groups of eight)
+constexpr int TS_SLOTS = 9;
+constexpr int TS_MAX_FF = 3072;                  // b1 staged in shared memory (ncu: the per-element __ldg of the bias was the
+constexpr int TSW_OFF = 65536;                   // epilogue's long-scoreboard stall and paced the whole kernel)
+constexpr int TSB1_OFF = TSW_OFF + TS_SLOTS * FF_SLOT_BYTES;
+constexpr int TSBAR_OFF = TSB1_OFF + TS_MAX_FF * 4;
+constexpr int TS_NBARS = 2 * TS_SLOTS + 2 + 6 + 2;
+constexpr int TS_SMEM = TSBAR_OFF + TS_NBARS * 8 + 16 + 1024;
+static_assert(TS_SMEM <= 232448, "shared memory budget exceeded");
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TS_THREADS, 1)
+ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+                    const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ FfnParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* slot_full = (uint64_t*)(smem + TSBAR_OFF);
+    uint64_t* slot_empty = slot_full + TS_SLOTS;
+    uint64_t* x_full = slot_empty + TS_SLOTS;
+    uint64_t* x_empty = x_full + 1;
+    uint64_t* hacc_full = x_empty + 1;          // [2] MMA -> epilogue group b: fp32 hidden accumulator ready
+    uint64_t* hts_full = hacc_full + 2;         // [2] epilogue group b -> MMA: bf16 hidden tile packed in TMEM
+    uint64_t* hfree = hts_full + 2;             // [2] GEMM2 has read the packed tile: the accumulator may be overwritten
+    uint64_t* y_full = hfree + 2;
+    uint64_t* y_empty = y_full + 1;
+    uint32_t* tmem_slot = (uint32_t*)(y_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nch = p.nch, half_uses = nch >> 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_w2);
+        for (int s = 0; s < TS_SLOTS; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 1); }
+        mbar_init(x_full, 1); mbar_init(x_empty, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&hacc_full[b], 1); mbar_init(&hts_full[b], 8); mbar_init(&hfree[b], 1); }
+        mbar_init(y_full, 1); mbar_init(y_empty, 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    float* sb1 = (float*)(smem + TSB1_OFF);
+    for (int i = threadIdx.x; i < nch * 128; i += TS_THREADS) sb1[i] = p.b1[i];        // weights: not produced by the predecessor
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_trigger();
+    pdl_wait();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t TM_Y = 0, TM_H = 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int slot = 0; uint32_t sphase = 0;
+            auto next_slot = [&](const CUtensorMap* m, int c0, int c1) {
+                mbar_wait(&slot_empty[slot], sphase ^ 1);
+                mbar_expect_tx(&slot_full[slot], FF_SLOT_BYTES);
+                tma_load_2d(m, smem + TSW_OFF + slot * FF_SLOT_BYTES, &slot_full[slot], c0, c1);
+                if (++slot == TS_SLOTS) { slot = 0; sphase ^= 1; }
+            };
+            int ti = 0;
+            for (int t = blockIdx.x; t < p.tiles_m; t += gridDim.x, ++ti) {
+                mbar_wait(x_empty, (ti & 1) ^ 1);
+                mbar_expect_tx(x_full, 4 * FF_SLOT_BYTES);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_x, smem + FX_OFF + kb * FF_SLOT_BYTES, x_full, kb * 64, t * 128);
+                for (int s = 0; s <= nch; ++s) {
+                    if (s < nch)
+                        for (int kb = 0; kb < 4; ++kb) next_slot(&map_w1, kb * 64, s * 128);
+                    if (s >= 1) {
+                        const int j = s - 1;
+                        for (int kb = 0; kb < 2; ++kb)
+                            for (int nh = 0; nh < 2; ++nh) next_slot(&map_w2, j * 128 + kb * 64, nh * 128);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 128);
+            int slot = 0; uint32_t sphase = 0;
+            int ti = 0;
+            for (int t = blockIdx.x; t < p.tiles_m; t += gridDim.x, ++ti) {
+                mbar_wait(x_full, ti & 1);
+                tc_fence_after();
+                for (int s = 0; s <= nch; ++s) {
+                    if (s < nch) {
+                        const int b = s & 1;
+                        const uint32_t u = (uint32_t)(ti * half_uses + (s >> 1));
+                        mbar_wait(&hfree[b], (u & 1) ^ 1);               // GEMM2 of this buffer's previous chunk has retired
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + TM_H + (uint32_t)(b * 128);
+                        for (int kb = 0; kb < 4; ++kb) {
+                            mbar_wait(&slot_full[slot], sphase);
+                            tc_fence_after();
+                            const uint32_t sa = smem_u32(smem + FX_OFF + kb * FF_SLOT_BYTES);
+                            const uint32_t sb = smem_u32(smem + TSW_OFF + slot * FF_SLOT_BYTES);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            umma_commit(&slot_empty[slot]);
+                            if (++slot == TS_SLOTS) { slot = 0; sphase ^= 1; }
+                        }
+                        umma_commit(&hacc_full[b]);
+                        if (s == nch - 1) umma_commit(x_empty);
+                    }
+                    if (s >= 1) {
+                        const int j = s - 1, b = j & 1;
+                        const uint32_t u = (uint32_t)(ti * half_uses + (j >> 1));
+                        if (j == 0) { mbar_wait(y_empty, (ti & 1) ^ 1); }
+                        mbar_wait(&hts_full[b], u & 1);
+                        tc_fence_after();
+                        const uint32_t ta = tmem_base + TM_H + (uint32_t)(b * 128);      // bf16 pairs: 8 columns per K = 16
+                        for (int kb = 0; kb < 2; ++kb) {
+                            for (int nh = 0; nh < 2; ++nh) {
+                                mbar_wait(&slot_full[slot], sphase);
+                                tc_fence_after();
+                                const uint32_t sb = smem_u32(smem + TSW_OFF + slot * FF_SLOT_BYTES);
+                                const uint32_t d = tmem_base + TM_Y + (uint32_t)(nh * 128);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16_ts(d, ta + (uint32_t)((kb * 4 + k) * 8), make_smem_desc(sb + k * 32), idesc,
+                                                 (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
+                                umma_commit(&slot_empty[slot]);
+                                if (++slot == TS_SLOTS) { slot = 0; sphase ^= 1; }
+                            }
+                        }
+                        umma_commit(&hfree[b]);
+                        if (j == nch - 1) umma_commit(y_full);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..17: group g = (warp - 2) >> 3 takes the chunks with j & 1 == g (accumulator buffer g); inside a
+        // group, warp & 3 = TMEM lane quadrant and ((warp - 2) & 7) >> 2 = which 64 of the 128 hidden columns.  The two warps
+        // of a quadrant meet at a named barrier between their loads and their in-place stores. =====
+        const int e = warp - 2;
+        const int quad = warp & 3, grp = e >> 3, half = (e & 7) >> 2;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int bar_id = 1 + grp * 4 + quad;
+        int ti = 0;
+        for (int t = blockIdx.x; t < p.tiles_m; t += gridDim.x, ++ti) {
+            for (int j = grp; j < nch; j += 2) {
+                const uint32_t u = (uint32_t)(ti * half_uses + (j >> 1));
+                mbar_wait(&hacc_full[grp], u & 1);
+                tc_fence_after();
+                const uint32_t ta = lane_base + TM_H + (uint32_t)(grp * 128);
+                uint32_t a0[32], a1[32];
+                tmem_ld32_nowait(ta + (uint32_t)(half * 64), a0);
+                tmem_ld32_nowait(ta + (uint32_t)(half * 64 + 32), a1);
+                tmem_ld_wait();
+                const float* bias = sb1 + j * 128 + half * 64;
+                uint32_t w[32];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float2 bb = *(reinterpret_cast<const float2*>(bias) + q);
+                    const __nv_bfloat162 hv = __floats2bfloat162_rn(fmaxf(__uint_as_float(a0[2 * q]) + bb.x, 0.f),
+                                                                    fmaxf(__uint_as_float(a0[2 * q + 1]) + bb.y, 0.f));
+                    w[q] = *reinterpret_cast<const uint32_t*>(&hv);
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float2 bb = *(reinterpret_cast<const float2*>(bias + 32) + q);
+                    const __nv_bfloat162 hv = __floats2bfloat162_rn(fmaxf(__uint_as_float(a1[2 * q]) + bb.x, 0.f),
+                                                                    fmaxf(__uint_as_float(a1[2 * q + 1]) + bb.y, 0.f));
+                    w[16 + q] = *reinterpret_cast<const uint32_t*>(&hv);
+                }
+                // both warps of this quadrant have read their fp32 columns: the packed tile may overwrite columns [0, 64)
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                tmem_st32(ta + (uint32_t)(half * 32), w);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hts_full[grp]);
+            }
+            mbar_wait(y_full, ti & 1);
+            tc_fence_after();
+            const int64_t m = (int64_t)t * 128 + r;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t acc[32];
+                const int col = (grp * 2 + half) * 64 + c * 32;
+                tmem_ld32(lane_base + TM_Y + (uint32_t)col, acc);
+                if (m < p.M) {
+                    const float4* res = reinterpret_cast<const float4*>(p.residual + m * p.ld_res + col);
+                    float4* dst = reinterpret_cast<float4*>(p.out + m * p.ldo + col);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + q);
+                        const float4 rr = res[q];
+                        dst[q] = make_float4(__uint_as_float(acc[4 * q]) + bb.x + rr.x, __uint_as_float(acc[4 * q + 1]) + bb.y + rr.y,
+                                             __uint_as_float(acc[4 * q + 2]) + bb.z + rr.z, __uint_as_float(acc[4 * q + 3]) + bb.w + rr.w);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(y_empty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace
+
+bool ffn_fused_supported(int d, int ff, int64_t M, const void* x, const void* w1, const void* w2, const float* residual, const float* out,
+                         int ld_res, int ldo)
+{
+    if (d != 256 || ff % 256 != 0 || ff < 256 || ff > 3072 || M < 1) return false;
+    if (((uintptr_t)x & 15) || ((uintptr_t)w1 & 15) || ((uintptr_t)w2 & 15) || ((uintptr_t)residual & 15) || ((uintptr_t)out & 15)) return false;
+    return ld_res % 4 == 0 && ldo % 4 == 0;
+}
+
+// out[M, 256] (fp32) = residual + relu(x W1^T + b1) W2^T + b2; x [M, 256] bf16 (row stride 256), W1 [ff, 256], W2 [256, ff] bf16
+int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual, int ld_res,
+                     float* out, int ldo, int64_t M, int ff, cudaStream_t stream)
+{
+    SEDT_REQUIRE(ffn_fused_supported(256, ff, M, x, w1, w2, residual, out, ld_res, ldo), "ffn_fused: unsupported shape / alignment");
+    SEDT_TRY(tc_init());
+    // variant: "ts" (default) keeps the hidden tile in tensor memory; "ss2" / "ss1" park it in shared memory (2-CTA multicast / plain)
+    static const int variant = [] {
+        const char* e = getenv("SEDT_FFN_VARIANT");
+        if (e == nullptr) return 0;
+        return e[0] == 's' && e[1] == 's' ? (e[2] == '1' ? 1 : 2) : 0;
+    }();
+    const int cl = variant == 1 ? 1 : 2;
+    CUtensorMap mx, m1, m2;
+    const uint32_t box[2] = {64u, 128u};
+    const uint32_t wbox[2] = {64u, variant == 2 ? 64u : 128u};   // ss2: each CTA loads half of a weight box
+    {
+        const uint64_t dims[2] = {256, (uint64_t)M}; const uint64_t strides[1] = {256 * 2};
+        SEDT_TRY(encode_map(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x, 2, dims, strides, box));
+    }
+    {
+        const uint64_t dims[2] = {256, (uint64_t)ff}; const uint64_t strides[1] = {256 * 2};
+        SEDT_TRY(encode_map(&m1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w1, 2, dims, strides, wbox));
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)ff, 256}; const uint64_t strides[1] = {(uint64_t)ff * 2};
+        SEDT_TRY(encode_map(&m2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w2, 2, dims, strides, wbox));
+    }
+    FfnParams p;
+    p.b1 = b1; p.b2 = b2; p.residual = residual; p.out = out; p.ld_res = ld_res; p.ldo = ldo;
+    p.M = (int)M; p.nch = ff / 128; p.tiles_m = (int)ceil_div(M, 128);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+        attr_set = true;
+    }
+    ProfScope _prof(PROF_GEMM_TC, stream);
+    if (variant == 0) {
+        const int grid = std::min(p.tiles_m, num_sms());
+        SEDT_CHECK_CUDA(launch_pdl(ffn_fused_ts_kernel, dim3((unsigned)grid), dim3(TS_THREADS), TS_SMEM, stream, 1, mx, m1, m2, p));
+    } else if (cl == 2) {
+        const int items = (p.tiles_m + 1) / 2;
+        const int grid = 2 * std::min(items, num_sms() / 2);
+        SEDT_CHECK_CUDA(launch_pdl(ffn_fused_kernel<2>, dim3((unsigned)grid), dim3(FF_THREADS), FF_SMEM, stream, 2, mx, m1, m2, p));
+    } else {
+        const int grid = std::min(p.tiles_m, num_sms());
+        SEDT_CHECK_CUDA(launch_pdl(ffn_fused_kernel<1>, dim3((unsigned)grid), dim3(FF_THREADS), FF_SMEM, stream, 1, mx, m1, m2, p));
+    }
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+}  // namespace sedt

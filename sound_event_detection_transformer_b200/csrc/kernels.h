@@ -206,6 +206,12 @@ private:
     cudaStream_t stream_;
 };
 
+// ---- ffn_fused.cu: out = residual + relu(x W1^T + b1) W2^T + b2 with the hidden activation kept on chip (eval forward)
+bool ffn_fused_supported(int d, int ff, int64_t M, const void* x, const void* w1, const void* w2, const float* residual, const float* out,
+                         int ld_res, int ldo);
+int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual, int ld_res,
+                     float* out, int ldo, int64_t M, int ff, cudaStream_t stream);
+
 // ---- matcher.cu
 int launch_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
                    const int32_t* offsets, int B, int Q, int C1, int Kmax, float w_class, float w_bbox, float w_giou,

@@ -570,6 +570,17 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
     float* x32 = (float*)ws.alloc((size_t)rows * d * 4);
     SEDT_TRY(linear(input_proj_, 0, d, feat, dt, 2048, rows, nullptr, x32, DT_F32, d, 0, s, dry));
 
+    // FFN: x32 += linear2(relu(linear1(in))).  SEDT_FFN_FUSED=1 keeps the hidden activation on chip (ffn_fused.cu).
+    static const bool ffn_fused = [] { const char* e = getenv("SEDT_FFN_FUSED"); return e != nullptr && atoi(e) != 0; }();
+    auto ffn = [&](const Linear& l1, const Linear& l2, const void* in, int64_t nrows, void* hidden, float* x) -> int {
+        if (ffn_fused && !dry && dt == DT_BF16 && cfg_.use_tensor_cores && !l1.f32_only && !l2.f32_only &&
+            ffn_fused_supported(d, ff, nrows, in, packed_ + l1.off_w, packed_ + l2.off_w, x, x, d, d))
+            return launch_ffn_fused(in, packed_ + l1.off_w, (const float*)(packed_ + l1.off_b), packed_ + l2.off_w,
+                                    (const float*)(packed_ + l2.off_b), x, d, x, d, nrows, ff, s);
+        SEDT_TRY(linear(l1, 0, ff, in, dt, d, nrows, nullptr, hidden, dt, ff, 1, s, dry));
+        return linear(l2, 0, d, hidden, dt, ff, nrows, x, x, DT_F32, d, 0, s, dry);
+    };
+
     // ---- encoder (transformer.py:98-111, :177-204)
     void* na = ws.alloc((size_t)rows * d * es);
     void* nap = ws.alloc((size_t)rows * d * es);
@@ -579,14 +590,12 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
             SEDT_TRY(LN(e.n1, x32, pos, pos_rows, na, nap, nullptr, rows));
             SEDT_TRY(mha(e.attn, true, nap, nap, na, B, S, S, mask_ds, nullptr, x32, x32, ws, s, dry));
             SEDT_TRY(LN(e.n2, x32, nullptr, 1, na, nullptr, nullptr, rows));
-            SEDT_TRY(linear(e.lin1, 0, ff, na, dt, d, rows, nullptr, ffh, dt, ff, 1, s, dry));
-            SEDT_TRY(linear(e.lin2, 0, d, ffh, dt, ff, rows, x32, x32, DT_F32, d, 0, s, dry));
+            SEDT_TRY(ffn(e.lin1, e.lin2, na, rows, ffh, x32));
         } else {
             if (!dry) SEDT_TRY(launch_cast_addpos(x32, pos, pos_rows, na, nap, dt, rows, s));
             SEDT_TRY(mha(e.attn, true, nap, nap, na, B, S, S, mask_ds, nullptr, x32, x32, ws, s, dry));
             SEDT_TRY(LN(e.n1, x32, nullptr, 1, na, nullptr, x32, rows));
-            SEDT_TRY(linear(e.lin1, 0, ff, na, dt, d, rows, nullptr, ffh, dt, ff, 1, s, dry));
-            SEDT_TRY(linear(e.lin2, 0, d, ffh, dt, ff, rows, x32, x32, DT_F32, d, 0, s, dry));
+            SEDT_TRY(ffn(e.lin1, e.lin2, na, rows, ffh, x32));
             SEDT_TRY(LN(e.n2, x32, nullptr, 1, nullptr, nullptr, x32, rows));
         }
     }
@@ -640,8 +649,7 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
             SEDT_TRY(cross_mha(e.cross_attn, dap, (const char*)ck_all + l * d * es, (const char*)cv_all + l * d * es, Dn_ * d, B, Qall, S,
                                mask_ds, t32, t32, ws, s, dry));
             SEDT_TRY(LN(e.n3, t32, nullptr, 1, da, nullptr, nullptr, qrows));
-            SEDT_TRY(linear(e.lin1, 0, ff, da, dt, d, qrows, nullptr, dffh, dt, ff, 1, s, dry));
-            SEDT_TRY(linear(e.lin2, 0, d, dffh, dt, ff, qrows, t32, t32, DT_F32, d, 0, s, dry));
+            SEDT_TRY(ffn(e.lin1, e.lin2, da, qrows, dffh, t32));
         } else {
             if (!dry) SEDT_TRY(launch_cast_addpos(t32, qpos, qpos_rows, da, dap, dt, qrows, s));
             SEDT_TRY(mha(e.self_attn, true, dap, dap, da, B, Qall, Qall, nullptr, amask, t32, t32, ws, s, dry));
@@ -649,8 +657,7 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
             SEDT_TRY(cross_mha(e.cross_attn, dap, (const char*)ck_all + l * d * es, (const char*)cv_all + l * d * es, Dn_ * d, B, Qall, S,
                                mask_ds, t32, t32, ws, s, dry));
             SEDT_TRY(LN(e.n2, t32, nullptr, 1, da, nullptr, t32, qrows));
-            SEDT_TRY(linear(e.lin1, 0, ff, da, dt, d, qrows, nullptr, dffh, dt, ff, 1, s, dry));
-            SEDT_TRY(linear(e.lin2, 0, d, dffh, dt, ff, qrows, t32, t32, DT_F32, d, 0, s, dry));
+            SEDT_TRY(ffn(e.lin1, e.lin2, da, qrows, dffh, t32));
             SEDT_TRY(LN(e.n3, t32, nullptr, 1, nullptr, nullptr, t32, qrows));
         }
         SEDT_TRY(LN(dec_norm_, t32, nullptr, 1, hs_tl, nullptr, hs_l, qrows));     // transformer.py:140-147
