@@ -287,7 +287,7 @@ constexpr int TS_MAX_FF = 3072;                  // b1 staged in shared memory (
 constexpr int TSW_OFF = 65536;                   // epilogue's long-scoreboard stall and paced the whole kernel)
 constexpr int TSB1_OFF = TSW_OFF + TS_SLOTS * FF_SLOT_BYTES;
 constexpr int TSBAR_OFF = TSB1_OFF + TS_MAX_FF * 4;
-constexpr int TS_NBARS = 2 * TS_SLOTS + 2 + 6 + 2;
+constexpr int TS_NBARS = 2 * TS_SLOTS + 2 + 6 + 2 + 3;
 constexpr int TS_SMEM = TSBAR_OFF + TS_NBARS * 8 + 16 + 1024;
 static_assert(TS_SMEM <= 232448, "shared memory budget exceeded");
 
@@ -308,11 +308,16 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(TS_THREADS, 1)
 ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
-                    const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ FfnParams p)
+                    const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
+                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ FfnParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -325,7 +330,9 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint64_t* hfree = hts_full + 2;             // [2] GEMM2 has read the packed tile: the accumulator may be overwritten
     uint64_t* y_full = hfree + 2;
     uint64_t* y_empty = y_full + 1;
-    uint32_t* tmem_slot = (uint32_t*)(y_empty + 1);
+    uint64_t* res_full = y_empty + 1;           // [2] residual half-tile has landed in the staging area (the x region)
+    uint64_t* stage_free = res_full + 2;        // group 0's output stores have left the staging area
+    uint32_t* tmem_slot = (uint32_t*)(stage_free + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nch = p.nch, half_uses = nch >> 1;
@@ -336,6 +343,8 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         mbar_init(x_full, 1); mbar_init(x_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(&hacc_full[b], 1); mbar_init(&hts_full[b], 8); mbar_init(&hfree[b], 1); }
         mbar_init(y_full, 1); mbar_init(y_empty, 16);
+        mbar_init(&res_full[0], 1); mbar_init(&res_full[1], 1); mbar_init(stage_free, 1);
+        prefetch_tmap(&map_res); prefetch_tmap(&map_out);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -401,7 +410,6 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                             if (++slot == TS_SLOTS) { slot = 0; sphase ^= 1; }
                         }
                         umma_commit(&hacc_full[b]);
-                        if (s == nch - 1) umma_commit(x_empty);
                     }
                     if (s >= 1) {
                         const int j = s - 1, b = j & 1;
@@ -474,29 +482,39 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hts_full[grp]);
             }
+            // ---- output tile: group g handles columns [128 g, 128 g + 128) = four 32-column chunks, staged through the x region
+            // (free once every GEMM1 of the tile has retired): TMA prefetches the residual half-tile into it, every thread adds
+            // its row's accumulator + b2 in place, TMA stores the half-tile.  Group 1 reuses the area after group 0's stores
+            // have been read out; the next x tile may only be loaded after that too (x_empty is arrived here). ----
             mbar_wait(y_full, ti & 1);
             tc_fence_after();
-            const int64_t m = (int64_t)t * 128 + r;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t acc[32];
-                const int col = (grp * 2 + half) * 64 + c * 32;
-                tmem_ld32(lane_base + TM_Y + (uint32_t)col, acc);
-                if (m < p.M) {
-                    const float4* res = reinterpret_cast<const float4*>(p.residual + m * p.ld_res + col);
-                    float4* dst = reinterpret_cast<float4*>(p.out + m * p.ldo + col);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + q);
-                        const float4 rr = res[q];
-                        dst[q] = make_float4(__uint_as_float(acc[4 * q]) + bb.x + rr.x, __uint_as_float(acc[4 * q + 1]) + bb.y + rr.y,
-                                             __uint_as_float(acc[4 * q + 2]) + bb.z + rr.z, __uint_as_float(acc[4 * q + 3]) + bb.w + rr.w);
-                    }
-                }
+            const bool leader = (e & 7) == 0 && lane == 0;
+            uint8_t* stage = smem + FX_OFF;
+            if (leader) {
+                if (grp == 1) mbar_wait(stage_free, ti & 1);
+                mbar_expect_tx(&res_full[grp], 4 * FF_SLOT_BYTES);
+                for (int c = 0; c < 4; ++c)
+                    tma_load_2d(&map_res, stage + c * FF_SLOT_BYTES, &res_full[grp], grp * 128 + c * 32, t * 128);
             }
+            uint32_t acc0[32], acc1[32];
+            tmem_ld32_nowait(lane_base + TM_Y + (uint32_t)(grp * 128 + half * 64), acc0);
+            tmem_ld32_nowait(lane_base + TM_Y + (uint32_t)(grp * 128 + half * 64 + 32), acc1);
+            tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(y_empty);
+            if (lane == 0) mbar_arrive(y_empty);                 // the accumulator is in registers: GEMM2 of the next tile may start
+            mbar_wait(&res_full[grp], ti & 1);
+            epilogue_slab<float, FF_SLOT_BYTES>(acc0, half * 2, grp * 128 + half * 64, nullptr, p.b2, true, 0, stage, r, r & 7);
+            epilogue_slab<float, FF_SLOT_BYTES>(acc1, half * 2 + 1, grp * 128 + half * 64 + 32, nullptr, p.b2, true, 0, stage, r, r & 7);
+            fence_async_smem();
+            asm volatile("bar.sync %0, 256;" ::"r"(9 + grp) : "memory");
+            if (leader) {
+                for (int c = 0; c < 4; ++c)
+                    tma_store_2d(&map_out, stage + c * FF_SLOT_BYTES, grp * 128 + c * 32, t * 128);
+                tma_store_commit();
+                tma_store_wait_read0();
+                if (grp == 0) mbar_arrive(stage_free); else mbar_arrive(x_empty);
+            }
         }
     }
 
@@ -558,8 +576,14 @@ int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void*
     }
     ProfScope _prof(PROF_GEMM_TC, stream);
     if (variant == 0) {
+        CUtensorMap mres, mout;
+        const uint32_t obox[2] = {32u, 128u};                     // 32 fp32 columns = one 128-byte swizzle row
+        const uint64_t odims[2] = {256, (uint64_t)M};
+        const uint64_t rstr[1] = {(uint64_t)ld_res * 4}, ostr[1] = {(uint64_t)ldo * 4};
+        SEDT_TRY(encode_map(&mres, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, residual, 2, odims, rstr, obox));
+        SEDT_TRY(encode_map(&mout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, 2, odims, ostr, obox));
         const int grid = std::min(p.tiles_m, num_sms());
-        SEDT_CHECK_CUDA(launch_pdl(ffn_fused_ts_kernel, dim3((unsigned)grid), dim3(TS_THREADS), TS_SMEM, stream, 1, mx, m1, m2, p));
+        SEDT_CHECK_CUDA(launch_pdl(ffn_fused_ts_kernel, dim3((unsigned)grid), dim3(TS_THREADS), TS_SMEM, stream, 1, mx, m1, m2, mres, mout, p));
     } else if (cl == 2) {
         const int items = (p.tiles_m + 1) / 2;
         const int grid = 2 * std::min(items, num_sms() / 2);
