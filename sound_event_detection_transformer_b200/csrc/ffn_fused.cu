@@ -274,13 +274,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 // 64 KiB of shared memory: the ring grows to 9 slots and b1 is staged in shared memory.  Two epilogue groups of eight warps
 // take alternate chunks, so two chunks are in the epilogue at once.
 //
-// Status: bit-for-bit the same result as the SS variants (tests/test_gpu_ffn.py), 108 us per encoder layer against 97 us for
-// the two GEMMs it replaces, so it is OFF by default (SEDT_FFN_FUSED=1 turns it on).  Timing breakdown with parts of the kernel
-// disabled (B200, M = 31744, ff = 2048): skeleton without MMAs and without the output pass 40 us (520 MB of weights through
-// TMA = 13 TB/s, the L2 -> SM limit), + MMAs 75 us (the N = 128 SS-mode MMAs of GEMM1 already saturate the shared-memory
-// read bandwidth, so the TMA writes do not overlap them), + output pass 111 us: the register -> global fp32 output with the
-// residual read (128 B per thread at a 1 KB stride, exposed at every tile boundary) costs 35 us and is the first thing to
-// replace by a TMA-staged store through the x region; then N = 256 MMAs for GEMM2 and the 2-CTA weight multicast.
+// Status: bit-for-bit the same result as the SS variants (tests/test_gpu_ffn.py); 90 us per encoder layer (M = 31744, ff = 2048)
+// against 97-99 us for the two GEMMs it replaces, so the encoder uses it (model.cu: M >= 128 x SM count; SEDT_FFN_FUSED=0/1
+// forces it off / on for every M).  How it got there, timed with parts of the kernel disabled: skeleton without MMAs and
+// without the output pass 40 us (520 MB of weights through TMA = 13 TB/s, the L2 -> SM limit), + MMAs 75 us (shared-memory
+// bandwidth: per chunk 128 KB of GEMM1 operand reads + 64 KB of GEMM2 B reads + 128 KB of TMA writes = 2560 cycles at 128 B/clk
+// against 2048 cycles of MMA), + a register -> global fp32 output pass 111 us (128 B per thread at a 1 KB stride = 32 L1
+// wavefronts per warp instruction, exposed at every tile boundary).  The output pass now goes through the x region with TMA
+// (residual prefetch, in-place add, TMA store): 92 us; the 2-CTA weight multicast changes nothing at this point (92.8 us).
+// Next: x tile as a TMEM-resident A operand for GEMM1 (halves its shared-memory reads), N = 256 MMAs for GEMM2.
 constexpr int TS_THREADS = 576;              // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue (two groups of eight)
 constexpr int TS_SLOTS = 9;
 constexpr int TS_MAX_FF = 3072;                  // b1 staged in shared memory (ncu: the per-element __ldg of the bias was the
@@ -314,6 +316,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+template <int CL>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                     const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
@@ -336,10 +339,16 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nch = p.nch, half_uses = nch >> 1;
+    // CL = 2: the two CTAs of a cluster take neighbouring row tiles and walk the weight sequence in lockstep; each loads half
+    // of every weight box and multicasts it to both (see the SS variant above)
+    const int cr = CL == 2 ? (int)cluster_ctarank() : 0;
+    const int ncl = (int)gridDim.x / CL, cl = (int)blockIdx.x / CL;
+    const int items = (p.tiles_m + CL - 1) / CL;
+    const int iters = cl < items ? (items - cl + ncl - 1) / ncl : 0;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_w2);
-        for (int s = 0; s < TS_SLOTS; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 1); }
+        for (int s = 0; s < TS_SLOTS; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], CL); }
         mbar_init(x_full, 1); mbar_init(x_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(&hacc_full[b], 1); mbar_init(&hts_full[b], 8); mbar_init(&hfree[b], 1); }
         mbar_init(y_full, 1); mbar_init(y_empty, 16);
@@ -352,6 +361,7 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     for (int i = threadIdx.x; i < nch * 128; i += TS_THREADS) sb1[i] = p.b1[i];        // weights: not produced by the predecessor
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();
     tc_fence_after();
     pdl_trigger();
     pdl_wait();
@@ -364,11 +374,15 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             auto next_slot = [&](const CUtensorMap* m, int c0, int c1) {
                 mbar_wait(&slot_empty[slot], sphase ^ 1);
                 mbar_expect_tx(&slot_full[slot], FF_SLOT_BYTES);
-                tma_load_2d(m, smem + TSW_OFF + slot * FF_SLOT_BYTES, &slot_full[slot], c0, c1);
+                if constexpr (CL == 2)
+                    tma_load_2d_mcast(m, smem + TSW_OFF + slot * FF_SLOT_BYTES + cr * (FF_SLOT_BYTES / 2), &slot_full[slot], c0, c1 + cr * 64,
+                                      (uint16_t)3);
+                else
+                    tma_load_2d(m, smem + TSW_OFF + slot * FF_SLOT_BYTES, &slot_full[slot], c0, c1);
                 if (++slot == TS_SLOTS) { slot = 0; sphase ^= 1; }
             };
-            int ti = 0;
-            for (int t = blockIdx.x; t < p.tiles_m; t += gridDim.x, ++ti) {
+            for (int ti = 0; ti < iters; ++ti) {
+                const int t = CL * (cl + ti * ncl) + cr;
                 mbar_wait(x_empty, (ti & 1) ^ 1);
                 mbar_expect_tx(x_full, 4 * FF_SLOT_BYTES);
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_x, smem + FX_OFF + kb * FF_SLOT_BYTES, x_full, kb * 64, t * 128);
@@ -387,8 +401,10 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(128, 128);
             int slot = 0; uint32_t sphase = 0;
-            int ti = 0;
-            for (int t = blockIdx.x; t < p.tiles_m; t += gridDim.x, ++ti) {
+            auto release_slot = [&](uint64_t* bar) {
+                if constexpr (CL == 2) umma_commit_mcast(bar, (uint16_t)3); else umma_commit(bar);
+            };
+            for (int ti = 0; ti < iters; ++ti) {
                 mbar_wait(x_full, ti & 1);
                 tc_fence_after();
                 for (int s = 0; s <= nch; ++s) {
@@ -406,7 +422,7 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 umma_bf16(d, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                            umma_commit(&slot_empty[slot]);
+                            release_slot(&slot_empty[slot]);
                             if (++slot == TS_SLOTS) { slot = 0; sphase ^= 1; }
                         }
                         umma_commit(&hacc_full[b]);
@@ -428,7 +444,7 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                                 for (int k = 0; k < 4; ++k)
                                     umma_bf16_ts(d, ta + (uint32_t)((kb * 4 + k) * 8), make_smem_desc(sb + k * 32), idesc,
                                                  (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
-                                umma_commit(&slot_empty[slot]);
+                                release_slot(&slot_empty[slot]);
                                 if (++slot == TS_SLOTS) { slot = 0; sphase ^= 1; }
                             }
                         }
@@ -447,8 +463,8 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const int r = quad * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int bar_id = 1 + grp * 4 + quad;
-        int ti = 0;
-        for (int t = blockIdx.x; t < p.tiles_m; t += gridDim.x, ++ti) {
+        for (int ti = 0; ti < iters; ++ti) {
+            const int t = CL * (cl + ti * ncl) + cr;
             for (int j = grp; j < nch; j += 2) {
                 const uint32_t u = (uint32_t)(ti * half_uses + (j >> 1));
                 mbar_wait(&hacc_full[grp], u & 1);
@@ -520,6 +536,7 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
@@ -527,6 +544,8 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 }
 
 }  // namespace
+
+int64_t ffn_fused_min_rows() { return (int64_t)128 * num_sms(); }
 
 bool ffn_fused_supported(int d, int ff, int64_t M, const void* x, const void* w1, const void* w2, const float* residual, const float* out,
                          int ld_res, int ldo)
@@ -549,9 +568,11 @@ int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void*
         return e[0] == 's' && e[1] == 's' ? (e[2] == '1' ? 1 : 2) : 0;
     }();
     const int cl = variant == 1 ? 1 : 2;
+    // 2-CTA weight multicast measured no faster than plain CTAs for the TS variant (92.8 vs 90.1 us): off unless asked for
+    static const int ts_cluster = [] { const char* e = getenv("SEDT_FFN_TS_CLUSTER"); return e != nullptr && atoi(e) == 2 ? 2 : 1; }();
     CUtensorMap mx, m1, m2;
     const uint32_t box[2] = {64u, 128u};
-    const uint32_t wbox[2] = {64u, variant == 2 ? 64u : 128u};   // ss2: each CTA loads half of a weight box
+    const uint32_t wbox[2] = {64u, (variant == 2 || (variant == 0 && ts_cluster == 2)) ? 64u : 128u};   // clusters: half boxes
     {
         const uint64_t dims[2] = {256, (uint64_t)M}; const uint64_t strides[1] = {256 * 2};
         SEDT_TRY(encode_map(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x, 2, dims, strides, box));
@@ -571,7 +592,8 @@ int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void*
     if (!attr_set) {
         SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM));
         SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM));
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
         attr_set = true;
     }
     ProfScope _prof(PROF_GEMM_TC, stream);
@@ -582,8 +604,16 @@ int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void*
         const uint64_t rstr[1] = {(uint64_t)ld_res * 4}, ostr[1] = {(uint64_t)ldo * 4};
         SEDT_TRY(encode_map(&mres, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, residual, 2, odims, rstr, obox));
         SEDT_TRY(encode_map(&mout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, 2, odims, ostr, obox));
-        const int grid = std::min(p.tiles_m, num_sms());
-        SEDT_CHECK_CUDA(launch_pdl(ffn_fused_ts_kernel, dim3((unsigned)grid), dim3(TS_THREADS), TS_SMEM, stream, 1, mx, m1, m2, mres, mout, p));
+        if (ts_cluster == 2) {
+            const int items = (p.tiles_m + 1) / 2;
+            const int grid = 2 * std::min(items, num_sms() / 2);
+            SEDT_CHECK_CUDA(launch_pdl(ffn_fused_ts_kernel<2>, dim3((unsigned)grid), dim3(TS_THREADS), TS_SMEM, stream, 2, mx, m1, m2, mres,
+                                       mout, p));
+        } else {
+            const int grid = std::min(p.tiles_m, num_sms());
+            SEDT_CHECK_CUDA(launch_pdl(ffn_fused_ts_kernel<1>, dim3((unsigned)grid), dim3(TS_THREADS), TS_SMEM, stream, 1, mx, m1, m2, mres,
+                                       mout, p));
+        }
     } else if (cl == 2) {
         const int items = (p.tiles_m + 1) / 2;
         const int grid = 2 * std::min(items, num_sms() / 2);

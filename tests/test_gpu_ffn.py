@@ -37,3 +37,33 @@ def test_ffn_fused_matches_torch(M, ff):
                                buf.data_ptr(), M, ff, _lib.current_stream()))
     torch.cuda.synchronize()
     assert torch.equal(buf, out)
+
+
+def test_model_forward_with_fused_ffn_matches_two_gemm_path(tmp_path):
+    """The whole bf16 forward with the fused FFN forced on (it is chosen by itself only from 128 x SM-count rows) against
+    the same forward with it forced off, each in a fresh process (the knob is read once): same rounding points, so the
+    outputs agree far inside the bf16 tier's tolerance."""
+    import os
+    import subprocess
+    import sys
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, torch, numpy as np; sys.path.insert(0, %r)\n"
+        "from sound_event_detection_transformer_b200 import spec, synth\n"
+        "from sound_event_detection_transformer_b200.sedt import build_model\n"
+        "args = spec.config_args('c2'); model, _, _ = build_model(args)\n"
+        "model.load_state_dict(synth.synth_state_dict(args, 12)); model = model.cuda().eval()\n"
+        "with torch.no_grad(): out = model(synth.synth_clips(3, 496, 64, seed=2).cuda())\n"
+        "np.savez(sys.argv[1], logits=out['pred_logits'].cpu().numpy(), boxes=out['pred_boxes'].cpu().numpy(), at=out['at'].cpu().numpy())\n"
+    ) % root
+    outs = {}
+    for mode in ("0", "1"):
+        fn = str(tmp_path / f"ffn{mode}.npz")
+        env = dict(os.environ, SEDT_FFN_FUSED=mode)
+        subprocess.run([sys.executable, "-c", code, fn], check=True, env=env, timeout=300)
+        outs[mode] = np.load(fn)
+    for k in ("logits", "boxes", "at"):
+        a, b = outs["0"][k], outs["1"][k]
+        assert np.isfinite(b).all()
+        assert np.linalg.norm(a - b) <= 2e-3 * np.linalg.norm(a), k
