@@ -313,14 +313,14 @@ def main():
     achieved = dom_flops / (dom_ms / 1e3) / 1e12
     step_tf = fl["total"] * B * K / (ms / 1e3) / 1e12 / world if world else 0.0
     # DRAM bytes of that kernel class per step come from the committed ncu capture of this same command / batch
-    # (profiles/r1j_class_summary.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the class's launches)
+    # (profiles/r1k_class_summary.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the class's launches)
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1j_class_summary.json")
+    tp = os.path.join(ROOT, "profiles", "r1k_class_summary.json")
     if os.path.exists(tp) and B == 256 and opts.precision == "bf16":
         c = json.load(open(tp)).get(dom)
         if c:
             traffic = (c["dram_read_MB"] + c["dram_write_MB"]) * 1e6
-            traffic_src = "profiles/r1j_class_summary.json (ncu, bytes per step over the class's launches)"
+            traffic_src = "profiles/r1k_class_summary.json (ncu, bytes per step over the class's launches)"
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,

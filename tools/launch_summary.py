@@ -25,7 +25,7 @@ def short(name):
 
 
 def klass(name):
-    if "conv_tc" in name: return "gemm_tcgen05"
+    if "conv_tc" in name or "ffn_fused" in name: return "gemm_tcgen05"
     if "stem" in name: return "stem"
     if "attention" in name: return "attention"
     if "layernorm" in name or "cast_addpos" in name: return "norm"
