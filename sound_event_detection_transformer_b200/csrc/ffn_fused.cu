@@ -3,19 +3,27 @@
 //   x [M, 256] bf16 (LayerNorm output), W1 [ff, 256], W2 [256, ff] bf16 (K-major as packed), fp32 biases, fp32 residual / out.
 //
 // The unfused path writes the [M, ff] hidden activation to HBM (130 MB per encoder layer at B = 256: linear1 is bound by that
-// write, linear2 by reading it back).  Here a CTA keeps a 128-row tile of x resident and walks over the hidden dimension in
-// chunks of 128: GEMM1 (x W1_j^T, K = 256) accumulates a 128 x 128 tile in TMEM, the epilogue warps add the bias, apply ReLU,
-// round to bf16 and park the tile in shared memory in the swizzled K-major layout, where it is the A operand of GEMM2
-// (h_j W2_j^T, K = 128) accumulating the 128 x 256 output tile in TMEM over all chunks.  Software-pipelined by one chunk
-// (GEMM1_{j+1} is issued before GEMM2_j) so the tensor core has work while chunk j goes through the epilogue.
+// write, linear2 by reading it back).  Here a CTA keeps a 128-row tile of x resident in shared memory and walks over the hidden
+// dimension in chunks of 128: GEMM1 (x W1_j^T, K = 256) accumulates a 128 x 128 tile in TMEM; the epilogue warps add the bias,
+// apply ReLU and pack the tile to bf16 IN PLACE in the accumulator's TMEM columns (tcgen05.st); GEMM2 (h_j W2_j^T, K = 128)
+// reads that tile as its A operand straight from tensor memory (tcgen05.mma with [a_tmem]) and accumulates the 128 x 256
+// output tile in TMEM over all chunks.  Software-pipelined by one chunk (GEMM1_{j+1} is issued before GEMM2_j) so the tensor
+// core has work while chunk j goes through the epilogue; two epilogue groups of eight warps take alternate chunks.
 //
-// The weights (2 MB per layer) stream through every CTA once per tile; from L2 alone that is the bound (measured: 112 us per
-// encoder layer against 100 us for the two separate GEMMs).  CL = 2: two CTAs of a cluster walk the weight sequence in
-// lockstep on different row tiles, each loads half of every weight box and multicasts it to both, and a ring slot is
-// recycled only when BOTH MMA warps have consumed it (commit multicast to both CTAs' empty barriers).
+// TMEM: Y 256 columns + 2 x 128 (hidden accumulator / packed tile, double buffered) = 512.  Shared memory: x 64 KiB, weight
+// ring 9 x 16 KiB ([128 rows x 64 k] boxes of W1 / W2), b1.  Warps: 0 TMA producer, 1 MMA issuer, 2..17 epilogue.  The output
+// tile goes through the x region (free once every GEMM1 of the tile has retired): TMA prefetches the residual half-tile, the
+// threads add accumulator + b2 in place, TMA stores it.
 //
-// TMEM: Y 256 columns + 2 x 128 (hidden accumulator, double buffered) = 512.  Shared memory: x 64 KiB, hidden 2 x 32 KiB,
-// weight ring 6 x 16 KiB ([128 rows x 64 k] boxes of W1 / W2).  Warps: 0 TMA producer, 1 MMA issuer, 2..9 epilogue.
+// History (all variants bit-identical, B200, M = 31744, ff = 2048; the two GEMMs this replaces: 97-99 us):
+//   * hidden tile parked in shared memory as the A operand (6-slot ring): 113 us; + 2-CTA weight multicast: 113 us;
+//   * hidden tile in TMEM, 9-slot ring, b1 in smem, 16 epilogue warps: 106-108 us.  Timed with parts disabled: skeleton without
+//     MMAs and output 40 us (520 MB of weights through TMA = 13 TB/s, the L2 -> SM limit); + MMAs 75 us (shared-memory bandwidth:
+//     per chunk 128 KB of GEMM1 operand reads + 64 KB of GEMM2 B reads + 128 KB of TMA writes = 2560 cycles at 128 B/clk against
+//     2048 cycles of MMA); + a register -> global fp32 output pass 111 us (128 B per thread at a 1 KB stride = 32 L1 wavefronts
+//     per warp instruction, exposed at every tile boundary);
+//   * output through the x region with TMA: 90-92 us (this file); + 2-CTA weight multicast on top: 92.8 us (dropped).
+// Next: x as a TMEM-resident A operand for GEMM1 (halves its shared-memory reads), N = 256 MMAs for GEMM2.
 #include "tc_common.cuh"
 #include <algorithm>
 #include <cstdlib>
@@ -25,273 +33,22 @@ namespace {
 
 using namespace tc;
 
-constexpr int FF_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int FF_SLOTS = 6;
-constexpr int FF_SLOT_BYTES = 16384;
-constexpr int FX_OFF = 0;                       // 4 k-blocks of [128 rows][64 k]
-constexpr int FH_OFF = 65536;                   // 2 buffers x 2 k-blocks
-constexpr int FW_OFF = 131072;                  // weight ring
-constexpr int FBAR_OFF = FW_OFF + FF_SLOTS * FF_SLOT_BYTES;
-constexpr int FF_NBARS = 2 * FF_SLOTS + 2 + 4 + 4 + 2;
-constexpr int FF_SMEM = FBAR_OFF + FF_NBARS * 8 + 16 + 1024;
-static_assert(FF_SMEM <= 232448, "shared memory budget exceeded");
-
-struct FfnParams {
-    const float* b1; const float* b2; const float* residual; float* out;
-    int ld_res, ldo, M, nch, tiles_m;
-};
-
-template <int CL>
-__global__ void __launch_bounds__(FF_THREADS, 1)
-ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
-                 const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ FfnParams p)
-{
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* slot_full = (uint64_t*)(smem + FBAR_OFF);
-    uint64_t* slot_empty = slot_full + FF_SLOTS;
-    uint64_t* x_full = slot_empty + FF_SLOTS;
-    uint64_t* x_empty = x_full + 1;
-    uint64_t* hacc_full = x_empty + 1;          // [2] MMA -> epilogue: hidden accumulator ready
-    uint64_t* hacc_empty = hacc_full + 2;       // [2] epilogue -> MMA: accumulator drained
-    uint64_t* hsm_full = hacc_empty + 2;        // [2] epilogue -> MMA: bf16 hidden tile parked in smem
-    uint64_t* hsm_empty = hsm_full + 2;         // [2] MMA -> epilogue: GEMM2 has read the tile
-    uint64_t* y_full = hsm_empty + 2;
-    uint64_t* y_empty = y_full + 1;
-    uint32_t* tmem_slot = (uint32_t*)(y_empty + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nch = p.nch, half_uses = nch >> 1;
-    // tile schedule: CTA cr of cluster c takes tiles CL * (c + i * nclusters) + cr, i = 0 .. iters - 1 (the same number of
-    // iterations in both CTAs of a cluster; a tile index past the end loads zeros and stores nothing)
-    const int cr = CL == 2 ? (int)cluster_ctarank() : 0;
-    const int ncl = (int)gridDim.x / CL, cl = (int)blockIdx.x / CL;
-    const int items = (p.tiles_m + CL - 1) / CL;
-    const int iters = cl < items ? (items - cl + ncl - 1) / ncl : 0;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_w2);
-        for (int s = 0; s < FF_SLOTS; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], CL); }
-        mbar_init(x_full, 1); mbar_init(x_empty, 1);
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&hacc_full[b], 1); mbar_init(&hacc_empty[b], 8);
-            mbar_init(&hsm_full[b], 8); mbar_init(&hsm_empty[b], 1);
-        }
-        mbar_init(y_full, 1); mbar_init(y_empty, 8);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) tmem_alloc<512>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    if constexpr (CL == 2) cluster_sync_all();     // the peer's barriers exist before anything is multicast to them
-    tc_fence_after();
-    pdl_trigger();
-    pdl_wait();
-    const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t TM_Y = 0, TM_H = 256;
-
-    if (warp == 0) {
-        // ===== TMA producer: x tile, then the weight boxes in exactly the order the MMA warp consumes them =====
-        if (lane == 0) {
-            int slot = 0; uint32_t sphase = 0;
-            auto next_slot = [&](const CUtensorMap* m, int c0, int c1) {
-                mbar_wait(&slot_empty[slot], sphase ^ 1);
-                mbar_expect_tx(&slot_full[slot], FF_SLOT_BYTES);
-                if constexpr (CL == 2)      // my 64 rows of the box, delivered to both CTAs (maps carry 64-row boxes)
-                    tma_load_2d_mcast(m, smem + FW_OFF + slot * FF_SLOT_BYTES + cr * (FF_SLOT_BYTES / 2), &slot_full[slot], c0, c1 + cr * 64,
-                                      (uint16_t)3);
-                else
-                    tma_load_2d(m, smem + FW_OFF + slot * FF_SLOT_BYTES, &slot_full[slot], c0, c1);
-                if (++slot == FF_SLOTS) { slot = 0; sphase ^= 1; }
-            };
-            for (int ti = 0; ti < iters; ++ti) {
-                const int t = CL * (cl + ti * ncl) + cr;
-                mbar_wait(x_empty, (ti & 1) ^ 1);
-                mbar_expect_tx(x_full, 4 * FF_SLOT_BYTES);
-                for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_x, smem + FX_OFF + kb * FF_SLOT_BYTES, x_full, kb * 64, t * 128);
-                for (int s = 0; s <= nch; ++s) {
-                    if (s < nch)
-                        for (int kb = 0; kb < 4; ++kb) next_slot(&map_w1, kb * 64, s * 128);
-                    if (s >= 1) {
-                        const int j = s - 1;
-                        for (int kb = 0; kb < 2; ++kb)
-                            for (int nh = 0; nh < 2; ++nh) next_slot(&map_w2, j * 128 + kb * 64, nh * 128);
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, 128);
-            int slot = 0; uint32_t sphase = 0;
-            auto release_slot = [&](uint64_t* bar) {
-                if constexpr (CL == 2) umma_commit_mcast(bar, (uint16_t)3); else umma_commit(bar);
-            };
-            for (int ti = 0; ti < iters; ++ti) {
-                mbar_wait(x_full, ti & 1);
-                tc_fence_after();
-                for (int s = 0; s <= nch; ++s) {
-                    if (s < nch) {
-                        // GEMM1_s: hidden accumulator (s & 1) = x W1_s^T
-                        const int b = s & 1;
-                        const uint32_t u = (uint32_t)(ti * half_uses + (s >> 1));
-                        mbar_wait(&hacc_empty[b], (u & 1) ^ 1);
-                        tc_fence_after();
-                        const uint32_t d = tmem_base + TM_H + (uint32_t)(b * 128);
-                        for (int kb = 0; kb < 4; ++kb) {
-                            mbar_wait(&slot_full[slot], sphase);
-                            tc_fence_after();
-                            const uint32_t sa = smem_u32(smem + FX_OFF + kb * FF_SLOT_BYTES);
-                            const uint32_t sb = smem_u32(smem + FW_OFF + slot * FF_SLOT_BYTES);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16(d, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                            release_slot(&slot_empty[slot]);
-                            if (++slot == FF_SLOTS) { slot = 0; sphase ^= 1; }
-                        }
-                        umma_commit(&hacc_full[b]);
-                        if (s == nch - 1) umma_commit(x_empty);          // the x tile may be replaced
-                    }
-                    if (s >= 1) {
-                        // GEMM2_j: Y += h_j W2_j^T
-                        const int j = s - 1, b = j & 1;
-                        const uint32_t u = (uint32_t)(ti * half_uses + (j >> 1));
-                        if (j == 0) { mbar_wait(y_empty, (ti & 1) ^ 1); }
-                        mbar_wait(&hsm_full[b], u & 1);
-                        tc_fence_after();
-                        for (int kb = 0; kb < 2; ++kb) {
-                            const uint32_t sa = smem_u32(smem + FH_OFF + (b * 2 + kb) * FF_SLOT_BYTES);
-                            for (int nh = 0; nh < 2; ++nh) {
-                                mbar_wait(&slot_full[slot], sphase);
-                                tc_fence_after();
-                                const uint32_t sb = smem_u32(smem + FW_OFF + slot * FF_SLOT_BYTES);
-                                const uint32_t d = tmem_base + TM_Y + (uint32_t)(nh * 128);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    umma_bf16(d, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc,
-                                              (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
-                                release_slot(&slot_empty[slot]);
-                                if (++slot == FF_SLOTS) { slot = 0; sphase ^= 1; }
-                            }
-                        }
-                        umma_commit(&hsm_empty[b]);
-                        if (j == nch - 1) umma_commit(y_full);
-                    }
-                }
-            }
-        }
-    } else {
-        // ===== epilogue warps 2..9: warp & 3 = TMEM lane quadrant, (warp - 2) >> 2 = column half =====
-        const int quad = warp & 3, half = (warp - 2) >> 2;
-        const int r = quad * 32 + lane;
-        const int sw = r & 7;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-        for (int ti = 0; ti < iters; ++ti) {
-            const int t = CL * (cl + ti * ncl) + cr;
-            for (int j = 0; j < nch; ++j) {
-                const int b = j & 1;
-                const uint32_t u = (uint32_t)(ti * half_uses + (j >> 1));
-                mbar_wait(&hacc_full[b], u & 1);
-                tc_fence_after();
-                uint32_t a0[32], a1[32];
-                const uint32_t ta = lane_base + TM_H + (uint32_t)(b * 128 + half * 64);
-                tmem_ld32_nowait(ta, a0);
-                tmem_ld32_nowait(ta + 32, a1);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&hacc_empty[b]);               // accumulator drained
-                // bias + ReLU + bf16
-                const float* bias = p.b1 + j * 128 + half * 64;
-                uint32_t w[32];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const float2 bb = __ldg(reinterpret_cast<const float2*>(bias) + q);
-                    const float v0 = fmaxf(__uint_as_float(a0[2 * q]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(a0[2 * q + 1]) + bb.y, 0.f);
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-                    w[q] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + 32) + q);
-                    const float v0 = fmaxf(__uint_as_float(a1[2 * q]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(a1[2 * q + 1]) + bb.y, 0.f);
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-                    w[16 + q] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                // park in the A-operand layout of GEMM2: k-block = half, row r, 16-byte piece XOR (r & 7)
-                mbar_wait(&hsm_empty[b], (u & 1) ^ 1);
-                uint8_t* row = smem + FH_OFF + (b * 2 + half) * FF_SLOT_BYTES + r * 128;
-#pragma unroll
-                for (int pc = 0; pc < 8; ++pc)
-                    *reinterpret_cast<uint4*>(row + ((pc ^ sw) << 4)) = make_uint4(w[4 * pc], w[4 * pc + 1], w[4 * pc + 2], w[4 * pc + 3]);
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&hsm_full[b]);
-            }
-            // ---- output tile: Y + b2 + residual -> fp32 global (32 contiguous floats per thread and slab) ----
-            mbar_wait(y_full, ti & 1);
-            tc_fence_after();
-            const int64_t m = (int64_t)t * 128 + r;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t acc[32];
-                const int col = half * 128 + c * 32;
-                tmem_ld32(lane_base + TM_Y + (uint32_t)col, acc);
-                if (m < p.M) {
-                    const float4* res = reinterpret_cast<const float4*>(p.residual + m * p.ld_res + col);
-                    float4* dst = reinterpret_cast<float4*>(p.out + m * p.ldo + col);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + q);
-                        const float4 rr = res[q];
-                        dst[q] = make_float4(__uint_as_float(acc[4 * q]) + bb.x + rr.x, __uint_as_float(acc[4 * q + 1]) + bb.y + rr.y,
-                                             __uint_as_float(acc[4 * q + 2]) + bb.z + rr.z, __uint_as_float(acc[4 * q + 3]) + bb.w + rr.w);
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(y_empty);
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if constexpr (CL == 2) cluster_sync_all();     // no CTA leaves while its peer may still multicast into it
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
-    }
-}
-
-
-// ---- variant TS: the bf16 hidden tile stays in TENSOR MEMORY ------------------------------------------------------------
-// Measured on the variant above: 113 us per encoder layer whatever the weight traffic (the 2-CTA multicast changed nothing):
-// the 6-slot weight ring (96 KB in flight) cannot cover TMA latency x consumption rate (8 boxes per ~1 us chunk), and the
-// rest of shared memory is taken by the hidden double buffer.  Here the epilogue packs relu(acc + b1) to bf16 IN PLACE in the
-// accumulator's TMEM columns (tcgen05.st) and GEMM2 reads its A operand from TMEM (tcgen05.mma with [a_tmem]), which frees
-// 64 KiB of shared memory: the ring grows to 9 slots and b1 is staged in shared memory.  Two epilogue groups of eight warps
-// take alternate chunks, so two chunks are in the epilogue at once.
-//
-// Status: bit-for-bit the same result as the SS variants (tests/test_gpu_ffn.py); 90 us per encoder layer (M = 31744, ff = 2048)
-// against 97-99 us for the two GEMMs it replaces, so the encoder uses it (model.cu: M >= 128 x SM count; SEDT_FFN_FUSED=0/1
-// forces it off / on for every M).  How it got there, timed with parts of the kernel disabled: skeleton without MMAs and
-// without the output pass 40 us (520 MB of weights through TMA = 13 TB/s, the L2 -> SM limit), + MMAs 75 us (shared-memory
-// bandwidth: per chunk 128 KB of GEMM1 operand reads + 64 KB of GEMM2 B reads + 128 KB of TMA writes = 2560 cycles at 128 B/clk
-// against 2048 cycles of MMA), + a register -> global fp32 output pass 111 us (128 B per thread at a 1 KB stride = 32 L1
-// wavefronts per warp instruction, exposed at every tile boundary).  The output pass now goes through the x region with TMA
-// (residual prefetch, in-place add, TMA store): 92 us; the 2-CTA weight multicast changes nothing at this point (92.8 us).
-// Next: x tile as a TMEM-resident A operand for GEMM1 (halves its shared-memory reads), N = 256 MMAs for GEMM2.
-constexpr int TS_THREADS = 576;              // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue (two groups of eight)
+constexpr int FF_SLOT_BYTES = 16384;            // one [128 rows][64 k] bf16 box
+constexpr int FX_OFF = 0;                       // x tile: 4 k-blocks; reused as the output staging area
+constexpr int TS_THREADS = 576;                 // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue (two groups of eight)
 constexpr int TS_SLOTS = 9;
-constexpr int TS_MAX_FF = 3072;                  // b1 staged in shared memory (ncu: the per-element __ldg of the bias was the
-constexpr int TSW_OFF = 65536;                   // epilogue's long-scoreboard stall and paced the whole kernel)
+constexpr int TS_MAX_FF = 3072;                 // b1 staged in shared memory (ncu: the per-element __ldg of the bias stalled the epilogue)
+constexpr int TSW_OFF = 65536;
 constexpr int TSB1_OFF = TSW_OFF + TS_SLOTS * FF_SLOT_BYTES;
 constexpr int TSBAR_OFF = TSB1_OFF + TS_MAX_FF * 4;
 constexpr int TS_NBARS = 2 * TS_SLOTS + 2 + 6 + 2 + 3;
 constexpr int TS_SMEM = TSBAR_OFF + TS_NBARS * 8 + 16 + 1024;
 static_assert(TS_SMEM <= 232448, "shared memory budget exceeded");
+
+struct FfnParams {
+    const float* b1; const float* b2; const float* residual; float* out;
+    int ld_res, ldo, M, nch, tiles_m;
+};
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -316,7 +73,6 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int CL>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                     const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
@@ -339,16 +95,11 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nch = p.nch, half_uses = nch >> 1;
-    // CL = 2: the two CTAs of a cluster take neighbouring row tiles and walk the weight sequence in lockstep; each loads half
-    // of every weight box and multicasts it to both (see the SS variant above)
-    const int cr = CL == 2 ? (int)cluster_ctarank() : 0;
-    const int ncl = (int)gridDim.x / CL, cl = (int)blockIdx.x / CL;
-    const int items = (p.tiles_m + CL - 1) / CL;
-    const int iters = cl < items ? (items - cl + ncl - 1) / ncl : 0;
+    const int iters = (int)blockIdx.x < p.tiles_m ? (p.tiles_m - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_x); prefetch_tmap(&map_w1); prefetch_tmap(&map_w2);
-        for (int s = 0; s < TS_SLOTS; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], CL); }
+        for (int s = 0; s < TS_SLOTS; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 1); }
         mbar_init(x_full, 1); mbar_init(x_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(&hacc_full[b], 1); mbar_init(&hts_full[b], 8); mbar_init(&hfree[b], 1); }
         mbar_init(y_full, 1); mbar_init(y_empty, 16);
@@ -361,7 +112,6 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     for (int i = threadIdx.x; i < nch * 128; i += TS_THREADS) sb1[i] = p.b1[i];        // weights: not produced by the predecessor
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL == 2) cluster_sync_all();
     tc_fence_after();
     pdl_trigger();
     pdl_wait();
@@ -374,15 +124,11 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             auto next_slot = [&](const CUtensorMap* m, int c0, int c1) {
                 mbar_wait(&slot_empty[slot], sphase ^ 1);
                 mbar_expect_tx(&slot_full[slot], FF_SLOT_BYTES);
-                if constexpr (CL == 2)
-                    tma_load_2d_mcast(m, smem + TSW_OFF + slot * FF_SLOT_BYTES + cr * (FF_SLOT_BYTES / 2), &slot_full[slot], c0, c1 + cr * 64,
-                                      (uint16_t)3);
-                else
-                    tma_load_2d(m, smem + TSW_OFF + slot * FF_SLOT_BYTES, &slot_full[slot], c0, c1);
+                tma_load_2d(m, smem + TSW_OFF + slot * FF_SLOT_BYTES, &slot_full[slot], c0, c1);
                 if (++slot == TS_SLOTS) { slot = 0; sphase ^= 1; }
             };
             for (int ti = 0; ti < iters; ++ti) {
-                const int t = CL * (cl + ti * ncl) + cr;
+                const int t = (int)blockIdx.x + ti * (int)gridDim.x;
                 mbar_wait(x_empty, (ti & 1) ^ 1);
                 mbar_expect_tx(x_full, 4 * FF_SLOT_BYTES);
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_x, smem + FX_OFF + kb * FF_SLOT_BYTES, x_full, kb * 64, t * 128);
@@ -401,9 +147,6 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(128, 128);
             int slot = 0; uint32_t sphase = 0;
-            auto release_slot = [&](uint64_t* bar) {
-                if constexpr (CL == 2) umma_commit_mcast(bar, (uint16_t)3); else umma_commit(bar);
-            };
             for (int ti = 0; ti < iters; ++ti) {
                 mbar_wait(x_full, ti & 1);
                 tc_fence_after();
@@ -422,7 +165,7 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 umma_bf16(d, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                            release_slot(&slot_empty[slot]);
+                            umma_commit(&slot_empty[slot]);
                             if (++slot == TS_SLOTS) { slot = 0; sphase ^= 1; }
                         }
                         umma_commit(&hacc_full[b]);
@@ -444,7 +187,7 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                                 for (int k = 0; k < 4; ++k)
                                     umma_bf16_ts(d, ta + (uint32_t)((kb * 4 + k) * 8), make_smem_desc(sb + k * 32), idesc,
                                                  (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
-                                release_slot(&slot_empty[slot]);
+                                umma_commit(&slot_empty[slot]);
                                 if (++slot == TS_SLOTS) { slot = 0; sphase ^= 1; }
                             }
                         }
@@ -464,7 +207,7 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int bar_id = 1 + grp * 4 + quad;
         for (int ti = 0; ti < iters; ++ti) {
-            const int t = CL * (cl + ti * ncl) + cr;
+            const int t = (int)blockIdx.x + ti * (int)gridDim.x;
             for (int j = grp; j < nch; j += 2) {
                 const uint32_t u = (uint32_t)(ti * half_uses + (j >> 1));
                 mbar_wait(&hacc_full[grp], u & 1);
@@ -536,7 +279,6 @@ ffn_fused_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL == 2) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
@@ -561,67 +303,38 @@ int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void*
 {
     SEDT_REQUIRE(ffn_fused_supported(256, ff, M, x, w1, w2, residual, out, ld_res, ldo), "ffn_fused: unsupported shape / alignment");
     SEDT_TRY(tc_init());
-    // variant: "ts" (default) keeps the hidden tile in tensor memory; "ss2" / "ss1" park it in shared memory (2-CTA multicast / plain)
-    static const int variant = [] {
-        const char* e = getenv("SEDT_FFN_VARIANT");
-        if (e == nullptr) return 0;
-        return e[0] == 's' && e[1] == 's' ? (e[2] == '1' ? 1 : 2) : 0;
-    }();
-    const int cl = variant == 1 ? 1 : 2;
-    // 2-CTA weight multicast measured no faster than plain CTAs for the TS variant (92.8 vs 90.1 us): off unless asked for
-    static const int ts_cluster = [] { const char* e = getenv("SEDT_FFN_TS_CLUSTER"); return e != nullptr && atoi(e) == 2 ? 2 : 1; }();
-    CUtensorMap mx, m1, m2;
+    CUtensorMap mx, m1, m2, mres, mout;
     const uint32_t box[2] = {64u, 128u};
-    const uint32_t wbox[2] = {64u, (variant == 2 || (variant == 0 && ts_cluster == 2)) ? 64u : 128u};   // clusters: half boxes
     {
         const uint64_t dims[2] = {256, (uint64_t)M}; const uint64_t strides[1] = {256 * 2};
         SEDT_TRY(encode_map(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x, 2, dims, strides, box));
     }
     {
         const uint64_t dims[2] = {256, (uint64_t)ff}; const uint64_t strides[1] = {256 * 2};
-        SEDT_TRY(encode_map(&m1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w1, 2, dims, strides, wbox));
+        SEDT_TRY(encode_map(&m1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w1, 2, dims, strides, box));
     }
     {
         const uint64_t dims[2] = {(uint64_t)ff, 256}; const uint64_t strides[1] = {(uint64_t)ff * 2};
-        SEDT_TRY(encode_map(&m2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w2, 2, dims, strides, wbox));
+        SEDT_TRY(encode_map(&m2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w2, 2, dims, strides, box));
+    }
+    {
+        const uint32_t obox[2] = {32u, 128u};                     // 32 fp32 columns = one 128-byte swizzle row
+        const uint64_t odims[2] = {256, (uint64_t)M};
+        const uint64_t rstr[1] = {(uint64_t)ld_res * 4}, ostr[1] = {(uint64_t)ldo * 4};
+        SEDT_TRY(encode_map(&mres, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, residual, 2, odims, rstr, obox));
+        SEDT_TRY(encode_map(&mout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, 2, odims, ostr, obox));
     }
     FfnParams p;
     p.b1 = b1; p.b2 = b2; p.residual = residual; p.out = out; p.ld_res = ld_res; p.ldo = ldo;
     p.M = (int)M; p.nch = ff / 128; p.tiles_m = (int)ceil_div(M, 128);
     static bool attr_set = false;
     if (!attr_set) {
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM));
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM));
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fused_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
         attr_set = true;
     }
+    const int grid = std::min(p.tiles_m, num_sms());
     ProfScope _prof(PROF_GEMM_TC, stream);
-    if (variant == 0) {
-        CUtensorMap mres, mout;
-        const uint32_t obox[2] = {32u, 128u};                     // 32 fp32 columns = one 128-byte swizzle row
-        const uint64_t odims[2] = {256, (uint64_t)M};
-        const uint64_t rstr[1] = {(uint64_t)ld_res * 4}, ostr[1] = {(uint64_t)ldo * 4};
-        SEDT_TRY(encode_map(&mres, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, residual, 2, odims, rstr, obox));
-        SEDT_TRY(encode_map(&mout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, 2, odims, ostr, obox));
-        if (ts_cluster == 2) {
-            const int items = (p.tiles_m + 1) / 2;
-            const int grid = 2 * std::min(items, num_sms() / 2);
-            SEDT_CHECK_CUDA(launch_pdl(ffn_fused_ts_kernel<2>, dim3((unsigned)grid), dim3(TS_THREADS), TS_SMEM, stream, 2, mx, m1, m2, mres,
-                                       mout, p));
-        } else {
-            const int grid = std::min(p.tiles_m, num_sms());
-            SEDT_CHECK_CUDA(launch_pdl(ffn_fused_ts_kernel<1>, dim3((unsigned)grid), dim3(TS_THREADS), TS_SMEM, stream, 1, mx, m1, m2, mres,
-                                       mout, p));
-        }
-    } else if (cl == 2) {
-        const int items = (p.tiles_m + 1) / 2;
-        const int grid = 2 * std::min(items, num_sms() / 2);
-        SEDT_CHECK_CUDA(launch_pdl(ffn_fused_kernel<2>, dim3((unsigned)grid), dim3(FF_THREADS), FF_SMEM, stream, 2, mx, m1, m2, p));
-    } else {
-        const int grid = std::min(p.tiles_m, num_sms());
-        SEDT_CHECK_CUDA(launch_pdl(ffn_fused_kernel<1>, dim3((unsigned)grid), dim3(FF_THREADS), FF_SMEM, stream, 1, mx, m1, m2, p));
-    }
+    SEDT_CHECK_CUDA(launch_pdl(ffn_fused_ts_kernel, dim3((unsigned)grid), dim3(TS_THREADS), TS_SMEM, stream, 1, mx, m1, m2, mres, mout, p));
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
