@@ -23,7 +23,11 @@
 //     2048 cycles of MMA); + a register -> global fp32 output pass 111 us (128 B per thread at a 1 KB stride = 32 L1 wavefronts
 //     per warp instruction, exposed at every tile boundary);
 //   * output through the x region with TMA: 90-92 us (this file); + 2-CTA weight multicast on top: 92.8 us (dropped).
-// Next: x as a TMEM-resident A operand for GEMM1 (halves its shared-memory reads), N = 256 MMAs for GEMM2.
+// Per 128-row tile the kernel takes 48 us (49.5 us at one tile per SM, 96.6 us at two, no tile-boundary cost); M = 31744 is 1.68
+// tiles per SM, i.e. two rounds with a third of the SMs idle in the second.  Dropping the wait for GEMM2_{j-2} before GEMM1_j
+// (in-order MMA execution would make it redundant) changed nothing (91.1 vs 91.3 us) and was not kept.
+// Next: x as a TMEM-resident A operand for GEMM1 (halves its shared-memory reads), N = 256 MMAs for GEMM2, a balanced split
+// of the last round.
 #include "tc_common.cuh"
 #include <algorithm>
 #include <cstdlib>
