@@ -203,6 +203,14 @@ SEDT_API int sedt_pseudo_labels(const float* logits, const float* boxes, const f
                                 int B, int Q, int C1, float min_width, int del_overlap, int64_t* labels, float* boxes_out,
                                 float* scores, int32_t* counts, void* stream);
 
+/* ---- The deterministic (evaluation) input pipeline of utilities/BoxTransforms.py:454-490: ApplyLog (librosa.amplitude_to_db:
+ * max(10 log10(max(1e-10, S^2)), clip maximum - 80)) -> PadOrTrunc(frames) (zero rows in the dB domain) -> ToTensor ->
+ * Normalize ((x - mean_[f]) / std_[f] in float64, utilities/Scaler.py:102-108).
+ *   raw [sum T_b, F] fp32 mel amplitudes, clip b = rows offsets[b] .. offsets[b+1] (int64 [B+1]); mean / std [F] float64 or
+ *   both null; out [B, 1, frames, F] fp32 = the tensor sedt_forward reads; apply_log = 0 skips the dB conversion. */
+SEDT_API int sedt_prepare_clips(const float* raw, const int64_t* offsets, const double* mean, const double* std, float* out,
+                                int B, int frames, int F, int apply_log, void* stream);
+
 /* ---- clip_grad_norm_ + AdamW: the optimizer half of the training step (engine.py:76-80; AdamW with two lr groups,
  * train_sedt.py:234-240,269-270; torch/optim/adamw.py _single_tensor_adamw arithmetic, amsgrad = maximize = False).
  * The caller keeps a device table of tensors and a device table of (tensor index, chunk index) pairs that splits

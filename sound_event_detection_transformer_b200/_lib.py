@@ -75,6 +75,7 @@ SIGNATURES = {
     "sedt_set_criterion": (_i, [_vp] * 9 + [_i] * 7 + [_f] * 5 + [_vp] * 10),
     "sedt_decode_events": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _f, _f] + [_vp] * 9),
     "sedt_pseudo_labels": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sedt_prepare_clips": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sedt_optim_chunk_elems": (_i, []),
     "sedt_grad_norm": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "sedt_clip_grads": (_i, [_vp, _vp, _i, _vp, _f, _vp]),

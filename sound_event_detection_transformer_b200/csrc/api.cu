@@ -227,6 +227,12 @@ int sedt_op_ffn(const void* x, const void* w1, const float* b1, const void* w2, 
     return launch_ffn_fused(x, w1, b1, w2, b2, residual, 256, out, 256, M, ff, (cudaStream_t)stream);
 }
 
+int sedt_prepare_clips(const float* raw, const int64_t* offsets, const double* mean, const double* std, float* out, int B, int frames,
+                       int F, int apply_log, void* stream)
+{
+    return launch_prepare_clips(raw, offsets, mean, std, out, B, frames, F, apply_log, (cudaStream_t)stream);
+}
+
 int sedt_optim_chunk_elems(void) { return optim_chunk_elems(); }
 
 int sedt_grad_norm(const sedt_optim_tensor* tensors, const int32_t* chunks, int nchunks, float* partials, float* norm_out, void* stream)

@@ -237,6 +237,10 @@ int launch_pseudo_labels(const float* logits, const float* boxes, const float* t
                          float min_width, int del_overlap, int64_t* out_labels, float* out_boxes, float* out_scores,
                          int32_t* out_count, cudaStream_t stream);
 
+// ---- prepare.cu: ApplyLog -> PadOrTrunc -> Normalize of the evaluation input pipeline (utilities/BoxTransforms.py:454-490)
+int launch_prepare_clips(const float* raw, const int64_t* offsets, const double* mean, const double* stdv, float* out, int B,
+                         int frames, int F, int apply_log, cudaStream_t stream);
+
 // ---- optim.cu: clip_grad_norm_ + AdamW over a (tensor, chunk) table (engine.py:76-80)
 int optim_chunk_elems();
 int launch_grad_norm(const void* tensors, const int32_t* chunks, int nchunks, float* partials, float* norm_out, cudaStream_t stream);

@@ -183,3 +183,9 @@ def synth_teacher_case(B: int, Q: int, C: int, seed: int):
     boxes[:, ::5, 1] *= 0.05
     at = torch.rand(B, C, generator=g)
     return logits, boxes, at
+
+
+def synth_db_clips(lengths, F: int, seed: int):
+    """dB-domain features of ragged lengths (same generator as tests/golden/make_golden.py: run_prepare)."""
+    g = torch.Generator().manual_seed(9500 + seed)
+    return [(torch.randn(t, F, generator=g) * 12.0 - 40.0).numpy().astype("float32") for t in lengths]

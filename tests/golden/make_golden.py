@@ -195,6 +195,34 @@ def run_pseudo_labels(tag, B, Q, C, seed, del_overlap=True):
     print(f"pseudo_{tag}: {B} clips, {sum(len(t['labels']) for t in out)} pseudo events")
 
 
+def synth_db_clips(lengths, F, seed):
+    g = torch.Generator().manual_seed(9500 + seed)
+    return [(torch.randn(t, F, generator=g) * 12.0 - 40.0).numpy().astype(np.float32) for t in lengths]
+
+
+def run_prepare(tag, lengths, frames, seed):
+    """The reference's own PadOrTrunc -> ToTensor -> Normalize (utilities/BoxTransforms.py:91-238, utilities/Scaler.py) on
+    seeded dB-domain features of ragged lengths.  ApplyLog is librosa (absent here) and is not part of this fixture."""
+    for name in ("librosa", "soundfile", "librosa.display", "librosa.feature"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    from utilities.BoxTransforms import Compose, Normalize, PadOrTrunc, ToTensor
+    from utilities.Scaler import Scaler
+    F = 64
+    g = torch.Generator().manual_seed(9600 + seed)
+    sc = Scaler()
+    sc.mean_ = (torch.randn(F, generator=g, dtype=torch.float64) * 5.0 - 40.0).numpy()
+    sc.std_ = (torch.rand(F, generator=g, dtype=torch.float64) * 10.0 + 5.0).numpy()
+    tf = Compose([PadOrTrunc(nb_frames=frames), ToTensor(unsqueeze_axis=0), Normalize(scaler=sc)])
+    outs = []
+    for clip in synth_db_clips(lengths, F, seed):
+        label = {"labels": np.zeros(0, np.int64), "boxes": np.zeros((0, 2), np.float32), "orig_size": np.asarray(10.0)}
+        x, _ = tf((clip, label))
+        outs.append(x.numpy())
+    np.savez_compressed(os.path.join(HERE, f"prepare_{tag}.npz"), out=np.stack(outs).astype(np.float32), mean=sc.mean_, std=sc.std_,
+                        lengths=np.asarray(lengths, np.int64), meta=np.asarray([frames, F, seed], np.int64))
+    print(f"prepare_{tag}: {len(lengths)} clips -> {np.stack(outs).shape}")
+
+
 def run_criterion(tag, args, B, seed, kmin=0, kmax=10, fine_tune=False, normalize=False, fl=False, rng_seed=1234):
     """Reference SetCriterion (sedt/sedt.py:134-352) built directly (build_model returns None for it
     without CUDA) on seeded model-shaped outputs: every loss value and the gradient of the weighted sum."""
@@ -228,6 +256,9 @@ def run_criterion(tag, args, B, seed, kmin=0, kmax=10, fine_tune=False, normaliz
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-prepare" in sys.argv:
+        run_prepare("ragged", [40, 64, 90, 1, 63, 65], 64, seed=41)
+        sys.exit(0)
     if "--only-pseudo" in sys.argv:
         run_pseudo_labels("q20", 48, 20, 10, seed=31)
         run_pseudo_labels("q10_keepall", 16, 10, 10, seed=32, del_overlap=False)

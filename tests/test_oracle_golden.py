@@ -140,3 +140,26 @@ def test_pseudo_label_oracle_matches_reference(tag):
     assert np.array_equal(np.asarray([len(l) for l, _ in out], np.int32), fx["counts"])
     assert np.array_equal(np.concatenate([l for l, _ in out]), fx["labels"])
     assert np.array_equal(np.concatenate([b.reshape(-1, 2) for _, b in out]), fx["boxes"])
+
+
+def test_prepare_oracle_matches_reference_transforms():
+    """pad / ToTensor / Normalize of oracle/prepare_oracle.py against the reference's own transform classes (prepare_ragged.npz)."""
+    from oracle import prepare_oracle
+    fx = np.load(os.path.join(GOLDEN, "prepare_ragged.npz"))
+    frames, F, seed = [int(v) for v in fx["meta"]]
+    clips = synth.synth_db_clips([int(v) for v in fx["lengths"]], F, seed)
+    out = np.stack([prepare_oracle.prepare_clip(c, frames, fx["mean"], fx["std"], apply_log=False) for c in clips])
+    assert out.dtype == np.float32 and np.array_equal(out, fx["out"])
+
+
+def test_amplitude_to_db_restatement_properties():
+    """librosa is absent (parity unpinned for this step): the restatement is checked against its published definition."""
+    from oracle import prepare_oracle
+    rng = np.random.default_rng(0)
+    S = np.abs(rng.standard_normal((50, 64))).astype(np.float32) * 3
+    S[0, 0] = 0.0
+    db = prepare_oracle.amplitude_to_db(S)
+    assert db.dtype == np.float32 and db.max() - db.min() <= 80.0 + 1e-4
+    big = (S > 1e-3) & (db > db.max() - 79.9)                    # above the amin floor and the top_db clip
+    assert np.allclose(db[big], 20 * np.log10(S[big]), atol=1e-4)
+    assert db[0, 0] == np.float32(db.max() - 80.0)
