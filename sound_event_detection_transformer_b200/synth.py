@@ -189,3 +189,16 @@ def synth_db_clips(lengths, F: int, seed: int):
     """dB-domain features of ragged lengths (same generator as tests/golden/make_golden.py: run_prepare)."""
     g = torch.Generator().manual_seed(9500 + seed)
     return [(torch.randn(t, F, generator=g) * 12.0 - 40.0).numpy().astype("float32") for t in lengths]
+
+
+def synth_decode_cases(n: int, Q: int, seed: int):
+    """Overlap-heavy PostProcess-shaped results (same generator as tests/golden/make_golden.py: run_decode_chains)."""
+    import numpy as np
+    rng = np.random.default_rng(9700 + seed)
+    cases = []
+    for _ in range(n):
+        onset = rng.uniform(0.0, 8.0, Q).astype(np.float32)
+        dur = rng.uniform(0.05, 3.0, Q).astype(np.float32)
+        cases.append({"scores": rng.uniform(0.3, 1.0, Q).astype(np.float32), "labels": rng.integers(0, 3, Q).astype(np.int64),
+                      "boxes": np.stack([onset, onset + dur], -1).astype(np.float32)})
+    return cases

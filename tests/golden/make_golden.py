@@ -195,6 +195,30 @@ def run_pseudo_labels(tag, B, Q, C, seed, del_overlap=True):
     print(f"pseudo_{tag}: {B} clips, {sum(len(t['labels']) for t in out)} pseudo events")
 
 
+def synth_decode_cases(n, Q, seed):
+    """PostProcess-shaped results with few classes and heavily overlapping intervals (chains of same-class overlaps)."""
+    rng = np.random.default_rng(9700 + seed)
+    cases = []
+    for _ in range(n):
+        onset = rng.uniform(0.0, 8.0, Q).astype(np.float32)
+        dur = rng.uniform(0.05, 3.0, Q).astype(np.float32)
+        cases.append({"scores": rng.uniform(0.3, 1.0, Q).astype(np.float32), "labels": rng.integers(0, 3, Q).astype(np.int64),
+                      "boxes": np.stack([onset, onset + dur], -1).astype(np.float32)})
+    return cases
+
+
+def run_decode_chains(tag, n, Q, seed):
+    """BoxEncoder.decode_strong (utilities/BoxEncoder.py:179-226) of the reference on overlap-heavy results: pins the order of the
+    suppression loop (delete the weaker neighbour, re-compare) that model outputs rarely exercise."""
+    enc = BoxEncoder(list(CLASSES), seconds=10.0)
+    out = []
+    for r in synth_decode_cases(n, Q, seed):
+        out.append([[e[0], float(e[1]), float(e[2]), float(e[3])] for e in enc.decode_strong(r, 0.5)])
+    with open(os.path.join(HERE, f"decode_{tag}.json"), "w") as f:
+        json.dump({"meta": [n, Q, seed], "events": out}, f)
+    print(f"decode_{tag}: {n} clips, {sum(len(c) for c in out)} events")
+
+
 def synth_db_clips(lengths, F, seed):
     g = torch.Generator().manual_seed(9500 + seed)
     return [(torch.randn(t, F, generator=g) * 12.0 - 40.0).numpy().astype(np.float32) for t in lengths]
@@ -256,6 +280,9 @@ def run_criterion(tag, args, B, seed, kmin=0, kmax=10, fine_tune=False, normaliz
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-decode" in sys.argv:
+        run_decode_chains("chains", 24, 20, seed=51)
+        sys.exit(0)
     if "--only-prepare" in sys.argv:
         run_prepare("ragged", [40, 64, 90, 1, 63, 65], 64, seed=41)
         sys.exit(0)

@@ -163,3 +163,19 @@ def test_amplitude_to_db_restatement_properties():
     big = (S > 1e-3) & (db > db.max() - 79.9)                    # above the amin floor and the top_db clip
     assert np.allclose(db[big], 20 * np.log10(S[big]), atol=1e-4)
     assert db[0, 0] == np.float32(db.max() - 80.0)
+
+
+def test_decode_oracle_matches_reference_on_overlap_chains():
+    """decode_oracle.decode_strong against the reference's BoxEncoder on overlap-heavy results (decode_chains.json)."""
+    fx = json.load(open(os.path.join(GOLDEN, "decode_chains.json")))
+    n, Q, seed = fx["meta"]
+    names = [f"class{i}" for i in range(10)]
+    total = 0
+    for r, gold in zip(synth.synth_decode_cases(n, Q, seed), fx["events"]):
+        ev = decode_oracle.decode_strong(r, names, 0.5)
+        assert [e[0] for e in ev] == [g[0] for g in gold]
+        for e, g in zip(ev, gold):
+            assert float(e[1]) == g[1] and float(e[2]) == g[2] and float(e[3]) == g[3]
+        total += len(ev)
+    kept = sum(int(((r["scores"] >= 0.5) & (r["boxes"][:, 1] - r["boxes"][:, 0] >= 0.2)).sum()) for r in synth.synth_decode_cases(n, Q, seed))
+    assert 0 < total < kept, "the fixture must exercise the overlap suppression"
