@@ -209,7 +209,7 @@ private:
 // ---- ffn_fused.cu: out = residual + relu(x W1^T + b1) W2^T + b2 with the hidden activation kept on chip (eval forward)
 bool ffn_fused_supported(int d, int ff, int64_t M, const void* x, const void* w1, const void* w2, const float* residual, const float* out,
                          int ld_res, int ldo);
-int64_t ffn_fused_min_rows();        // one 128-row tile per SM: below that the two-GEMM path is faster
+bool ffn_fused_preferred(int64_t M);  // true where the fused kernel beats the two GEMMs (whole rounds of tiles over the SMs)
 int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual, int ld_res,
                      float* out, int ldo, int64_t M, int ff, cudaStream_t stream);
 

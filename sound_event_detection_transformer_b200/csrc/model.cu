@@ -570,11 +570,12 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
     float* x32 = (float*)ws.alloc((size_t)rows * d * 4);
     SEDT_TRY(linear(input_proj_, 0, d, feat, dt, 2048, rows, nullptr, x32, DT_F32, d, 0, s, dry));
 
-    // FFN: x32 += linear2(relu(linear1(in))).  With at least one 128-row tile per SM the fused kernel keeps the hidden activation
-    // on chip (ffn_fused.cu: 90 vs 97 us per encoder layer at B = 256); SEDT_FFN_FUSED=0 / 1 forces it off / on for every size.
+    // FFN: x32 += linear2(relu(linear1(in))).  Where it pays (ffn_fused_preferred: whole rounds of 128-row tiles over the SMs) the
+    // fused kernel keeps the hidden activation on chip (90 vs 97 us per encoder layer at B = 256); SEDT_FFN_FUSED=0 / 1 forces it
+    // off / on for every size.
     static const int ffn_mode = [] { const char* e = getenv("SEDT_FFN_FUSED"); return e == nullptr ? -1 : atoi(e); }();
     auto ffn = [&](const Linear& l1, const Linear& l2, const void* in, int64_t nrows, void* hidden, float* x) -> int {
-        const bool ffn_fused = ffn_mode == 1 || (ffn_mode == -1 && nrows >= ffn_fused_min_rows());
+        const bool ffn_fused = ffn_mode == 1 || (ffn_mode == -1 && ffn_fused_preferred(nrows));
         if (ffn_fused && !dry && dt == DT_BF16 && cfg_.use_tensor_cores && !l1.f32_only && !l2.f32_only &&
             ffn_fused_supported(d, ff, nrows, in, packed_ + l1.off_w, packed_ + l2.off_w, x, x, d, d))
             return launch_ffn_fused(in, packed_ + l1.off_w, (const float*)(packed_ + l1.off_b), packed_ + l2.off_w,
