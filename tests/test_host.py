@@ -101,3 +101,37 @@ def test_postprocess_has_no_cpu_path():
     out = {"pred_logits": torch.randn(2, 20, 11), "pred_boxes": torch.rand(2, 20, 2)}
     with pytest.raises(RuntimeError):
         PostProcess()(out, torch.full((2,), 10.0))
+
+
+def test_new_entry_points_have_no_cpu_path():
+    """FusedAdamW / clip_grad_norm_ / prepare_clips / pseudo_labels refuse CPU tensors instead of falling back."""
+    from sound_event_detection_transformer_b200.optim import FusedAdamW, clip_grad_norm_
+    from sound_event_detection_transformer_b200.prepare import prepare_clips
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        FusedAdamW([p]).step(max_norm=0.1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        clip_grad_norm_([p], 0.1)
+    with pytest.raises(ValueError):
+        FusedAdamW([p], betas=(0.3, 0.999))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            prepare_clips([torch.zeros(4, 64)], 8, device="cpu")
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            PostProcess().pseudo_labels({"pred_logits": torch.zeros(1, 4, 11), "pred_boxes": torch.zeros(1, 4, 2)}, torch.ones(1), torch.ones(10))
+
+
+def test_fused_criterion_gate_is_host_logic():
+    """The fused set-criterion path is only taken for the supervised default recipe; everything else routes to the per-clip
+    path (sedt/sedt.py:309-352 semantics) -- checked on the predicate alone, no kernels involved."""
+    import numpy as np
+    args = spec.config_args("c1")
+    _, criterion, _ = build_model(args)
+    out = {"pred_logits": torch.zeros(2, 10, 11), "pred_boxes": torch.zeros(2, 10, 2)}
+    tg = np.array([{"labels": torch.zeros(1, dtype=torch.int64), "boxes": torch.zeros(1, 2)}] * 2, dtype=object)
+    assert not criterion._fused_ok(out, tg, slice(2), None, False, False)            # CPU tensors
+    assert not criterion._fused_ok(out, tg, None, None, False, False)                # no strong clips
+    assert not criterion._fused_ok(out, tg, slice(1, 2), None, False, False)         # strong set not at the front
+    assert not criterion._fused_ok(out, tg, slice(2), None, True, False)             # fine_tune
+    assert not criterion._fused_ok(out, tg, slice(2), None, False, True)             # normalize
