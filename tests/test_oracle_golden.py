@@ -179,3 +179,21 @@ def test_decode_oracle_matches_reference_on_overlap_chains():
         total += len(ev)
     kept = sum(int(((r["scores"] >= 0.5) & (r["boxes"][:, 1] - r["boxes"][:, 0] >= 0.2)).sum()) for r in synth.synth_decode_cases(n, Q, seed))
     assert 0 < total < kept, "the fixture must exercise the overlap suppression"
+
+
+@pytest.mark.parametrize("tag,cfg", [("c2", "c2"), ("c1_edges", "c1")])
+def test_criterion_oracle_matches_reference(tag, cfg):
+    """oracle/criterion_oracle.py against every loss value the reference's own SetCriterion produced (criterion_*.npz)."""
+    from oracle import criterion_oracle
+    fx = np.load(os.path.join(GOLDEN, f"criterion_{tag}.npz"))
+    B, kmin, kmax, seed = [int(v) for v in fx["meta"]]
+    args = spec.config_args(cfg)
+    outputs, targets = synth.synth_criterion_case(B, args.num_queries, args.num_classes, args.dec_layers, kmin, kmax, seed)
+    out = {"pred_logits": outputs["pred_logits"].numpy(), "pred_boxes": outputs["pred_boxes"].numpy(), "at": outputs["at"].numpy(),
+           "aux_outputs": [{k: v.numpy() for k, v in a.items()} for a in outputs["aux_outputs"]]}
+    tg = [{k: v.numpy() for k, v in t.items()} for t in targets]
+    losses = criterion_oracle.set_criterion(out, tg, args.num_classes, args.eos_coef)
+    names = [str(n) for n in fx["loss_names"]]
+    assert sorted(losses) == names
+    for n, v in zip(names, fx["loss_values"]):
+        assert abs(float(losses[n]) - v) <= 2e-5 * max(1.0, abs(v)), (n, float(losses[n]), v)
