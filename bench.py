@@ -16,9 +16,14 @@ data-path collective).  Rank 0 prints ONE JSON line.
           algorithmic FLOPs per step / its summed launch durations per step,
           measured with CUDA events on the launching stream (a second, profiled
           pass over the same steps); peak = MEASURED_PEAKS.json.
-`cpu_baseline` / `--impl reference`: the oracle port of the reference's fp32
-          PyTorch path on the host cores (the reference itself is Python under
-          /root/reference, which does not exist on the GPU box), bounded sample.
+`cpu_baseline` / `--impl reference`: the reference's own fp32 PyTorch modules
+          (oracle/_ref: an unmodified copy made by oracle/make_ref.py, kind
+          "reference"; the oracle port, kind "port", only when that copy is
+          missing) on the host cores, the same 256-clip batches per step.
+`gpu_eager_baseline`: the same reference modules in stock PyTorch eager on the
+          same B200 (fp32, TF32 and bf16 autocast), CUDA-event timed -- the
+          comparison SURVEY.md section 2.1 sets; reported, not the target.
+`--mode train`: the config-4 training step (tools/train_bench.py) with the same keys.
 """
 import argparse
 import ctypes as C
@@ -92,53 +97,118 @@ class ClockSampler(threading.Thread):
                 "samples_in_timed_region": len(timed), "interval_ms": 20}
 
 
-def cpu_port_clips_per_sec(args, sd, sample_clips, repeats):
-    """The oracle port of the reference forward on the host cores."""
+def bench_config(B, world, graph=True, nrot=None, in_bytes=None):
+    """`config` of the JSON line: the same dict on both arms (the reference arm runs the same workload)."""
+    cfg = {"workload": WORKLOAD, "clips_per_gpu_per_step": B, "global_batch": B * world, "parallelism": f"dp{world}"}
+    return cfg
+
+
+def reference_forward(args, sd, device="cpu", autocast=None):
+    """(fn(x) -> outputs, kind): the reference's own SEDT module from oracle/_ref (kind "reference") or, when that copy
+    is missing, the oracle port (kind "port", CPU only)."""
     import torch
+    from oracle import ref_loader
+    if ref_loader.reference_root() is not None:
+        model = ref_loader.build_reference_model(args, sd, device)
+
+        def fn(x):
+            with torch.no_grad():
+                if autocast is not None:
+                    with torch.autocast("cuda", dtype=autocast):
+                        return model(x)
+                return model(x)
+        return fn, "reference"
+    if str(device) != "cpu":
+        return None, "port"
     from oracle import sedt_oracle
+    return (lambda x: sedt_oracle.sedt_forward(sd, args, x)), "port"
+
+
+def cpu_clips_per_sec(args, sd, sample_clips, repeats):
+    """The reference forward on the host cores: 1 warm-up + best of `repeats` (cpu_baseline leg of our arm)."""
+    import torch
     from sound_event_detection_transformer_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    fn, kind = reference_forward(args, sd)
     x = synth.synth_clips(sample_clips, T_FRAMES, N_MELS, seed=77)
-    sedt_oracle.sedt_forward(sd, args, x)                 # warm-up
+    fn(x)
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
-        sedt_oracle.sedt_forward(sd, args, x)
+        fn(x)
         best = min(best, time.perf_counter() - t0)
-    return sample_clips / best, cores, best
+    return sample_clips / best, cores, best, kind
+
+
+def gpu_eager_baseline(args, sd, dev, B, steps=5):
+    """Stock PyTorch eager of the reference modules on the same GPU (SURVEY 2.1's bar), CUDA-event timed."""
+    import torch
+    from sound_event_detection_transformer_b200 import synth
+    out = {"kind": None, "unit": UNIT, "clips_per_step": B, "steps": steps, "timing": "CUDA events, 2 warm-up steps"}
+    x = synth.synth_clips(B, T_FRAMES, N_MELS, seed=78).to(dev)
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for name, allow_tf32, ac in (("fp32", False, None), ("tf32", True, None), ("bf16_autocast", True, torch.bfloat16)):
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = allow_tf32
+            fn, kind = reference_forward(args, sd, dev, ac)
+            out["kind"] = kind
+            if fn is None:
+                out["unavailable"] = "oracle/_ref missing: the oracle port is CPU-only"
+                return out
+            for _ in range(2):
+                fn(x)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                fn(x)
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = B * steps / (e0.elapsed_time(e1) / 1e3)
+            del fn
+            torch.cuda.empty_cache()
+    except Exception as exc:          # a baseline leg must never take the measurement down
+        out["error"] = repr(exc)[:200]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return out
 
 
 def run_reference(opts):
-    """`--impl reference`: the reference's CPU path (oracle port), rank 0 only."""
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores, rank 0 only; the same
+    workload, batch and step counts as our arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     from sound_event_detection_transformer_b200 import spec, synth
+    if opts.mode == "train":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_bench
+        return emit(train_bench.run_reference(opts))
     args = spec.config_args("c2")
     sd = synth.synth_state_dict(args, 12)
-    sample = 64
-    from oracle import sedt_oracle
+    B, K, W = opts.batch, opts.steps, opts.warmup
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    x = synth.synth_clips(sample, T_FRAMES, N_MELS, seed=77)
-    for _ in range(max(1, min(opts.warmup, 2))):
-        sedt_oracle.sedt_forward(sd, args, x)
-    steps = max(1, min(opts.steps, 10))
+    fn, kind = reference_forward(args, sd)
+    xs = [synth.synth_clips(B, T_FRAMES, N_MELS, seed=100 + i) for i in range(2)]
+    for i in range(W):
+        fn(xs[i % 2])
     t0 = time.perf_counter()
-    for _ in range(steps):
-        sedt_oracle.sedt_forward(sd, args, x)
+    for i in range(K):
+        fn(xs[i % 2])
     dt = time.perf_counter() - t0
-    v = sample * steps / dt
-    smp = f"{sample} clips of the same workload per step, fp32 torch on {cores} host threads"
+    v = B * K / dt
+    what = "the unmodified reference modules (oracle/_ref)" if kind == "reference" else "the oracle port of the reference"
+    smp = f"{B} clips per step x {K} steps of the same workload, {what}, fp32 torch eager on {cores} host threads"
     emit({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": opts.gpus, "steps": steps,
-        "warmup": opts.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": opts.gpus, "steps": K,
+        "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_clips_per_step": sample,
-                   "note": "reference is pure Python under /root/reference (absent on the GPU box): timed the oracle port"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": smp},
+        "config": bench_config(B, max(1, opts.gpus)),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": smp},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -179,15 +249,17 @@ def main():
                     help="eval: the headline metric (configs[1]); train: the config-4 training step (batch 64 per GPU by default)")
     opts = ap.parse_args()
     opts.warmup = max(opts.warmup, 3)
+    if opts.mode == "train" and opts.batch == 256:
+        opts.batch = 64                  # config 4: 64 clips per GPU
     if opts.impl == "reference":
         return run_reference(opts)
     if opts.mode == "train":
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import train_bench
         import torch.distributed as dist
-        opts.batch = 64 if opts.batch == 256 else opts.batch
         opts.profile = False
         opts.dropout = 0.1
+        opts.bench_keys = True           # roofline / cpu_baseline / e2e / clocks like the eval line
         res = train_bench.run(opts)
         if res is not None:
             emit(res)
@@ -312,42 +384,51 @@ def main():
     dom_flops = fl["tensor_core_gemm"] * B if dom == "gemm_tcgen05" else fl["total"] * B
     achieved = dom_flops / (dom_ms / 1e3) / 1e12
     step_tf = fl["total"] * B * K / (ms / 1e3) / 1e12 / world if world else 0.0
-    # DRAM bytes of that kernel class per step come from the committed ncu capture of this same command / batch
-    # (profiles/r1k_class_summary.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the class's launches)
+    # DRAM bytes of that kernel class per step: from the committed ncu capture of this same command / batch (ncu cannot run
+    # inside the timed region); the newest profiles/r*_class_summary.json, its name and age stated next to the number
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1k_class_summary.json")
-    if os.path.exists(tp) and B == 256 and opts.precision == "bf16":
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_class_summary.json")))
+    if cands and B == 256 and opts.precision == "bf16":
+        tp = cands[-1]
         c = json.load(open(tp)).get(dom)
         if c:
             traffic = (c["dram_read_MB"] + c["dram_write_MB"]) * 1e6
-            traffic_src = "profiles/r1k_class_summary.json (ncu, bytes per step over the class's launches)"
+            traffic_src = (f"profiles/{os.path.basename(tp)} (ncu dram__bytes_read.sum + dram__bytes_write.sum over the class's "
+                           "launches of one step of this command; captured earlier, not in this run)")
+    peak_burst = float(peaks.get("bf16_tflops", peak_tf))
+    step_ach = fl["total"] * B / ((ms / K) / 1e3) / 1e12
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
-        "peak_source": f"{peak_src} bf16_tflops_sustained",
+        "peak_source": f"{peak_src} bf16_tflops_sustained (the kernel runs inside a long step); burst peak {peak_burst} -> "
+                       f"frac {achieved / peak_burst:.3f}",
+        "frac_vs_burst_peak": achieved / peak_burst,
         "algorithmic_flops_per_clip": fl["total"], "kernel_flops_per_step": dom_flops, "kernel_ms_per_step": dom_ms,
         "kernel_share_of_step": dom_ms / sum(v["ms_per_step"] for v in per_class.values()),
-        "whole_step": {"achieved": fl["total"] * B / ((ms / K) / 1e3) / 1e12, "frac": fl["total"] * B / ((ms / K) / 1e3) / 1e12 / peak_tf},
+        "whole_step": {"achieved": step_ach, "frac": step_ach / peak_tf, "frac_vs_burst_peak": step_ach / peak_burst},
         "per_class": per_class,
     }
 
-    cpu = None
+    cpu = eager = None
     if not opts.no_cpu_baseline:
-        v, cores, best = cpu_port_clips_per_sec(args, sd, 256, 3)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"one 256-clip batch of the same workload, fp32 torch port of the reference on {cores} host threads, "
-                         f"1 warm-up + best of 3 ({best:.2f} s per batch)"}
+        v, cores, best, kind = cpu_clips_per_sec(args, sd, 256, 2)
+        what = "the unmodified reference modules (oracle/_ref)" if kind == "reference" else "oracle port of the reference"
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"one 256-clip batch of the same workload, {what}, fp32 torch eager on {cores} host threads, "
+                         f"1 warm-up + best of 2 ({best:.2f} s per batch)"}
+        eager = gpu_eager_baseline(args, sd, dev, B)
 
     emit({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if opts.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": B, "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": not opts.no_graph,
-                   "l2": f"inputs rotate over {nrot} distinct {in_bytes / 2**20:.1f} MiB batches; per-step activation traffic "
-                         "(>1 GB) exceeds the 126 MB L2"},
+        "config": bench_config(B, world),
+        "cuda_graph": not opts.no_graph,
+        "l2": f"inputs rotate over {nrot} distinct {in_bytes / 2**20:.1f} MiB batches; per-step activation traffic (>1 GB) exceeds the 126 MB L2",
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": eager,
     })
     if world > 1:
         dist.destroy_process_group()

@@ -74,6 +74,11 @@ SEDT_API const char* sedt_last_error(void);
 SEDT_API int sedt_abi_version(void);
 /* number of kernels this library has launched since load (bench.py reports the delta) */
 SEDT_API unsigned long long sedt_launch_count(void);
+/* eager launches per kernel kind (the size-dependent choices of the dispatcher: "conv_tc2", "conv_tc3_2sm", "conv_tc4_ws",
+ * "ffn_fused", "enc_attn_fused", "bottleneck_fused", ...): lets a parity test assert which kernels produced the output it checked */
+SEDT_API int sedt_kernel_kinds(void);
+SEDT_API const char* sedt_kernel_kind_name(int kind);
+SEDT_API unsigned long long sedt_kernel_kind_count(int kind);
 
 /* Per-kernel-class device timing for roofline evidence (bench.py).  While enabled every launch is
  * bracketed by CUDA events on its stream; sedt_profile_read synchronises the device and returns

@@ -51,6 +51,9 @@ SIGNATURES = {
     "sedt_last_error": (C.c_char_p, []),
     "sedt_abi_version": (_i, []),
     "sedt_launch_count": (C.c_ulonglong, []),
+    "sedt_kernel_kinds": (_i, []),
+    "sedt_kernel_kind_name": (C.c_char_p, [_i]),
+    "sedt_kernel_kind_count": (C.c_ulonglong, [_i]),
     "sedt_profile_enable": (_i, [_i]),
     "sedt_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "sedt_model_create": (_i, [C.POINTER(SedtConfig), C.POINTER(_vp)]),
@@ -130,6 +133,12 @@ def load() -> C.CDLL:
             raise RuntimeError(f"libsedt_b200.so ABI {lib.sedt_abi_version()} != expected {ABI_VERSION}; rebuild")
         _lib = lib
         return lib
+
+
+def kernel_kind_counts() -> dict:
+    """Eager launches so far per size-dependent kernel kind (graph replays are not counted)."""
+    lib = load()
+    return {lib.sedt_kernel_kind_name(i).decode(): int(lib.sedt_kernel_kind_count(i)) for i in range(lib.sedt_kernel_kinds())}
 
 
 def check(rc: int) -> None:

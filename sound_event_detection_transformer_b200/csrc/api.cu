@@ -24,6 +24,9 @@ extern "C" {
 const char* sedt_last_error(void) { return get_error(); }
 int sedt_abi_version(void) { return SEDT_ABI_VERSION; }
 unsigned long long sedt_launch_count(void) { return g_launch_count; }
+int sedt_kernel_kinds(void) { return KK_NKINDS; }
+const char* sedt_kernel_kind_name(int kind) { return kernel_kind_name(kind); }
+unsigned long long sedt_kernel_kind_count(int kind) { return kind >= 0 && kind < KK_NKINDS ? g_kind_count[kind] : 0ull; }
 
 int sedt_profile_enable(int on) { g_prof_on = on != 0; return SEDT_OK; }
 int sedt_profile_read(double* ms_per_class, long long* launches_per_class)

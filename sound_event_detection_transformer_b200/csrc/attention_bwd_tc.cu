@@ -310,7 +310,7 @@ static int launch_ab_variant(const void* Q, int ldq, const void* K, int ldk, con
     attention_bwd_tc_kernel<AM, DR><<<grid, block, AB_SMEM_TC, stream>>>(
         (const bf16*)Q, ldq, (const bf16*)K, ldk, (const bf16*)V, ldv, (const bf16*)dO, ldo, (bf16*)dQ, lddq, (bf16*)dK, lddk,
         (bf16*)dV, lddv, kpm, amask, Lq, Lk, scale, drop);
-    SEDT_COUNT_LAUNCH();
+    SEDT_COUNT_KIND(KK_ATTENTION_BWD_TC);
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
 }

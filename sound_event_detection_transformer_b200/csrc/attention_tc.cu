@@ -260,7 +260,7 @@ static int launch_att_variant(const void* Q, int ldq, const void* K, int ldk, co
     SEDT_CHECK_CUDA(launch_pdl(attention_tc_kernel<AM, DR>, grid, block, ATT_SMEM, stream, 1, (const __nv_bfloat16*)Q, ldq,
                                (const __nv_bfloat16*)K, ldk, (const __nv_bfloat16*)V, ldv, (__nv_bfloat16*)O, ldo, kpm, amask, Lq, Lk,
                                scale, drop));
-    SEDT_COUNT_LAUNCH();
+    SEDT_COUNT_KIND(KK_ATTENTION_TC);
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
 }

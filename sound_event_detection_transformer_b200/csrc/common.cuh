@@ -53,6 +53,13 @@ static inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b
 // launch counter: bench.py reports how many of OUR kernels ran in the timed region
 extern unsigned long long g_launch_count;
 #define SEDT_COUNT_LAUNCH() (++::sedt::g_launch_count)
+// per-kernel launch counters for the kernels whose selection depends on the problem size (launch_conv_tc dispatch, fused
+// blocks): the parity tests assert that the launch sequence they checked is the one the benchmark times
+enum KernelKind : int { KK_CONV_TC2 = 0, KK_CONV_TC3_2SM, KK_CONV_TC4_WS, KK_CONV_TC_V1, KK_FFN_FUSED, KK_ATTENTION_TC, KK_STEM_TC,
+                        KK_WGRAD_TC, KK_ATTENTION_BWD_TC, KK_ENC_ATTN_FUSED, KK_BOTTLENECK_FUSED, KK_DEC_LAYER_FUSED, KK_NKINDS };
+extern unsigned long long g_kind_count[KK_NKINDS];
+const char* kernel_kind_name(int kind);
+#define SEDT_COUNT_KIND(kind) (++::sedt::g_launch_count, ++::sedt::g_kind_count[kind])
 
 // ---- optional per-kernel-class device timing (bench.py roofline evidence) ---------------
 // When enabled, every launcher brackets its kernel with two CUDA events on the launching

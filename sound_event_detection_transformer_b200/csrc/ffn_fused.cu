@@ -348,7 +348,7 @@ int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void*
     const int grid = std::min(p.tiles_m, num_sms());
     ProfScope _prof(PROF_GEMM_TC, stream);
     SEDT_CHECK_CUDA(launch_pdl(ffn_fused_ts_kernel, dim3((unsigned)grid), dim3(TS_THREADS), TS_SMEM, stream, 1, mx, m1, m2, mres, mout, p));
-    SEDT_COUNT_LAUNCH();
+    SEDT_COUNT_KIND(KK_FFN_FUSED);
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
 }

@@ -208,7 +208,7 @@ int launch_v1(const TcProblem& pr, dim3 grid, cudaStream_t stream)
     }
     ProfScope _prof(PROF_GEMM_TC, stream);
     kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(pr.map_a[0], pr.map_a[1], pr.map_a[2], pr.map_a[3], pr.map_b, pr.p);
-    SEDT_COUNT_LAUNCH();
+    SEDT_COUNT_KIND(KK_CONV_TC_V1);
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
 }

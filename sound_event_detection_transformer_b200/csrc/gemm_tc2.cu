@@ -244,7 +244,7 @@ int launch_v2(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr,
     ProfScope _prof(PROF_GEMM_TC, stream);
     SEDT_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(NUM_THREADS2), L::TOTAL, stream, 1, pr.map_a[0], pr.map_a[1],
                                pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p, pr.tiles_nc, total));
-    SEDT_COUNT_LAUNCH();
+    SEDT_COUNT_KIND(KK_CONV_TC2);
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
 }

@@ -283,7 +283,7 @@ int launch_v3(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr,
     ProfScope _prof(PROF_GEMM_TC, stream);
     SEDT_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(T3_THREADS), L::TOTAL, stream, 2, pr.map_a[0], pr.map_a[1], pr.map_a[2],
                                pr.map_a[3], pr.map_b, mo, mr, pr.p, pr.tiles_nc, total));
-    SEDT_COUNT_LAUNCH();
+    SEDT_COUNT_KIND(KK_CONV_TC3_2SM);
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
 }

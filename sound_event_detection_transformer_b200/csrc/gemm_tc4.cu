@@ -286,7 +286,7 @@ int launch_v4(const TcProblem& pr, const CUtensorMap& mo, const CUtensorMap& mr,
     ProfScope _prof(PROF_GEMM_TC, stream);
     SEDT_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(NUM_THREADS4), L::TOTAL, stream, 1, pr.map_a[0], pr.map_a[1],
                                pr.map_a[2], pr.map_a[3], pr.map_b, mo, mr, pr.p, pr.tiles_nc, pr.tiles_m));
-    SEDT_COUNT_LAUNCH();
+    SEDT_COUNT_KIND(KK_CONV_TC4_WS);
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
 }

@@ -175,7 +175,7 @@ int launch_wg(const TcProblem& pr, const CUtensorMap& mdy, const WgParams& p, in
     }
     ProfScope _prof(PROF_GEMM_TC, stream);
     kern<<<grid, WG_THREADS, L::TOTAL, stream>>>(pr.map_a[0], pr.map_a[1], pr.map_a[2], pr.map_a[3], mdy, p);
-    SEDT_COUNT_LAUNCH();
+    SEDT_COUNT_KIND(KK_WGRAD_TC);
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
 }

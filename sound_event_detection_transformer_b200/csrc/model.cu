@@ -12,6 +12,13 @@ namespace sedt {
 // ---- error string / launch counter ------------------------------------------------
 static thread_local char g_err[1024] = "";
 unsigned long long g_launch_count = 0;
+unsigned long long g_kind_count[KK_NKINDS] = {};
+const char* kernel_kind_name(int kind)
+{
+    static const char* names[KK_NKINDS] = {"conv_tc2", "conv_tc3_2sm", "conv_tc4_ws", "conv_tc_v1", "ffn_fused", "attention_tc", "stem_tc",
+                                           "wgrad_tc", "attention_bwd_tc", "enc_attn_fused", "bottleneck_fused", "dec_layer_fused"};
+    return kind >= 0 && kind < KK_NKINDS ? names[kind] : nullptr;
+}
 
 bool pdl_enabled()
 {

@@ -5,6 +5,7 @@
 #pragma once
 #include "kernels.h"
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace sedt {
@@ -146,8 +147,7 @@ private:
     // by the following ones while the weight / workspace addresses stay put (train.cu: Model::backward)
     struct DgradPlan { std::vector<DgradJob> jobs; unsigned long long key = 0; bool ready = false; };
     DgradPlan dgrad_plan_;
-    const void* rng_tape_ = nullptr;          // tape whose dropout RNG state {seed, step} has been initialised
-    unsigned long long rng_seed_ = 0;
+    std::unordered_map<const void*, unsigned long long> rng_tapes_;   // tape -> seed its dropout RNG state {seed, step} was initialised with
 };
 
 }  // namespace sedt

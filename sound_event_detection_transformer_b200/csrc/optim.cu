@@ -84,7 +84,8 @@ grad_norm_finish_kernel(const float* __restrict__ partials, int n, float* __rest
 // torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (total_norm + 1e-6))
 __device__ __forceinline__ float clip_coef(const float* norm, float max_norm) {
     if (norm == nullptr || !(max_norm > 0.f)) return 1.f;
-    return fminf(max_norm / (norm[0] + 1e-6f), 1.f);
+    const float c = max_norm / (norm[0] + 1e-6f);
+    return c < 1.f ? c : (c != c ? c : 1.f);            // torch clamps with max = 1: a NaN norm propagates to every gradient
 }
 
 __global__ void __launch_bounds__(kThreads)

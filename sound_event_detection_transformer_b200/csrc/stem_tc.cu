@@ -341,7 +341,7 @@ int launch_stem_tc(const float* x, const void* wtc, const float* bn_bias, const 
         SEDT_CHECK_CUDA(launch_pdl(stem_tc_kernel<false>, grid, block, ST_SMEM, stream, 1, x, (const uint8_t*)wtc, bn_bias, bn_scale, sat,
                                    (__nv_bfloat16*)out, (uint8_t*)nullptr, T, Hc, Hp));
     }
-    SEDT_COUNT_LAUNCH();
+    SEDT_COUNT_KIND(KK_STEM_TC);
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;
 }

@@ -183,11 +183,14 @@ int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int 
         // records the per-step increment), so that every replayed step draws fresh masks
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         SEDT_CHECK_CUDA(cudaStreamIsCapturing(s, &cap));
-        if (cap == cudaStreamCaptureStatusNone && (rng_tape_ != tape || rng_seed_ != seed)) {
+        // several tapes may be alive at once (two forwards before one backward, engine.py:134-170): each keeps its own state
+        auto it = rng_tapes_.find(tape);
+        if (cap == cudaStreamCaptureStatusNone && (it == rng_tapes_.end() || it->second != seed)) {
             SEDT_TRY(launch_rng_init(tp.rng, seed, s));
-            rng_tape_ = tape; rng_seed_ = seed;
+            rng_tapes_[tape] = seed;
+            it = rng_tapes_.find(tape);
         }
-        SEDT_REQUIRE(rng_tape_ == tape, "forward_train: dropout RNG state of this tape was not initialised before graph capture");
+        SEDT_REQUIRE(it != rng_tapes_.end(), "forward_train: dropout RNG state of this tape was not initialised before graph capture");
         SEDT_TRY(launch_rng_step(tp.rng, s));
     }
     auto site = [&](uint32_t id) { return make_drop_site(tp.rng, id, dropout); };
@@ -434,7 +437,7 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
         return SEDT_OK;
     };
     const bool drop = dropout > 0.f;
-    SEDT_REQUIRE(!drop || rng_tape_ == tape, "backward: forward_train with dropout has not run on this tape");
+    SEDT_REQUIRE(!drop || rng_tapes_.count(tape) != 0, "backward: forward_train with dropout has not run on this tape");
     auto site = [&](uint32_t id) { return make_drop_site(tp.rng, id, dropout); };
     if (drop) SEDT_TRY(launch_fill_value(bb.vscale, 1.f / (1.f - dropout), ff, s));
     // bf16 copy of a gradient that enters a GEMM whose forward output went through dropout site `id`

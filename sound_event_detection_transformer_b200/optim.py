@@ -42,7 +42,13 @@ class _Table:
         self.chunks = torch.tensor(chunks if chunks else [0, 0], dtype=torch.int32).to(dev)
         self.partials = torch.empty(max(self.n, 1), dtype=torch.float32, device=dev)
         self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.key = tuple((p.data_ptr(), g.data_ptr()) for p, g, *_ in entries)
+        self.key = _table_key(entries)
+
+
+def _table_key(entries):
+    """Addresses AND sizes AND group ids: the table stores numel / group at build time, and the allocator may hand a freed
+    address to a tensor of another size (a second model in the same process)."""
+    return tuple((p.data_ptr(), g.data_ptr(), p.numel(), grp) for p, g, _, _, grp in entries)
 
 
 def _check(p: torch.Tensor, g: torch.Tensor):
@@ -66,11 +72,12 @@ def clip_grad_norm_(parameters: Iterable[torch.Tensor], max_norm: float) -> torc
     for p in ps:
         _check(p, p.grad)
     dev = ps[0].device
-    key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+    ent = [(p, p.grad, None, None, 0) for p in ps]
+    key = _table_key(ent)
     tab = _clip_tables.get(key)
     if tab is None:
         _clip_tables.clear()                      # one live table: the training loop clips the same list every step
-        tab = _clip_tables[key] = _Table([(p, p.grad, None, None, 0) for p in ps], dev)
+        tab = _clip_tables[key] = _Table(ent, dev)
     lib = _lib.load()
     with torch.cuda.device(dev):
         s = _lib.current_stream()
@@ -96,7 +103,11 @@ class FusedAdamW(torch.optim.Optimizer):
         self.last_grad_norm: Optional[torch.Tensor] = None       # device scalar of the last step(max_norm > 0)
 
     def _entries(self):
-        ent = []
+        """(param, grad, exp_avg, exp_avg_sq, virtual group) per parameter with a gradient, plus the hyper-parameters of
+        every virtual group.  torch.optim.AdamW keeps `step` per parameter: parameters of one param_group whose step counts
+        differ (a gradient that first appears mid-run, e.g. weak_class_embed once the weak loss is switched on, or a
+        checkpoint with mixed steps) get their own virtual group, i.e. their own bias correction."""
+        ent, vgroups, steps = [], {}, []
         for gi, group in enumerate(self.param_groups):
             for p in group["params"]:
                 if p.grad is None:
@@ -107,8 +118,13 @@ class FusedAdamW(torch.optim.Optimizer):
                     st["step"] = torch.tensor(0.0, dtype=torch.float32)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                ent.append((p, p.grad, st["exp_avg"], st["exp_avg_sq"], gi))
-        return ent
+                step = float(st["step"])
+                vg = vgroups.setdefault((gi, step), len(vgroups))
+                ent.append((p, p.grad, st["exp_avg"], st["exp_avg_sq"], vg))
+                steps.append(st["step"])
+        if len(vgroups) > 8:
+            raise ValueError(f"FusedAdamW: {len(vgroups)} distinct (param_group, step) pairs; the kernel takes up to 8")
+        return ent, vgroups, steps
 
     @torch.no_grad()
     def step(self, closure=None, max_norm: float = 0.0):
@@ -116,30 +132,29 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        ent = self._entries()
+        ent, vgroups, steps = self._entries()
         if not ent:
             return loss
         dev = ent[0][0].device
-        key = tuple((p.data_ptr(), g.data_ptr()) for p, g, *_ in ent)
+        key = _table_key(ent)
         if self._table is None or self._table.key != key or \
                 self._table_state != tuple((m.data_ptr(), v.data_ptr()) for _, _, m, v, _ in ent):
             self._table = _Table(ent, dev)
             self.table_builds += 1
             self._table_state = tuple((m.data_ptr(), v.data_ptr()) for _, _, m, v, _ in ent)
         tab = self._table
-        groups = (_lib.SedtAdamWGroup * len(self.param_groups))()
-        for gi, group in enumerate(self.param_groups):
-            steps = [self.state[p]["step"] for p in group["params"] if p.grad is not None]
-            step = (float(steps[0]) if steps else 0.0) + 1.0
-            if steps:
-                torch._foreach_add_(steps, 1.0)
+        groups = (_lib.SedtAdamWGroup * len(vgroups))()
+        for (gi, step0), vg in vgroups.items():
+            group = self.param_groups[gi]
+            step = step0 + 1.0
             b1, b2 = group["betas"]
             lr = float(group["lr"])
-            groups[gi].decay = 1.0 - lr * group["weight_decay"]
-            groups[gi].w1, groups[gi].beta2, groups[gi].w2 = 1.0 - b1, b2, 1.0 - b2
-            groups[gi].bc2_sqrt = math.sqrt(1.0 - b2 ** step)
-            groups[gi].eps = group["eps"]
-            groups[gi].neg_step = -(lr / (1.0 - b1 ** step))
+            groups[vg].decay = 1.0 - lr * group["weight_decay"]
+            groups[vg].w1, groups[vg].beta2, groups[vg].w2 = 1.0 - b1, b2, 1.0 - b2
+            groups[vg].bc2_sqrt = math.sqrt(1.0 - b2 ** step)
+            groups[vg].eps = group["eps"]
+            groups[vg].neg_step = -(lr / (1.0 - b1 ** step))
+        torch._foreach_add_(steps, 1.0)
         lib = _lib.load()
         with torch.cuda.device(dev):
             s = _lib.current_stream()
@@ -150,7 +165,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 norm_ptr = tab.norm.data_ptr()
                 self.last_grad_norm = tab.norm
             _lib.check(lib.sedt_adamw_step(tab.tensors.data_ptr(), tab.chunks.data_ptr(), tab.n, groups,
-                                           len(self.param_groups), norm_ptr, float(max_norm or 0.0), s))
+                                           len(vgroups), norm_ptr, float(max_norm or 0.0), s))
         # the update wrote the parameters behind autograd's back: bump the version counters so that the runtime
         # re-packs its bf16 weight snapshot (runtime.ensure_packed keys on _version)
         self._bump(ent)

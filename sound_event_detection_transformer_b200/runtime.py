@@ -5,11 +5,33 @@ PyTorch is used for device memory and streams only."""
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, Optional
 
 import torch
 
 from . import _lib
+
+
+class _TrainSlot:
+    """Resources of one forward_train / backward pair in flight (see ForwardRuntime._acquire_slot)."""
+
+    def __init__(self, index: int, seed: int):
+        self.index, self.seed = index, seed
+        self.tape: Optional[torch.Tensor] = None
+        self.owner = None          # weakref to the token of the forward that holds the slot
+        self.gen = 0               # bumped by every forward_train on this slot
+        self.g: Optional[dict] = None      # graph mode: static buffers + captured graphs
+
+    def busy(self) -> bool:
+        return self.owner is not None and self.owner() is not None
+
+
+class _TrainCtx:
+    __slots__ = ("slot", "gen", "x", "m8", "B", "T", "F", "dropout", "graph")
+
+    def __init__(self, slot, gen, x, m8, B, T, F, dropout, graph):
+        self.slot, self.gen, self.x, self.m8, self.B, self.T, self.F, self.dropout, self.graph = slot, gen, x, m8, B, T, F, dropout, graph
 
 
 class ForwardRuntime:
@@ -29,6 +51,7 @@ class ForwardRuntime:
         # CUDA-graph replay of the whole forward (one graph per input shape); see forward(use_graph=True)
         self._graphs: Dict[tuple, dict] = {}
         self.graph_kernel_launches = 0     # kernels executed through graph replays (the library counter only sees eager launches)
+        self.max_train_slots = 4           # forward_train calls that may wait for their backward at the same time (per input shape)
 
     def __del__(self):
         try:
@@ -78,8 +101,8 @@ class ForwardRuntime:
         # graphs bake in the packed-buffer and parameter addresses (not the values): re-capture only when those move
         if realloc or keep or getattr(self, "_ptr_key", None) != pkey:
             self._graphs.clear()
-            self._train_graphs = {}
             self._pack_graph_key = None
+            self._pack_epoch = getattr(self, "_pack_epoch", 0) + 1      # train slots re-capture when this moves
         self._ptr_key = pkey
         if use_graph and not keep and self._pack_graph_key != pkey:
             with torch.cuda.device(dev):
@@ -215,68 +238,98 @@ class ForwardRuntime:
             self._grad_layout = (n, offs)
         return self._grad_layout
 
-    def forward_train(self, x: torch.Tensor, mask: Optional[torch.Tensor], use_graph: bool = False, dropout: float = 0.0):
-        """Forward in train mode: same outputs as forward(); the activations stay in a runtime-owned tape until
-        backward() (one forward/backward pair in flight per runtime).  use_graph replays the launch sequence as a
-        CUDA graph per input shape (static input / output buffers, overwritten by the next step)."""
+    # Train slots.  One forward_train / backward pair owns one slot: its own activation tape and dropout RNG stream and, in
+    # graph mode, its own static input / output / gradient buffers and captured graphs.  A forward issued while earlier
+    # forwards still wait for their backward (the semi-supervised loop runs the labelled and the unlabelled batch through
+    # the model before ONE total_losses.backward(), engine.py:134-170) takes a fresh slot instead of overwriting the tape.
+    # A slot is busy while the autograd node that owns it (its token) is alive and has not run backward.
+    def _slot_seed(self, index: int) -> int:
+        if getattr(self, "_seed", None) is None:
+            self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF        # fixed per runtime: graphs bake it in
+        return (self._seed + index * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF   # slot 0 keeps the runtime's seed
+
+    def _acquire_slot(self, key, token) -> "_TrainSlot":
+        slots = self._train_slots.setdefault(key, []) if hasattr(self, "_train_slots") else None
+        if slots is None:
+            self._train_slots = {key: []}
+            slots = self._train_slots[key]
+        for sl in slots:
+            if not sl.busy():
+                break
+        else:
+            if len(slots) >= self.max_train_slots:
+                raise RuntimeError(f"{len(slots)} train-mode forwards are waiting for their backward: outputs of grad-enabled "
+                                   "forwards are being kept alive without ever calling backward() (each holds an activation tape); "
+                                   "run such forwards under torch.no_grad(), or raise runtime.max_train_slots")
+            n = sum(len(v) for v in self._train_slots.values())
+            sl = _TrainSlot(n, self._slot_seed(n))
+            slots.append(sl)
+        sl.owner = weakref.ref(token) if token is not None else None
+        sl.gen += 1
+        return sl
+
+    def train_slots_in_use(self) -> int:
+        return sum(1 for v in getattr(self, "_train_slots", {}).values() for sl in v if sl.busy())
+
+    def forward_train(self, x: torch.Tensor, mask: Optional[torch.Tensor], use_graph: bool = False, dropout: float = 0.0,
+                      token=None):
+        """Forward in train mode: same outputs as forward(); the activations stay in the slot's tape until backward().
+        `token`: the object whose lifetime marks the slot busy (the autograd context); None = fire and forget (a train-mode
+        forward without gradients: dropout is applied, nothing is kept).  use_graph replays the launch sequence as a CUDA
+        graph per (input shape, slot): static buffers, overwritten by the slot's next step.  Returns (res, ctx)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 1
         x = x.contiguous()
         B, _, T, F = x.shape
         dev = x.device
-        self._dropout = float(dropout)
-        if getattr(self, "_seed", None) is None:
-            self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF        # fixed per runtime: graphs bake it in
+        dropout = float(dropout)
         if use_graph:
-            return self._forward_train_graph(x, mask)
+            return self._forward_train_graph(x, mask, dropout, token)
+        sl = self._acquire_slot(("eager", dev.index), token)
         need = int(self.lib.sedt_train_tape_bytes(self.handle, B, T, F, int(mask is not None)))
         if need < 0:
             _lib.check(need)
-        tape = getattr(self, "_tape", None)
-        if tape is None or tape.numel() < need + 256 or tape.device != dev:
-            self._tape = None
-            self._tape = tape = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        if sl.tape is None or sl.tape.numel() < need + 256 or sl.tape.device != dev:
+            sl.tape = None
+            sl.tape = torch.empty(need + 256, dtype=torch.uint8, device=dev)
         m8 = None
         if mask is not None:
             m8 = mask.to(dev).contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(dev, torch.uint8).contiguous()
         res = self._alloc_outputs(B, T, F, 0, dev)
         outs = _lib.SedtOutputs(**{k: _lib.ptr(res.get(k)) or None for k, _ in _lib.SedtOutputs._fields_})
         with torch.cuda.device(dev):
-            _lib.check(self.lib.sedt_forward_train(self.handle, x.data_ptr(), _lib.ptr(m8) or None, B, T, F, self._aligned(tape),
-                                                   tape.numel() - 256, C.byref(outs), self._dropout, self._seed,
+            _lib.check(self.lib.sedt_forward_train(self.handle, x.data_ptr(), _lib.ptr(m8) or None, B, T, F, self._aligned(sl.tape),
+                                                   sl.tape.numel() - 256, C.byref(outs), dropout, sl.seed,
                                                    _lib.current_stream()))
-        return res, (x, m8, B, T, F)
+        return res, _TrainCtx(sl, sl.gen, x, m8, B, T, F, dropout, False)
 
-    def _train_graph_state(self, B, T, F, has_mask, dev):
-        key = (B, T, F, has_mask, dev.index, self._dropout)
-        g = getattr(self, "_train_graphs", {}).get(key)
+    def _forward_train_graph(self, x, mask, dropout, token):
+        B, _, T, F = x.shape
+        dev = x.device
+        has_mask = mask is not None
+        sl = self._acquire_slot((B, T, F, has_mask, dev.index, dropout), token)
+        g = sl.g
         if g is None:
-            if not hasattr(self, "_train_graphs"):
-                self._train_graphs = {}
             need = int(self.lib.sedt_train_tape_bytes(self.handle, B, T, F, int(has_mask)))
             if need < 0:
                 _lib.check(need)
-            self._tape = torch.empty(need + 256, dtype=torch.uint8, device=dev)
-            g = {"x": torch.empty(B, 1, T, F, dtype=torch.float32, device=dev),
-                 "mask": torch.empty(B, T, F, dtype=torch.uint8, device=dev) if has_mask else None,
-                 "res": self._alloc_outputs(B, T, F, 0, dev), "fwd": None, "bwd": None}
-            self._train_graphs[key] = g
-        return g
-
-    def _forward_train_graph(self, x, mask):
-        B, _, T, F = x.shape
-        dev = x.device
-        g = self._train_graph_state(B, T, F, mask is not None, dev)
+            sl.tape = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+            g = sl.g = {"x": torch.empty(B, 1, T, F, dtype=torch.float32, device=dev),
+                        "mask": torch.empty(B, T, F, dtype=torch.uint8, device=dev) if has_mask else None,
+                        "res": self._alloc_outputs(B, T, F, 0, dev), "fwd": None, "bwd": None, "epoch": self._pack_epoch}
+        elif g["epoch"] != self._pack_epoch:           # the parameters / packed buffer moved: the captured addresses are stale
+            g["fwd"] = g["bwd"] = None
+            g["epoch"] = self._pack_epoch
         g["x"].copy_(x, non_blocking=True)
-        if mask is not None:
+        if has_mask:
             g["mask"].copy_(mask.view(torch.uint8) if mask.dtype == torch.bool else mask, non_blocking=True)
         if g["fwd"] is None:
-            res, tape = g["res"], self._tape
+            res, tape = g["res"], sl.tape
             outs = _lib.SedtOutputs(**{k: _lib.ptr(res.get(k)) or None for k, _ in _lib.SedtOutputs._fields_})
 
             def launch():
                 _lib.check(self.lib.sedt_forward_train(self.handle, g["x"].data_ptr(), _lib.ptr(g["mask"]) or None, B, T, F,
-                                                       self._aligned(tape), tape.numel() - 256, C.byref(outs), self._dropout,
-                                                       self._seed, _lib.current_stream()))
+                                                       self._aligned(tape), tape.numel() - 256, C.byref(outs), dropout,
+                                                       sl.seed, _lib.current_stream()))
             with torch.cuda.device(dev):
                 launch()                                  # lazy one-time setup must not be captured
                 torch.cuda.synchronize(dev)
@@ -288,10 +341,11 @@ class ForwardRuntime:
             g["fwd"] = graph
         g["fwd"].replay()
         self.graph_kernel_launches += g["fwd_launches"]
-        return g["res"], (g["x"], g["mask"], B, T, F, g)
+        return g["res"], _TrainCtx(sl, sl.gen, g["x"], g["mask"], B, T, F, dropout, True)
 
     def _backward_graph(self, ctx, d_logits, d_boxes, d_at, train_backbone):
-        x, m8, B, T, F, g = ctx
+        sl, x, m8, B, T, F = ctx.slot, ctx.x, ctx.m8, ctx.B, ctx.T, ctx.F
+        g = sl.g
         dev = x.device
         if g["bwd"] is None or g.get("bwd_tb") != bool(train_backbone):
             need = int(self.lib.sedt_backward_workspace_bytes(self.handle, B, T, F))
@@ -305,13 +359,13 @@ class ForwardRuntime:
             g["da"] = torch.zeros_like(res["at"]) if "at" in res else None
             shift = ((-g["flat"].data_ptr()) % 256) // 4
             g["grads"] = g["flat"][shift:shift + n]
-            tape, ws = self._tape, g["ws"]
+            tape, ws = sl.tape, g["ws"]
 
             def launch():
                 _lib.check(self.lib.sedt_backward(self.handle, self._ptrs, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
                                                   self._aligned(tape), tape.numel() - 256, self._aligned(ws), ws.numel() - 256,
                                                   g["dl"].data_ptr(), g["db"].data_ptr(), _lib.ptr(g["da"]) or None,
-                                                  g["grads"].data_ptr(), int(train_backbone), self._dropout, _lib.current_stream()))
+                                                  g["grads"].data_ptr(), int(train_backbone), ctx.dropout, _lib.current_stream()))
             with torch.cuda.device(dev):
                 launch()
                 torch.cuda.synchronize(dev)
@@ -331,34 +385,43 @@ class ForwardRuntime:
         self.graph_kernel_launches += g["bwd_launches"]
         return g["grads"]
 
-    def backward(self, ctx, d_logits, d_boxes, d_at, train_backbone: bool) -> torch.Tensor:
-        """Gradients of every trainable state_dict entry in one flat fp32 tensor (see grad_layout())."""
-        if len(ctx) == 6:
-            return self._backward_graph(ctx, d_logits, d_boxes, d_at, train_backbone)
-        x, m8, B, T, F = ctx
-        dev = x.device
-        need = int(self.lib.sedt_backward_workspace_bytes(self.handle, B, T, F))
-        if need < 0:
-            _lib.check(need)
-        ws = getattr(self, "_bws", None)
-        if ws is None or ws.numel() < need + 256 or ws.device != dev:
-            self._bws = None
-            self._bws = ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
-        n, _ = self.grad_layout()
-        flat = torch.empty(n + 64, dtype=torch.float32, device=dev)
-        shift = ((-flat.data_ptr()) % 256) // 4
-        grads = flat[shift:shift + n]
+    def backward(self, ctx: "_TrainCtx", d_logits, d_boxes, d_at, train_backbone: bool) -> torch.Tensor:
+        """Gradients of every trainable state_dict entry in one flat fp32 tensor (see grad_layout()).  In graph mode the
+        tensor is the slot's static buffer: the next backward of the same slot overwrites it (callers that hand views of
+        it to autograd must copy, see sedt/model.py: _TrainStep)."""
+        sl = ctx.slot
+        if sl.gen != ctx.gen:
+            raise RuntimeError("backward: the activation tape of this forward has been overwritten by a later forward_train "
+                               "(backward called twice, or after the autograd graph had been released)")
+        try:
+            if ctx.graph:
+                return self._backward_graph(ctx, d_logits, d_boxes, d_at, train_backbone)
+            x, m8, B, T, F = ctx.x, ctx.m8, ctx.B, ctx.T, ctx.F
+            dev = x.device
+            need = int(self.lib.sedt_backward_workspace_bytes(self.handle, B, T, F))
+            if need < 0:
+                _lib.check(need)
+            ws = getattr(self, "_bws", None)
+            if ws is None or ws.numel() < need + 256 or ws.device != dev:
+                self._bws = None
+                self._bws = ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+            n, _ = self.grad_layout()
+            flat = torch.empty(n + 64, dtype=torch.float32, device=dev)
+            shift = ((-flat.data_ptr()) % 256) // 4
+            grads = flat[shift:shift + n]
 
-        def f32(t):
-            return None if t is None else t.detach().to(torch.float32).contiguous()
-        d_logits, d_boxes, d_at = f32(d_logits), f32(d_boxes), f32(d_at)
-        tape = self._tape
-        with torch.cuda.device(dev):
-            _lib.check(self.lib.sedt_backward(self.handle, self._ptrs, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
-                                              self._aligned(tape), tape.numel() - 256, self._aligned(ws), ws.numel() - 256,
-                                              _lib.ptr(d_logits) or None, _lib.ptr(d_boxes) or None, _lib.ptr(d_at) or None,
-                                              grads.data_ptr(), int(train_backbone), self._dropout, _lib.current_stream()))
-        return grads
+            def f32(t):
+                return None if t is None else t.detach().to(torch.float32).contiguous()
+            d_logits, d_boxes, d_at = f32(d_logits), f32(d_boxes), f32(d_at)
+            tape = sl.tape
+            with torch.cuda.device(dev):
+                _lib.check(self.lib.sedt_backward(self.handle, self._ptrs, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
+                                                  self._aligned(tape), tape.numel() - 256, self._aligned(ws), ws.numel() - 256,
+                                                  _lib.ptr(d_logits) or None, _lib.ptr(d_boxes) or None, _lib.ptr(d_at) or None,
+                                                  grads.data_ptr(), int(train_backbone), ctx.dropout, _lib.current_stream()))
+            return grads
+        finally:
+            sl.owner = None                    # the pair is complete: the slot may serve the next forward
 
     def kernel_launches(self) -> int:
         """Kernels of this library executed so far on behalf of this process (eager + graph replays)."""

@@ -15,17 +15,44 @@ from .modules import MLP
 PRECISIONS = {"fp32": 0, "bf16": 1}
 
 
+class _Token:
+    """Lifetime marker of one forward's autograd context: the runtime slot (tape) it holds stays busy while it is alive
+    and backward has not run."""
+    __slots__ = ("__weakref__",)
+
+
+def _detach_grads_from(static, params, names, shapes, rt):
+    if static is None:
+        return
+    lo, hi = static.data_ptr(), static.data_ptr() + static.numel() * 4
+    if not any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in params):
+        return
+    keep = static.clone()
+    _, offs = rt.grad_layout()
+    for p, n, shp in zip(params, names, shapes):
+        if p.grad is not None and lo <= p.grad.data_ptr() < hi:
+            p.grad = keep[offs[n]:offs[n] + p.numel()].view(shp)
+
+
 class _TrainStep(torch.autograd.Function):
     """forward = sedt_forward_train, backward = sedt_backward (hand-written kernels both ways); the trainable
-    parameters are inputs so that autograd hands their gradients to the optimizer as usual (engine.py:70-80)."""
+    parameters are inputs so that autograd hands their gradients to the optimizer as usual (engine.py:70-80).
+    Each forward takes its own runtime slot (tape + dropout stream), so several forwards may precede one backward
+    (engine.py:134-170)."""
 
     @staticmethod
     def forward(ctx, model, x, mask, names, *params):
         rt = model.runtime(use_graph=model.use_cuda_graph)
-        res, tctx = rt.forward_train(x, mask, use_graph=model.use_cuda_graph, dropout=float(model.transformer.dropout))
-        ctx.model, ctx.tctx, ctx.names, ctx.shapes = model, tctx, names, [p.shape for p in params]
+        ctx.token = _Token()
+        res, tctx = rt.forward_train(x, mask, use_graph=model.use_cuda_graph, dropout=float(model.transformer.dropout),
+                                     token=ctx.token)
+        ctx.model, ctx.tctx, ctx.names, ctx.shapes, ctx.params = model, tctx, names, [p.shape for p in params], params
         ctx.has_at = "at" in res
         outs = (res["logits"], res["boxes"]) + ((res["at"],) if ctx.has_at else ())
+        if tctx.graph:
+            # the slot's static output buffers are overwritten by its next replay; a second forward in flight uses another
+            # slot, but outputs that outlive their backward (logging, EMA targets) must not alias them
+            outs = tuple(o.clone() for o in outs)
         return outs
 
     @staticmethod
@@ -33,6 +60,12 @@ class _TrainStep(torch.autograd.Function):
         model = ctx.model
         rt = model._rt
         train_backbone = any(n.startswith("backbone.") for n in ctx.names)
+        if ctx.tctx.graph:
+            # graph mode: the gradients land in the slot's static buffer and views of it become p.grad.  If a p.grad still
+            # aliases that buffer (gradient accumulation over micro-batches, engine.py:75-80, or zero_grad(set_to_none=False)),
+            # the replay below would overwrite it and autograd would then add the buffer to itself: move those gradients to
+            # their own storage first (one flat copy, only in that case).
+            _detach_grads_from(ctx.tctx.slot.g.get("grads"), ctx.params, ctx.names, ctx.shapes, rt)
         flat = rt.backward(ctx.tctx, d_logits, d_boxes, d_at, train_backbone)
         if model.grad_allreduce:
             from ..parallel import allreduce_mean_
@@ -122,20 +155,22 @@ class SEDT(nn.Module):
     def _wants_grad(self) -> bool:
         return torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
 
+    def _train_unsupported(self) -> Optional[str]:
+        """Why the native training kernels cannot run this module (None = they can)."""
+        if self.precision != "bf16" or not self.use_tensor_cores:
+            return "the training kernels exist for the bf16 tcgen05 tier only"
+        if not self.transformer.normalize_before:
+            return "the training kernels implement the pre-norm layers only"
+        if not 0.0 <= float(self.transformer.dropout) < 1.0:
+            return f"dropout must be in [0, 1), got {self.transformer.dropout}"
+        return None
+
     def _check_mode(self):
-        """Training with gradients runs through the native backward (SEDT only, bf16 tier, pre-norm);
-        everything else that would need autograd raises instead of silently falling back."""
+        """Training with gradients runs through the native backward (bf16 tier, pre-norm); everything else that
+        would need autograd raises instead of silently falling back."""
         if not self._wants_grad():
             return
-        why = None
-        if self._self_sup:
-            why = "SP-SEDT training (random query drop, feature loss) has no backward kernels yet"
-        elif self.precision != "bf16" or not self.use_tensor_cores:
-            why = "the backward kernels exist for the bf16 tcgen05 tier only"
-        elif not self.transformer.normalize_before:
-            why = "the backward kernels implement the pre-norm layers only"
-        elif not 0.0 <= float(self.transformer.dropout) < 1.0:
-            why = f"dropout must be in [0, 1), got {self.transformer.dropout}"
+        why = self._train_unsupported()
         if why is not None:
             raise NotImplementedError(why + ". Call model.eval() / torch.no_grad() for inference.")
 
@@ -176,6 +211,11 @@ class SEDT(nn.Module):
         x, mask = self._prepare(samples)
         if self._wants_grad():
             res = self._forward_train(x, mask)
+        elif self.training and float(self.transformer.dropout) > 0.0 and self._train_unsupported() is None:
+            # train() mode without gradients (the mean-teacher forward, engine.py:146-147): the reference keeps dropout
+            # active there, so this runs the training forward (fresh Philox masks, nothing kept for a backward).  Where the
+            # training kernels do not apply (fp32 tier, post-norm) the eval kernels run instead, i.e. dropout is off.
+            res, _ = self.runtime().forward_train(x, mask, use_graph=False, dropout=float(self.transformer.dropout), token=None)
         else:
             res = self.runtime().forward(x, mask, use_graph=self.use_cuda_graph)
         out = {"pred_logits": res["logits"][-1], "pred_boxes": res["boxes"][-1]}
@@ -214,6 +254,9 @@ class SPSEDT(SEDT):
 
     def forward(self, samples, patches: torch.Tensor):
         self._check_mode()
+        if self._wants_grad():
+            raise NotImplementedError("SP-SEDT training (random query drop, feature loss) has no backward kernels yet. "
+                                      "Call model.eval() / torch.no_grad() for inference.")
         if isinstance(samples, (list, tuple)) and len(samples) == 2 and torch.is_tensor(samples[0]) and samples[0].dim() == 4:
             samples = NestedTensor(samples[0], samples[1])          # engine.py:59 passes .decompose()
         x, mask = self._prepare(samples)

@@ -105,3 +105,33 @@ def test_cpu_tensors_raise():
     p.grad = torch.ones(4)
     with pytest.raises(RuntimeError):
         FusedAdamW([p]).step()
+
+
+def test_fused_adamw_mixed_step_counts_and_nan_norm():
+    """A parameter whose gradient first appears later keeps its own bias correction (torch.optim.AdamW: per-parameter
+    `step`); a NaN gradient norm propagates to every parameter like torch's clip_grad_norm_."""
+    from sound_event_detection_transformer_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    a = [torch.nn.Parameter(torch.randn(300, 7, device="cuda")), torch.nn.Parameter(torch.randn(64, device="cuda"))]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    fused = FusedAdamW(a, lr=1e-2, weight_decay=1e-2)
+    ref = torch.optim.AdamW(b, lr=1e-2, weight_decay=1e-2)
+    for step in range(4):
+        for i, (p, q) in enumerate(zip(a, b)):
+            if i == 1 and step < 2:                 # the second parameter gets its first gradient at step 2
+                p.grad = q.grad = None
+                continue
+            g = torch.randn_like(p)
+            p.grad, q.grad = g.clone(), g.clone()
+        torch.nn.utils.clip_grad_norm_(b, 0.1)
+        ref.step()
+        fused.step(max_norm=0.1)
+    torch.cuda.synchronize()
+    for p, q in zip(a, b):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+    assert float(fused.state[a[0]]["step"]) == 4.0 and float(fused.state[a[1]]["step"]) == 2.0
+    a[0].grad = torch.full_like(a[0], float("nan"))
+    a[1].grad = torch.zeros_like(a[1])
+    fused.step(max_norm=0.1)
+    torch.cuda.synchronize()
+    assert torch.isnan(a[0]).all() and torch.isnan(a[1]).all()

@@ -217,3 +217,89 @@ def test_dropout_masks_change_every_step_and_eval_is_unaffected():
         e1 = model(x)["pred_logits"].clone()
         e2 = model(x)["pred_logits"].clone()
     assert torch.equal(e1, e2)
+
+
+# ---- several forwards in flight / gradient accumulation -----------------------------------------------------
+def _small_train_model(seed, dropout=0.0):
+    args = spec.config_args("c1")
+    args.enc_layers, args.dec_layers = 1, 1
+    sd, model, _, _ = _setup(args, seed, 2, 160)
+    model.transformer.dropout = dropout
+    return args, sd, model
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_two_forwards_then_one_backward(graph):
+    """engine.py:134-170: model(labelled), model(unlabelled), ONE total.backward().  Each forward owns its tape: the summed
+    gradient equals the sum of the two single-batch gradients."""
+    args, sd, model = _small_train_model(25)
+    model.use_cuda_graph = graph
+    xa, xb = synth.synth_clips(2, 160, 64, seed=40).cuda(), synth.synth_clips(2, 160, 64, seed=41).cuda()
+    g = torch.Generator().manual_seed(7)
+    D, Q, C = args.dec_layers, args.num_queries, args.num_classes
+    R = {"l": torch.randn(D, 2, Q, C + 1, generator=g).cuda(), "b": torch.randn(D, 2, Q, 2, generator=g).cuda(),
+         "a": torch.randn(2, C, generator=g).cuda()}
+    single = []
+    for x in (xa, xb):
+        model.zero_grad(set_to_none=True)
+        _loss(model(x), R).backward()
+        torch.cuda.synchronize()
+        single.append({n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad})
+    model.zero_grad(set_to_none=True)
+    oa = model(xa)
+    ob = model(xb)
+    assert model._rt.train_slots_in_use() == 2
+    (_loss(oa, R) + _loss(ob, R)).backward()
+    torch.cuda.synchronize()
+    assert model._rt.train_slots_in_use() == 0
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            want = single[0][n] + single[1][n]
+            assert ((p.grad - want).norm() / want.norm().clamp_min(1e-20)).item() < 2e-3, n     # fp32 atomics order only
+
+
+def test_backward_twice_raises_instead_of_using_a_stale_tape():
+    args, sd, model = _small_train_model(26)
+    x = synth.synth_clips(2, 160, 64, seed=42).cuda()
+    out = model(x)
+    loss = out["pred_logits"].sum()
+    loss.backward(retain_graph=True)
+    model(x)["pred_logits"].sum().backward()          # reuses the slot
+    with pytest.raises(RuntimeError, match="overwritten"):
+        loss.backward()
+
+
+def test_gradient_accumulation_in_graph_mode():
+    """engine.py:75-80 (accumrating_gradient_steps): two micro-batches accumulated into p.grad, and zero_grad(set_to_none=False)
+    between steps, must not alias the graph's static gradient buffer."""
+    args, sd, model = _small_train_model(27)
+    model.use_cuda_graph = True
+    xa, xb = synth.synth_clips(2, 160, 64, seed=43).cuda(), synth.synth_clips(2, 160, 64, seed=44).cuda()
+    single = []
+    for x in (xa, xb):
+        model.zero_grad(set_to_none=True)
+        model(x)["pred_logits"].square().sum().backward()
+        torch.cuda.synchronize()
+        single.append({n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad})
+    for set_to_none in (True, False):
+        model.zero_grad(set_to_none=set_to_none)
+        for x in (xa, xb):
+            model(x)["pred_logits"].square().sum().backward()
+        torch.cuda.synchronize()
+        for n, p in model.named_parameters():
+            if p.requires_grad:
+                want = single[0][n] + single[1][n]
+                assert ((p.grad - want).norm() / want.norm().clamp_min(1e-20)).item() < 2e-3, (set_to_none, n)
+
+
+def test_no_grad_train_mode_keeps_dropout_active():
+    """engine.py:146-147: the mean-teacher forward runs under no_grad with the module in train() mode."""
+    args, sd, model = _small_train_model(28, dropout=0.1)
+    x = synth.synth_clips(2, 160, 64, seed=45).cuda()
+    with torch.no_grad():
+        a = model(x)["pred_logits"].clone()
+        b = model(x)["pred_logits"].clone()
+        model.eval()
+        e = model(x)["pred_logits"].clone()
+    assert (a - b).abs().max() > 1e-3 and (a - e).abs().max() > 1e-3
+    assert model._rt.train_slots_in_use() == 0
