@@ -284,6 +284,13 @@ SEDT_API int sedt_op_conv_wgrad(const void* x, const void* dy, float* dw, int B,
 SEDT_API int sedt_op_conv_tc_supported(const sedt_conv_desc* d);
 /* Fused transformer FFN of the eval forward (sedt/transformer.py:202-203): out[M,256] fp32 = residual + relu(x W1^T + b1) W2^T + b2,
  * x [M,256] bf16, W1 [ff,256] / W2 [256,ff] bf16 (nn.Linear layout), ff % 256 == 0; the [M,ff] hidden activation never leaves the SM. */
+/* fused encoder self-attention block (csrc/enc_attn_fused.cu; sedt/transformer.py:192-198): in place
+ * x[B*S,256] (fp32) += out_proj(MHA(q = k = nap, v = na)), na / nap [B*S,256] bf16 = LN(x) / LN(x)+pos, w_in [768,256] and
+ * w_out [256,256] bf16 as nn.MultiheadAttention stores them, b_in [768] / b_out [256] fp32, kpm [B,S] uint8 (1 = padded key)
+ * or NULL; S <= 128 tokens per clip, 8 heads of 32 */
+SEDT_API int sedt_op_enc_attn(const void* na, const void* nap, const void* w_in, const float* b_in, const void* w_out,
+                              const float* b_out, const uint8_t* kpm, float* x, int B, int S, void* stream);
+
 SEDT_API int sedt_op_ffn(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual,
                          float* out, int64_t M, int ff, void* stream);
 /* OIHW fp32 -> O(HW)I in `dtype` */

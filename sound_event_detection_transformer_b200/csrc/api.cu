@@ -230,6 +230,13 @@ int sedt_op_ffn(const void* x, const void* w1, const float* b1, const void* w2, 
     return launch_ffn_fused(x, w1, b1, w2, b2, residual, 256, out, 256, M, ff, (cudaStream_t)stream);
 }
 
+int sedt_op_enc_attn(const void* na, const void* nap, const void* w_in, const float* b_in, const void* w_out, const float* b_out,
+                     const uint8_t* kpm, float* x, int B, int S, void* stream)
+{
+    SEDT_REQUIRE(na && nap && w_in && b_in && w_out && b_out && x, "op_enc_attn: null argument");
+    return launch_enc_attn_fused(na, nap, w_in, b_in, w_out, b_out, kpm, x, B, S, 0.17677669529663687f, (cudaStream_t)stream);
+}
+
 int sedt_prepare_clips(const float* raw, const int64_t* offsets, const double* mean, const double* std, float* out, int B, int frames,
                        int F, int apply_log, void* stream)
 {

@@ -1,0 +1,501 @@
+// Fused encoder self-attention block (eval):   x += out_proj( MHA( q = k = (LN(x)+pos) Wq/Wk, v = LN(x) Wv ) )
+// (sedt/transformer.py:192-198 forward_pre, torch/nn/functional.py:5833-5867 in-proj split, :6630-6659 attention core.)
+//
+// One persistent CTA per SM walks over the clips; a clip is ONE 128-row tile (S = H*W <= 128 tokens), so every intermediate of
+// the block stays on chip:
+//
+//   TMA      LN(x)+pos  -> bufA, LN(x) -> bufB          (bf16 [128 x 256] K-major A operands, 64 KiB each, from layernorm_kernel)
+//   tcgen05  Q = bufA Wq^T -> TMEM [0,256)              K = bufA Wk^T -> TMEM [256,512)        (weights streamed through a TMA ring)
+//   rows     Q + bq -> bf16 packed IN PLACE in TMEM [0,128): the A operand of S = Q K^T is read from tensor memory
+//            K + bk -> bf16 -> bufA (LN(x)+pos is dead)   [128 keys x 256] K-major = B operand of S
+//   tcgen05  V = bufB Wv^T -> TMEM [256,512)
+//   rows     V + bv -> bf16 -> bufB transposed per head ([32 dims x 128 keys] K-major = B operand of P V; LN(x) is dead)
+//   per head h (two teams of four warps take alternate heads, each with its own S / O buffers):
+//     tcgen05  S_h = Q_h K_h^T                          -> TMEM S[team] (128 columns)
+//     rows     softmax over the thread's own TMEM lane (masks as shared-memory vectors), un-normalised P packed to bf16 IN PLACE
+//     tcgen05  O_h = P V_h  (A from TMEM)                -> TMEM Otmp[team] (32 columns)
+//     rows     O_h / sum -> bf16 -> TMEM [16h, 16h+16)  (the columns Q_h occupied: dead once S_h has been issued)
+//   tcgen05  Y = O Wo^T  (A = the packed [128 x 256] O in TMEM, Wo streamed)   -> TMEM [128,384)
+//   rows     Y + bo + residual x (TMA-prefetched into bufA/bufB as soon as K / V^T are dead) -> fp32 -> TMA store (S rows only)
+//
+// Replaces four launches per encoder layer (V projection, Q/K projection, attention_tc_kernel, out_proj + residual: 102 us at
+// B = 256, 11 % of the tensor peak, six HBM round trips of [rows, 256..512] tensors) by one that reads LN(x), LN(x)+pos and x once
+// and writes x once.  Rounding points are those of the unfused path (Q, K, V, P, O in bf16; everything else fp32), so the two
+// agree up to fp32 summation order.
+//
+// 320 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 "row" warps (warp & 3 = TMEM lane quadrant; team = (warp-2)/4).
+#include "tc_common.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <math_constants.h>
+
+namespace sedt {
+namespace {
+
+using namespace tc;
+
+constexpr int EA_THREADS = 320;
+constexpr int EA_SLOT = 16384;                   // one [128 rows][64 k] bf16 box / one [128 rows][32 fp32] box
+constexpr int EA_NSLOTS = 5;
+constexpr int EA_BUFA = 0;
+constexpr int EA_BUFB = 65536;
+constexpr int EA_RING = 131072;
+constexpr int EA_BIAS = EA_RING + EA_NSLOTS * EA_SLOT;          // in_proj bias [768] fp32
+constexpr int EA_MASK = EA_BIAS + 768 * 4;                      // key validity 0/1 [128], 0/-1e30 [128]
+constexpr int EA_BAR = EA_MASK + 1024;
+constexpr int EA_NBARS = 2 * EA_NSLOTS + 21;
+constexpr int EA_SMEM = EA_BAR + EA_NBARS * 8 + 16 + 1024;
+static_assert(EA_SMEM <= 232448, "shared memory budget exceeded");
+
+// TMEM columns
+constexpr uint32_t TM_Q = 0;          // Q accumulator [0,256) -> packed Q / O bf16 [0,128)
+constexpr uint32_t TM_KV = 256;       // K, then V accumulator [256,512)
+constexpr uint32_t TM_S = 128;        // S / P buffers of the two teams: [128,256), [256,384)
+constexpr uint32_t TM_OT = 384;       // O_h accumulators of the two teams: [384,416), [416,448)
+constexpr uint32_t TM_Y = 128;        // out_proj accumulator [128,384)
+
+struct EaParams {
+    const float* b_in;        // [768]
+    const float* b_out;       // [256]
+    const uint8_t* kpm;       // [B, S] (1 = padded key) or null
+    int B, S;
+    float scale;
+};
+
+__device__ __forceinline__ uint32_t ea_swz(int row, int byte_in_row) {
+    return (uint32_t)(row * 128 + ((((byte_in_row >> 4) ^ (row & 7)) << 4) | (byte_in_row & 15)));
+}
+__device__ __forceinline__ uint32_t ea_pack2(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(EA_THREADS, 1)
+enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_constant__ CUtensorMap map_na,
+                      const __grid_constant__ CUtensorMap map_win, const __grid_constant__ CUtensorMap map_wo,
+                      const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out,
+                      const __grid_constant__ EaParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* slot_full = (uint64_t*)(smem + EA_BAR);
+    uint64_t* slot_empty = slot_full + EA_NSLOTS;
+    uint64_t* act_full = slot_empty + EA_NSLOTS;
+    uint64_t* q_full = act_full + 1;
+    uint64_t* k_full = q_full + 1;
+    uint64_t* v_full = k_full + 1;
+    uint64_t* q_drained = v_full + 1;
+    uint64_t* k_drained = q_drained + 1;
+    uint64_t* v_drained = k_drained + 1;
+    uint64_t* s_full = v_drained + 1;        // [2]
+    uint64_t* p_ready = s_full + 2;          // [2]
+    uint64_t* o_full = p_ready + 2;          // [2]
+    uint64_t* o_done = o_full + 2;           // [2]
+    uint64_t* kv_dead = o_done + 2;
+    uint64_t* y_full = kv_dead + 1;
+    uint64_t* res_full = y_full + 1;         // [2]
+    uint64_t* y_drained = res_full + 2;
+    uint64_t* stage_free = y_drained + 1;
+    uint32_t* tmem_slot = (uint32_t*)(stage_free + 1);
+    float* s_bias = (float*)(smem + EA_BIAS);
+    float* s_mask = (float*)(smem + EA_MASK);
+    float* s_neg = s_mask + 128;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.S;
+    const int iters = (int)blockIdx.x < p.B ? (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_nap); prefetch_tmap(&map_na); prefetch_tmap(&map_win); prefetch_tmap(&map_wo);
+        prefetch_tmap(&map_res); prefetch_tmap(&map_out);
+        for (int s = 0; s < EA_NSLOTS; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 1); }
+        mbar_init(act_full, 1); mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1);
+        mbar_init(q_drained, 8); mbar_init(k_drained, 8); mbar_init(v_drained, 8);
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&s_full[g], 1); mbar_init(&p_ready[g], 4); mbar_init(&o_full[g], 1); mbar_init(&o_done[g], 4);
+            mbar_init(&res_full[g], 1);
+        }
+        mbar_init(kv_dead, 1); mbar_init(y_full, 1); mbar_init(y_drained, 8); mbar_init(stage_free, 2);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    for (int i = threadIdx.x; i < 768; i += EA_THREADS) s_bias[i] = p.b_in[i];             // weights: not produced by the predecessor
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_trigger();
+    pdl_wait();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int slot = 0; uint32_t sphase = 0;
+            auto next_slot = [&](const CUtensorMap* m, int c0, int c1) {
+                mbar_wait(&slot_empty[slot], sphase ^ 1);
+                mbar_expect_tx(&slot_full[slot], EA_SLOT);
+                tma_load_2d(m, smem + EA_RING + slot * EA_SLOT, &slot_full[slot], c0, c1);
+                if (++slot == EA_NSLOTS) { slot = 0; sphase ^= 1; }
+            };
+            for (int it = 0; it < iters; ++it) {
+                const int b = (int)blockIdx.x + it * (int)gridDim.x;
+                const int row0 = b * S;
+                mbar_wait(stage_free, (it & 1) ^ 1);                // the previous clip's output stores have left bufA / bufB
+                mbar_expect_tx(act_full, 8 * EA_SLOT);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_nap, smem + EA_BUFA + kb * EA_SLOT, act_full, kb * 64, row0);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_na, smem + EA_BUFB + kb * EA_SLOT, act_full, kb * 64, row0);
+                for (int m = 0; m < 3; ++m)                         // Wq, Wk, Wv: [N half][k block]
+                    for (int nh = 0; nh < 2; ++nh)
+                        for (int kb = 0; kb < 4; ++kb) next_slot(&map_win, kb * 64, m * 256 + nh * 128);
+                for (int i = 0; i < 8; ++i) {                       // Wo: [k block][N half]
+                    if (i == EA_NSLOTS) {
+                        // K and V^T are dead once the last P V has retired: prefetch the residual tile over them
+                        mbar_wait(kv_dead, it & 1);
+                        for (int g = 0; g < 2; ++g) {
+                            mbar_expect_tx(&res_full[g], 4 * EA_SLOT);
+                            for (int c = 0; c < 4; ++c)
+                                tma_load_2d(&map_res, smem + (g ? EA_BUFB : EA_BUFA) + c * EA_SLOT, &res_full[g], (4 * g + c) * 32, row0);
+                        }
+                    }
+                    next_slot(&map_wo, (i >> 1) * 64, (i & 1) * 128);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc128 = make_idesc(128, 128);
+            constexpr uint32_t idesc32 = make_idesc(128, 32);
+            int slot = 0; uint32_t sphase = 0;
+            const uint32_t sA = smem_u32(smem + EA_BUFA), sB = smem_u32(smem + EA_BUFB);
+            const int ksteps_pv = (S + UMMA_K - 1) / UMMA_K;
+            // one projection: D[128 x 256] = A[128 x 256] W^T, W rows streamed as [N half][k block] boxes
+            auto project = [&](uint32_t a_base, uint32_t d_col) {
+                for (int nh = 0; nh < 2; ++nh)
+                    for (int kb = 0; kb < 4; ++kb) {
+                        mbar_wait(&slot_full[slot], sphase);
+                        tc_fence_after();
+                        const uint32_t sa = a_base + kb * EA_SLOT;
+                        const uint32_t sb = smem_u32(smem + EA_RING + slot * EA_SLOT);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_base + d_col + (uint32_t)(nh * 128), make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32),
+                                      idesc128, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&slot_empty[slot]);
+                        if (++slot == EA_NSLOTS) { slot = 0; sphase ^= 1; }
+                    }
+            };
+            for (int it = 0; it < iters; ++it) {
+                const uint32_t par = (uint32_t)(it & 1);
+                mbar_wait(act_full, par);
+                mbar_wait(y_drained, par ^ 1);                      // the previous clip's Y has left TMEM
+                tc_fence_after();
+                project(sA, TM_Q);  umma_commit(q_full);
+                project(sA, TM_KV); umma_commit(k_full);
+                mbar_wait(k_drained, par);                          // K is in bufA, its accumulator may be overwritten
+                tc_fence_after();
+                project(sB, TM_KV); umma_commit(v_full);
+                mbar_wait(q_drained, par);
+                mbar_wait(v_drained, par);
+                tc_fence_after();
+                auto issue_s = [&](int h) {
+                    const int g = h & 1;
+                    const uint32_t d = tmem_base + TM_S + (uint32_t)(g * 128);
+                    const uint32_t kaddr = sA + (h >> 1) * EA_SLOT + (h & 1) * 64;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        umma_bf16_ts(d, tmem_base + TM_Q + (uint32_t)(16 * h + 8 * k), make_smem_desc(kaddr + k * 32), idesc128, k > 0 ? 1u : 0u);
+                    umma_commit(&s_full[g]);
+                };
+                issue_s(0);
+                issue_s(1);
+                for (int h = 0; h < 8; ++h) {
+                    const int g = h & 1;
+                    const uint32_t u = (uint32_t)(it * 4 + (h >> 1));
+                    mbar_wait(&p_ready[g], u & 1);
+                    if (h >= 2) mbar_wait(&o_done[g], (u - 1) & 1);  // this team's O accumulator has been read
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + TM_OT + (uint32_t)(g * 32);
+                    const uint32_t pa = tmem_base + TM_S + (uint32_t)(g * 128);
+                    const uint32_t vaddr = sB + h * 8192;
+                    for (int ks = 0; ks < ksteps_pv; ++ks)
+                        umma_bf16_ts(d, pa + (uint32_t)(8 * ks), make_smem_desc(vaddr + (ks >> 2) * 4096 + (ks & 3) * 32), idesc32, ks > 0 ? 1u : 0u);
+                    umma_commit(&o_full[g]);
+                    if (h + 2 < 8) issue_s(h + 2);                  // in-order execution: P_h has been consumed by then
+                }
+                umma_commit(kv_dead);
+                mbar_wait(&o_done[0], (uint32_t)(it * 4 + 3) & 1);
+                mbar_wait(&o_done[1], (uint32_t)(it * 4 + 3) & 1);
+                tc_fence_after();
+                for (int i = 0; i < 8; ++i) {                       // Y = O Wo^T, A = packed O in TMEM
+                    const int kb = i >> 1, nh = i & 1;
+                    mbar_wait(&slot_full[slot], sphase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + EA_RING + slot * EA_SLOT);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ts(tmem_base + TM_Y + (uint32_t)(nh * 128), tmem_base + TM_Q + (uint32_t)(kb * 32 + k * 8),
+                                     make_smem_desc(sb + k * 32), idesc128, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&slot_empty[slot]);
+                    if (++slot == EA_NSLOTS) { slot = 0; sphase ^= 1; }
+                }
+                umma_commit(y_full);
+            }
+        }
+    } else {
+        // ===================== row warps =====================
+        const int e = warp - 2, team = e >> 2, quad = warp & 3;
+        const int r = quad * 32 + lane;                              // row of the tile = TMEM lane
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int nkc = (S + 31) >> 5;
+        const bool row_warp = quad * 32 < S;
+        const float cs = p.scale * 1.4426950408889634f;
+        uint8_t* bufA = smem + EA_BUFA;
+        uint8_t* bufB = smem + EA_BUFB;
+        for (int it = 0; it < iters; ++it) {
+            const int b = (int)blockIdx.x + it * (int)gridDim.x;
+            const uint32_t par = (uint32_t)(it & 1);
+            if (team == 0) {
+                float mk = 1.f;                                      // validity of key r
+                if (r >= S) mk = 0.f;
+                else if (p.kpm != nullptr && p.kpm[(size_t)b * S + r]) mk = 0.f;
+                s_mask[r] = mk;
+                s_neg[r] = (mk - 1.f) * 1e30f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+
+            // ---- Q: fp32 accumulator + bias -> bf16, packed in place (team t: columns [128t, 128t+128) -> [64t, 64t+64))
+            mbar_wait(q_full, par);
+            tc_fence_after();
+            {
+                uint32_t w[64];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t acc[32];
+                    tmem_ld32(lane_base + TM_Q + (uint32_t)(team * 128 + c * 32), acc);
+                    const float* bq = s_bias + team * 128 + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        w[16 * c + j] = ea_pack2(__uint_as_float(acc[2 * j]) + bq[2 * j], __uint_as_float(acc[2 * j + 1]) + bq[2 * j + 1]);
+                }
+                // the partner warp of the other team (same TMEM lanes) has read its fp32 columns too
+                asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+                uint32_t w0[32], w1[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { w0[j] = w[j]; w1[j] = w[32 + j]; }
+                tmem_st32(lane_base + TM_Q + (uint32_t)(team * 64), w0);
+                tmem_st32(lane_base + TM_Q + (uint32_t)(team * 64 + 32), w1);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_drained);
+
+            // ---- K: + bias -> bf16 -> bufA in the K-major operand layout (LN(x)+pos is dead: both projections have retired)
+            mbar_wait(k_full, par);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int col = team * 128 + c * 32;
+                uint32_t acc[32];
+                tmem_ld32(lane_base + TM_KV + (uint32_t)col, acc);
+                const float* bk = s_bias + 256 + col;
+                uint8_t* rowp = bufA + (col >> 6) * EA_SLOT + r * 128;
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    uint32_t q4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        q4[q] = ea_pack2(__uint_as_float(acc[8 * j8 + 2 * q]) + bk[8 * j8 + 2 * q],
+                                         __uint_as_float(acc[8 * j8 + 2 * q + 1]) + bk[8 * j8 + 2 * q + 1]);
+                    *reinterpret_cast<uint4*>(rowp + ((((c & 1) * 4 + j8) ^ (r & 7)) << 4)) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(k_drained);
+
+            // ---- V: + bias -> bf16 -> bufB, transposed per head: element (d, key r) of head h -> [h][r / 64][d][r % 64]
+            mbar_wait(v_full, par);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int h = team * 4 + c;
+                uint32_t acc[32];
+                tmem_ld32(lane_base + TM_KV + (uint32_t)(h * 32), acc);
+                const float* bv = s_bias + 512 + h * 32;
+                uint8_t* vb = bufB + h * 8192 + (r >> 6) * 4096;
+                const int col_b = (r & 63) * 2;
+#pragma unroll
+                for (int d = 0; d < 32; ++d)
+                    *reinterpret_cast<__nv_bfloat16*>(vb + ea_swz(d, col_b)) = __float2bfloat16_rn(__uint_as_float(acc[d]) + bv[d]);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(v_drained);
+
+            // ---- heads h = 2 hh + team
+#pragma unroll 1
+            for (int hh = 0; hh < 4; ++hh) {
+                const int h = 2 * hh + team;
+                const uint32_t u = (uint32_t)(it * 4 + hh);
+                const uint32_t sbase = lane_base + TM_S + (uint32_t)(team * 128);
+                mbar_wait(&s_full[team], u & 1);
+                tc_fence_after();
+                // p_j = 2^(c (s_j - m)) * valid_j, c = scale * log2 e, m = max over the valid keys (attention_tc.cu)
+                float m = -CUDART_INF_F;
+#pragma unroll 1
+                for (int c = 0; c < (row_warp ? nkc : 0); ++c) {
+                    uint32_t acc[32];
+                    tmem_ld32(sbase + (uint32_t)(c * 32), acc);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 ng = *reinterpret_cast<const float4*>(s_neg + c * 32 + j4 * 4);
+                        m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(acc[4 * j4]) + ng.x, __uint_as_float(acc[4 * j4 + 1]) + ng.y),
+                                           fmaxf(__uint_as_float(acc[4 * j4 + 2]) + ng.z, __uint_as_float(acc[4 * j4 + 3]) + ng.w)));
+                    }
+                }
+                const float mc = m * cs;
+                float l = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < (row_warp ? nkc : 0); ++c) {
+                    uint32_t acc[32], pk[16];
+                    tmem_ld32(sbase + (uint32_t)(c * 32), acc);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 vm = *reinterpret_cast<const float4*>(s_mask + c * 32 + j4 * 4);
+                        const float vmv[4] = {vm.x, vm.y, vm.z, vm.w};
+                        float pv[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float ex;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(__uint_as_float(acc[4 * j4 + q]), cs, -mc)));
+                            pv[q] = ex * vmv[q];
+                            l += pv[q];
+                        }
+                        pk[2 * j4] = ea_pack2(pv[0], pv[1]);
+                        pk[2 * j4 + 1] = ea_pack2(pv[2], pv[3]);
+                    }
+                    tmem_st16(sbase + (uint32_t)(c * 16), pk);       // lands in columns of S chunks <= c, all consumed already
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_ready[team]);
+
+                mbar_wait(&o_full[team], u & 1);
+                tc_fence_after();
+                {
+                    uint32_t acc[32], pk[16];
+                    tmem_ld32(lane_base + TM_OT + (uint32_t)(team * 32), acc);
+                    const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = ea_pack2(__uint_as_float(acc[2 * j]) * inv, __uint_as_float(acc[2 * j + 1]) * inv);
+                    tmem_st16(lane_base + TM_Q + (uint32_t)(16 * h), pk);
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&o_done[team]);
+            }
+
+            // ---- output: Y + bo + x -> fp32, staged through the residual tile (team t: columns [128t, 128t+128) in bufA / bufB)
+            mbar_wait(y_full, par);
+            tc_fence_after();
+            uint8_t* stage = team ? bufB : bufA;
+            mbar_wait(&res_full[team], par);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t acc[32];
+                tmem_ld32(lane_base + TM_Y + (uint32_t)(team * 128 + c * 32), acc);
+                epilogue_slab<float, EA_SLOT>(acc, c, team * 128 + c * 32, nullptr, p.b_out, true, 0, stage, r, r & 7);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(y_drained);
+            fence_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(6 + team) : "memory");
+            if ((e & 3) == 0 && lane == 0) {
+                for (int c = 0; c < 4; ++c) tma_store_3d(&map_out, stage + c * EA_SLOT, (4 * team + c) * 32, 0, b);
+                tma_store_commit();
+                tma_store_wait_read0();
+                mbar_arrive(stage_free);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace
+
+bool enc_attn_fused_supported(int d, int nheads, int S, const void* na, const void* nap, const void* w_in, const void* w_out,
+                              const float* x, int dt)
+{
+    if (dt != DT_BF16 || d != 256 || nheads != 8 || S < 1 || S > 128) return false;
+    if (((uintptr_t)na & 15) || ((uintptr_t)nap & 15) || ((uintptr_t)w_in & 15) || ((uintptr_t)w_out & 15) || ((uintptr_t)x & 15)) return false;
+    return true;
+}
+
+// SEDT_ENC_ATTN_FUSED: unset / 1 = use the fused block wherever it is supported, 0 = the four separate launches
+bool enc_attn_fused_enabled()
+{
+    static const bool on = [] { const char* e = getenv("SEDT_ENC_ATTN_FUSED"); return e == nullptr || atoi(e) != 0; }();
+    return on;
+}
+
+// x[B*S, 256] (fp32, in place) += out_proj(attention(q = k = nap Wq/Wk^T, v = na Wv^T)); na / nap [B*S, 256] bf16,
+// w_in [768, 256] / w_out [256, 256] bf16 (row-major [out, in] as packed), b_in [768] / b_out [256] fp32, kpm [B, S] or null
+int launch_enc_attn_fused(const void* na, const void* nap, const void* w_in, const float* b_in, const void* w_out, const float* b_out,
+                          const uint8_t* kpm, float* x, int B, int S, float scale, cudaStream_t stream)
+{
+    SEDT_REQUIRE(enc_attn_fused_supported(256, 8, S, na, nap, w_in, w_out, x, DT_BF16), "enc_attn_fused: unsupported shape / alignment");
+    SEDT_REQUIRE(B >= 1, "enc_attn_fused: B=%d", B);
+    SEDT_TRY(tc_init());
+    const uint64_t rows = (uint64_t)B * (uint64_t)S;
+    CUtensorMap mnap, mna, mwin, mwo, mres, mout;
+    const uint32_t box[2] = {64u, 128u};
+    {
+        const uint64_t dims[2] = {256, rows}; const uint64_t strides[1] = {256 * 2};
+        SEDT_TRY(encode_map(&mnap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, nap, 2, dims, strides, box));
+        SEDT_TRY(encode_map(&mna, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, na, 2, dims, strides, box));
+    }
+    {
+        const uint64_t dims[2] = {256, 768}; const uint64_t strides[1] = {256 * 2};
+        SEDT_TRY(encode_map(&mwin, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_in, 2, dims, strides, box));
+        const uint64_t dims2[2] = {256, 256};
+        SEDT_TRY(encode_map(&mwo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_out, 2, dims2, strides, box));
+    }
+    {
+        const uint32_t rbox[2] = {32u, 128u};                     // 32 fp32 columns = one 128-byte swizzle row
+        const uint64_t dims[2] = {256, rows}; const uint64_t strides[1] = {256 * 4};
+        SEDT_TRY(encode_map(&mres, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, 2, dims, strides, rbox));
+        // the store sees the clip as [B][S][256] so that a tile never writes into the next clip's rows
+        const uint32_t obox[3] = {32u, (uint32_t)S, 1u};
+        const uint64_t odims[3] = {256, (uint64_t)S, (uint64_t)B}; const uint64_t ostr[2] = {256 * 4, (uint64_t)S * 256 * 4};
+        SEDT_TRY(encode_map(&mout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, 3, odims, ostr, obox));
+    }
+    EaParams p;
+    p.b_in = b_in; p.b_out = b_out; p.kpm = kpm; p.B = B; p.S = S; p.scale = scale;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
+        attr_set = true;
+    }
+    const int grid = std::min(B, num_sms());
+    ProfScope _prof(PROF_ATTENTION, stream);
+    SEDT_CHECK_CUDA(launch_pdl(enc_attn_fused_kernel, dim3((unsigned)grid), dim3(EA_THREADS), EA_SMEM, stream, 1, mnap, mna, mwin, mwo, mres,
+                               mout, p));
+    SEDT_COUNT_KIND(KK_ENC_ATTN_FUSED);
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+}  // namespace sedt

@@ -213,6 +213,13 @@ bool ffn_fused_preferred(int64_t M);  // true where the fused kernel beats the t
 int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual, int ld_res,
                      float* out, int ldo, int64_t M, int ff, cudaStream_t stream);
 
+// ---- enc_attn_fused.cu: x += out_proj(MHA(q = k = nap, v = na)) for one <= 128-token clip per tile, everything on chip
+bool enc_attn_fused_supported(int d, int nheads, int S, const void* na, const void* nap, const void* w_in, const void* w_out,
+                              const float* x, int dt);
+bool enc_attn_fused_enabled();        // SEDT_ENC_ATTN_FUSED (default on)
+int launch_enc_attn_fused(const void* na, const void* nap, const void* w_in, const float* b_in, const void* w_out, const float* b_out,
+                          const uint8_t* kpm, float* x, int B, int S, float scale, cudaStream_t stream);
+
 // ---- matcher.cu
 int launch_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,
                    const int32_t* offsets, int B, int Q, int C1, int Kmax, float w_class, float w_bbox, float w_giou,

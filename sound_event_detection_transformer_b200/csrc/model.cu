@@ -485,6 +485,15 @@ int Model::mha(const Mha& A, bool self_attn, const void* q_in, const void* k_in,
     const size_t es = dtype_size(dt);
     const size_t mark = ws.off;
     const float scale = (float)std::sqrt(1.0 / (double)(d / cfg_.nheads));
+    // self-attention of a <= 128-token clip with q = k: the whole block (three projections, attention core, out_proj + residual)
+    // as one launch with every intermediate on chip (enc_attn_fused.cu); the launches below remain for the other shapes,
+    // the SP-SEDT decoder mask and the fp32 tier
+    if (!dry && self_attn && q_in == k_in && amask == nullptr && Lq == Lk && resid32 == out32 && cfg_.use_tensor_cores &&
+        enc_attn_fused_enabled() && !A.in_proj.f32_only &&
+        enc_attn_fused_supported(d, cfg_.nheads, Lq, v_in, q_in, packed_ + A.in_proj.off_w, packed_ + A.out_proj.off_w, out32, dt))
+        return launch_enc_attn_fused(v_in, q_in, packed_ + A.in_proj.off_w, (const float*)(packed_ + A.in_proj.off_b),
+                                     packed_ + A.out_proj.off_w, (const float*)(packed_ + A.out_proj.off_b), kpm, out32, (int)B, Lq,
+                                     scale, s);
     const void *Qp, *Kp, *Vp; int ldq, ldk;
     void* vbuf = ws.alloc((size_t)B * Lk * d * es);
     SEDT_TRY(linear(A.in_proj, 2 * d, d, v_in, dt, d, B * Lk, nullptr, vbuf, dt, d, 0, s, dry));
