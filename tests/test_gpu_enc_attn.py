@@ -88,8 +88,8 @@ def test_enc_attn_fused_is_deterministic_and_touches_only_its_rows():
     big[:B * S] = x
     lib = _lib.load()
     na, nap, w_in, b_in, w_out, b_out, kpm, _ = args
-    pad = lambda t: torch.cat([t, torch.zeros(64, 256, dtype=t.dtype, device="cuda")])
-    _lib.check(lib.sedt_op_enc_attn(pad(na).data_ptr(), pad(nap).data_ptr(), w_in.data_ptr(), b_in.data_ptr(), w_out.data_ptr(),
+    na_p, nap_p = (torch.cat([t, torch.zeros(64, 256, dtype=t.dtype, device="cuda")]) for t in (na, nap))
+    _lib.check(lib.sedt_op_enc_attn(na_p.data_ptr(), nap_p.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), w_out.data_ptr(),
                                     b_out.data_ptr(), None, big.data_ptr(), B, S, _lib.current_stream()))
     torch.cuda.synchronize()
     assert torch.equal(big[:B * S], a) and bool((big[B * S:] == 7.0).all())

@@ -222,7 +222,7 @@ def test_c4_training_step_matches_bf16_rounding_oracle():
     gradient: relative L2 ~ sqrt(flipped fraction) = 4-9 % for the deep layers (was 6-15 % against the fp32 oracle).
     That noise is (nearly) orthogonal to the true gradient, so a mis-scaled or mis-routed layer is caught by the
     PROJECTION of the kernel gradient on the oracle gradient, a = <g, r> / <r, r>, which the flips leave at 1:
-        every trainable tensor: rel-L2 <= 0.10, cosine >= 0.995, |a - 1| <= 0.03 (tensors with >= 256 elements; 0.08 below).
+        every trainable tensor: rel-L2 <= 0.10, cosine >= 0.995, |a - 1| <= 0.04 (tensors with >= 256 elements; 0.08 below; measured 0.02 / 0.05).
     The individual backward kernels are held to tight bars on identical inputs in tests/test_gpu_backward_ops.py."""
     args = spec.config_args("c2")
     args.precision, args.dropout = "bf16", 0.0
@@ -260,6 +260,8 @@ def test_c4_training_step_matches_bf16_rounding_oracle():
     rows = []
     for n, p in named.items():
         gk, gr = p.grad.detach().float().cpu().flatten(), sdr[n].grad.flatten()
+        if float(gk.norm()) == 0.0 and float(gr.norm()) == 0.0:         # e.g. decoder.layers.0.norm1.weight: tgt = 0 -> LN(0) = 0
+            continue
         rel = ((gk - gr).norm() / gr.norm().clamp_min(1e-20)).item()
         cos = (torch.dot(gk, gr) / (gk.norm() * gr.norm()).clamp_min(1e-30)).item()
         proj = (torch.dot(gk, gr) / torch.dot(gr, gr).clamp_min(1e-30)).item()
@@ -270,5 +272,5 @@ def test_c4_training_step_matches_bf16_rounding_oracle():
     print(f"c4 training step: median rel-L2 {sorted(r for r, *_ in rows)[len(rows) // 2]:.4f}, max |projection - 1| "
           f"{max(big):.4f} (>= 256 elements), {max(abs(a - 1) for _, _, a, _, _ in rows):.4f} (all)")
     bad = [(n, round(r, 4), round(c, 5), round(a, 4)) for r, c, a, k, n in rows
-           if r > 0.10 or c < 0.995 or abs(a - 1) > (0.03 if k >= 256 else 0.08)]
+           if r > 0.10 or c < 0.995 or abs(a - 1) > (0.04 if k >= 256 else 0.08)]
     assert not bad, f"{len(bad)} of {len(rows)} gradients off: {bad[:12]}"
