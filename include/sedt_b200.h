@@ -216,6 +216,26 @@ SEDT_API int sedt_pseudo_labels(const float* logits, const float* boxes, const f
 SEDT_API int sedt_prepare_clips(const float* raw, const int64_t* offsets, const double* mean, const double* std, float* out,
                                 int B, int frames, int F, int apply_log, void* stream);
 
+/* ---- training-time input transforms (csrc/augment.cu) ------------------------------------------------
+ * sedt_augment_clips: TimeMask -> FreqMask -> FreqShift (utilities/BoxTransforms.py:363-452) in place on x [B, T, F] fp32 (the
+ * padded log-mel clips BEFORE Normalize).  One record per clip, the integer bands as the reference computes them on the host
+ * (int(fraction * n)); tm_t == 0 / fm_mode == 0 / fs_shift == 0 skip a transform.  fm_mode: 1 = constant fill (fm_const),
+ * 2 = mean of the band (np.mean in float32, reproduced bit for bit).  scratch: B * T floats. */
+typedef struct sedt_augment_params {
+    int32_t tm_t0, tm_t;          /* TimeMask: rows [tm_t0, tm_t0 + tm_t) are multiplied by 0 */
+    int32_t fm_f0, fm_f, fm_mode; /* FreqMask: bins [fm_f0, fm_f0 + fm_f) */
+    float fm_const;
+    int32_t fs_shift, reserved;   /* FreqShift: np.roll by fs_shift bins, wrapped bins zeroed */
+} sedt_augment_params;
+SEDT_API int sedt_augment_clips(float* x, const sedt_augment_params* params, int B, int T, int F, float* scratch, void* stream);
+/* mixup's data path (utilities/mixup.py:35): out[k] = a * x[i1] + b * x[i2] over rows of row_elems fp32 (b == 0: copy of x[i1]) */
+typedef struct sedt_mix_row { int32_t i1, i2; float a, b; } sedt_mix_row;
+SEDT_API int sedt_mix_rows(const float* x, float* out, const sedt_mix_row* rows, int n_out, int64_t row_elems, void* stream);
+/* SP-SEDT patch crop + resize (utilities/BoxTransforms.py:315-360, Query): x [B, 1, T, F] fp32, bounds [B*P][2] = (s_idx, e_idx)
+ * frame range of every patch, out [B, P, 1, 128, F]; Pillow's 8-bit antialiased bilinear resample, bit-exact */
+SEDT_API int sedt_query_patches(const float* x, const int32_t* bounds, float* out, int B, int P, int T, int F, int fixed_patch_size,
+                                void* stream);
+
 /* ---- clip_grad_norm_ + AdamW: the optimizer half of the training step (engine.py:76-80; AdamW with two lr groups,
  * train_sedt.py:234-240,269-270; torch/optim/adamw.py _single_tensor_adamw arithmetic, amsgrad = maximize = False).
  * The caller keeps a device table of tensors and a device table of (tensor index, chunk index) pairs that splits

@@ -40,6 +40,15 @@ class SedtOptimTensor(C.Structure):
                 ("numel", C.c_int64), ("group", C.c_int32), ("reserved", C.c_int32)]
 
 
+class SedtAugmentParams(C.Structure):
+    _fields_ = [("tm_t0", C.c_int32), ("tm_t", C.c_int32), ("fm_f0", C.c_int32), ("fm_f", C.c_int32), ("fm_mode", C.c_int32),
+                ("fm_const", C.c_float), ("fs_shift", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SedtMixRow(C.Structure):
+    _fields_ = [("i1", C.c_int32), ("i2", C.c_int32), ("a", C.c_float), ("b", C.c_float)]
+
+
 class SedtAdamWGroup(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("decay", "w1", "beta2", "w2", "bc2_sqrt", "eps", "neg_step", "reserved")]
 
@@ -79,6 +88,9 @@ SIGNATURES = {
     "sedt_decode_events": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _f, _f] + [_vp] * 9),
     "sedt_pseudo_labels": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "sedt_prepare_clips": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sedt_augment_clips": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "sedt_mix_rows": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
+    "sedt_query_patches": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sedt_optim_chunk_elems": (_i, []),
     "sedt_grad_norm": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "sedt_clip_grads": (_i, [_vp, _vp, _i, _vp, _f, _vp]),

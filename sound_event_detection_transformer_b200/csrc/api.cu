@@ -243,6 +243,23 @@ int sedt_prepare_clips(const float* raw, const int64_t* offsets, const double* m
     return launch_prepare_clips(raw, offsets, mean, std, out, B, frames, F, apply_log, (cudaStream_t)stream);
 }
 
+static_assert(sizeof(sedt_augment_params) == sizeof(AugmentParams) && sizeof(sedt_mix_row) == sizeof(MixRow), "augment structs out of step");
+
+int sedt_augment_clips(float* x, const sedt_augment_params* params, int B, int T, int F, float* scratch, void* stream)
+{
+    return launch_augment_clips(x, (const AugmentParams*)params, B, T, F, scratch, (cudaStream_t)stream);
+}
+
+int sedt_mix_rows(const float* x, float* out, const sedt_mix_row* rows, int n_out, int64_t row_elems, void* stream)
+{
+    return launch_mix_rows(x, out, (const MixRow*)rows, n_out, row_elems, (cudaStream_t)stream);
+}
+
+int sedt_query_patches(const float* x, const int32_t* bounds, float* out, int B, int P, int T, int F, int fixed_patch_size, void* stream)
+{
+    return launch_query_patches(x, bounds, out, B, P, T, F, fixed_patch_size, (cudaStream_t)stream);
+}
+
 int sedt_optim_chunk_elems(void) { return optim_chunk_elems(); }
 
 int sedt_grad_norm(const sedt_optim_tensor* tensors, const int32_t* chunks, int nchunks, float* partials, float* norm_out, void* stream)

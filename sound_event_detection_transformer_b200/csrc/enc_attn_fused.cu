@@ -60,7 +60,11 @@ struct EaParams {
     const uint8_t* kpm;       // [B, S] (1 = padded key) or null
     int B, S;
     float scale;
+    long long* dbg;           // optional phase timestamps of CTA 0 (SEDT_EA_DEBUG=1, see launch_enc_attn_fused); null in production
 };
+
+// debug timeline: slot = role * 64 + event, clock64() of the first two clips of CTA 0
+#define EA_T(role, ev) do { if (p.dbg != nullptr && blockIdx.x == 0 && it < 2) p.dbg[(it * 3 + (role)) * 64 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t ea_swz(int row, int byte_in_row) {
     return (uint32_t)(row * 128 + ((((byte_in_row >> 4) ^ (row & 7)) << 4) | (byte_in_row & 15)));
@@ -141,16 +145,20 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 const int b = (int)blockIdx.x + it * (int)gridDim.x;
                 const int row0 = b * S;
                 mbar_wait(stage_free, (it & 1) ^ 1);                // the previous clip's output stores have left bufA / bufB
+                EA_T(0, 0);
                 mbar_expect_tx(act_full, 8 * EA_SLOT);
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_nap, smem + EA_BUFA + kb * EA_SLOT, act_full, kb * 64, row0);
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_na, smem + EA_BUFB + kb * EA_SLOT, act_full, kb * 64, row0);
                 for (int m = 0; m < 3; ++m)                         // Wq, Wk, Wv: [N half][k block]
                     for (int nh = 0; nh < 2; ++nh)
                         for (int kb = 0; kb < 4; ++kb) next_slot(&map_win, kb * 64, m * 256 + nh * 128);
+                EA_T(0, 1);
                 for (int i = 0; i < 8; ++i) {                       // Wo: [k block][N half]
                     if (i == EA_NSLOTS) {
                         // K and V^T are dead once the last P V has retired: prefetch the residual tile over them
+                        EA_T(0, 2);
                         mbar_wait(kv_dead, it & 1);
+                        EA_T(0, 3);
                         for (int g = 0; g < 2; ++g) {
                             mbar_expect_tx(&res_full[g], 4 * EA_SLOT);
                             for (int c = 0; c < 4; ++c)
@@ -159,6 +167,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                     }
                     next_slot(&map_wo, (i >> 1) * 64, (i & 1) * 128);
                 }
+                EA_T(0, 4);
             }
         }
     } else if (warp == 1) {
@@ -187,17 +196,25 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
             };
             for (int it = 0; it < iters; ++it) {
                 const uint32_t par = (uint32_t)(it & 1);
+                EA_T(1, 0);
                 mbar_wait(act_full, par);
+                EA_T(1, 1);
                 mbar_wait(y_drained, par ^ 1);                      // the previous clip's Y has left TMEM
                 tc_fence_after();
+                EA_T(1, 2);
                 project(sA, TM_Q);  umma_commit(q_full);
+                EA_T(1, 3);
                 project(sA, TM_KV); umma_commit(k_full);
+                EA_T(1, 4);
                 mbar_wait(k_drained, par);                          // K is in bufA, its accumulator may be overwritten
                 tc_fence_after();
+                EA_T(1, 5);
                 project(sB, TM_KV); umma_commit(v_full);
+                EA_T(1, 6);
                 mbar_wait(q_drained, par);
                 mbar_wait(v_drained, par);
                 tc_fence_after();
+                EA_T(1, 7);
                 auto issue_s = [&](int h) {
                     const int g = h & 1;
                     const uint32_t d = tmem_base + TM_S + (uint32_t)(g * 128);
@@ -224,9 +241,11 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                     if (h + 2 < 8) issue_s(h + 2);                  // in-order execution: P_h has been consumed by then
                 }
                 umma_commit(kv_dead);
+                EA_T(1, 8);
                 mbar_wait(&o_done[0], (uint32_t)(it * 4 + 3) & 1);
                 mbar_wait(&o_done[1], (uint32_t)(it * 4 + 3) & 1);
                 tc_fence_after();
+                EA_T(1, 9);
                 for (int i = 0; i < 8; ++i) {                       // Y = O Wo^T, A = packed O in TMEM
                     const int kb = i >> 1, nh = i & 1;
                     mbar_wait(&slot_full[slot], sphase);
@@ -240,6 +259,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                     if (++slot == EA_NSLOTS) { slot = 0; sphase ^= 1; }
                 }
                 umma_commit(y_full);
+                EA_T(1, 10);
             }
         }
     } else {
@@ -263,10 +283,13 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 s_neg[r] = (mk - 1.f) * 1e30f;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
+#define EA_TT(ev) do { if (quad == 0 && lane == 0) EA_T(2, team * 32 + (ev)); } while (0)
+            EA_TT(0);
 
             // ---- Q: fp32 accumulator + bias -> bf16, packed in place (team t: columns [128t, 128t+128) -> [64t, 64t+64))
             mbar_wait(q_full, par);
             tc_fence_after();
+            EA_TT(1);
             {
                 uint32_t w[64];
 #pragma unroll
@@ -290,10 +313,12 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(q_drained);
+            EA_TT(2);
 
             // ---- K: + bias -> bf16 -> bufA in the K-major operand layout (LN(x)+pos is dead: both projections have retired)
             mbar_wait(k_full, par);
             tc_fence_after();
+            EA_TT(3);
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int col = team * 128 + c * 32;
@@ -315,10 +340,12 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(k_drained);
+            EA_TT(4);
 
             // ---- V: + bias -> bf16 -> bufB, transposed per head: element (d, key r) of head h -> [h][r / 64][d][r % 64]
             mbar_wait(v_full, par);
             tc_fence_after();
+            EA_TT(5);
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int h = team * 4 + c;
@@ -335,6 +362,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(v_drained);
+            EA_TT(6);
 
             // ---- heads h = 2 hh + team
 #pragma unroll 1
@@ -344,6 +372,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 const uint32_t sbase = lane_base + TM_S + (uint32_t)(team * 128);
                 mbar_wait(&s_full[team], u & 1);
                 tc_fence_after();
+                EA_TT(8 + 4 * hh);
                 // p_j = 2^(c (s_j - m)) * valid_j, c = scale * log2 e, m = max over the valid keys (attention_tc.cu)
                 float m = -CUDART_INF_F;
 #pragma unroll 1
@@ -384,9 +413,11 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_ready[team]);
+                EA_TT(9 + 4 * hh);
 
                 mbar_wait(&o_full[team], u & 1);
                 tc_fence_after();
+                EA_TT(10 + 4 * hh);
                 {
                     uint32_t acc[32], pk[16];
                     tmem_ld32(lane_base + TM_OT + (uint32_t)(team * 32), acc);
@@ -399,13 +430,16 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&o_done[team]);
+                EA_TT(11 + 4 * hh);
             }
 
             // ---- output: Y + bo + x -> fp32, staged through the residual tile (team t: columns [128t, 128t+128) in bufA / bufB)
             mbar_wait(y_full, par);
             tc_fence_after();
+            EA_TT(24);
             uint8_t* stage = team ? bufB : bufA;
             mbar_wait(&res_full[team], par);
+            EA_TT(25);
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t acc[32];
@@ -415,6 +449,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(y_drained);
+            EA_TT(26);
             fence_async_smem();
             asm volatile("bar.sync %0, 128;" ::"r"(6 + team) : "memory");
             if ((e & 3) == 0 && lane == 0) {
@@ -422,6 +457,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 tma_store_commit();
                 tma_store_wait_read0();
                 mbar_arrive(stage_free);
+                if (p.dbg != nullptr && blockIdx.x == 0 && it < 2) p.dbg[(it * 3 + 2) * 64 + team * 32 + 27] = clock64();
             }
         }
     }
@@ -483,7 +519,15 @@ int launch_enc_attn_fused(const void* na, const void* nap, const void* w_in, con
         SEDT_TRY(encode_map(&mout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, 3, odims, ostr, obox));
     }
     EaParams p;
-    p.b_in = b_in; p.b_out = b_out; p.kpm = kpm; p.B = B; p.S = S; p.scale = scale;
+    p.b_in = b_in; p.b_out = b_out; p.kpm = kpm; p.B = B; p.S = S; p.scale = scale; p.dbg = nullptr;
+    // SEDT_EA_DEBUG=1 (development only; synchronises): phase timeline of CTA 0's first two clips on stderr, in cycles
+    static const bool debug = [] { const char* e = getenv("SEDT_EA_DEBUG"); return e != nullptr && atoi(e) != 0; }();
+    long long* dbg_dev = nullptr;
+    if (debug) {
+        SEDT_CHECK_CUDA(cudaMalloc(&dbg_dev, 6 * 64 * sizeof(long long)));
+        SEDT_CHECK_CUDA(cudaMemsetAsync(dbg_dev, 0, 6 * 64 * sizeof(long long), stream));
+        p.dbg = dbg_dev;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         SEDT_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EA_SMEM));
@@ -495,6 +539,22 @@ int launch_enc_attn_fused(const void* na, const void* nap, const void* w_in, con
                                mout, p));
     SEDT_COUNT_KIND(KK_ENC_ATTN_FUSED);
     SEDT_CHECK_CUDA(cudaGetLastError());
+    if (debug) {
+        long long h[6 * 64];
+        SEDT_CHECK_CUDA(cudaStreamSynchronize(stream));
+        SEDT_CHECK_CUDA(cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(dbg_dev);
+        long long t0 = 0;
+        for (int i = 0; i < 6 * 64; ++i) if (h[i] != 0 && (t0 == 0 || h[i] < t0)) t0 = h[i];
+        static const char* roles[3] = {"tma", "mma", "row"};
+        fprintf(stderr, "[enc_attn_fused B=%d S=%d] cycles since the first event of CTA 0\n", B, S);
+        for (int it = 0; it < 2; ++it)
+            for (int role = 0; role < 3; ++role) {
+                fprintf(stderr, "  clip %d %s:", it, roles[role]);
+                for (int ev = 0; ev < 64; ++ev) if (h[(it * 3 + role) * 64 + ev] != 0) fprintf(stderr, " %d=%lld", ev, h[(it * 3 + role) * 64 + ev] - t0);
+                fprintf(stderr, "\n");
+            }
+    }
     return SEDT_OK;
 }
 

@@ -248,6 +248,14 @@ int launch_pseudo_labels(const float* logits, const float* boxes, const float* t
 int launch_prepare_clips(const float* raw, const int64_t* offsets, const double* mean, const double* stdv, float* out, int B,
                          int frames, int F, int apply_log, cudaStream_t stream);
 
+// ---- augment.cu: TimeMask / FreqMask / FreqShift, mixup rows, SP-SEDT patch crop + resize (utilities/BoxTransforms.py:315-452,
+// utilities/mixup.py:13-127); the structs mirror include/sedt_b200.h
+struct AugmentParams { int32_t tm_t0, tm_t, fm_f0, fm_f, fm_mode; float fm_const; int32_t fs_shift, reserved; };
+struct MixRow { int32_t i1, i2; float a, b; };
+int launch_augment_clips(float* x, const AugmentParams* params, int B, int T, int F, float* row_sums, cudaStream_t stream);
+int launch_mix_rows(const float* x, float* out, const MixRow* rows, int n_out, int64_t row_elems, cudaStream_t stream);
+int launch_query_patches(const float* x, const int32_t* bounds, float* out, int B, int P, int T, int F, int fixed, cudaStream_t stream);
+
 // ---- optim.cu: clip_grad_norm_ + AdamW over a (tensor, chunk) table (engine.py:76-80)
 int optim_chunk_elems();
 int launch_grad_norm(const void* tensors, const int32_t* chunks, int nchunks, float* partials, float* norm_out, cudaStream_t stream);

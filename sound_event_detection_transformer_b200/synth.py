@@ -202,3 +202,35 @@ def synth_decode_cases(n: int, Q: int, seed: int):
         cases.append({"scores": rng.uniform(0.3, 1.0, Q).astype(np.float32), "labels": rng.integers(0, 3, Q).astype(np.int64),
                       "boxes": np.stack([onset, onset + dur], -1).astype(np.float32)})
     return cases
+
+
+def synth_patch_boxes(B: int, P: int, seed: int, fixed_len=None):
+    """(center, width) boxes that stay inside the clip, as SedData.get_random_patch draws them (data_utils/DataLoad.py:57-77):
+    widths in [0.0005, 0.8) (or fixed_len), plus the degenerate / full-width cases at the front of clip 0."""
+    g = torch.Generator().manual_seed(9800 + seed)
+    l = torch.rand(B, P, generator=g) * 0.8 + 0.0005 if fixed_len is None else torch.full((B, P), float(fixed_len))
+    c = l / 2 + torch.rand(B, P, generator=g) * (1 - l)
+    boxes = torch.stack([c, l], -1)
+    if fixed_len is None and P >= 4:
+        boxes[0, :4] = torch.tensor([[0.3, 0.0005], [0.5, 1.0], [0.5, 0.26], [0.129, 0.258]])
+    return boxes
+
+
+def synth_mixup_case(n_strong: int, n_weak: int, n_unl: int, T: int, F: int, seed: int, C: int = 10):
+    """A batch laid out [strong | weak | unlabelled] like the semi-supervised loader (train_ss_sedt.py): clips + label dicts.
+    Strong clips carry 0..12 events (so that > max_events and same-class overlaps occur), weak / unlabelled ones only tags."""
+    g = torch.Generator().manual_seed(9900 + seed)
+    bs = n_strong + n_weak + n_unl
+    x = torch.randn(bs, 1, T, F, generator=g)
+    y = []
+    for i in range(bs):
+        if i < n_strong:
+            k = int(torch.randint(0, 13, (1,), generator=g))
+            l = torch.rand(k, generator=g) * 0.15 + 0.01
+            c = l / 2 + torch.rand(k, generator=g) * (1 - l)
+            y.append({"labels": torch.randint(0, C, (k,), generator=g), "boxes": torch.stack([c, l], -1).reshape(k, 2),
+                      "orig_size": torch.tensor(10.0)})
+        else:
+            k = int(torch.randint(0, 3, (1,), generator=g)) if i < n_strong + n_weak else 0
+            y.append({"labels": torch.randint(0, C, (k,), generator=g), "boxes": torch.zeros(0, 2), "orig_size": torch.tensor(10.0)})
+    return x, y

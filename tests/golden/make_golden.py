@@ -247,6 +247,67 @@ def run_prepare(tag, lengths, frames, seed):
     print(f"prepare_{tag}: {len(lengths)} clips -> {np.stack(outs).shape}")
 
 
+def _stub_audio_modules():
+    for name in ("librosa", "soundfile", "librosa.display", "librosa.feature"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+
+
+def run_augment(tag, B, T, seed):
+    """TimeMask -> FreqMask(fill_mode="mean") -> FreqShift exactly as get_transforms chains them (utilities/BoxTransforms.py:
+    471-478), probabilities raised so that every transform fires often; np.random seeded per batch."""
+    _stub_audio_modules()
+    from utilities.BoxTransforms import FreqMask, FreqShift, TimeMask
+    clips = synth.synth_db_clips([T] * B, 64, seed)
+    tfs = [TimeMask(p=0.7), FreqMask(fill_mode="mean", p=0.7), FreqShift(p=0.7)]
+    np.random.seed(4200 + seed)
+    outs = []
+    for c in clips:
+        d = c.copy()
+        for tf in tfs:
+            d = tf.transform_data(d)
+        outs.append(d)
+    np.savez_compressed(os.path.join(HERE, f"augment_{tag}.npz"), out=np.stack(outs).astype(np.float32), meta=np.asarray([B, T, seed]))
+    print(f"augment_{tag}: {np.stack(outs).shape}")
+
+
+def run_query(tag, B, P, T, seed, fixed=False):
+    """Query.transform_label (utilities/BoxTransforms.py:315-360) on normalised clips."""
+    _stub_audio_modules()
+    from utilities.BoxTransforms import Query
+    x = synth.synth_clips(B, T, 64, seed=seed)
+    boxes = synth.synth_patch_boxes(B, P, seed, fixed_len=(128 / T) if fixed else None)
+    q = Query(fixed)
+    outs = []
+    for b in range(B):
+        _, lab = q.transform_label((x[b], {"patches": 1, "boxes": boxes[b]}))
+        outs.append(lab["patches"].numpy())
+    np.savez_compressed(os.path.join(HERE, f"query_{tag}.npz"), out=np.stack(outs).astype(np.float32), meta=np.asarray([B, P, T, seed, int(fixed)]))
+    print(f"query_{tag}: {np.stack(outs).shape}")
+
+
+def run_mixup(tag, n_strong, n_weak, n_unl, T, seed, with_weak=True):
+    """utilities/mixup.py: mixup_data on a [strong | weak | unlabelled] batch (np.random seeded)."""
+    from utilities.mixup import mixup_data
+
+    class NT:
+        pass
+    x, y = synth.synth_mixup_case(n_strong, n_weak, n_unl, T, 64, seed)
+    nt = NT(); nt.tensors = x.clone()
+    np.random.seed(4300 + seed)
+    mask_weak = slice(n_strong, n_strong + n_weak) if with_weak else None
+    xo, yo, s_sl, w_sl = mixup_data(nt, np.array(y, dtype=object), slice(n_strong), mask_weak, mix_up_ratio=0.5, max_events=20, alpha=3)
+    fx = {"out": xo.tensors.numpy().astype(np.float32), "meta": np.asarray([n_strong, n_weak, n_unl, T, seed, int(with_weak)]),
+          "slices": np.asarray([s_sl.start or 0, s_sl.stop, w_sl.start, w_sl.stop]),
+          "n_labels": np.asarray([len(l["labels"]) for l in yo]), "n_boxes": np.asarray([len(l["boxes"]) for l in yo]),
+          "labels": np.concatenate([l["labels"].numpy().reshape(-1) for l in yo] + [np.zeros(0, np.int64)]),
+          "boxes": np.concatenate([l["boxes"].numpy().reshape(-1, 2) for l in yo if len(l["boxes"])] + [np.zeros((0, 2), np.float32)]),
+          "ratio": np.concatenate([(l["ratio"].numpy() if "ratio" in l else -np.ones(len(l["labels"]), np.float32)).reshape(-1)
+                                   for l in yo] + [np.zeros(0, np.float32)])}
+    np.savez_compressed(os.path.join(HERE, f"mixup_{tag}.npz"), **fx)
+    print(f"mixup_{tag}: {fx['out'].shape}, strong {s_sl}, weak {w_sl}, mixed rows {(fx['ratio'] >= 0).sum()}")
+
+
+
 def run_criterion(tag, args, B, seed, kmin=0, kmax=10, fine_tune=False, normalize=False, fl=False, rng_seed=1234):
     """Reference SetCriterion (sedt/sedt.py:134-352) built directly (build_model returns None for it
     without CUDA) on seeded model-shaped outputs: every loss value and the gradient of the weighted sum."""
@@ -282,6 +343,14 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     if "--only-decode" in sys.argv:
         run_decode_chains("chains", 24, 20, seed=51)
+        sys.exit(0)
+    if "--only-augment" in sys.argv:
+        run_augment("b12", 12, 96, seed=51)
+        run_query("p6", 3, 6, 200, seed=52)
+        run_query("fixed", 2, 3, 300, seed=53, fixed=True)
+        run_mixup("ss", 12, 6, 6, 40, seed=54)
+        run_mixup("strong_only", 10, 0, 0, 40, seed=55, with_weak=False)
+        run_mixup("weak_mix", 4, 10, 6, 24, seed=56)
         sys.exit(0)
     if "--only-prepare" in sys.argv:
         run_prepare("ragged", [40, 64, 90, 1, 63, 65], 64, seed=41)
@@ -325,3 +394,9 @@ if __name__ == "__main__":
     run_matcher("c3_normalize", 32, 20, 10, 0, 10, seed=6, normalize=True)
     run_criterion("c2", spec.config_args("c2"), 48, seed=1)
     run_criterion("c1_edges", spec.config_args("c1"), 16, seed=2, kmin=8, kmax=14)
+    run_augment("b12", 12, 96, seed=51)
+    run_query("p6", 3, 6, 200, seed=52)
+    run_query("fixed", 2, 3, 300, seed=53, fixed=True)
+    run_mixup("ss", 12, 6, 6, 40, seed=54)
+    run_mixup("strong_only", 10, 0, 0, 40, seed=55, with_weak=False)
+    run_mixup("weak_mix", 4, 10, 6, 24, seed=56)

@@ -239,3 +239,63 @@ def test_oracle_matches_live_reference_copy():
     got = sedt_oracle.sedt_forward(sd, args, clips)
     for k in ("pred_logits", "pred_boxes", "at"):
         assert (got[k] - want[k]).abs().max().item() <= 2e-6 * max(1.0, want[k].abs().max().item()), k
+
+
+# ---- training-time input transforms: oracle/augment_oracle.py against the reference's own classes ----------------
+def _unpack_mixup_labels(fx):
+    out, lo, bo = [], 0, 0
+    for nl, nb in zip(fx["n_labels"], fx["n_boxes"]):
+        out.append({"labels": fx["labels"][lo:lo + nl], "boxes": fx["boxes"][bo:bo + nb], "ratio": fx["ratio"][lo:lo + nl]})
+        lo += nl; bo += nb
+    return out
+
+
+def test_augment_oracle_matches_reference_transforms():
+    from oracle import augment_oracle as ao
+    fx = np.load(os.path.join(GOLDEN, "augment_b12.npz"))
+    B, T, seed = [int(v) for v in fx["meta"]]
+    np.random.seed(4200 + seed)
+    fired = 0
+    for clip, want in zip(synth.synth_db_clips([T] * B, 64, seed), fx["out"]):
+        p = ao.draw_params(np.random, tm=(0.0, 0.1, 0.7), fm=(0.03, 0.4, 0.7), fs=(0.7, 4, 0.0, 2.0))
+        got = ao.augment(clip.copy(), p)
+        assert np.array_equal(got, want)
+        fired += int(bool(p["tm_apply"])) + int(bool(p["fm_apply"])) + int(bool(p["fs_apply"] and p["fs_shift"]))
+    assert fired >= B                                      # the fixture exercises all three transforms
+
+
+@pytest.mark.parametrize("tag", ["p6", "fixed"])
+def test_query_oracle_matches_reference_pil_path(tag):
+    """Bit-exact: Pillow's 8-bit antialiased bilinear resample restated in integers."""
+    from oracle import augment_oracle as ao
+    fx = np.load(os.path.join(GOLDEN, f"query_{tag}.npz"))
+    B, P, T, seed, fixed = [int(v) for v in fx["meta"]]
+    x = synth.synth_clips(B, T, 64, seed=seed).numpy()
+    boxes = synth.synth_patch_boxes(B, P, seed, fixed_len=(128 / T) if fixed else None).numpy()
+    for b in range(B):
+        assert np.array_equal(ao.query_patches(x[b], boxes[b], bool(fixed)), fx["out"][b])
+
+
+@pytest.mark.parametrize("tag", ["ss", "strong_only", "weak_mix"])
+def test_mixup_oracle_matches_reference(tag):
+    from oracle import augment_oracle as ao
+    fx = np.load(os.path.join(GOLDEN, f"mixup_{tag}.npz"))
+    n_strong, n_weak, n_unl, T, seed, with_weak = [int(v) for v in fx["meta"]]
+    x, y = synth.synth_mixup_case(n_strong, n_weak, n_unl, T, 64, seed)
+    yn = [{k: v.numpy() for k, v in t.items()} for t in y]
+    np.random.seed(4300 + seed)
+    lam = np.random.beta(3, 3)
+    index = np.asarray(list(range(len(y))))
+    np.random.shuffle(index)
+    rows, labels, ns, nw = ao.mixup_plan(yn, n_strong, n_weak if with_weak else None, lam, index)
+    assert [0, ns, ns, ns + nw] == fx["slices"].tolist()
+    assert np.array_equal(ao.mixup_rows(x.numpy(), rows), fx["out"])
+    want = _unpack_mixup_labels(fx)
+    assert len(labels) == len(want)
+    for got, w in zip(labels, want):
+        assert np.array_equal(np.asarray(got["labels"]), w["labels"])
+        assert np.array_equal(np.asarray(got["boxes"], np.float32).reshape(-1, 2), w["boxes"])
+        if "ratio" in got:
+            assert np.allclose(got["ratio"], w["ratio"], rtol=1e-6)
+        else:
+            assert (w["ratio"] < 0).all()
