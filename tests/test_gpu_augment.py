@@ -112,10 +112,10 @@ def test_mixup_label_unlabel_rows():
     got = out.tensors.cpu()
     assert got.shape == x2.shape and len(labels) == 8
     for i in range(8):
+        took_l1 = i < 4 and "ratio" not in labels[i] and labels[i]["labels"].data_ptr() == y1c[i]["labels"].data_ptr()
         if i < 4 and "ratio" in labels[i]:
             want = np.float32(lam) * x1[i].numpy() + np.float32(1 - lam) * x2[i].numpy()
-        elif i < 4 and len(labels[i]["labels"]) == len(y1[i]["labels"]) and torch.equal(labels[i]["labels"].cpu(), y1[i]["labels"]) \\
-                and not torch.equal(labels[i]["labels"].cpu(), y2[i]["labels"]):
+        elif took_l1:
             want = x1[i].numpy()
         else:
             want = x2[i].numpy()
