@@ -74,6 +74,44 @@ def freq_mask(data: np.ndarray, f_frac: float, f0_frac: float, fill_mode: str = 
     return data
 
 
+def _pairwise_sum_f32(a: np.ndarray) -> np.float32:
+    """numpy/core/src/umath/loops_utils.h.src: FLOAT_pairwise_sum."""
+    n = len(a)
+    if n < 8:
+        res = f32(0)
+        for v in a:
+            res = f32(res + v)
+        return res
+    if n <= 128:
+        r = [f32(a[j]) for j in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for j in range(8):
+                r[j] = f32(r[j] + a[i + j])
+            i += 8
+        res = f32(f32(f32(r[0] + r[1]) + f32(r[2] + r[3])) + f32(f32(r[4] + r[5]) + f32(r[6] + r[7])))
+        while i < n:
+            res = f32(res + a[i])
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return f32(_pairwise_sum_f32(a[:n2]) + _pairwise_sum_f32(a[n2:]))
+
+
+def numpy_mean_f32(s: np.ndarray) -> np.float32:
+    """np.mean of a non-contiguous [T, n] float32 slice, operation by operation (what csrc/augment.cu reproduces): C-order
+    chunks of (8192 // n) * n elements through the pairwise sum, chunk sums accumulated in float32, float32(double(sum) / count).
+    Checked against np.mean itself in tests/test_oracle_golden.py."""
+    n = s.shape[1]
+    chunk = (8192 // n) * n
+    flat = np.ascontiguousarray(s).reshape(-1)
+    acc = f32(0)
+    for i in range(0, len(flat), chunk):
+        acc = f32(acc + _pairwise_sum_f32(flat[i:i + chunk]))
+    return f32(np.float64(acc) / np.float64(s.size))
+
+
 def freq_shift(data: np.ndarray, shift: int) -> np.ndarray:
     data = np.roll(data, shift, axis=1)
     if shift >= 0:

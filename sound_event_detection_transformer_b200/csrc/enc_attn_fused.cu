@@ -9,7 +9,7 @@
 //   rows     Q + bq -> bf16 packed IN PLACE in TMEM [0,128): the A operand of S = Q K^T is read from tensor memory
 //            K + bk -> bf16 -> bufA (LN(x)+pos is dead)   [128 keys x 256] K-major = B operand of S
 //   tcgen05  V = bufB Wv^T -> TMEM [256,512)
-//   rows     V + bv -> bf16 -> bufB transposed per head ([32 dims x 128 keys] K-major = B operand of P V; LN(x) is dead)
+//   rows     V + bv -> bf16 -> bufB as stored ([128 keys x 256] = an MN-major B operand of P V: no transpose; LN(x) is dead)
 //   per head h (two teams of four warps take alternate heads, each with its own S / O buffers):
 //     tcgen05  S_h = Q_h K_h^T                          -> TMEM S[team] (128 columns)
 //     rows     softmax over the thread's own TMEM lane (masks as shared-memory vectors), un-normalised P packed to bf16 IN PLACE
@@ -40,10 +40,10 @@ constexpr int EA_NSLOTS = 5;
 constexpr int EA_BUFA = 0;
 constexpr int EA_BUFB = 65536;
 constexpr int EA_RING = 131072;
-constexpr int EA_BIAS = EA_RING + EA_NSLOTS * EA_SLOT;          // in_proj bias [768] fp32
-constexpr int EA_MASK = EA_BIAS + 768 * 4;                      // key validity 0/1 [128], 0/-1e30 [128]
+constexpr int EA_BIAS = EA_RING + EA_NSLOTS * EA_SLOT;          // in_proj bias [768] + out_proj bias [256] fp32
+constexpr int EA_MASK = EA_BIAS + 1024 * 4;                     // key validity 0/1 [128], 0/-1e30 [128]
 constexpr int EA_BAR = EA_MASK + 1024;
-constexpr int EA_NBARS = 2 * EA_NSLOTS + 21;
+constexpr int EA_NBARS = 2 * EA_NSLOTS + 23;
 constexpr int EA_SMEM = EA_BAR + EA_NBARS * 8 + 16 + 1024;
 static_assert(EA_SMEM <= 232448, "shared memory budget exceeded");
 
@@ -84,8 +84,9 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* slot_full = (uint64_t*)(smem + EA_BAR);
     uint64_t* slot_empty = slot_full + EA_NSLOTS;
-    uint64_t* act_full = slot_empty + EA_NSLOTS;
-    uint64_t* q_full = act_full + 1;
+    uint64_t* nap_full = slot_empty + EA_NSLOTS;      // LN(x)+pos has landed in bufA
+    uint64_t* na_full = nap_full + 1;                 // LN(x) has landed in bufB
+    uint64_t* q_full = na_full + 1;
     uint64_t* k_full = q_full + 1;
     uint64_t* v_full = k_full + 1;
     uint64_t* q_drained = v_full + 1;
@@ -99,8 +100,8 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
     uint64_t* y_full = kv_dead + 1;
     uint64_t* res_full = y_full + 1;         // [2]
     uint64_t* y_drained = res_full + 2;
-    uint64_t* stage_free = y_drained + 1;
-    uint32_t* tmem_slot = (uint32_t*)(stage_free + 1);
+    uint64_t* stage_free = y_drained + 1;    // [2] the output stores of bufA / bufB have been read out
+    uint32_t* tmem_slot = (uint32_t*)(stage_free + 2);
     float* s_bias = (float*)(smem + EA_BIAS);
     float* s_mask = (float*)(smem + EA_MASK);
     float* s_neg = s_mask + 128;
@@ -113,17 +114,18 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
         prefetch_tmap(&map_nap); prefetch_tmap(&map_na); prefetch_tmap(&map_win); prefetch_tmap(&map_wo);
         prefetch_tmap(&map_res); prefetch_tmap(&map_out);
         for (int s = 0; s < EA_NSLOTS; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 1); }
-        mbar_init(act_full, 1); mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1);
+        mbar_init(nap_full, 1); mbar_init(na_full, 1); mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1);
         mbar_init(q_drained, 8); mbar_init(k_drained, 8); mbar_init(v_drained, 8);
         for (int g = 0; g < 2; ++g) {
             mbar_init(&s_full[g], 1); mbar_init(&p_ready[g], 4); mbar_init(&o_full[g], 1); mbar_init(&o_done[g], 4);
             mbar_init(&res_full[g], 1);
         }
-        mbar_init(kv_dead, 1); mbar_init(y_full, 1); mbar_init(y_drained, 8); mbar_init(stage_free, 2);
+        mbar_init(kv_dead, 1); mbar_init(y_full, 1); mbar_init(y_drained, 8);
+        mbar_init(&stage_free[0], 1); mbar_init(&stage_free[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
-    for (int i = threadIdx.x; i < 768; i += EA_THREADS) s_bias[i] = p.b_in[i];             // weights: not produced by the predecessor
+    for (int i = threadIdx.x; i < 1024; i += EA_THREADS) s_bias[i] = i < 768 ? p.b_in[i] : p.b_out[i - 768];   // weights: not produced by the predecessor
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -144,11 +146,14 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
             for (int it = 0; it < iters; ++it) {
                 const int b = (int)blockIdx.x + it * (int)gridDim.x;
                 const int row0 = b * S;
-                mbar_wait(stage_free, (it & 1) ^ 1);                // the previous clip's output stores have left bufA / bufB
+                // bufA / bufB are free once the previous clip's output stores have been read out of them; Q / K only need bufA
+                mbar_wait(&stage_free[0], (it & 1) ^ 1);
                 EA_T(0, 0);
-                mbar_expect_tx(act_full, 8 * EA_SLOT);
-                for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_nap, smem + EA_BUFA + kb * EA_SLOT, act_full, kb * 64, row0);
-                for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_na, smem + EA_BUFB + kb * EA_SLOT, act_full, kb * 64, row0);
+                mbar_expect_tx(nap_full, 4 * EA_SLOT);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_nap, smem + EA_BUFA + kb * EA_SLOT, nap_full, kb * 64, row0);
+                mbar_wait(&stage_free[1], (it & 1) ^ 1);
+                mbar_expect_tx(na_full, 4 * EA_SLOT);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_na, smem + EA_BUFB + kb * EA_SLOT, na_full, kb * 64, row0);
                 for (int m = 0; m < 3; ++m)                         // Wq, Wk, Wv: [N half][k block]
                     for (int nh = 0; nh < 2; ++nh)
                         for (int kb = 0; kb < 4; ++kb) next_slot(&map_win, kb * 64, m * 256 + nh * 128);
@@ -174,7 +179,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc128 = make_idesc(128, 128);
-            constexpr uint32_t idesc32 = make_idesc(128, 32);
+            constexpr uint32_t idesc32 = make_idesc(128, 32) | (1u << 16);      // B (= V, [keys][dims]) is MN-major
             int slot = 0; uint32_t sphase = 0;
             const uint32_t sA = smem_u32(smem + EA_BUFA), sB = smem_u32(smem + EA_BUFB);
             const int ksteps_pv = (S + UMMA_K - 1) / UMMA_K;
@@ -197,7 +202,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
             for (int it = 0; it < iters; ++it) {
                 const uint32_t par = (uint32_t)(it & 1);
                 EA_T(1, 0);
-                mbar_wait(act_full, par);
+                mbar_wait(nap_full, par);
                 EA_T(1, 1);
                 mbar_wait(y_drained, par ^ 1);                      // the previous clip's Y has left TMEM
                 tc_fence_after();
@@ -207,6 +212,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 project(sA, TM_KV); umma_commit(k_full);
                 EA_T(1, 4);
                 mbar_wait(k_drained, par);                          // K is in bufA, its accumulator may be overwritten
+                mbar_wait(na_full, par);
                 tc_fence_after();
                 EA_T(1, 5);
                 project(sB, TM_KV); umma_commit(v_full);
@@ -234,9 +240,9 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                     tc_fence_after();
                     const uint32_t d = tmem_base + TM_OT + (uint32_t)(g * 32);
                     const uint32_t pa = tmem_base + TM_S + (uint32_t)(g * 128);
-                    const uint32_t vaddr = sB + h * 8192;
-                    for (int ks = 0; ks < ksteps_pv; ++ks)
-                        umma_bf16_ts(d, pa + (uint32_t)(8 * ks), make_smem_desc(vaddr + (ks >> 2) * 4096 + (ks & 3) * 32), idesc32, ks > 0 ? 1u : 0u);
+                    const uint32_t vaddr = sB + (h >> 1) * EA_SLOT + (h & 1) * 64;       // 32 dims = 64 bytes of every 128-byte key row
+                    for (int ks = 0; ks < ksteps_pv; ++ks)                               // 16 keys = 16 rows of 128 bytes per step
+                        umma_bf16_ts(d, pa + (uint32_t)(8 * ks), make_smem_desc_mn(vaddr + ks * UMMA_K * 128, EA_SLOT), idesc32, ks > 0 ? 1u : 0u);
                     umma_commit(&o_full[g]);
                     if (h + 2 < 8) issue_s(h + 2);                  // in-order execution: P_h has been consumed by then
                 }
@@ -342,21 +348,26 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
             if (lane == 0) mbar_arrive(k_drained);
             EA_TT(4);
 
-            // ---- V: + bias -> bf16 -> bufB, transposed per head: element (d, key r) of head h -> [h][r / 64][d][r % 64]
+            // ---- V: + bias -> bf16 -> bufB in the same [keys][256] image (read by P V as an MN-major operand; LN(x) is dead)
             mbar_wait(v_full, par);
             tc_fence_after();
             EA_TT(5);
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
-                const int h = team * 4 + c;
+                const int col = team * 128 + c * 32;
                 uint32_t acc[32];
-                tmem_ld32(lane_base + TM_KV + (uint32_t)(h * 32), acc);
-                const float* bv = s_bias + 512 + h * 32;
-                uint8_t* vb = bufB + h * 8192 + (r >> 6) * 4096;
-                const int col_b = (r & 63) * 2;
+                tmem_ld32(lane_base + TM_KV + (uint32_t)col, acc);
+                const float* bv = s_bias + 512 + col;
+                uint8_t* rowp = bufB + (col >> 6) * EA_SLOT + r * 128;
 #pragma unroll
-                for (int d = 0; d < 32; ++d)
-                    *reinterpret_cast<__nv_bfloat16*>(vb + ea_swz(d, col_b)) = __float2bfloat16_rn(__uint_as_float(acc[d]) + bv[d]);
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    uint32_t q4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        q4[q] = ea_pack2(__uint_as_float(acc[8 * j8 + 2 * q]) + bv[8 * j8 + 2 * q],
+                                         __uint_as_float(acc[8 * j8 + 2 * q + 1]) + bv[8 * j8 + 2 * q + 1]);
+                    *reinterpret_cast<uint4*>(rowp + ((((c & 1) * 4 + j8) ^ (r & 7)) << 4)) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+                }
             }
             fence_async_smem();
             tc_fence_before();
@@ -374,16 +385,22 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 tc_fence_after();
                 EA_TT(8 + 4 * hh);
                 // p_j = 2^(c (s_j - m)) * valid_j, c = scale * log2 e, m = max over the valid keys (attention_tc.cu)
+                // chunks whose 32 keys are all real (no padding mask, below S) skip the mask vectors
                 float m = -CUDART_INF_F;
 #pragma unroll 1
                 for (int c = 0; c < (row_warp ? nkc : 0); ++c) {
                     uint32_t acc[32];
                     tmem_ld32(sbase + (uint32_t)(c * 32), acc);
+                    if (p.kpm == nullptr && c * 32 + 32 <= S) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 ng = *reinterpret_cast<const float4*>(s_neg + c * 32 + j4 * 4);
-                        m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(acc[4 * j4]) + ng.x, __uint_as_float(acc[4 * j4 + 1]) + ng.y),
-                                           fmaxf(__uint_as_float(acc[4 * j4 + 2]) + ng.z, __uint_as_float(acc[4 * j4 + 3]) + ng.w)));
+                        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1])));
+                    } else {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 ng = *reinterpret_cast<const float4*>(s_neg + c * 32 + j4 * 4);
+                            m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(acc[4 * j4]) + ng.x, __uint_as_float(acc[4 * j4 + 1]) + ng.y),
+                                               fmaxf(__uint_as_float(acc[4 * j4 + 2]) + ng.z, __uint_as_float(acc[4 * j4 + 3]) + ng.w)));
+                        }
                     }
                 }
                 const float mc = m * cs;
@@ -392,20 +409,31 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 for (int c = 0; c < (row_warp ? nkc : 0); ++c) {
                     uint32_t acc[32], pk[16];
                     tmem_ld32(sbase + (uint32_t)(c * 32), acc);
+                    if (p.kpm == nullptr && c * 32 + 32 <= S) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 vm = *reinterpret_cast<const float4*>(s_mask + c * 32 + j4 * 4);
-                        const float vmv[4] = {vm.x, vm.y, vm.z, vm.w};
-                        float pv[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float ex;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(__uint_as_float(acc[4 * j4 + q]), cs, -mc)));
-                            pv[q] = ex * vmv[q];
-                            l += pv[q];
+                        for (int j = 0; j < 16; ++j) {
+                            float e0, e1;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(acc[2 * j]), cs, -mc)));
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(acc[2 * j + 1]), cs, -mc)));
+                            l += e0; l += e1;
+                            pk[j] = ea_pack2(e0, e1);
                         }
-                        pk[2 * j4] = ea_pack2(pv[0], pv[1]);
-                        pk[2 * j4 + 1] = ea_pack2(pv[2], pv[3]);
+                    } else {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 vm = *reinterpret_cast<const float4*>(s_mask + c * 32 + j4 * 4);
+                            const float vmv[4] = {vm.x, vm.y, vm.z, vm.w};
+                            float pv[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float ex;
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(__uint_as_float(acc[4 * j4 + q]), cs, -mc)));
+                                pv[q] = ex * vmv[q];
+                                l += pv[q];
+                            }
+                            pk[2 * j4] = ea_pack2(pv[0], pv[1]);
+                            pk[2 * j4 + 1] = ea_pack2(pv[2], pv[3]);
+                        }
                     }
                     tmem_st16(sbase + (uint32_t)(c * 16), pk);       // lands in columns of S chunks <= c, all consumed already
                 }
@@ -444,7 +472,16 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
             for (int c = 0; c < 4; ++c) {
                 uint32_t acc[32];
                 tmem_ld32(lane_base + TM_Y + (uint32_t)(team * 128 + c * 32), acc);
-                epilogue_slab<float, EA_SLOT>(acc, c, team * 128 + c * 32, nullptr, p.b_out, true, 0, stage, r, r & 7);
+                const float* bo = s_bias + 768 + team * 128 + c * 32;
+                uint8_t* rowp = stage + c * EA_SLOT + r * 128;                        // 32 fp32 columns = one 128-byte row of chunk c
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float4* slot = reinterpret_cast<float4*>(rowp + ((j4 ^ (r & 7)) << 4));
+                    const float4 r4 = *slot;
+                    const float4 b4 = *reinterpret_cast<const float4*>(bo + 4 * j4);
+                    *slot = make_float4(__uint_as_float(acc[4 * j4]) + b4.x + r4.x, __uint_as_float(acc[4 * j4 + 1]) + b4.y + r4.y,
+                                        __uint_as_float(acc[4 * j4 + 2]) + b4.z + r4.z, __uint_as_float(acc[4 * j4 + 3]) + b4.w + r4.w);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -456,7 +493,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 for (int c = 0; c < 4; ++c) tma_store_3d(&map_out, stage + c * EA_SLOT, (4 * team + c) * 32, 0, b);
                 tma_store_commit();
                 tma_store_wait_read0();
-                mbar_arrive(stage_free);
+                mbar_arrive(&stage_free[team]);
                 if (p.dbg != nullptr && blockIdx.x == 0 && it < 2) p.dbg[(it * 3 + 2) * 64 + team * 32 + 27] = clock64();
             }
         }

@@ -35,14 +35,6 @@ struct WgParams {
     int8_t tap_map[9], tap_dh[9], tap_dw[9];
 };
 
-// MN-major, 128-byte swizzle descriptor (cute::UMMA::make_umma_desc<Major::MN>): canonical layout
-// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units - 64 channels contiguous per pixel row (128 B), 8 pixel rows
-// per 1024-byte swizzle atom (SBO = 1024), the next 64-channel box LBO bytes further on.
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-
 template <int BLOCK_N, int STAGES>
 struct SmemWg {
     static constexpr int A_BYTES = 2 * WG_BOX_BYTES;                       // 128 output channels of dY

@@ -127,6 +127,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// MN-major, 128-byte swizzle descriptor (cute::UMMA::make_umma_desc<Major::MN>): canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units - 64 elements of the M / N index contiguous per K row (128 B), 8 K rows per 1024-byte swizzle atom (SBO = 1024),
+// the next 64-element box LBO bytes further on.  Pair with idesc bit 15 (A) / 16 (B).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

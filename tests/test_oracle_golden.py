@@ -299,3 +299,16 @@ def test_mixup_oracle_matches_reference(tag):
             assert np.allclose(got["ratio"], w["ratio"], rtol=1e-6)
         else:
             assert (w["ratio"] < 0).all()
+
+
+def test_numpy_mean_restatement_is_exact():
+    """FreqMask(fill_mode="mean") fills with np.mean of a strided float32 slice; the device kernel reproduces numpy's
+    summation order (oracle/augment_oracle.py: numpy_mean_f32).  This pins that restatement against np.mean itself."""
+    from oracle import augment_oracle as ao
+    rng = np.random.RandomState(3)
+    for _ in range(120):
+        T, n = int(rng.randint(1, 700)), int(rng.randint(1, 26))
+        f0 = int(rng.randint(0, 64 - n))
+        d = (rng.randn(T, 64) * 12 - 40).astype(np.float32)
+        s = d[:, f0:f0 + n]
+        assert ao.numpy_mean_f32(s) == np.mean(s), (T, n, f0)
