@@ -134,6 +134,19 @@ SEDT_API int64_t sedt_train_tape_bytes(sedt_model* m, int B, int T, int F, int h
 SEDT_API int64_t sedt_backward_workspace_bytes(sedt_model* m, int B, int T, int F);
 SEDT_API int64_t sedt_grad_numel(const sedt_model* m);
 SEDT_API int64_t sedt_grad_offset(const sedt_model* m, int slot);
+/* SP-SEDT pretraining step (sedt/spsedt.py:34-91 in train mode; the backbone is frozen, train_spsedt.py:50): the training
+ * branch of SPSEDT.forward -- query positions 2 * query_embed + query_keep * patch2query(avgpool(backbone(patch))) with
+ * query_keep [B, Q] uint8 = (torch.rand(Q, bs, 1) > mask_ratio) drawn by the caller (spsedt.py:65), block-diagonal decoder mask,
+ * dropout -- and its backward: gradients of input_proj, the transformer, the heads (class_embed, bbox_embed, feature_align),
+ * query_embed and patch2query from d(pred_logits), d(pred_boxes), d(pred_feature [D,B,Q,2048]).  P must equal num_patches. */
+SEDT_API int64_t sedt_train_tape_bytes_sp(sedt_model* m, int B, int T, int F, int has_mask, int P, int PT);
+SEDT_API int64_t sedt_backward_workspace_bytes_sp(sedt_model* m, int B, int T, int F, int P, int PT);
+SEDT_API int sedt_forward_train_sp(sedt_model* m, const float* x, const uint8_t* mask, int B, int T, int F, const float* patches, int P,
+                                   int PT, const uint8_t* query_keep, void* tape, int64_t tape_bytes, const sedt_outputs* out,
+                                   float dropout, uint64_t seed, void* stream);
+SEDT_API int sedt_backward_sp(sedt_model* m, const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F, int P,
+                              int PT, void* tape, int64_t tape_bytes, void* workspace, int64_t workspace_bytes, const float* d_logits,
+                              const float* d_boxes, const float* d_pred_feature, float* grads, float dropout, void* stream);
 SEDT_API int sedt_forward_train(sedt_model* m, const float* x, const uint8_t* mask, int B, int T, int F, void* tape,
                                 int64_t tape_bytes, const sedt_outputs* out, float dropout, uint64_t seed, void* stream);
 SEDT_API int sedt_backward(sedt_model* m, const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F,

@@ -294,8 +294,11 @@ def spsedt_attention_mask(num_queries: int, num_patches: int) -> Tensor:
 
 
 @torch.no_grad()
-def spsedt_forward(sd: SD, args, x: Tensor, mask: Tensor, patches: Tensor, taps: Optional[dict] = None) -> dict:
-    """sedt/spsedt.py:34-91, eval branch (:70-75), query_shuffle=False."""
+def spsedt_forward(sd: SD, args, x: Tensor, mask: Tensor, patches: Tensor, taps: Optional[dict] = None,
+                   query_keep: Optional[Tensor] = None) -> dict:
+    """sedt/spsedt.py:34-91, query_shuffle=False: the eval branch (:70-75) or, with query_keep [B, Q] (1 = keep; the
+    reference draws torch.rand(Q, bs, 1) > mask_ratio at :65), the training branch (:63-69):
+    decoder_input = query_embed; decoder_input += patches_feature * mask + decoder_input, i.e. 2 * query_embed + mask * patch."""
     feat = backbone_forward(sd, x, args.dilation, taps)
     m = resize_mask(mask, feat.shape[-2:])
     pos = position_sine(m, args.hidden_dim)
@@ -307,7 +310,12 @@ def spsedt_forward(sd: SD, args, x: Tensor, mask: Tensor, patches: Tensor, taps:
         .repeat(1, 1, qpp, 1).flatten(1, 2).permute(1, 0, 2).contiguous()
     start = 1 if args.dec_at else 0
     nq = P * args.num_queries // args.num_patches
-    dec_in = pq + sd["query_embed.weight"][start:nq, :].unsqueeze(1).repeat(1, bs, 1)
+    if query_keep is not None:
+        assert nq == args.num_queries - start, "the training branch uses num_patches patches"
+        qe = sd["query_embed.weight"][start:, :].unsqueeze(1).repeat(1, bs, 1)
+        dec_in = qe + (pq * query_keep.t().to(pq.dtype).unsqueeze(-1) + qe)
+    else:
+        dec_in = pq + sd["query_embed.weight"][start:nq, :].unsqueeze(1).repeat(1, bs, 1)
     tgt_mask = spsedt_attention_mask(args.num_queries, args.num_patches)[:nq, :nq]
     src = F.conv2d(feat, sd["input_proj.weight"], sd["input_proj.bias"])
     hs, memory = transformer_forward(sd, src, m, dec_in, pos, nheads=args.nheads, enc_layers=args.enc_layers,

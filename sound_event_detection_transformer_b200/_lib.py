@@ -81,6 +81,10 @@ SIGNATURES = {
     "sedt_grad_offset": (_i64, [_vp, _i]),
     "sedt_forward_train": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i64, C.POINTER(SedtOutputs), _f, C.c_uint64, _vp]),
     "sedt_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i, _f, _vp]),
+    "sedt_train_tape_bytes_sp": (_i64, [_vp, _i, _i, _i, _i, _i, _i]),
+    "sedt_backward_workspace_bytes_sp": (_i64, [_vp, _i, _i, _i, _i, _i]),
+    "sedt_forward_train_sp": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i64, C.POINTER(SedtOutputs), _f, C.c_uint64, _vp]),
+    "sedt_backward_sp": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _f, _vp]),
     "sedt_matcher": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sedt_matcher_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sedt_lsap": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -119,16 +119,47 @@ int sedt_forward(sedt_model* m, const float* x, const uint8_t* mask, int B, int 
 }
 
 // ---- training step ---------------------------------------------------------------------------------------
-int64_t sedt_train_tape_bytes(sedt_model* m, int B, int T, int F, int has_mask)
+int64_t sedt_train_tape_bytes(sedt_model* m, int B, int T, int F, int has_mask) { return sedt_train_tape_bytes_sp(m, B, T, F, has_mask, 0, 0); }
+int64_t sedt_backward_workspace_bytes(sedt_model* m, int B, int T, int F) { return sedt_backward_workspace_bytes_sp(m, B, T, F, 0, 0); }
+
+int64_t sedt_train_tape_bytes_sp(sedt_model* m, int B, int T, int F, int has_mask, int P, int PT)
 {
     if (m == nullptr) { set_error("train_tape_bytes: null model"); return SEDT_ERR_INVALID; }
-    return m->impl->tape_bytes(B, T, F, has_mask != 0);
+    return m->impl->tape_bytes(B, T, F, has_mask != 0, P, PT);
 }
 
-int64_t sedt_backward_workspace_bytes(sedt_model* m, int B, int T, int F)
+int64_t sedt_backward_workspace_bytes_sp(sedt_model* m, int B, int T, int F, int P, int PT)
 {
     if (m == nullptr) { set_error("backward_workspace_bytes: null model"); return SEDT_ERR_INVALID; }
-    return m->impl->backward_workspace_bytes(B, T, F);
+    return m->impl->backward_workspace_bytes(B, T, F, P, PT);
+}
+
+int sedt_forward_train_sp(sedt_model* m, const float* x, const uint8_t* mask, int B, int T, int F, const float* patches, int P, int PT,
+                          const uint8_t* query_keep, void* tape, int64_t tape_bytes, const sedt_outputs* out, float dropout,
+                          uint64_t seed, void* stream)
+{
+    SEDT_REQUIRE(m != nullptr && x != nullptr && out != nullptr && tape != nullptr && patches != nullptr && query_keep != nullptr,
+                 "forward_train_sp: null argument");
+    SEDT_REQUIRE(out->hs != nullptr && out->logits != nullptr && out->boxes != nullptr, "forward_train_sp: hs/logits/boxes outputs are required");
+    SEDT_REQUIRE(((uintptr_t)tape & 255) == 0, "forward_train_sp: tape must be 256-byte aligned");
+    ForwardOut o{out->hs, out->logits, out->boxes, nullptr, out->memory, out->pred_feature, out->gt_feature, nullptr};
+    Model::SpTrain sp;
+    sp.patches = patches; sp.P = P; sp.PT = PT; sp.query_keep = query_keep;
+    return m->impl->forward_train(x, mask, B, T, F, tape, (size_t)tape_bytes, o, dropout, (unsigned long long)seed, (cudaStream_t)stream, &sp);
+}
+
+int sedt_backward_sp(sedt_model* m, const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F, int P, int PT,
+                     void* tape, int64_t tape_bytes, void* workspace, int64_t workspace_bytes, const float* d_logits,
+                     const float* d_boxes, const float* d_pred_feature, float* grads, float dropout, void* stream)
+{
+    SEDT_REQUIRE(m != nullptr && weights != nullptr && x != nullptr && tape != nullptr && workspace != nullptr && grads != nullptr,
+                 "backward_sp: null argument");
+    SEDT_REQUIRE(((uintptr_t)tape & 255) == 0 && ((uintptr_t)workspace & 255) == 0 && ((uintptr_t)grads & 255) == 0,
+                 "backward_sp: tape, workspace and grads must be 256-byte aligned");
+    Model::SpTrain sp;
+    sp.P = P; sp.PT = PT; sp.d_pred_feature = d_pred_feature;
+    return m->impl->backward(weights, x, mask, B, T, F, tape, (size_t)tape_bytes, workspace, (size_t)workspace_bytes, d_logits,
+                             d_boxes, nullptr, grads, 0, dropout, (cudaStream_t)stream, &sp);
 }
 
 int64_t sedt_grad_numel(const sedt_model* m) { return m == nullptr ? (int64_t)SEDT_ERR_INVALID : m->impl->grad_numel(); }

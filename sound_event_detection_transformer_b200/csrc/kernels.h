@@ -169,8 +169,14 @@ int launch_heads_finalize(const float* cls_raw, const float* box_raw, const floa
 // [N, HW, C] -> [N, C] mean (SP-SEDT avgpool), fp32 out
 int launch_avgpool(const void* x, int dt, float* out, int N, int HW, int C, cudaStream_t stream);
 // query_pos[b, q, :] = pq[b, q / qpp, :] + query_embed[start + q, :]
+// training branch (spsedt.py:63-67): keep [B, P*qpp] 1 = add the patch feature; qe_scale = 2 (decoder_input += ... + decoder_input)
 int launch_patch_query(const float* pq, const float* query_embed, float* out, int B, int P, int qpp, int start,
-                       cudaStream_t stream);
+                       cudaStream_t stream, const uint8_t* keep = nullptr, float qe_scale = 1.f);
+// acc[i] += g[i] (bf16 -> fp32), and the backward of launch_patch_query's training branch:
+//   d_qe[q, :] += qe_scale * sum_b dq[b, q, :],   d_pq[b, p, :] = sum_{q in patch p} keep[b, q] * dq[b, q, :]
+int launch_accum_bf16(const void* g, float* acc, int64_t n, cudaStream_t stream);
+int launch_patch_query_bwd(const float* dq, const uint8_t* keep, float* d_qe, float* d_pq, int B, int P, int qpp, float qe_scale,
+                           cudaStream_t stream);
 
 // additive block-diagonal 0/-inf decoder mask [Q,Q] (sedt/spsedt.py:27-32)
 int launch_blockdiag_mask(float* m, int Q, int qpp, cudaStream_t stream);

@@ -81,20 +81,27 @@ public:
                 Arena& ws, const ForwardOut& out, cudaStream_t stream, bool dry);
     static void feature_shape(int T, int F, bool dilation, int* H, int* W);
 
-    // ---- training step (train.cu): bf16 tier, pre-norm, supervised model, dropout = 0
-    int64_t tape_bytes(int B, int T, int F, bool has_mask) const;
-    int64_t backward_workspace_bytes(int B, int T, int F) const;
+    // ---- training step (train.cu): bf16 tier, pre-norm; SEDT (backbone trainable from layer2 / conv0) and SP-SEDT pretraining
+    // (frozen backbone, train_spsedt.py:50; patches + query-drop mask through SpTrain)
+    struct SpTrain {                       // SP-SEDT extras of one training step (all null / 0 for SEDT)
+        const float* patches = nullptr;    // [B, P, 1, PT, F]
+        int P = 0, PT = 0;
+        const uint8_t* query_keep = nullptr;     // [B, Q] 1 = the patch feature is added to this query (spsedt.py:65-67)
+        const float* d_pred_feature = nullptr;   // backward: gradient of pred_feature [D, B, Q, 2048] or null
+    };
+    int64_t tape_bytes(int B, int T, int F, bool has_mask, int P = 0, int PT = 0);
+    int64_t backward_workspace_bytes(int B, int T, int F, int P = 0, int PT = 0);
     int64_t grad_offset(int slot) const;       // element offset of a state_dict entry in the flat fp32 gradient buffer
     int64_t grad_numel() const;
     int forward_train(const float* x, const uint8_t* mask, int B, int T, int F, void* tape, size_t tape_bytes,
-                      const ForwardOut& out, float dropout, unsigned long long seed, cudaStream_t stream);
+                      const ForwardOut& out, float dropout, unsigned long long seed, cudaStream_t stream, const SpTrain* sp = nullptr);
     int backward(const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F, void* tape,
                  size_t tape_bytes, void* workspace, size_t ws_bytes, const float* d_logits, const float* d_boxes,
-                 const float* d_at, float* grads, int train_backbone, float dropout, cudaStream_t stream);
+                 const float* d_at, float* grads, int train_backbone, float dropout, cudaStream_t stream, const SpTrain* sp = nullptr);
 
 private:
     struct BlockTape; struct EncTape; struct DecTape; struct Tape; struct BwdBufs;
-    void tape_layout(int B, int T, int F, bool has_mask, Arena& a, Tape& tp) const;
+    void tape_layout(int B, int T, int F, bool has_mask, int P, int PT, Arena& a, Tape& tp);
     void bwd_layout(int B, const Tape& tp, Arena& a, BwdBufs& bb) const;
     int check_train_config() const;
     int add_slot(const std::string& name, int64_t numel);

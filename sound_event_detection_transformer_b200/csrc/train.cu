@@ -43,6 +43,11 @@ struct Model::Tape {
     void* hs_t;                 // [D, B*Qall, d] bf16 decoder states after decoder.norm
     void *hh1; float* hh2;      // box MLP hidden layers (bf16 / fp32)
     float *cls_raw, *box_raw, *weak_raw, *boxes, *at;
+    // SP-SEDT pretraining (frozen backbone: no block tape, the clip / patch backbones run through the eval launch sequence
+    // in `scratch`; only the layer4 feature map `feat` is kept for input_proj's weight gradient)
+    void* scratch; size_t scratch_bytes; const void* feat;
+    float *gt, *pq, *qpos, *amask; uint8_t* keep; void* fh1;
+    int Q;                      // queries per clip of this model (qall_, or num_queries for SP-SEDT)
 };
 
 struct Model::BwdBufs {
@@ -58,31 +63,54 @@ struct Model::BwdBufs {
     void *dck, *dcv;
     // backbone
     void *G0, *G1, *gh2, *gh1, *up;
+    // SP-SEDT: d(pred_feature) as a bf16 GEMM operand, d(feature_align hidden), per-clip d(query_pos), d(patch feature), bf16 copies
+    void *dfeat, *dfh1, *dpq16, *gt16; float *dqpos32, *dpq32;
 };
 
 // Every buffer of the tape, in a fixed order: forward_train and backward derive the same pointers from the
 // same base address.
-void Model::tape_layout(int B, int T, int F, bool has_mask, Arena& a, Tape& tp) const
+void Model::tape_layout(int B, int T, int F, bool has_mask, int P, int PT, Arena& a, Tape& tp)
 {
     const int d = cfg_.hidden_dim, ff = cfg_.dim_feedforward;
     const size_t es = 2;
+    const bool sp = cfg_.self_sup != 0;
     tp.H0 = conv_out_dim(conv_out_dim(T, 7, 2, 3, 1), 3, 2, 1, 1);
     tp.W0 = conv_out_dim(conv_out_dim(F, 7, 2, 3, 1), 3, 2, 1, 1);
     tp.rng = (unsigned long long*)a.alloc(256);
-    tp.stem_out = a.alloc((size_t)B * tp.H0 * tp.W0 * 64 * es);
-    tp.stem_amax = (uint8_t*)a.alloc((size_t)B * tp.H0 * tp.W0 * 64);
-    int h = tp.H0, w = tp.W0;
     tp.blk.clear();
-    for (const Block& b : blocks_) {
-        BlockTape bt{};
-        bt.H = h; bt.W = w;
-        bt.Ho = conv_out_dim(h, 3, b.c2.stride, b.c2.pad, b.c2.dil); bt.Wo = conv_out_dim(w, 3, b.c2.stride, b.c2.pad, b.c2.dil);
-        bt.h1 = a.alloc((size_t)B * h * w * b.c1.cout * es);
-        bt.h2 = a.alloc((size_t)B * bt.Ho * bt.Wo * b.c2.cout * es);
-        bt.ds = b.has_ds ? a.alloc((size_t)B * bt.Ho * bt.Wo * b.ds.cout * es) : nullptr;
-        bt.out = a.alloc((size_t)B * bt.Ho * bt.Wo * b.c3.cout * es);
-        tp.blk.push_back(bt);
-        h = bt.Ho; w = bt.Wo;
+    tp.scratch = nullptr; tp.scratch_bytes = 0; tp.feat = nullptr;
+    tp.gt = tp.pq = tp.qpos = tp.amask = nullptr; tp.keep = nullptr; tp.fh1 = nullptr;
+    tp.Q = sp ? cfg_.num_queries : qall_;
+    int h = tp.H0, w = tp.W0;
+    if (!sp) {
+        tp.stem_out = a.alloc((size_t)B * tp.H0 * tp.W0 * 64 * es);
+        tp.stem_amax = (uint8_t*)a.alloc((size_t)B * tp.H0 * tp.W0 * 64);
+        for (const Block& b : blocks_) {
+            BlockTape bt{};
+            bt.H = h; bt.W = w;
+            bt.Ho = conv_out_dim(h, 3, b.c2.stride, b.c2.pad, b.c2.dil); bt.Wo = conv_out_dim(w, 3, b.c2.stride, b.c2.pad, b.c2.dil);
+            bt.h1 = a.alloc((size_t)B * h * w * b.c1.cout * es);
+            bt.h2 = a.alloc((size_t)B * bt.Ho * bt.Wo * b.c2.cout * es);
+            bt.ds = b.has_ds ? a.alloc((size_t)B * bt.Ho * bt.Wo * b.ds.cout * es) : nullptr;
+            bt.out = a.alloc((size_t)B * bt.Ho * bt.Wo * b.c3.cout * es);
+            tp.blk.push_back(bt);
+            h = bt.Ho; w = bt.Wo;
+        }
+    } else {
+        tp.stem_out = nullptr; tp.stem_amax = nullptr;
+        feature_shape(T, F, cfg_.dilation != 0, &h, &w);
+        // scratch = the larger of the two eval backbones' workspaces; the clip backbone runs last, so its layer4 output stays valid
+        Arena dry1(nullptr, 0), dry2(nullptr, 0);
+        void* f = nullptr; int fh = 0, fw = 0;
+        (void)backbone(nullptr, B * P, PT, F, dry1, &f, &fh, &fw, nullptr, true);
+        (void)backbone(nullptr, B, T, F, dry2, &f, &fh, &fw, nullptr, true);
+        tp.scratch_bytes = std::max(dry1.peak, dry2.peak) + 256;
+        tp.scratch = a.alloc(tp.scratch_bytes);
+        tp.gt = (float*)a.alloc((size_t)B * P * 2048 * 4);
+        tp.pq = (float*)a.alloc((size_t)B * P * d * 4);
+        tp.qpos = (float*)a.alloc((size_t)B * tp.Q * d * 4);
+        tp.keep = (uint8_t*)a.alloc((size_t)B * tp.Q);
+        tp.amask = (float*)a.alloc((size_t)tp.Q * tp.Q * 4);
     }
     tp.H = h; tp.W = w; tp.S = h * w;
     const int64_t rows = (int64_t)B * tp.S;
@@ -106,7 +134,7 @@ void Model::tape_layout(int B, int T, int F, bool has_mask, Arena& a, Tape& tp) 
     const size_t Dn = dec_.size();
     tp.mem = a.alloc((size_t)rows * d * es); tp.mempos = a.alloc((size_t)rows * d * es);
     tp.ck = a.alloc((size_t)rows * Dn * d * es); tp.cv = a.alloc((size_t)rows * Dn * d * es);
-    const int64_t qrows = (int64_t)B * qall_;
+    const int64_t qrows = (int64_t)B * tp.Q;
     tp.dec.clear();
     float* t = (float*)a.alloc((size_t)qrows * d * 4);          // tgt = 0
     for (size_t l = 0; l < Dn; ++l) {
@@ -123,7 +151,7 @@ void Model::tape_layout(int B, int T, int F, bool has_mask, Arena& a, Tape& tp) 
         t = e.t_out;
     }
     const int64_t hrows = (int64_t)Dn * qrows;
-    const int ncls = cfg_.num_classes, C1 = ncls + 1;
+    const int ncls = sp ? 1 : cfg_.num_classes, C1 = ncls + 1;
     tp.hs_t = a.alloc((size_t)hrows * d * es);
     tp.hh1 = a.alloc((size_t)hrows * d * es);
     tp.hh2 = (float*)a.alloc((size_t)hrows * d * 4);
@@ -133,23 +161,24 @@ void Model::tape_layout(int B, int T, int F, bool has_mask, Arena& a, Tape& tp) 
     tp.tmp32 = (float*)a.alloc((size_t)std::max(rows, qrows) * d * 4);
     tp.boxes = (float*)a.alloc((size_t)Dn * B * cfg_.num_queries * 2 * 4);
     tp.at = cfg_.dec_at ? (float*)a.alloc((size_t)B * ncls * 4) : nullptr;
+    if (sp && cfg_.feature_recon) tp.fh1 = a.alloc((size_t)hrows * d * es);
 }
 
 int Model::check_train_config() const
 {
     SEDT_REQUIRE(cfg_.precision == 1 && cfg_.use_tensor_cores, "training kernels exist for the bf16 tcgen05 tier only");
     SEDT_REQUIRE(cfg_.pre_norm, "training kernels implement the pre-norm layers only (transformer.py:192-204, :263-284)");
-    SEDT_REQUIRE(!cfg_.self_sup, "training kernels implement the supervised SEDT model only");
+    SEDT_REQUIRE(!(cfg_.self_sup && cfg_.dec_at), "SP-SEDT has no audio query (sedt/spsedt.py:59,72)");
     SEDT_REQUIRE(cfg_.hidden_dim == 256 && cfg_.nheads == 8, "kernels are built for hidden_dim 256 / 8 heads");
     SEDT_REQUIRE(cfg_.num_classes + 1 <= 128, "head gradients are padded to 128 columns: num_classes <= 127");
     return SEDT_OK;
 }
 
-int64_t Model::tape_bytes(int B, int T, int F, bool has_mask) const
+int64_t Model::tape_bytes(int B, int T, int F, bool has_mask, int P, int PT)
 {
     Arena a(nullptr, 0);
     Tape tp;
-    tape_layout(B, T, F, has_mask, a, tp);
+    tape_layout(B, T, F, has_mask, P, PT, a, tp);
     return (int64_t)a.peak + 256;
 }
 
@@ -160,15 +189,22 @@ static inline uint32_t enc_site(int l, int k) { return (uint32_t)(8 * l + k); }
 static inline uint32_t dec_site(int l, int k) { return (uint32_t)(1024 + 8 * l + k); }
 
 int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int F, void* tape, size_t tape_bytes_,
-                         const ForwardOut& out, float dropout, unsigned long long seed, cudaStream_t s)
+                         const ForwardOut& out, float dropout, unsigned long long seed, cudaStream_t s, const SpTrain* sp)
 {
+    const bool spm = cfg_.self_sup != 0;
+    const SpTrain none;
+    if (sp == nullptr) sp = &none;
+    SEDT_REQUIRE(!spm || (sp->patches != nullptr && sp->query_keep != nullptr), "forward_train: SP-SEDT needs patches and the query-drop mask");
+    SEDT_REQUIRE(!spm || sp->P == cfg_.num_patches, "forward_train: the training branch uses exactly num_patches = %d patches per clip (sedt/spsedt.py:63-69), got %d",
+                 cfg_.num_patches, sp->P);
+    SEDT_REQUIRE(!spm || !cfg_.feature_recon || (out.pred_feature != nullptr && out.gt_feature != nullptr), "forward_train: pred_feature / gt_feature outputs are required");
     SEDT_REQUIRE(dropout >= 0.f && dropout < 1.f, "forward_train: dropout=%f", dropout);
     SEDT_TRY(check_train_config());
     SEDT_REQUIRE(packed_ != nullptr, "forward_train: sedt_model_pack has not been called");
     SEDT_REQUIRE(F == 64, "stem: the fused stem kernel needs 64 mel bins, got F=%d", F);
     Arena a(tape, tape_bytes_);
     Tape tp;
-    tape_layout(B, T, F, mask != nullptr, a, tp);
+    tape_layout(B, T, F, mask != nullptr, sp->P, sp->PT, a, tp);
     if (a.overflow) { set_error("forward_train: tape too small (%zu bytes needed, %zu given)", a.peak, a.cap); return SEDT_ERR_WORKSPACE; }
     const int d = cfg_.hidden_dim, ff = cfg_.dim_feedforward, dt = DT_BF16;
     const size_t es = 2;
@@ -201,27 +237,52 @@ int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int 
         return launch_dropout_add(tp.tmp32, resid, y, R * L.out, site(id), s);
     };
     auto attention = [&](const void* Qp, int ldq, const void* Kp, int ldk, const void* Vp, int ldv, void* Op, const uint8_t* kpm,
-                         int Lq, int Lk, uint32_t id) -> int {
-        if (!drop) return launch_attention(Qp, ldq, Kp, ldk, Vp, ldv, Op, d, dt, kpm, nullptr, B, cfg_.nheads, Lq, Lk, scale, s);
-        return launch_attention_tc_drop(Qp, ldq, Kp, ldk, Vp, ldv, Op, d, kpm, nullptr, B, cfg_.nheads, Lq, Lk, scale, site(id), s);
+                         int Lq, int Lk, uint32_t id, const float* am = nullptr) -> int {
+        if (!drop) return launch_attention(Qp, ldq, Kp, ldk, Vp, ldv, Op, d, dt, kpm, am, B, cfg_.nheads, Lq, Lk, scale, s);
+        return launch_attention_tc_drop(Qp, ldq, Kp, ldk, Vp, ldv, Op, d, kpm, am, B, cfg_.nheads, Lq, Lk, scale, site(id), s);
     };
 
     // ---- backbone
-    SEDT_TRY(launch_stem_tc(x, packed_ + off_stem_wtc, P_(off_stem_bias), P_(off_stem_scale), P_(off_sat), tp.stem_out, B, T, F, s,
-                            tp.stem_amax));
-    const void* cur = tp.stem_out;
-    for (size_t i = 0; i < blocks_.size(); ++i) {
-        const Block& b = blocks_[i];
-        const BlockTape& bt = tp.blk[i];
-        int ho, wo;
-        SEDT_TRY(conv(b.c1, cur, B, bt.H, bt.W, nullptr, bt.h1, &ho, &wo, s, false));
-        SEDT_TRY(conv(b.c2, bt.h1, B, bt.H, bt.W, nullptr, bt.h2, &ho, &wo, s, false));
-        const void* idn = cur;
-        if (b.has_ds) { SEDT_TRY(conv(b.ds, cur, B, bt.H, bt.W, nullptr, bt.ds, &ho, &wo, s, false)); idn = bt.ds; }
-        SEDT_TRY(conv(b.c3, bt.h2, B, bt.Ho, bt.Wo, idn, bt.out, &ho, &wo, s, false));
-        cur = bt.out;
+    const void* feat = nullptr;
+    if (!spm) {
+        SEDT_TRY(launch_stem_tc(x, packed_ + off_stem_wtc, P_(off_stem_bias), P_(off_stem_scale), P_(off_sat), tp.stem_out, B, T, F, s,
+                                tp.stem_amax));
+        const void* cur = tp.stem_out;
+        for (size_t i = 0; i < blocks_.size(); ++i) {
+            const Block& b = blocks_[i];
+            const BlockTape& bt = tp.blk[i];
+            int ho, wo;
+            SEDT_TRY(conv(b.c1, cur, B, bt.H, bt.W, nullptr, bt.h1, &ho, &wo, s, false));
+            SEDT_TRY(conv(b.c2, bt.h1, B, bt.H, bt.W, nullptr, bt.h2, &ho, &wo, s, false));
+            const void* idn = cur;
+            if (b.has_ds) { SEDT_TRY(conv(b.ds, cur, B, bt.H, bt.W, nullptr, bt.ds, &ho, &wo, s, false)); idn = bt.ds; }
+            SEDT_TRY(conv(b.c3, bt.h2, B, bt.Ho, bt.Wo, idn, bt.out, &ho, &wo, s, false));
+            cur = bt.out;
+        }
+        feat = cur;
+    } else {
+        // frozen backbone (train_spsedt.py:50): patches first (avgpool -> gt_feature -> patch2query), then the clips, whose
+        // layer4 output stays in the scratch arena until backward (spsedt.py:40-57)
+        const int qpp = cfg_.num_queries / cfg_.num_patches;
+        {
+            Arena ws(tp.scratch, tp.scratch_bytes);
+            void* pfeat = nullptr; int ph = 0, pw = 0;
+            SEDT_TRY(backbone(sp->patches, B * sp->P, sp->PT, F, ws, &pfeat, &ph, &pw, s, false));
+            SEDT_REQUIRE(!ws.overflow, "forward_train: patch backbone scratch too small");
+            SEDT_TRY(launch_avgpool(pfeat, dt, tp.gt, B * sp->P, ph * pw, 2048, s));
+            SEDT_TRY(linear(patch2query_, 0, d, tp.gt, DT_F32, 2048, (int64_t)B * sp->P, nullptr, tp.pq, DT_F32, d, 0, s, false));
+        }
+        SEDT_CHECK_CUDA(cudaMemcpyAsync(tp.keep, sp->query_keep, (size_t)B * tp.Q, cudaMemcpyDeviceToDevice, s));
+        SEDT_TRY(launch_patch_query(tp.pq, P_(off_query_embed), tp.qpos, B, sp->P, qpp, 0, s, tp.keep, 2.f));
+        SEDT_TRY(launch_blockdiag_mask(tp.amask, tp.Q, qpp, s));
+        if (out.gt_feature != nullptr)
+            SEDT_CHECK_CUDA(cudaMemcpyAsync(out.gt_feature, tp.gt, (size_t)B * sp->P * 2048 * 4, cudaMemcpyDeviceToDevice, s));
+        Arena ws(tp.scratch, tp.scratch_bytes);
+        void* cfeat = nullptr; int ch = 0, cw = 0;
+        SEDT_TRY(backbone(x, B, T, F, ws, &cfeat, &ch, &cw, s, false));
+        SEDT_REQUIRE(!ws.overflow && ch == tp.H && cw == tp.W, "forward_train: clip backbone scratch / shape mismatch");
+        feat = cfeat;
     }
-    const void* feat = cur;
     const int S = tp.S;
     const int64_t rows = (int64_t)B * S;
 
@@ -264,19 +325,21 @@ int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int 
     }
 
     // ---- decoder
-    const int Qall = qall_;
+    const int Qall = tp.Q;
     const int64_t qrows = (int64_t)B * Qall;
-    const float* qpos = P_(off_query_embed);
+    const float* qpos = spm ? tp.qpos : P_(off_query_embed);
+    const int64_t qpos_rows = spm ? qrows : Qall;
+    const float* amask = spm ? tp.amask : nullptr;                       // block-diagonal decoder mask (spsedt.py:27-32)
     SEDT_TRY(launch_fill_zero(tp.dec[0].t_in, (size_t)qrows * d * 4, s));
     for (int l = 0; l < Dn; ++l) {
         const DecLayer& e = dec_[l];
         const DecTape& t = tp.dec[l];
-        SEDT_TRY(LN(e.n1, t.t_in, qpos, Qall, t.da, t.dap, nullptr, qrows));
+        SEDT_TRY(LN(e.n1, t.t_in, qpos, qpos_rows, t.da, t.dap, nullptr, qrows));
         SEDT_TRY(linear(e.self_attn.in_proj, 2 * d, d, t.da, dt, d, qrows, nullptr, t.v, dt, d, 0, s, false));
         SEDT_TRY(linear(e.self_attn.in_proj, 0, 2 * d, t.dap, dt, d, qrows, nullptr, t.qk, dt, 2 * d, 0, s, false));
-        SEDT_TRY(attention(t.qk, 2 * d, (const char*)t.qk + d * es, 2 * d, t.v, d, t.ao1, nullptr, Qall, Qall, dec_site(l, 0)));
+        SEDT_TRY(attention(t.qk, 2 * d, (const char*)t.qk + d * es, 2 * d, t.v, d, t.ao1, nullptr, Qall, Qall, dec_site(l, 0), amask));
         SEDT_TRY(linear_drop_add(e.self_attn.out_proj, t.ao1, d, qrows, t.t_in, t.t_mid1, dec_site(l, 1)));
-        SEDT_TRY(LN(e.n2, t.t_mid1, qpos, Qall, nullptr, t.dap2, nullptr, qrows));
+        SEDT_TRY(LN(e.n2, t.t_mid1, qpos, qpos_rows, nullptr, t.dap2, nullptr, qrows));
         SEDT_TRY(linear(e.cross_attn.in_proj, 0, d, t.dap2, dt, d, qrows, nullptr, t.qb, dt, d, 0, s, false));
         SEDT_TRY(attention(t.qb, d, (const char*)tp.ck + (size_t)l * d * es, Dn * d, (const char*)tp.cv + (size_t)l * d * es, Dn * d,
                            t.ao2, tp.mask_ds, Qall, S, dec_site(l, 2)));
@@ -291,12 +354,16 @@ int Model::forward_train(const float* x, const uint8_t* mask, int B, int T, int 
 
     // ---- heads
     const int64_t hrows = (int64_t)Dn * qrows;
-    const int ncls = cfg_.num_classes, C1 = ncls + 1, start = cfg_.dec_at ? 1 : 0;
+    const int ncls = spm ? 1 : cfg_.num_classes, C1 = ncls + 1, start = cfg_.dec_at ? 1 : 0;
     SEDT_TRY(linear(bbox0_, 0, d, tp.hs_t, dt, d, hrows, nullptr, tp.hh1, dt, d, 1, s, false));
     SEDT_TRY(linear(bbox1_, 0, d, tp.hh1, dt, d, hrows, nullptr, tp.hh2, DT_F32, d, 1, s, false));
     SEDT_TRY(launch_heads_out(out.hs, tp.hh2, P_(class_embed_.off_w), P_(class_embed_.off_b), P_(bbox2_.off_w), P_(bbox2_.off_b),
                               cfg_.dec_at ? P_(weak_.off_w) : nullptr, cfg_.dec_at ? P_(weak_.off_b) : nullptr, out.logits, out.boxes,
                               cfg_.dec_at ? out.at : nullptr, Dn, B, Qall, start, C1, ncls, s));
+    if (spm && cfg_.feature_recon) {                                     // feature_align MLP (spsedt.py:80)
+        SEDT_TRY(linear(falign0_, 0, d, tp.hs_t, dt, d, hrows, nullptr, tp.fh1, dt, d, 1, s, false));
+        SEDT_TRY(linear(falign1_, 0, 2048, tp.fh1, dt, d, hrows, nullptr, out.pred_feature, DT_F32, 2048, 0, s, false));
+    }
     // sigmoid outputs for the backward pass (the caller's tensors may be modified by then)
     SEDT_CHECK_CUDA(cudaMemcpyAsync(tp.boxes, out.boxes, (size_t)Dn * B * cfg_.num_queries * 2 * 4, cudaMemcpyDeviceToDevice, s));
     if (cfg_.dec_at) SEDT_CHECK_CUDA(cudaMemcpyAsync(tp.at, out.at, (size_t)B * ncls * 4, cudaMemcpyDeviceToDevice, s));
@@ -312,13 +379,13 @@ int64_t Model::grad_offset(int slot) const
 }
 int64_t Model::grad_numel() const { return grad_offset((int)slots_.size()); }
 
-int64_t Model::backward_workspace_bytes(int B, int T, int F) const
+int64_t Model::backward_workspace_bytes(int B, int T, int F, int P, int PT)
 {
     Arena a(nullptr, 0);
     BwdBufs bb;
     Arena ta(nullptr, 0);
     Tape tp;
-    tape_layout(B, T, F, false, ta, tp);
+    tape_layout(B, T, F, false, P, PT, ta, tp);
     bwd_layout(B, tp, a, bb);
     return (int64_t)a.peak + 256;
 }
@@ -330,7 +397,7 @@ void Model::bwd_layout(int B, const Tape& tp, Arena& a, BwdBufs& bb) const
     const size_t es = 2;
     size_t wmax = (size_t)std::max(ff * d, (int)dec_.size() * d * d), dwmax = (size_t)128 * d;
     size_t g_max = 0, h2_max = 0, h1_max = 0, up_max = 0;
-    for (size_t i = 0; i < blocks_.size(); ++i) {
+    for (size_t i = 0; i < tp.blk.size(); ++i) {              // (empty for SP-SEDT: frozen backbone, no block tape)
         const Block& b = blocks_[i];
         const BlockTape& bt = tp.blk[i];
         for (const ConvLayer* L : {&b.c1, &b.c2, &b.c3, b.has_ds ? &b.ds : nullptr}) {
@@ -356,7 +423,7 @@ void Model::bwd_layout(int B, const Tape& tp, Arena& a, BwdBufs& bb) const
     bb.wd_all = (char*)a.alloc(bb.wd_all_bytes);
     bb.dw = (float*)a.alloc(dwmax * 4);
     bb.vscale = (float*)a.alloc((size_t)ff * 4);
-    const int64_t rows = (int64_t)B * tp.S, qrows = (int64_t)B * qall_, hrows = (int64_t)dec_.size() * qrows;
+    const int64_t rows = (int64_t)B * tp.S, qrows = (int64_t)B * tp.Q, hrows = (int64_t)dec_.size() * qrows;
     bb.dcls = a.alloc((size_t)hrows * 128 * es); bb.dbox = a.alloc((size_t)hrows * 128 * es);
     bb.dweak = a.alloc((size_t)std::max(B, 1) * 128 * es);
     bb.dh2 = a.alloc((size_t)hrows * d * es); bb.dh1 = a.alloc((size_t)hrows * d * es); bb.hh2b = a.alloc((size_t)hrows * d * es);
@@ -367,21 +434,34 @@ void Model::bwd_layout(int B, const Tape& tp, Arena& a, BwdBufs& bb) const
     bb.dn_a = a.alloc(r * d * es); bb.dn_b = a.alloc(r * d * es); bb.dao = a.alloc(r * d * es);
     bb.dqk = a.alloc(r * 2 * d * es); bb.dv = a.alloc(r * d * es); bb.dq = a.alloc(r * d * es);
     bb.dck = a.alloc((size_t)rows * dec_.size() * d * es); bb.dcv = a.alloc((size_t)rows * dec_.size() * d * es);
-    bb.G0 = a.alloc(std::max(g_max, (size_t)rows * 2048) * es); bb.G1 = a.alloc(g_max * es);
-    bb.gh2 = a.alloc(h2_max * es); bb.gh1 = a.alloc(h1_max * es); bb.up = a.alloc(std::max<size_t>(up_max, 8) * es);
+    bb.G0 = a.alloc(std::max(g_max, (size_t)rows * 2048) * es); bb.G1 = a.alloc(std::max<size_t>(g_max, 8) * es);
+    bb.gh2 = a.alloc(std::max<size_t>(h2_max, 8) * es); bb.gh1 = a.alloc(std::max<size_t>(h1_max, 8) * es);
+    bb.up = a.alloc(std::max<size_t>(up_max, 8) * es);
+    bb.dfeat = bb.dfh1 = bb.dpq16 = bb.gt16 = nullptr; bb.dqpos32 = bb.dpq32 = nullptr;
+    if (cfg_.self_sup) {
+        const size_t np = (size_t)B * cfg_.num_patches;
+        bb.dfeat = a.alloc((size_t)hrows * 2048 * es); bb.dfh1 = a.alloc((size_t)hrows * d * es);
+        bb.dqpos32 = (float*)a.alloc((size_t)qrows * d * 4); bb.dpq32 = (float*)a.alloc(np * d * 4);
+        bb.dpq16 = a.alloc(np * d * es); bb.gt16 = a.alloc(np * 2048 * es);
+    }
 }
 
 int Model::backward(const void* const* weights, const float* x, const uint8_t* mask, int B, int T, int F, void* tape, size_t tape_bytes_,
                     void* workspace, size_t ws_bytes, const float* d_logits, const float* d_boxes, const float* d_at,
-                    float* grads, int train_backbone, float dropout, cudaStream_t s)
+                    float* grads, int train_backbone, float dropout, cudaStream_t s, const SpTrain* sp)
 {
+    const bool spm = cfg_.self_sup != 0;
+    const SpTrain none;
+    if (sp == nullptr) sp = &none;
+    SEDT_REQUIRE(!spm || !train_backbone, "backward: SP-SEDT pretraining keeps the backbone frozen (train_spsedt.py:50)");
+    SEDT_REQUIRE(!spm || sp->P == cfg_.num_patches, "backward: SP-SEDT needs the patch configuration of the forward");
     SEDT_TRY(check_train_config());
     SEDT_REQUIRE(dropout >= 0.f && dropout < 1.f, "backward: dropout=%f", dropout);
     SEDT_REQUIRE(packed_ != nullptr, "backward: sedt_model_pack has not been called");
     SEDT_TRY(tc_init());
     Arena ta(tape, tape_bytes_);
     Tape tp;
-    tape_layout(B, T, F, mask != nullptr, ta, tp);
+    tape_layout(B, T, F, mask != nullptr, sp->P, sp->PT, ta, tp);
     if (ta.overflow) { set_error("backward: tape too small (%zu bytes needed, %zu given)", ta.peak, ta.cap); return SEDT_ERR_WORKSPACE; }
     Arena wa(workspace, ws_bytes);
     BwdBufs bb;
@@ -390,7 +470,7 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
 
     const int d = cfg_.hidden_dim, ff = cfg_.dim_feedforward, dt = DT_BF16;
     const size_t es = 2;
-    const int S = tp.S, Qall = qall_, Dn = (int)dec_.size();
+    const int S = tp.S, Qall = tp.Q, Dn = (int)dec_.size();
     const int64_t rows = (int64_t)B * S, qrows = (int64_t)B * Qall, hrows = (int64_t)Dn * qrows;
     const float scale = (float)std::sqrt(1.0 / (double)(d / cfg_.nheads));
     auto Wp = [&](int slot) { return (const float*)weights[slot]; };
@@ -476,7 +556,7 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     };
 
     // ================= heads (sedt/sedt.py:89-95) =====================================================
-    const int ncls = cfg_.num_classes, C1 = ncls + 1, start = cfg_.dec_at ? 1 : 0;
+    const int ncls = spm ? 1 : cfg_.num_classes, C1 = ncls + 1, start = cfg_.dec_at ? 1 : 0;
     SEDT_TRY(launch_heads_bwd_prepare(d_logits, d_boxes, d_at, tp.boxes, tp.at, bb.dcls, bb.dbox, cfg_.dec_at ? bb.dweak : nullptr, Dn,
                                       B, Qall, start, C1, ncls, s));
     auto padded_param_grads = [&](const Linear& L, const void* x, int lda, const void* dy_pad, int64_t M) -> int {
@@ -503,6 +583,14 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
         SEDT_TRY(dgrad_lin(Wp(weak_.w_slot), ncls, 128, d, bb.dweak, 128, B, dst, Qall * d, 0, dst, DT_F32, Qall * d));
     }
 
+    if (spm && cfg_.feature_recon && sp->d_pred_feature != nullptr) {        // feature_align: pred_feature = W1 relu(W0 hs + b0) + b1
+        SEDT_TRY(to16(sp->d_pred_feature, bb.dfeat, hrows * 2048));
+        SEDT_TRY(lin_param_grads(falign1_, 0, 2048, tp.fh1, d, bb.dfeat, 2048, hrows));
+        SEDT_TRY(dgrad_lin(Wp(falign1_.w_slot), 2048, 2048, d, bb.dfeat, 2048, hrows, tp.fh1, d, 2, bb.dfh1, dt, d));
+        SEDT_TRY(lin_param_grads(falign0_, 0, d, tp.hs_t, d, bb.dfh1, d, hrows));
+        SEDT_TRY(dgrad_lin(Wp(falign0_.w_slot), d, d, d, bb.dfh1, d, hrows, bb.dhs32, d, 0, bb.dhs32, DT_F32, d));
+    }
+
     // attention core backward: tcgen05 kernel (SEDT_ATT_BWD_SIMT=1 selects the CUDA-core one)
     static const bool att_simt = [] { const char* e = getenv("SEDT_ATT_BWD_SIMT"); return e != nullptr && e[0] == '1'; }();
     auto attn_bwd = [&](const void* Qp, int ldq, const void* Kp, int ldk, const void* Vp, int ldv, const void* dOp, int ldo, void* dQp,
@@ -519,19 +607,26 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     // ================= decoder (transformer.py:263-284), last layer first ===============================
     // self-attention + its LayerNorm, shared by encoder and decoder layers.
     //   in : gx = d(loss)/d(x_mid) fp32 (x_mid = x_in + out_proj(attn))      out: gout = d(loss)/d(x_in) fp32
+    // query-position gradient: summed over the batch into query_embed's slot (SEDT), kept per clip for SP-SEDT (the positions
+    // are batch dependent there: 2 * query_embed + keep * patch2query(patch feature))
+    if (spm) SEDT_TRY(launch_fill_zero(bb.dqpos32, (size_t)qrows * d * 4, s));
+    auto add_dqpos = [&](const void* g16, float* dqpos_acc, int L) -> int {
+        if (spm) return launch_accum_bf16(g16, bb.dqpos32, (int64_t)B * L * d, s);
+        return launch_colsum(g16, dt, (int64_t)L * d, dqpos_acc, B, L * d, s);
+    };
     auto self_attn_bwd = [&](const Mha& A, const Norm& n1, const float* x_in, const void* na, const void* nap, const void* qk,
                              const void* v, const void* ao, const uint8_t* kpm, int L, int64_t R, const float* gx, float* gout,
-                             float* dqpos_acc, uint32_t site_p, uint32_t site_o) -> int {
+                             float* dqpos_acc, uint32_t site_p, uint32_t site_o, const float* am = nullptr) -> int {
         SEDT_TRY(to16_drop(gx, bb.g16, R * d, site_o));
         SEDT_TRY(lin_param_grads(A.out_proj, 0, d, ao, d, bb.g16, d, R));
         SEDT_TRY(dgrad_lin(Wp(A.out_proj.w_slot), d, d, d, bb.g16, d, R, nullptr, 0, 0, bb.dao, dt, d));
         SEDT_TRY(attn_bwd(qk, 2 * d, (const char*)qk + d * es, 2 * d, v, d, bb.dao, d, bb.dqk, 2 * d,
-                          (char*)bb.dqk + d * es, 2 * d, bb.dv, d, kpm, nullptr, B, cfg_.nheads, L, L, scale, site_p, s));
+                          (char*)bb.dqk + d * es, 2 * d, bb.dv, d, kpm, am, B, cfg_.nheads, L, L, scale, site_p, s));
         SEDT_TRY(lin_param_grads(A.in_proj, 0, 2 * d, nap, d, bb.dqk, 2 * d, R));
         SEDT_TRY(lin_param_grads(A.in_proj, 2 * d, d, na, d, bb.dv, d, R));
         SEDT_TRY(dgrad_lin(Wp(A.in_proj.w_slot), 2 * d, 2 * d, d, bb.dqk, 2 * d, R, nullptr, 0, 0, bb.dn_b, dt, d));     // d(LN + pos)
         SEDT_TRY(dgrad_lin(Wp(A.in_proj.w_slot) + (size_t)2 * d * d, d, d, d, bb.dv, d, R, nullptr, 0, 0, bb.dn_a, dt, d));   // d(LN)
-        if (dqpos_acc != nullptr) SEDT_TRY(launch_colsum(bb.dn_b, dt, (int64_t)L * d, dqpos_acc, B, L * d, s));
+        if (dqpos_acc != nullptr) SEDT_TRY(add_dqpos(bb.dn_b, dqpos_acc, L));
         return launch_layernorm_bwd(x_in, P_(n1.off_g), bb.dn_a, bb.dn_b, nullptr, gx, gout, Gp(n1.w_slot), Gp(n1.b_slot), R, s);
     };
     // FFN + its LayerNorm:  in: gy = d/d(x_out) fp32, x_out = x_mid + lin2(relu(lin1(LN(x_mid))))   out: gout = d/d(x_mid)
@@ -569,7 +664,7 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
                                       dec_site(l, 2), s));
         SEDT_TRY(lin_param_grads(e.cross_attn.in_proj, 0, d, t.dap2, d, bb.dq, d, qrows));
         SEDT_TRY(dgrad_lin(Wp(e.cross_attn.in_proj.w_slot), d, d, d, bb.dq, d, qrows, nullptr, 0, 0, bb.dn_b, dt, d));
-        SEDT_TRY(launch_colsum(bb.dn_b, dt, (int64_t)Qall * d, dqpos, B, Qall * d, s));
+        SEDT_TRY(add_dqpos(bb.dn_b, dqpos, Qall));
         SEDT_TRY(launch_layernorm_bwd(t.t_mid1, P_(e.n2.off_g), nullptr, bb.dn_b, nullptr, gcur, gnext, Gp(e.n2.w_slot), Gp(e.n2.b_slot),
                                       qrows, s));
         std::swap(gcur, gnext);
@@ -578,8 +673,19 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
         SEDT_TRY(lin_param_grads(e.cross_attn.in_proj, 2 * d, d, tp.mem, d, (const char*)bb.dcv + (size_t)l * d * es, Dn * d, rows));
         // self attention
         SEDT_TRY(self_attn_bwd(e.self_attn, e.n1, t.t_in, t.da, t.dap, t.qk, t.v, t.ao1, nullptr, Qall, qrows, gcur, gnext, dqpos,
-                               dec_site(l, 0), dec_site(l, 1)));
+                               dec_site(l, 0), dec_site(l, 1), spm ? tp.amask : nullptr));
         std::swap(gcur, gnext);
+    }
+    if (spm) {
+        // query positions = 2 * query_embed + keep * patch2query(gt_feature) (spsedt.py:63-67): query_embed gets twice the batch sum,
+        // patch2query the kept queries' gradient summed per patch; gt_feature itself only leads into the frozen backbone
+        const int qpp = cfg_.num_queries / cfg_.num_patches;
+        const int64_t np = (int64_t)B * sp->P;
+        SEDT_TRY(launch_patch_query_bwd(bb.dqpos32, tp.keep, dqpos, bb.dpq32, B, sp->P, qpp, 2.f, s));
+        SEDT_TRY(to16(bb.dpq32, bb.dpq16, np * d));
+        SEDT_TRY(to16(tp.gt, bb.gt16, np * 2048));
+        SEDT_TRY(wgrad_lin(bb.gt16, 2048, 2048, bb.dpq16, d, d, np, Gp(patch2query_.w_slot)));
+        SEDT_TRY(launch_colsum(bb.dpq32, DT_F32, d, Gp(patch2query_.b_slot), np, d, s));
     }
     // memory: d(mem + pos) = sum_l dK_l Wk_l, d(mem) = sum_l dV_l Wv_l  -> encoder.norm backward
     {
@@ -611,7 +717,15 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     }
 
     // ================= input_proj (sedt/sedt.py:36,88) ===================================================
-    const void* feat = tp.blk.back().out;
+    const void* feat = nullptr;
+    if (spm) {                                        // same arena, same order as forward_train: the clip backbone's layer4 output
+        Arena ws(tp.scratch, tp.scratch_bytes);
+        void* cfeat = nullptr; int ch = 0, cw = 0;
+        SEDT_TRY(backbone(nullptr, B, T, F, ws, &cfeat, &ch, &cw, s, true));
+        feat = cfeat;
+    } else {
+        feat = tp.blk.back().out;
+    }
     SEDT_TRY(to16(gcur, bb.g16, rows * d));
     SEDT_TRY(lin_param_grads(input_proj_, 0, d, feat, 2048, bb.g16, d, rows));
     if (!train_backbone) return finish_plan();

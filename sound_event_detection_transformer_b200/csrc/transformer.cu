@@ -332,7 +332,7 @@ __global__ void avgpool_kernel(const T* __restrict__ x, float* __restrict__ out,
 }
 
 __global__ void patch_query_kernel(const float* __restrict__ pq, const float* __restrict__ qe, float* __restrict__ out,
-                                   int B, int P, int qpp, int start)
+                                   int B, int P, int qpp, int start, const uint8_t* __restrict__ keep, float qe_scale)
 {
     const int Q = P * qpp;
     const int64_t total = (int64_t)B * Q * D;
@@ -340,7 +340,40 @@ __global__ void patch_query_kernel(const float* __restrict__ pq, const float* __
         const int d = (int)(i % D);
         const int q = (int)((i / D) % Q);
         const int b = (int)(i / ((int64_t)D * Q));
-        out[i] = pq[((size_t)b * P + q / qpp) * D + d] + qe[(size_t)(start + q) * D + d];
+        const float pf = pq[((size_t)b * P + q / qpp) * D + d];
+        const float k = keep == nullptr ? 1.f : (keep[(size_t)b * Q + q] ? 1.f : 0.f);
+        out[i] = pf * k + qe_scale * qe[(size_t)(start + q) * D + d];
+    }
+}
+
+__global__ void accum_bf16_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ acc, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc[i] += __bfloat162float(g[i]);
+}
+
+// one thread per (q or (b, p), d): fixed summation order, no atomics
+__global__ void patch_query_bwd_kernel(const float* __restrict__ dq, const uint8_t* __restrict__ keep, float* __restrict__ d_qe,
+                                       float* __restrict__ d_pq, int B, int P, int qpp, float qe_scale)
+{
+    const int Q = P * qpp;
+    const int64_t n_qe = (int64_t)Q * D, n_pq = (int64_t)B * P * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_qe + n_pq; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n_qe) {
+            const int d = (int)(i % D), q = (int)(i / D);
+            float s = 0.f;
+            for (int b = 0; b < B; ++b) s += dq[((size_t)b * Q + q) * D + d];
+            d_qe[i] += qe_scale * s;
+        } else {
+            const int64_t j = i - n_qe;
+            const int d = (int)(j % D), p = (int)((j / D) % P), b = (int)(j / ((int64_t)D * P));
+            float s = 0.f;
+            for (int k = 0; k < qpp; ++k) {
+                const int q = p * qpp + k;
+                if (keep == nullptr || keep[(size_t)b * Q + q]) s += dq[((size_t)b * Q + q) * D + d];
+            }
+            d_pq[j] = s;
+        }
     }
 }
 
@@ -488,14 +521,36 @@ int launch_avgpool(const void* x, int dt, float* out, int N, int HW, int C, cuda
     return SEDT_OK;
 }
 
+int launch_accum_bf16(const void* g, float* acc, int64_t n, cudaStream_t stream)
+{
+    if (n == 0) return SEDT_OK;
+    int64_t gr = ceil_div(n, 256); if (gr > 148 * 8) gr = 148 * 8;
+    accum_bf16_kernel<<<(unsigned)gr, 256, 0, stream>>>((const __nv_bfloat16*)g, acc, n);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
+int launch_patch_query_bwd(const float* dq, const uint8_t* keep, float* d_qe, float* d_pq, int B, int P, int qpp, float qe_scale,
+                           cudaStream_t stream)
+{
+    const int64_t n = (int64_t)(P * qpp + B * P) * D;
+    if (n == 0) return SEDT_OK;
+    int64_t gr = ceil_div(n, 256); if (gr > 148 * 8) gr = 148 * 8;
+    patch_query_bwd_kernel<<<(unsigned)gr, 256, 0, stream>>>(dq, keep, d_qe, d_pq, B, P, qpp, qe_scale);
+    SEDT_COUNT_LAUNCH();
+    SEDT_CHECK_CUDA(cudaGetLastError());
+    return SEDT_OK;
+}
+
 int launch_patch_query(const float* pq, const float* query_embed, float* out, int B, int P, int qpp, int start,
-                       cudaStream_t stream)
+                       cudaStream_t stream, const uint8_t* keep, float qe_scale)
 {
     const int64_t n = (int64_t)B * P * qpp * D;
     if (n == 0) return SEDT_OK;
     int64_t g = ceil_div(n, 256); if (g > 148 * 8) g = 148 * 8;
     ProfScope _prof(PROF_OTHER, stream);
-    patch_query_kernel<<<(unsigned)g, 256, 0, stream>>>(pq, query_embed, out, B, P, qpp, start);
+    patch_query_kernel<<<(unsigned)g, 256, 0, stream>>>(pq, query_embed, out, B, P, qpp, start, keep, qe_scale);
     SEDT_COUNT_LAUNCH();
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;

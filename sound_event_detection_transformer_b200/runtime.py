@@ -28,10 +28,11 @@ class _TrainSlot:
 
 
 class _TrainCtx:
-    __slots__ = ("slot", "gen", "x", "m8", "B", "T", "F", "dropout", "graph")
+    __slots__ = ("slot", "gen", "x", "m8", "B", "T", "F", "dropout", "graph", "P", "PT")
 
-    def __init__(self, slot, gen, x, m8, B, T, F, dropout, graph):
+    def __init__(self, slot, gen, x, m8, B, T, F, dropout, graph, P=0, PT=0):
         self.slot, self.gen, self.x, self.m8, self.B, self.T, self.F, self.dropout, self.graph = slot, gen, x, m8, B, T, F, dropout, graph
+        self.P, self.PT = P, PT
 
 
 class ForwardRuntime:
@@ -272,7 +273,7 @@ class ForwardRuntime:
         return sum(1 for v in getattr(self, "_train_slots", {}).values() for sl in v if sl.busy())
 
     def forward_train(self, x: torch.Tensor, mask: Optional[torch.Tensor], use_graph: bool = False, dropout: float = 0.0,
-                      token=None):
+                      token=None, patches: Optional[torch.Tensor] = None, query_keep: Optional[torch.Tensor] = None):
         """Forward in train mode: same outputs as forward(); the activations stay in the slot's tape until backward().
         `token`: the object whose lifetime marks the slot busy (the autograd context); None = fire and forget (a train-mode
         forward without gradients: dropout is applied, nothing is kept).  use_graph replays the launch sequence as a CUDA
@@ -282,10 +283,19 @@ class ForwardRuntime:
         B, _, T, F = x.shape
         dev = x.device
         dropout = float(dropout)
+        P = PT = 0
+        if self.cfg.self_sup:
+            # SP-SEDT pretraining step (spsedt.py:63-69): patches [B, P, 1, PT, F] and the query-drop mask [B, Q] (1 = keep);
+            # eager launches only (the graph path keeps static buffers for the supervised model)
+            assert patches is not None and patches.dim() == 5 and query_keep is not None
+            patches = patches.to(dev, torch.float32).contiguous()
+            query_keep = query_keep.to(dev, torch.uint8).contiguous()
+            P, PT = int(patches.shape[1]), int(patches.shape[3])
+            use_graph = False
         if use_graph:
             return self._forward_train_graph(x, mask, dropout, token)
         sl = self._acquire_slot(("eager", dev.index), token)
-        need = int(self.lib.sedt_train_tape_bytes(self.handle, B, T, F, int(mask is not None)))
+        need = int(self.lib.sedt_train_tape_bytes_sp(self.handle, B, T, F, int(mask is not None), P, PT))
         if need < 0:
             _lib.check(need)
         if sl.tape is None or sl.tape.numel() < need + 256 or sl.tape.device != dev:
@@ -294,13 +304,18 @@ class ForwardRuntime:
         m8 = None
         if mask is not None:
             m8 = mask.to(dev).contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(dev, torch.uint8).contiguous()
-        res = self._alloc_outputs(B, T, F, 0, dev)
+        res = self._alloc_outputs(B, T, F, P, dev)
         outs = _lib.SedtOutputs(**{k: _lib.ptr(res.get(k)) or None for k, _ in _lib.SedtOutputs._fields_})
         with torch.cuda.device(dev):
-            _lib.check(self.lib.sedt_forward_train(self.handle, x.data_ptr(), _lib.ptr(m8) or None, B, T, F, self._aligned(sl.tape),
-                                                   sl.tape.numel() - 256, C.byref(outs), dropout, sl.seed,
-                                                   _lib.current_stream()))
-        return res, _TrainCtx(sl, sl.gen, x, m8, B, T, F, dropout, False)
+            if self.cfg.self_sup:
+                _lib.check(self.lib.sedt_forward_train_sp(self.handle, x.data_ptr(), _lib.ptr(m8) or None, B, T, F, patches.data_ptr(),
+                                                          P, PT, query_keep.data_ptr(), self._aligned(sl.tape), sl.tape.numel() - 256,
+                                                          C.byref(outs), dropout, sl.seed, _lib.current_stream()))
+            else:
+                _lib.check(self.lib.sedt_forward_train(self.handle, x.data_ptr(), _lib.ptr(m8) or None, B, T, F, self._aligned(sl.tape),
+                                                       sl.tape.numel() - 256, C.byref(outs), dropout, sl.seed,
+                                                       _lib.current_stream()))
+        return res, _TrainCtx(sl, sl.gen, x, m8, B, T, F, dropout, False, P, PT)
 
     def _forward_train_graph(self, x, mask, dropout, token):
         B, _, T, F = x.shape
@@ -385,7 +400,7 @@ class ForwardRuntime:
         self.graph_kernel_launches += g["bwd_launches"]
         return g["grads"]
 
-    def backward(self, ctx: "_TrainCtx", d_logits, d_boxes, d_at, train_backbone: bool) -> torch.Tensor:
+    def backward(self, ctx: "_TrainCtx", d_logits, d_boxes, d_at, train_backbone: bool, d_pred_feature=None) -> torch.Tensor:
         """Gradients of every trainable state_dict entry in one flat fp32 tensor (see grad_layout()).  In graph mode the
         tensor is the slot's static buffer: the next backward of the same slot overwrites it (callers that hand views of
         it to autograd must copy, see sedt/model.py: _TrainStep)."""
@@ -398,7 +413,7 @@ class ForwardRuntime:
                 return self._backward_graph(ctx, d_logits, d_boxes, d_at, train_backbone)
             x, m8, B, T, F = ctx.x, ctx.m8, ctx.B, ctx.T, ctx.F
             dev = x.device
-            need = int(self.lib.sedt_backward_workspace_bytes(self.handle, B, T, F))
+            need = int(self.lib.sedt_backward_workspace_bytes_sp(self.handle, B, T, F, ctx.P, ctx.PT))
             if need < 0:
                 _lib.check(need)
             ws = getattr(self, "_bws", None)
@@ -412,8 +427,16 @@ class ForwardRuntime:
 
             def f32(t):
                 return None if t is None else t.detach().to(torch.float32).contiguous()
-            d_logits, d_boxes, d_at = f32(d_logits), f32(d_boxes), f32(d_at)
+            d_logits, d_boxes, d_at, d_pred_feature = f32(d_logits), f32(d_boxes), f32(d_at), f32(d_pred_feature)
             tape = sl.tape
+            if self.cfg.self_sup:
+                with torch.cuda.device(dev):
+                    _lib.check(self.lib.sedt_backward_sp(self.handle, self._ptrs, x.data_ptr(), _lib.ptr(m8) or None, B, T, F, ctx.P, ctx.PT,
+                                                         self._aligned(tape), tape.numel() - 256, self._aligned(ws), ws.numel() - 256,
+                                                         _lib.ptr(d_logits) or None, _lib.ptr(d_boxes) or None,
+                                                         _lib.ptr(d_pred_feature) or None, grads.data_ptr(), ctx.dropout,
+                                                         _lib.current_stream()))
+                return grads
             with torch.cuda.device(dev):
                 _lib.check(self.lib.sedt_backward(self.handle, self._ptrs, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
                                                   self._aligned(tape), tape.numel() - 256, self._aligned(ws), ws.numel() - 256,

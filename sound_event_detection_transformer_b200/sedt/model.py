@@ -80,6 +80,41 @@ class _TrainStep(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+class _TrainStepSP(torch.autograd.Function):
+    """SP-SEDT pretraining step (sedt/spsedt.py:34-91 in train mode, frozen backbone): forward = sedt_forward_train_sp,
+    backward = sedt_backward_sp.  Outputs: pred_logits, pred_boxes, pred_feature of all decoder layers (differentiable) and
+    gt_feature (the frozen backbone's patch features: a constant)."""
+
+    @staticmethod
+    def forward(ctx, model, x, mask, patches, query_keep, names, *params):
+        rt = model.runtime()
+        ctx.token = _Token()
+        res, tctx = rt.forward_train(x, mask, use_graph=False, dropout=float(model.transformer.dropout), token=ctx.token,
+                                     patches=patches, query_keep=query_keep)
+        ctx.model, ctx.tctx, ctx.names, ctx.shapes = model, tctx, names, [p.shape for p in params]
+        ctx.has_feat = "pred_feature" in res
+        outs = (res["logits"], res["boxes"], res["gt_feature"]) + ((res["pred_feature"],) if ctx.has_feat else ())
+        ctx.mark_non_differentiable(res["gt_feature"])
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_logits, d_boxes, d_gt=None, d_feat=None):
+        model = ctx.model
+        rt = model._rt
+        flat = rt.backward(ctx.tctx, d_logits, d_boxes, None, False, d_pred_feature=d_feat)
+        if model.grad_allreduce:
+            from ..parallel import allreduce_mean_
+            allreduce_mean_(flat)
+        _, offs = rt.grad_layout()
+        grads = []
+        for n, shp in zip(ctx.names, ctx.shapes):
+            k = 1
+            for v in shp:
+                k *= v
+            grads.append(flat[offs[n]:offs[n] + k].view(shp))
+        return (None, None, None, None, None, None, *grads)
+
+
 class SEDT(nn.Module):
     """Drop-in for sedt.sedt.SEDT.  Extra keyword `precision`: "bf16" (default: bf16 operands,
     fp32 accumulation on tcgen05 tensor cores) or "fp32" (CUDA-core tier held to 1e-4 parity)."""
@@ -228,8 +263,8 @@ class SEDT(nn.Module):
 
 
 class SPSEDT(SEDT):
-    """Drop-in for sedt.spsedt.SPSEDT (eval branch of forward; the training branch draws a random
-    query-drop mask and needs the backward kernels, see SEDT._check_mode)."""
+    """Drop-in for sedt.spsedt.SPSEDT: the test branch in eval(), the pretraining branch (random query drop, doubled query
+    embedding, feature reconstruction head) with its backward in train()."""
 
     def __init__(self, backbone, transformer, num_classes, num_queries, aux_loss=False, dec_at=False, feature_recon=True,
                  query_shuffle=False, mask_ratio=0.1, num_patches=10, pooling=None, precision: str = "bf16",
@@ -252,15 +287,42 @@ class SPSEDT(SEDT):
         assert num_queries % num_patches == 0
         self._self_sup, self._feature_recon, self._num_patches = True, bool(feature_recon), num_patches
 
-    def forward(self, samples, patches: torch.Tensor):
-        self._check_mode()
-        if self._wants_grad():
-            raise NotImplementedError("SP-SEDT training (random query drop, feature loss) has no backward kernels yet. "
-                                      "Call model.eval() / torch.no_grad() for inference.")
+    def draw_query_keep(self, bs: int, device) -> torch.Tensor:
+        """The reference's draw, verbatim (spsedt.py:65): torch.rand(num_queries, bs, 1) > mask_ratio, returned as [bs, Q] uint8.
+        A run seeded like the reference draws the same mask."""
+        m = (torch.rand(self.num_queries, bs, 1, device=device) > self.mask_ratio)
+        return m[:, :, 0].t().contiguous().to(torch.uint8)
+
+    def forward(self, samples, patches: torch.Tensor, query_keep: Optional[torch.Tensor] = None):
+        """sedt/spsedt.py:34-91.  eval(): the test branch (any number of patches <= num_patches).  train(): the training branch
+        (num_patches patches, random query drop, doubled query embedding, dropout) through the native training kernels --
+        with gradients (loss.backward() fills .grad of every trainable parameter; the backbone is frozen, train_spsedt.py:50)
+        or without (torch.no_grad()).  query_keep [B, Q] (1 = keep the patch feature) overrides the random draw (tests)."""
         if isinstance(samples, (list, tuple)) and len(samples) == 2 and torch.is_tensor(samples[0]) and samples[0].dim() == 4:
             samples = NestedTensor(samples[0], samples[1])          # engine.py:59 passes .decompose()
         x, mask = self._prepare(samples)
-        res = self.runtime().forward(x, mask, patches=patches, use_graph=self.use_cuda_graph)
+        if self.training:
+            why = self._train_unsupported()
+            if why is None and any(p.requires_grad for n, p in self.named_parameters() if n.startswith("backbone.")):
+                why = "SP-SEDT pretraining keeps the backbone frozen (train_spsedt.py:50: lr_backbone = 0)"
+            if why is None and int(patches.shape[1]) != self.num_patches:
+                why = f"the training branch needs exactly num_patches = {self.num_patches} patches per clip (spsedt.py:63-69)"
+            if why is not None:
+                raise NotImplementedError(why + ". Call model.eval() for inference.")
+            if query_keep is None:
+                query_keep = self.draw_query_keep(x.shape[0], x.device)
+            patches = patches.to(x.device, torch.float32)
+            if torch.is_grad_enabled():
+                named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+                outs = _TrainStepSP.apply(self, x, mask, patches, query_keep, tuple(n for n, _ in named), *[p for _, p in named])
+                res = {"logits": outs[0], "boxes": outs[1], "gt_feature": outs[2]}
+                if self.feature_recon:
+                    res["pred_feature"] = outs[3]
+            else:
+                res, _ = self.runtime().forward_train(x, mask, dropout=float(self.transformer.dropout), token=None, patches=patches,
+                                                      query_keep=query_keep)
+        else:
+            res = self.runtime().forward(x, mask, patches=patches, use_graph=self.use_cuda_graph)
         out = {"pred_logits": res["logits"][-1], "pred_boxes": res["boxes"][-1]}
         if self.feature_recon:
             out["pred_feature"] = res["pred_feature"][-1]

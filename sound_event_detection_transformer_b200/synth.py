@@ -234,3 +234,21 @@ def synth_mixup_case(n_strong: int, n_weak: int, n_unl: int, T: int, F: int, see
             k = int(torch.randint(0, 3, (1,), generator=g)) if i < n_strong + n_weak else 0
             y.append({"labels": torch.randint(0, C, (k,), generator=g), "boxes": torch.zeros(0, 2), "orig_size": torch.tensor(10.0)})
     return x, y
+
+
+# ---- SP-SEDT pretraining step: the parameters whose gradients the golden fixture samples, and the functional it differentiates
+SP_TRAIN_PARAMS = ("patch2query.weight", "patch2query.bias", "query_embed.weight", "feature_align.layers.1.weight",
+                   "feature_align.layers.0.bias", "class_embed.weight", "bbox_embed.layers.0.weight", "input_proj.weight",
+                   "transformer.decoder.layers.0.self_attn.in_proj_weight", "transformer.encoder.layers.1.linear1.weight")
+
+
+def sp_train_functional(out, B, Q, seed):
+    """A fixed random linear functional of every output of the pretraining forward (all decoder layers)."""
+    g = torch.Generator().manual_seed(8800 + seed)
+    tot = 0.0
+    for o in [out] + list(out["aux_outputs"]):
+        tot = tot + (o["pred_logits"] * torch.randn(B, Q, 2, generator=g)).sum() + (o["pred_boxes"] * torch.randn(B, Q, 2, generator=g)).sum() \
+            + (o["pred_feature"] * torch.randn(B, Q, 2048, generator=g)).sum() * 0.05
+    return tot
+
+

@@ -308,6 +308,40 @@ def run_mixup(tag, n_strong, n_weak, n_unl, T, seed, with_weak=True):
 
 
 
+SP_TRAIN_PARAMS, sp_train_functional = synth.SP_TRAIN_PARAMS, synth.sp_train_functional
+
+
+def run_spsedt_train(tag, B, T, seed, drop_ratio=0.3):
+    """SPSEDT.forward in train() mode (sedt/spsedt.py:63-69) with dropout 0 and an injected query-drop mask (torch.rand is
+    patched for the one call at :65), outputs + gradients of a fixed functional w.r.t. a sample of the trainable parameters."""
+    torch.Tensor.cuda = lambda self, *a, **k: self          # spsedt.py:37-38
+    args = spec.config_args("c5"); args.dropout = 0.0; args.enc_layers = 2; args.dec_layers = 2
+    model = build_ref(args, seed)
+    model.train()
+    x = synth.synth_clips(B, T, 64, seed=seed)
+    patches = synth.synth_patches(B, 10, 128, 64, seed=seed)
+    mask = torch.zeros(B, T, 64, dtype=torch.bool)
+    keep = torch.rand(20, B, 1, generator=torch.Generator().manual_seed(8700 + seed)) > drop_ratio
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: torch.where(keep, torch.ones(1), torch.zeros(1))     # > mask_ratio exactly where keep
+    try:
+        out = model((x, mask), patches)
+    finally:
+        torch.rand = real_rand
+    sp_train_functional(out, B, 20, seed).backward()
+    named = dict(model.named_parameters())
+    fx = {"keep": keep[:, :, 0].t().numpy().astype(np.uint8), "meta": np.asarray([B, T, seed]),
+          "pred_logits": out["pred_logits"].detach().numpy(), "pred_boxes": out["pred_boxes"].detach().numpy(),
+          "pred_feature": sample(out["pred_feature"]), "gt_feature": sample(out["gt_feature"]),
+          "aux0_pred_logits": out["aux_outputs"][0]["pred_logits"].detach().numpy()}
+    for n in SP_TRAIN_PARAMS:
+        fx["grad_" + n] = sample(named[n].grad) if named[n].grad.numel() > 20000 else named[n].grad.numpy()
+    assert all(not p.requires_grad for n, p in named.items() if n.startswith("backbone."))
+    np.savez_compressed(os.path.join(HERE, f"spsedt_train_{tag}.npz"), **fx)
+    print(f"spsedt_train_{tag}: kept {int(keep.sum())} of {keep.numel()} queries")
+
+
+
 def run_criterion(tag, args, B, seed, kmin=0, kmax=10, fine_tune=False, normalize=False, fl=False, rng_seed=1234):
     """Reference SetCriterion (sedt/sedt.py:134-352) built directly (build_model returns None for it
     without CUDA) on seeded model-shaped outputs: every loss value and the gradient of the weighted sum."""
@@ -343,6 +377,9 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     if "--only-decode" in sys.argv:
         run_decode_chains("chains", 24, 20, seed=51)
+        sys.exit(0)
+    if "--only-sptrain" in sys.argv:
+        run_spsedt_train("c5_b2", 2, 200, seed=15)
         sys.exit(0)
     if "--only-augment" in sys.argv:
         run_augment("b12", 12, 96, seed=51)
@@ -400,3 +437,4 @@ if __name__ == "__main__":
     run_mixup("ss", 12, 6, 6, 40, seed=54)
     run_mixup("strong_only", 10, 0, 0, 40, seed=55, with_weak=False)
     run_mixup("weak_mix", 4, 10, 6, 24, seed=56)
+    run_spsedt_train("c5_b2", 2, 200, seed=15)

@@ -312,3 +312,28 @@ def test_numpy_mean_restatement_is_exact():
         d = (rng.randn(T, 64) * 12 - 40).astype(np.float32)
         s = d[:, f0:f0 + n]
         assert ao.numpy_mean_f32(s) == np.mean(s), (T, n, f0)
+
+
+def test_spsedt_training_branch_oracle_matches_reference():
+    """sedt/spsedt.py:63-69 (train() mode: query drop + doubled query embedding) and autograd through it: the oracle against
+    outputs and gradients of the reference's own SPSEDT (fixture spsedt_train_c5_b2.npz, mask injected at spsedt.py:65)."""
+    mg_names = synth                                                  # the functional / parameter list shared with make_golden.py
+    fx = np.load(os.path.join(GOLDEN, "spsedt_train_c5_b2.npz"))
+    B, T, seed = [int(v) for v in fx["meta"]]
+    args = spec.config_args("c5"); args.dropout = 0.0; args.enc_layers = 2; args.dec_layers = 2
+    sd = {k: v.clone() for k, v in synth.synth_state_dict(args, seed).items()}
+    for n in mg_names.SP_TRAIN_PARAMS:
+        sd[n].requires_grad_(True)
+    x, patches = synth.synth_clips(B, T, 64, seed=seed), synth.synth_patches(B, 10, 128, 64, seed=seed)
+    mask = torch.zeros(B, T, 64, dtype=torch.bool)
+    with torch.enable_grad():
+        out = sedt_oracle.spsedt_forward.__wrapped__(sd, args, x, mask, patches, query_keep=torch.from_numpy(fx["keep"]).bool())
+        mg_names.sp_train_functional(out, B, 20, seed).backward()
+    assert np.array_equal(out["pred_logits"].detach().numpy(), fx["pred_logits"])
+    assert np.array_equal(out["pred_boxes"].detach().numpy(), fx["pred_boxes"])
+    assert np.allclose(out["pred_feature"].detach().flatten()[::97].numpy(), fx["pred_feature"], rtol=0, atol=1e-6)
+    for n in mg_names.SP_TRAIN_PARAMS:
+        g = sd[n].grad
+        got = g.flatten()[::97].numpy() if g.numel() > 20000 else g.numpy()
+        want = fx["grad_" + n]
+        assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), n
