@@ -130,6 +130,11 @@ SEDT_API int sedt_forward(sedt_model* m, const float* x, const uint8_t* mask, in
  * after linear2): masks are counter-based (Philox keyed by `seed`, the dropout site and a per-tape step counter that
  * sedt_forward_train advances), so the backward pass regenerates exactly the forward's masks; pass the same
  * dropout to both calls. */
+/* Data-parallel training (train_spsedt.py:157-158 wraps the model in DistributedDataParallel): sedt_backward records
+ * `cuda_event` (a cudaEvent_t, or NULL to stop) on its stream as soon as every gradient outside the backbone (transformer, heads,
+ * input_proj, query_embed: slots below the first "backbone." entry and from query_embed on) is final, so that the caller can
+ * all-reduce that bucket on a side stream while the backbone backward is still running. */
+SEDT_API int sedt_model_set_bucket_event(sedt_model* m, void* cuda_event);
 SEDT_API int64_t sedt_train_tape_bytes(sedt_model* m, int B, int T, int F, int has_mask);
 SEDT_API int64_t sedt_backward_workspace_bytes(sedt_model* m, int B, int T, int F);
 SEDT_API int64_t sedt_grad_numel(const sedt_model* m);

@@ -75,6 +75,7 @@ SIGNATURES = {
     "sedt_feature_shape": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "sedt_workspace_bytes": (_i64, [_vp, _i, _i, _i, _i, _i]),
     "sedt_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i64, C.POINTER(SedtOutputs), _vp]),
+    "sedt_model_set_bucket_event": (_i, [_vp, _vp]),
     "sedt_train_tape_bytes": (_i64, [_vp, _i, _i, _i, _i]),
     "sedt_backward_workspace_bytes": (_i64, [_vp, _i, _i, _i]),
     "sedt_grad_numel": (_i64, [_vp]),

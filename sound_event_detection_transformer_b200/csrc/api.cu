@@ -162,6 +162,13 @@ int sedt_backward_sp(sedt_model* m, const void* const* weights, const float* x, 
                              d_boxes, nullptr, grads, 0, dropout, (cudaStream_t)stream, &sp);
 }
 
+int sedt_model_set_bucket_event(sedt_model* m, void* cuda_event)
+{
+    SEDT_REQUIRE(m != nullptr, "set_bucket_event: null model");
+    m->impl->set_bucket_event((cudaEvent_t)cuda_event);
+    return SEDT_OK;
+}
+
 int64_t sedt_grad_numel(const sedt_model* m) { return m == nullptr ? (int64_t)SEDT_ERR_INVALID : m->impl->grad_numel(); }
 
 int64_t sedt_grad_offset(const sedt_model* m, int slot)

@@ -80,6 +80,9 @@ public:
     int forward(const float* x, const uint8_t* mask, int B, int T, int F, const float* patches, int P, int PT,
                 Arena& ws, const ForwardOut& out, cudaStream_t stream, bool dry);
     static void feature_shape(int T, int F, bool dilation, int* H, int* W);
+    // data-parallel training: backward() records this event on its stream once every gradient outside the backbone (transformer,
+    // heads, input_proj, query_embed) is final, so that the caller can all-reduce that bucket while the backbone backward runs
+    void set_bucket_event(cudaEvent_t ev) { bucket_event_ = ev; }
 
     // ---- training step (train.cu): bf16 tier, pre-norm; SEDT (backbone trainable from layer2 / conv0) and SP-SEDT pretraining
     // (frozen backbone, train_spsedt.py:50; patches + query-drop mask through SpTrain)
@@ -154,6 +157,7 @@ private:
     // by the following ones while the weight / workspace addresses stay put (train.cu: Model::backward)
     struct DgradPlan { std::vector<DgradJob> jobs; unsigned long long key = 0; bool ready = false; };
     DgradPlan dgrad_plan_;
+    cudaEvent_t bucket_event_ = nullptr;
     std::unordered_map<const void*, unsigned long long> rng_tapes_;   // tape -> seed its dropout RNG state {seed, step} was initialised with
 };
 

@@ -728,6 +728,8 @@ int Model::backward(const void* const* weights, const float* x, const uint8_t* m
     }
     SEDT_TRY(to16(gcur, bb.g16, rows * d));
     SEDT_TRY(lin_param_grads(input_proj_, 0, d, feat, 2048, bb.g16, d, rows));
+    // everything outside the backbone is final: the first all-reduce bucket may go (see Model::set_bucket_event)
+    if (bucket_event_ != nullptr) SEDT_CHECK_CUDA(cudaEventRecord(bucket_event_, s));
     if (!train_backbone) return finish_plan();
     // gradient w.r.t. the layer4 output, already masked by its ReLU
     SEDT_TRY(dgrad_lin(Wp(input_proj_.w_slot), d, d, 2048, bb.g16, d, rows, feat, 2048, 2, bb.G0, dt, 2048));

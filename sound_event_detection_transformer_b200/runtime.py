@@ -239,6 +239,27 @@ class ForwardRuntime:
             self._grad_layout = (n, offs)
         return self._grad_layout
 
+    def backbone_grad_range(self):
+        """[lo, hi) element range of the `backbone.*` gradients in the flat buffer (they are contiguous in state_dict order)."""
+        n, offs = self.grad_layout()
+        bb = [i for i, name in enumerate(self.names) if name.startswith("backbone.")]
+        lo = offs[self.names[bb[0]]]
+        hi = offs[self.names[bb[-1] + 1]] if bb[-1] + 1 < len(self.names) else n
+        return lo, hi
+
+    def bucket_event(self, enable: bool = True):
+        """The event sedt_backward records once the non-backbone gradients are final (overlapped all-reduce, see
+        sedt/model.py: _allreduce_buckets); enable=False detaches it."""
+        if not enable:
+            _lib.check(self.lib.sedt_model_set_bucket_event(self.handle, None))
+            return None
+        ev = getattr(self, "_bucket_event", None)
+        if ev is None:
+            ev = self._bucket_event = torch.cuda.Event()
+            ev.record()                                   # forces the lazy creation of the cudaEvent_t (outside any capture)
+        _lib.check(self.lib.sedt_model_set_bucket_event(self.handle, ev.cuda_event))
+        return ev
+
     # Train slots.  One forward_train / backward pair owns one slot: its own activation tape and dropout RNG stream and, in
     # graph mode, its own static input / output / gradient buffers and captured graphs.  A forward issued while earlier
     # forwards still wait for their backward (the semi-supervised loop runs the labelled and the unlabelled batch through
@@ -358,11 +379,14 @@ class ForwardRuntime:
         self.graph_kernel_launches += g["fwd_launches"]
         return g["res"], _TrainCtx(sl, sl.gen, g["x"], g["mask"], B, T, F, dropout, True)
 
-    def _backward_graph(self, ctx, d_logits, d_boxes, d_at, train_backbone):
+    def _backward_graph(self, ctx, d_logits, d_boxes, d_at, train_backbone, post=None):
+        """post(grads): optional work captured into the same graph right after the backward launches (the data-parallel
+        gradient all-reduce: NCCL collectives are capturable).  If capturing it fails the graph is re-captured without it and
+        g["post_captured"] stays False: the caller then runs it eagerly after the replay."""
         sl, x, m8, B, T, F = ctx.slot, ctx.x, ctx.m8, ctx.B, ctx.T, ctx.F
         g = sl.g
         dev = x.device
-        if g["bwd"] is None or g.get("bwd_tb") != bool(train_backbone):
+        if g["bwd"] is None or g.get("bwd_tb") != bool(train_backbone) or g.get("bwd_post") != (post is not None):
             need = int(self.lib.sedt_backward_workspace_bytes(self.handle, B, T, F))
             if need < 0:
                 _lib.check(need)
@@ -383,13 +407,32 @@ class ForwardRuntime:
                                                   g["grads"].data_ptr(), int(train_backbone), ctx.dropout, _lib.current_stream()))
             with torch.cuda.device(dev):
                 launch()
+                if post is not None:
+                    post(g["grads"])                       # warm-up outside the capture (communicator setup)
                 torch.cuda.synchronize(dev)
-                graph = torch.cuda.CUDAGraph()
-                n0 = self.lib.sedt_launch_count()
-                with torch.cuda.graph(graph):
-                    launch()
+                g["post_captured"] = False
+                graph = None
+                if post is not None:
+                    try:
+                        graph = torch.cuda.CUDAGraph()
+                        n0 = self.lib.sedt_launch_count()
+                        with torch.cuda.graph(graph):
+                            launch()
+                            post(g["grads"])
+                        g["post_captured"] = True
+                    except Exception as exc:               # e.g. a collective backend that cannot be captured
+                        import warnings
+                        warnings.warn(f"gradient all-reduce could not be captured into the backward graph ({exc!r}); "
+                                      "it runs eagerly after the replay")
+                        torch.cuda.synchronize(dev)
+                        graph = None
+                if graph is None:
+                    graph = torch.cuda.CUDAGraph()
+                    n0 = self.lib.sedt_launch_count()
+                    with torch.cuda.graph(graph):
+                        launch()
                 g["bwd_launches"] = int(self.lib.sedt_launch_count() - n0)
-            g["bwd"], g["bwd_tb"] = graph, bool(train_backbone)
+            g["bwd"], g["bwd_tb"], g["bwd_post"] = graph, bool(train_backbone), post is not None
         for dst, src in ((g["dl"], d_logits), (g["db"], d_boxes), (g["da"], d_at)):
             if dst is not None:
                 if src is None:
@@ -398,9 +441,11 @@ class ForwardRuntime:
                     dst.copy_(src, non_blocking=True)
         g["bwd"].replay()
         self.graph_kernel_launches += g["bwd_launches"]
+        if post is not None and not g["post_captured"]:
+            post(g["grads"])
         return g["grads"]
 
-    def backward(self, ctx: "_TrainCtx", d_logits, d_boxes, d_at, train_backbone: bool, d_pred_feature=None) -> torch.Tensor:
+    def backward(self, ctx: "_TrainCtx", d_logits, d_boxes, d_at, train_backbone: bool, d_pred_feature=None, post=None) -> torch.Tensor:
         """Gradients of every trainable state_dict entry in one flat fp32 tensor (see grad_layout()).  In graph mode the
         tensor is the slot's static buffer: the next backward of the same slot overwrites it (callers that hand views of
         it to autograd must copy, see sedt/model.py: _TrainStep)."""
@@ -410,7 +455,7 @@ class ForwardRuntime:
                                "(backward called twice, or after the autograd graph had been released)")
         try:
             if ctx.graph:
-                return self._backward_graph(ctx, d_logits, d_boxes, d_at, train_backbone)
+                return self._backward_graph(ctx, d_logits, d_boxes, d_at, train_backbone, post)
             x, m8, B, T, F = ctx.x, ctx.m8, ctx.B, ctx.T, ctx.F
             dev = x.device
             need = int(self.lib.sedt_backward_workspace_bytes_sp(self.handle, B, T, F, ctx.P, ctx.PT))
@@ -436,12 +481,16 @@ class ForwardRuntime:
                                                          _lib.ptr(d_logits) or None, _lib.ptr(d_boxes) or None,
                                                          _lib.ptr(d_pred_feature) or None, grads.data_ptr(), ctx.dropout,
                                                          _lib.current_stream()))
+                if post is not None:
+                    post(grads)
                 return grads
             with torch.cuda.device(dev):
                 _lib.check(self.lib.sedt_backward(self.handle, self._ptrs, x.data_ptr(), _lib.ptr(m8) or None, B, T, F,
                                                   self._aligned(tape), tape.numel() - 256, self._aligned(ws), ws.numel() - 256,
                                                   _lib.ptr(d_logits) or None, _lib.ptr(d_boxes) or None, _lib.ptr(d_at) or None,
                                                   grads.data_ptr(), int(train_backbone), ctx.dropout, _lib.current_stream()))
+            if post is not None:
+                post(grads)
             return grads
         finally:
             sl.owner = None                    # the pair is complete: the slot may serve the next forward

@@ -21,6 +21,38 @@ class _Token:
     __slots__ = ("__weakref__",)
 
 
+def _allreduce_buckets(rt, train_backbone: bool):
+    """The training step's one exchange as two buckets: the gradients outside the backbone are averaged on a side
+    stream as soon as sedt_backward signals them final (bucket event), overlapping the backbone backward; the backbone bucket
+    follows on the main stream.  Returns post(flat) for ForwardRuntime.backward, or None for a single process."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        rt.bucket_event(False)
+        return None
+    from ..parallel import allreduce_mean_
+    lo, hi = rt.backbone_grad_range()
+    ev = rt.bucket_event(True)
+    if getattr(rt, "_side_stream", None) is None:
+        rt._side_stream = torch.cuda.Stream()
+    side = rt._side_stream
+
+    def post(flat):
+        main = torch.cuda.current_stream()
+        if train_backbone:
+            with torch.cuda.stream(side):
+                side.wait_event(ev)                      # recorded by sedt_backward after input_proj's weight gradient
+                allreduce_mean_(flat[:lo])
+                if hi < flat.numel():
+                    allreduce_mean_(flat[hi:])
+            allreduce_mean_(flat[lo:hi])                 # main stream: after the backbone backward
+            main.wait_stream(side)
+        else:
+            allreduce_mean_(flat[:lo])
+            if hi < flat.numel():
+                allreduce_mean_(flat[hi:])
+    return post
+
+
 def _detach_grads_from(static, params, names, shapes, rt):
     if static is None:
         return
@@ -66,10 +98,8 @@ class _TrainStep(torch.autograd.Function):
             # the replay below would overwrite it and autograd would then add the buffer to itself: move those gradients to
             # their own storage first (one flat copy, only in that case).
             _detach_grads_from(ctx.tctx.slot.g.get("grads"), ctx.params, ctx.names, ctx.shapes, rt)
-        flat = rt.backward(ctx.tctx, d_logits, d_boxes, d_at, train_backbone)
-        if model.grad_allreduce:
-            from ..parallel import allreduce_mean_
-            allreduce_mean_(flat)                 # one NCCL all-reduce of the whole gradient bucket
+        post = _allreduce_buckets(rt, train_backbone) if model.grad_allreduce else None
+        flat = rt.backward(ctx.tctx, d_logits, d_boxes, d_at, train_backbone, post=post)
         _, offs = rt.grad_layout()
         grads = []
         for n, shp in zip(ctx.names, ctx.shapes):
@@ -101,10 +131,8 @@ class _TrainStepSP(torch.autograd.Function):
     def backward(ctx, d_logits, d_boxes, d_gt=None, d_feat=None):
         model = ctx.model
         rt = model._rt
-        flat = rt.backward(ctx.tctx, d_logits, d_boxes, None, False, d_pred_feature=d_feat)
-        if model.grad_allreduce:
-            from ..parallel import allreduce_mean_
-            allreduce_mean_(flat)
+        post = _allreduce_buckets(rt, False) if model.grad_allreduce else None
+        flat = rt.backward(ctx.tctx, d_logits, d_boxes, None, False, d_pred_feature=d_feat, post=post)
         _, offs = rt.grad_layout()
         grads = []
         for n, shp in zip(ctx.names, ctx.shapes):
