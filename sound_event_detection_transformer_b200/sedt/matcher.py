@@ -8,12 +8,54 @@ from __future__ import annotations
 
 import ctypes as C
 from collections import Counter
+from collections.abc import Sequence as _Seq
 from typing import List, Sequence, Tuple
 
 import torch
 from torch import nn
 
 from .. import _lib
+
+
+class MatchIndices(_Seq):
+    """The matcher's `indices` result, `indices[i] == (rows_i int64 ascending, cols_i int64)` (sedt/matcher.py:92-97), backed by
+    the two padded [B, Q] matrices the kernel writes: clip i's pairs are the first counts[i] entries of row i, so every item
+    is a view that is only created when somebody asks for it (8192 clips -> no 16384 small tensors up front)."""
+
+    def __init__(self, rows: torch.Tensor, cols: torch.Tensor, counts: Sequence[int]):
+        self.rows, self.cols, self.counts = rows, cols, counts
+
+    def __len__(self):
+        return len(self.counts)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        n = self.counts[i]
+        return self.rows[i, :n], self.cols[i, :n]
+
+
+class OnesCoef(_Seq):
+    """Coef of the default recipe (sedt/matcher.py:131): ones(len(indices[i])) per clip, as views of one vector."""
+
+    def __init__(self, counts: Sequence[int], q: int):
+        self.counts, self.ones = counts, torch.ones(max(q, 1), dtype=torch.float32)
+
+    def __len__(self):
+        return len(self.counts)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return self.ones[:self.counts[i]]
 
 
 class HungarianMatcher(nn.Module):
@@ -29,11 +71,23 @@ class HungarianMatcher(nn.Module):
     def forward(self, outputs, targets: Sequence[dict], fine_tune=False, normalize=False, fl=False):
         """Returns (indices, Coef): indices[i] = (int64 rows ascending, int64 cols) with
         len = min(num_queries, K_i); Coef[i] fp32 (ones | 1/multiplicity | targets[i]['ratio'])."""
+        # targets: the reference's list of dicts, or a pack_targets() result (labels / boxes / offsets already on the device:
+        # a training loop packs once per batch and reuses it for the matcher calls of all decoder layers)
+        packed = targets if isinstance(targets, dict) and "offsets" in targets else None
+        tlist = [None] * len(packed["sizes"]) if packed is not None else targets
         if fine_tune:
-            rows, cols, counts, lmin, largmin = self.match(outputs["pred_logits"], outputs["pred_boxes"], targets, fl=fl,
-                                                           want_lmin=True)
+            rows, cols, counts, lmin, largmin = self.match(outputs["pred_logits"], outputs["pred_boxes"], tlist, fl=fl,
+                                                           want_lmin=True, packed=packed)
         else:
-            rows, cols, counts = self.match(outputs["pred_logits"], outputs["pred_boxes"], targets, fl=fl)
+            rows, cols, counts = self.match(outputs["pred_logits"], outputs["pred_boxes"], tlist, fl=fl, packed=packed)
+        if not fine_tune and not normalize and (packed is not None or not any("ratio" in t for t in targets)):
+            # default recipe: the padded [B, Q] matrices ARE the result (pairs first, sorted by query): one D2H copy of each
+            # (reference contract: CPU tensors) or none (device_indices), per-clip views on demand
+            if not self.device_indices:
+                rows, cols = rows.cpu(), cols.cpu()
+            return MatchIndices(rows, cols, counts), OnesCoef(counts, rows.shape[1])
+        if packed is not None:
+            raise ValueError("fine_tune / normalize / ratio matching needs the per-clip target dicts")
         # compact the padded [B,Q] index matrices once on the device, then one split on the host
         valid = rows >= 0
         flat_r, flat_c = rows[valid], cols[valid]

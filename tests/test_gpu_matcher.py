@@ -145,3 +145,26 @@ def test_matcher_full_size_properties():
         k = len(targets[b]["boxes"])
         r, c = linear_sum_assignment(cost[b, :, :k])
         assert np.array_equal(rows[b, :n[b]], r) and np.array_equal(cols[b, :n[b]], c)
+
+
+def test_packed_targets_and_lazy_indices_match_the_list_api():
+    """matcher(outputs, pack_targets(...)) == matcher(outputs, list of dicts): same pairs, per-clip items are views of the two
+    [B, Q] result matrices created on demand (sedt/matcher.py:92-97 contract: (rows ascending, cols), CPU int64)."""
+    from sound_event_detection_transformer_b200.sedt.matcher import MatchIndices
+    outputs, targets = synth.synth_matcher_case(300, 20, 10, 0, 24, seed=9)        # incl. K = 0 and K > Q
+    o = {k: v.cuda() for k, v in outputs.items()}
+    t = [{k: v.cuda() for k, v in tg.items()} for tg in targets]
+    matcher = build_matcher(spec.default_args())
+    idx_list, coef_list = matcher(o, t)
+    packed = matcher.pack_targets(t, o["pred_logits"].device)
+    idx, coef = matcher(o, packed)
+    assert isinstance(idx, MatchIndices) and len(idx) == 300 and len(coef) == 300
+    for i in range(300):
+        (r, c), (r2, c2) = idx[i], idx_list[i]
+        assert r.dtype == torch.int64 and not r.is_cuda and torch.equal(r, r2) and torch.equal(c, c2)
+        assert len(r) == min(20, len(targets[i]["boxes"])) and torch.equal(coef[i], torch.ones(len(r)))
+    assert [len(r) for r, _ in idx[5:9]] == [len(idx[i][0]) for i in range(5, 9)] and len(idx[-1][0]) == len(idx[299][0])
+    assert float(torch.cat(list(coef)).sum()) == sum(len(r) for r, _ in idx_list)
+    matcher.device_indices = True
+    idx_dev, _ = matcher(o, packed)
+    assert idx_dev[3][0].is_cuda and torch.equal(idx_dev[3][0].cpu(), idx[3][0])

@@ -133,9 +133,12 @@ def run(o):
             sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
             from bench import ClockSampler
             sampler = ClockSampler(local); sampler.start()
-            t_w = time.perf_counter()
-            while time.perf_counter() - t_w < 1.0 and len(sampler.rows) < 2:
-                x = x_keep; step(); torch.cuda.synchronize()
+        # keep every GPU under the bench load while nvidia-smi starts sampling: the SAME number of extra steps on every rank
+        # (a step contains the gradient all-reduce: a rank-dependent count would dead-lock the collective)
+        for _ in range(40):
+            x = x_keep; step()
+        torch.cuda.synchronize()
+        if sampler is not None:
             sampler.mark()
         parallel.barrier()
         t0 = time.perf_counter()
