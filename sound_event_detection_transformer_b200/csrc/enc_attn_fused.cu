@@ -309,11 +309,8 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 }
                 // the partner warp of the other team (same TMEM lanes) has read its fp32 columns too
                 asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
-                uint32_t w0[32], w1[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) { w0[j] = w[j]; w1[j] = w[32 + j]; }
-                tmem_st32(lane_base + TM_Q + (uint32_t)(team * 64), w0);
-                tmem_st32(lane_base + TM_Q + (uint32_t)(team * 64 + 32), w1);
+                tmem_st32(lane_base + TM_Q + (uint32_t)(team * 64), *reinterpret_cast<const uint32_t(*)[32]>(&w[0]));
+                tmem_st32(lane_base + TM_Q + (uint32_t)(team * 64 + 32), *reinterpret_cast<const uint32_t(*)[32]>(&w[32]));
                 tmem_st_wait();
             }
             tc_fence_before();
@@ -385,49 +382,62 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 tc_fence_after();
                 EA_TT(8 + 4 * hh);
                 // p_j = 2^(c (s_j - m)) * valid_j, c = scale * log2 e, m = max over the valid keys (attention_tc.cu)
-                // chunks whose 32 keys are all real (no padding mask, below S) skip the mask vectors
+                // chunks whose 32 keys are all real (no padding mask, below S) skip the mask vectors; the TMEM load of chunk c + 1 is
+                // in flight while chunk c is processed
+                const int nch = row_warp ? nkc : 0;
+                const bool nomask = p.kpm == nullptr;
                 float m = -CUDART_INF_F;
-#pragma unroll 1
-                for (int c = 0; c < (row_warp ? nkc : 0); ++c) {
-                    uint32_t acc[32];
-                    tmem_ld32(sbase + (uint32_t)(c * 32), acc);
-                    if (p.kpm == nullptr && c * 32 + 32 <= S) {
+                auto max_chunk = [&](const uint32_t (&a)[32], int cc) {
+                    if (nomask && cc * 32 + 32 <= S) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1])));
+                        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(a[j]), __uint_as_float(a[j + 1])));
                     } else {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 ng = *reinterpret_cast<const float4*>(s_neg + c * 32 + j4 * 4);
-                            m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(acc[4 * j4]) + ng.x, __uint_as_float(acc[4 * j4 + 1]) + ng.y),
-                                               fmaxf(__uint_as_float(acc[4 * j4 + 2]) + ng.z, __uint_as_float(acc[4 * j4 + 3]) + ng.w)));
+                            const float4 ng = *reinterpret_cast<const float4*>(s_neg + cc * 32 + j4 * 4);
+                            m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(a[4 * j4]) + ng.x, __uint_as_float(a[4 * j4 + 1]) + ng.y),
+                                               fmaxf(__uint_as_float(a[4 * j4 + 2]) + ng.z, __uint_as_float(a[4 * j4 + 3]) + ng.w)));
                         }
+                    }
+                };
+                uint32_t acc0[32], acc1[32];
+                if (nch > 0) tmem_ld32_nowait(sbase, acc0);
+#pragma unroll 1
+                for (int c = 0; c < nch; c += 2) {
+                    tmem_ld_wait();
+                    if (c + 1 < nch) tmem_ld32_nowait(sbase + (uint32_t)((c + 1) * 32), acc1);
+                    max_chunk(acc0, c);
+                    if (c + 1 < nch) {
+                        tmem_ld_wait();
+                        if (c + 2 < nch) tmem_ld32_nowait(sbase + (uint32_t)((c + 2) * 32), acc0);
+                        max_chunk(acc1, c + 1);
                     }
                 }
                 const float mc = m * cs;
                 float l = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < (row_warp ? nkc : 0); ++c) {
-                    uint32_t acc[32], pk[16];
-                    tmem_ld32(sbase + (uint32_t)(c * 32), acc);
-                    if (p.kpm == nullptr && c * 32 + 32 <= S) {
+                // P chunk cc goes to columns [16 cc, 16 cc + 16): inside S chunks <= cc / 2, all consumed, and never the columns of
+                // the load in flight (chunk cc + 1)
+                auto exp_chunk = [&](const uint32_t (&a)[32], int cc) {
+                    uint32_t pk[16];
+                    if (nomask && cc * 32 + 32 <= S) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float e0, e1;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(acc[2 * j]), cs, -mc)));
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(acc[2 * j + 1]), cs, -mc)));
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(a[2 * j]), cs, -mc)));
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(a[2 * j + 1]), cs, -mc)));
                             l += e0; l += e1;
                             pk[j] = ea_pack2(e0, e1);
                         }
                     } else {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 vm = *reinterpret_cast<const float4*>(s_mask + c * 32 + j4 * 4);
+                            const float4 vm = *reinterpret_cast<const float4*>(s_mask + cc * 32 + j4 * 4);
                             const float vmv[4] = {vm.x, vm.y, vm.z, vm.w};
                             float pv[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 float ex;
-                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(__uint_as_float(acc[4 * j4 + q]), cs, -mc)));
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(__uint_as_float(a[4 * j4 + q]), cs, -mc)));
                                 pv[q] = ex * vmv[q];
                                 l += pv[q];
                             }
@@ -435,7 +445,19 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                             pk[2 * j4 + 1] = ea_pack2(pv[2], pv[3]);
                         }
                     }
-                    tmem_st16(sbase + (uint32_t)(c * 16), pk);       // lands in columns of S chunks <= c, all consumed already
+                    tmem_st16(sbase + (uint32_t)(cc * 16), pk);
+                };
+                if (nch > 0) tmem_ld32_nowait(sbase, acc0);
+#pragma unroll 1
+                for (int c = 0; c < nch; c += 2) {
+                    tmem_ld_wait();
+                    if (c + 1 < nch) tmem_ld32_nowait(sbase + (uint32_t)((c + 1) * 32), acc1);
+                    exp_chunk(acc0, c);
+                    if (c + 1 < nch) {
+                        tmem_ld_wait();
+                        if (c + 2 < nch) tmem_ld32_nowait(sbase + (uint32_t)((c + 2) * 32), acc0);
+                        exp_chunk(acc1, c + 1);
+                    }
                 }
                 tmem_st_wait();
                 tc_fence_before();

@@ -488,7 +488,9 @@ int Model::mha(const Mha& A, bool self_attn, const void* q_in, const void* k_in,
     // self-attention of a <= 128-token clip with q = k: the whole block (three projections, attention core, out_proj + residual)
     // as one launch with every intermediate on chip (enc_attn_fused.cu); the launches below remain for the other shapes,
     // the SP-SEDT decoder mask and the fp32 tier
-    if (!dry && self_attn && q_in == k_in && amask == nullptr && Lq == Lk && resid32 == out32 && cfg_.use_tensor_cores &&
+    // (one 128-row tile per clip: pays from ~64 tokens per clip on; the decoder's 11 / 21 queries pack 6 clips into one GEMM tile
+    // in the separate launches below -- measured 47 vs 51 us for the decoder self-attention at B = 256)
+    if (!dry && self_attn && q_in == k_in && amask == nullptr && Lq == Lk && Lq >= 64 && resid32 == out32 && cfg_.use_tensor_cores &&
         enc_attn_fused_enabled() && !A.in_proj.f32_only &&
         enc_attn_fused_supported(d, cfg_.nheads, Lq, v_in, q_in, packed_ + A.in_proj.off_w, packed_ + A.out_proj.off_w, out32, dt))
         return launch_enc_attn_fused(v_in, q_in, packed_ + A.in_proj.off_w, (const float*)(packed_ + A.in_proj.off_b),
