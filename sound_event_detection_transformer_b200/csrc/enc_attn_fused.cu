@@ -136,7 +136,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int slot = 0; uint32_t sphase = 0;
+            int slot = 0, pre = 0; uint32_t sphase = 0;
             auto next_slot = [&](const CUtensorMap* m, int c0, int c1) {
                 mbar_wait(&slot_empty[slot], sphase ^ 1);
                 mbar_expect_tx(&slot_full[slot], EA_SLOT);
@@ -154,12 +154,16 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 mbar_wait(&stage_free[1], (it & 1) ^ 1);
                 mbar_expect_tx(na_full, 4 * EA_SLOT);
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(&map_na, smem + EA_BUFB + kb * EA_SLOT, na_full, kb * 64, row0);
-                for (int m = 0; m < 3; ++m)                         // Wq, Wk, Wv: [N half][k block]
-                    for (int nh = 0; nh < 2; ++nh)
-                        for (int kb = 0; kb < 4; ++kb) next_slot(&map_win, kb * 64, m * 256 + nh * 128);
+                // weight boxes of one clip in consumption order: 0..23 = Wq, Wk, Wv as [N half][k block], 24..31 = Wo as [k block][N half];
+                // the first `pre` boxes of this clip were issued during the previous clip's tail (they do not need bufA / bufB)
+                auto issue_w = [&](int i) {
+                    if (i < 24) next_slot(&map_win, (i & 3) * 64, (i >> 3) * 256 + ((i >> 2) & 1) * 128);
+                    else next_slot(&map_wo, ((i - 24) >> 1) * 64, ((i - 24) & 1) * 128);
+                };
+                for (int i = pre; i < 24; ++i) issue_w(i);
                 EA_T(0, 1);
-                for (int i = 0; i < 8; ++i) {                       // Wo: [k block][N half]
-                    if (i == EA_NSLOTS) {
+                for (int i = 24; i < 32; ++i) {
+                    if (i == 24 + EA_NSLOTS) {
                         // K and V^T are dead once the last P V has retired: prefetch the residual tile over them
                         EA_T(0, 2);
                         mbar_wait(kv_dead, it & 1);
@@ -170,8 +174,11 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                                 tma_load_2d(&map_res, smem + (g ? EA_BUFB : EA_BUFA) + c * EA_SLOT, &res_full[g], (4 * g + c) * 32, row0);
                         }
                     }
-                    next_slot(&map_wo, (i >> 1) * 64, (i & 1) * 128);
+                    issue_w(i);
                 }
+                pre = 0;
+                if (it + 1 < iters)                                 // the ring drains while the epilogue runs: the next clip's first weights go now
+                    for (; pre < EA_NSLOTS; ++pre) issue_w(pre);
                 EA_T(0, 4);
             }
         }
@@ -386,17 +393,21 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 // in flight while chunk c is processed
                 const int nch = row_warp ? nkc : 0;
                 const bool nomask = p.kpm == nullptr;
-                float m = -CUDART_INF_F;
+                // four independent partial maxima / sums: a single accumulator would serialise 128 dependent FMNMX / FADD per head
+                float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
                 auto max_chunk = [&](const uint32_t (&a)[32], int cc) {
                     if (nomask && cc * 32 + 32 <= S) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(a[j]), __uint_as_float(a[j + 1])));
+                        for (int j = 0; j < 32; j += 4) {
+                            m0 = fmaxf(m0, __uint_as_float(a[j])); m1 = fmaxf(m1, __uint_as_float(a[j + 1]));
+                            m2 = fmaxf(m2, __uint_as_float(a[j + 2])); m3 = fmaxf(m3, __uint_as_float(a[j + 3]));
+                        }
                     } else {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
                             const float4 ng = *reinterpret_cast<const float4*>(s_neg + cc * 32 + j4 * 4);
-                            m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(a[4 * j4]) + ng.x, __uint_as_float(a[4 * j4 + 1]) + ng.y),
-                                               fmaxf(__uint_as_float(a[4 * j4 + 2]) + ng.z, __uint_as_float(a[4 * j4 + 3]) + ng.w)));
+                            m0 = fmaxf(m0, __uint_as_float(a[4 * j4]) + ng.x); m1 = fmaxf(m1, __uint_as_float(a[4 * j4 + 1]) + ng.y);
+                            m2 = fmaxf(m2, __uint_as_float(a[4 * j4 + 2]) + ng.z); m3 = fmaxf(m3, __uint_as_float(a[4 * j4 + 3]) + ng.w);
                         }
                     }
                 };
@@ -413,20 +424,23 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                         max_chunk(acc1, c + 1);
                     }
                 }
-                const float mc = m * cs;
-                float l = 0.f;
+                const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * cs;
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                 // P chunk cc goes to columns [16 cc, 16 cc + 16): inside S chunks <= cc / 2, all consumed, and never the columns of
                 // the load in flight (chunk cc + 1)
                 auto exp_chunk = [&](const uint32_t (&a)[32], int cc) {
                     uint32_t pk[16];
                     if (nomask && cc * 32 + 32 <= S) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float e0, e1;
+                        for (int j = 0; j < 16; j += 2) {
+                            float e0, e1, e2, e3;
                             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(a[2 * j]), cs, -mc)));
                             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(a[2 * j + 1]), cs, -mc)));
-                            l += e0; l += e1;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(__uint_as_float(a[2 * j + 2]), cs, -mc)));
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fmaf(__uint_as_float(a[2 * j + 3]), cs, -mc)));
+                            l0 += e0; l1 += e1; l2 += e2; l3 += e3;
                             pk[j] = ea_pack2(e0, e1);
+                            pk[j + 1] = ea_pack2(e2, e3);
                         }
                     } else {
 #pragma unroll
@@ -439,8 +453,8 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                                 float ex;
                                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(__uint_as_float(a[4 * j4 + q]), cs, -mc)));
                                 pv[q] = ex * vmv[q];
-                                l += pv[q];
                             }
+                            l0 += pv[0]; l1 += pv[1]; l2 += pv[2]; l3 += pv[3];
                             pk[2 * j4] = ea_pack2(pv[0], pv[1]);
                             pk[2 * j4 + 1] = ea_pack2(pv[2], pv[3]);
                         }
@@ -471,6 +485,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                 {
                     uint32_t acc[32], pk[16];
                     tmem_ld32(lane_base + TM_OT + (uint32_t)(team * 32), acc);
+                    const float l = (l0 + l1) + (l2 + l3);
                     const float inv = l > 0.f ? 1.f / l : 0.f;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) pk[j] = ea_pack2(__uint_as_float(acc[2 * j]) * inv, __uint_as_float(acc[2 * j + 1]) * inv);
@@ -494,6 +509,11 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
             for (int c = 0; c < 4; ++c) {
                 uint32_t acc[32];
                 tmem_ld32(lane_base + TM_Y + (uint32_t)(team * 128 + c * 32), acc);
+                if (c == 3) {                                                          // the whole accumulator is in registers / staged
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(y_drained);
+                }
                 const float* bo = s_bias + 768 + team * 128 + c * 32;
                 uint8_t* rowp = stage + c * EA_SLOT + r * 128;                        // 32 fp32 columns = one 128-byte row of chunk c
 #pragma unroll
@@ -504,16 +524,16 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                     *slot = make_float4(__uint_as_float(acc[4 * j4]) + b4.x + r4.x, __uint_as_float(acc[4 * j4 + 1]) + b4.y + r4.y,
                                         __uint_as_float(acc[4 * j4 + 2]) + b4.z + r4.z, __uint_as_float(acc[4 * j4 + 3]) + b4.w + r4.w);
                 }
+                // chunk c leaves through TMA while chunk c + 1 is being computed
+                fence_async_smem();
+                asm volatile("bar.sync %0, 128;" ::"r"(6 + team) : "memory");
+                if ((e & 3) == 0 && lane == 0) {
+                    tma_store_3d(&map_out, stage + c * EA_SLOT, (4 * team + c) * 32, 0, b);
+                    tma_store_commit();
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(y_drained);
             EA_TT(26);
-            fence_async_smem();
-            asm volatile("bar.sync %0, 128;" ::"r"(6 + team) : "memory");
             if ((e & 3) == 0 && lane == 0) {
-                for (int c = 0; c < 4; ++c) tma_store_3d(&map_out, stage + c * EA_SLOT, (4 * team + c) * 32, 0, b);
-                tma_store_commit();
                 tma_store_wait_read0();
                 mbar_arrive(&stage_free[team]);
                 if (p.dbg != nullptr && blockIdx.x == 0 && it < 2) p.dbg[(it * 3 + 2) * 64 + team * 32 + 27] = clock64();

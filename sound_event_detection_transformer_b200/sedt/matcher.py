@@ -39,23 +39,12 @@ class MatchIndices(_Seq):
         return self.rows[i, :n], self.cols[i, :n]
 
 
-class OnesCoef(_Seq):
-    """Coef of the default recipe (sedt/matcher.py:131): ones(len(indices[i])) per clip, as views of one vector."""
-
-    def __init__(self, counts: Sequence[int], q: int):
-        self.counts, self.ones = counts, torch.ones(max(q, 1), dtype=torch.float32)
-
-    def __len__(self):
-        return len(self.counts)
-
-    def __getitem__(self, i):
-        if isinstance(i, slice):
-            return [self[j] for j in range(*i.indices(len(self)))]
-        if i < 0:
-            i += len(self)
-        if not 0 <= i < len(self):
-            raise IndexError(i)
-        return self.ones[:self.counts[i]]
+def ones_coef(counts: Sequence[int], q: int) -> List[torch.Tensor]:
+    """Coef of the default recipe (sedt/matcher.py:131): ones(len(indices[i])) per clip.  A real list (consumers call
+    torch.cat(coef), sedt/sedt.py:322) whose entries are shared: one tensor per distinct length."""
+    ones = torch.ones(max(q, 1), dtype=torch.float32)
+    cache = [ones[:n] for n in range(max(q, 1) + 1)]
+    return [cache[n] for n in counts]
 
 
 class HungarianMatcher(nn.Module):
@@ -85,7 +74,7 @@ class HungarianMatcher(nn.Module):
             # (reference contract: CPU tensors) or none (device_indices), per-clip views on demand
             if not self.device_indices:
                 rows, cols = rows.cpu(), cols.cpu()
-            return MatchIndices(rows, cols, counts), OnesCoef(counts, rows.shape[1])
+            return MatchIndices(rows, cols, counts), ones_coef(counts, rows.shape[1])
         if packed is not None:
             raise ValueError("fine_tune / normalize / ratio matching needs the per-clip target dicts")
         # compact the padded [B,Q] index matrices once on the device, then one split on the host

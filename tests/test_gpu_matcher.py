@@ -164,7 +164,7 @@ def test_packed_targets_and_lazy_indices_match_the_list_api():
         assert r.dtype == torch.int64 and not r.is_cuda and torch.equal(r, r2) and torch.equal(c, c2)
         assert len(r) == min(20, len(targets[i]["boxes"])) and torch.equal(coef[i], torch.ones(len(r)))
     assert [len(r) for r, _ in idx[5:9]] == [len(idx[i][0]) for i in range(5, 9)] and len(idx[-1][0]) == len(idx[299][0])
-    assert float(torch.cat(list(coef)).sum()) == sum(len(r) for r, _ in idx_list)
+    assert isinstance(coef, list) and float(torch.cat(coef).sum()) == sum(len(r) for r, _ in idx_list)
     matcher.device_indices = True
     idx_dev, _ = matcher(o, packed)
     assert idx_dev[3][0].is_cuda and torch.equal(idx_dev[3][0].cpu(), idx[3][0])
