@@ -21,15 +21,22 @@ class _Token:
     __slots__ = ("__weakref__",)
 
 
-def _allreduce_buckets(rt, train_backbone: bool):
-    """The training step's one exchange as two buckets: the gradients outside the backbone are averaged on a side
-    stream as soon as sedt_backward signals them final (bucket event), overlapping the backbone backward; the backbone bucket
-    follows on the main stream.  Returns post(flat) for ForwardRuntime.backward, or None for a single process."""
+def _allreduce_buckets(rt, train_backbone: bool, overlap: bool):
+    """The training step's one exchange: the mean all-reduce of the flat gradient buffer inside backward.
+    overlap=False (default): one collective after the last backward kernel.  overlap=True: two buckets -- the gradients outside
+    the backbone are averaged on a side stream as soon as sedt_backward signals them final (bucket event), while the backbone
+    backward is still running; the backbone bucket follows on the main stream.  Measured on 2 x B200 (B = 64 / GPU): 9.51 ms per
+    step overlapped vs ~9.25 ms sequential vs 8.94 ms without any exchange -- the persistent 148-CTA GEMM kernels of the backbone
+    backward lose SMs to NCCL's CTAs and run a second wave, which costs more than the 0.3 ms the overlap hides; hence the default.
+    Returns post(flat) for ForwardRuntime.backward, or None for a single process."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
         rt.bucket_event(False)
         return None
     from ..parallel import allreduce_mean_
+    if not overlap or not train_backbone:
+        rt.bucket_event(False)
+        return allreduce_mean_
     lo, hi = rt.backbone_grad_range()
     ev = rt.bucket_event(True)
     if getattr(rt, "_side_stream", None) is None:
@@ -38,18 +45,13 @@ def _allreduce_buckets(rt, train_backbone: bool):
 
     def post(flat):
         main = torch.cuda.current_stream()
-        if train_backbone:
-            with torch.cuda.stream(side):
-                side.wait_event(ev)                      # recorded by sedt_backward after input_proj's weight gradient
-                allreduce_mean_(flat[:lo])
-                if hi < flat.numel():
-                    allreduce_mean_(flat[hi:])
-            allreduce_mean_(flat[lo:hi])                 # main stream: after the backbone backward
-            main.wait_stream(side)
-        else:
+        with torch.cuda.stream(side):
+            side.wait_event(ev)                      # recorded by sedt_backward after input_proj's weight gradient
             allreduce_mean_(flat[:lo])
             if hi < flat.numel():
                 allreduce_mean_(flat[hi:])
+        allreduce_mean_(flat[lo:hi])                 # main stream: after the backbone backward
+        main.wait_stream(side)
     return post
 
 
@@ -98,7 +100,7 @@ class _TrainStep(torch.autograd.Function):
             # the replay below would overwrite it and autograd would then add the buffer to itself: move those gradients to
             # their own storage first (one flat copy, only in that case).
             _detach_grads_from(ctx.tctx.slot.g.get("grads"), ctx.params, ctx.names, ctx.shapes, rt)
-        post = _allreduce_buckets(rt, train_backbone) if model.grad_allreduce else None
+        post = _allreduce_buckets(rt, train_backbone, model.grad_allreduce_overlap) if model.grad_allreduce else None
         flat = rt.backward(ctx.tctx, d_logits, d_boxes, d_at, train_backbone, post=post)
         _, offs = rt.grad_layout()
         grads = []
@@ -131,7 +133,7 @@ class _TrainStepSP(torch.autograd.Function):
     def backward(ctx, d_logits, d_boxes, d_gt=None, d_feat=None):
         model = ctx.model
         rt = model._rt
-        post = _allreduce_buckets(rt, False) if model.grad_allreduce else None
+        post = _allreduce_buckets(rt, False, False) if model.grad_allreduce else None
         flat = rt.backward(ctx.tctx, d_logits, d_boxes, None, False, d_pred_feature=d_feat, post=post)
         _, offs = rt.grad_layout()
         grads = []
@@ -179,6 +181,9 @@ class SEDT(nn.Module):
         # data-parallel training: average the flat gradient bucket over the ranks inside backward (the model is then
         # NOT wrapped in DistributedDataParallel; one all-reduce instead of DDP's per-bucket hooks)
         self.grad_allreduce = False
+        # True: two buckets, the non-backbone one overlapped with the backbone backward (measured slower on B200, see
+        # _allreduce_buckets); False: one all-reduce after the last backward kernel
+        self.grad_allreduce_overlap = False
         self._rt: Optional[ForwardRuntime] = None
         self._self_sup = False
         self._feature_recon = False

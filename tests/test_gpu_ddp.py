@@ -20,11 +20,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_two_rank_gradients_equal_single_process(graph):
+@pytest.mark.parametrize("graph,overlap", [(False, False), (True, False), (False, True), (True, True)])
+def test_two_rank_gradients_equal_single_process(graph, overlap):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "ddp_grad_check.py")] + (["--graph"] if graph else [])
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "ddp_grad_check.py")] + (["--graph"] if graph else []) + (["--overlap"] if overlap else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "DDP_GRAD_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

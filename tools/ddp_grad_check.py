@@ -25,6 +25,7 @@ def loss_fn(out, R, sl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--overlap", action="store_true", help="bucketed all-reduce overlapped with the backbone backward")
     ap.add_argument("--per-rank", type=int, default=2)
     o = ap.parse_args()
     rank, world, local = parallel.env_ranks()
@@ -45,7 +46,7 @@ def main():
         model, _, _ = build_model(args)
         model.load_state_dict(sd, strict=True)
         model = model.to(dev).train()
-        model.grad_allreduce, model.use_cuda_graph = allreduce, o.graph
+        model.grad_allreduce, model.use_cuda_graph, model.grad_allreduce_overlap = allreduce, o.graph, o.overlap
         out = None
         for _ in range(3 if o.graph else 1):                 # graph mode: capture, then replays
             model.zero_grad(set_to_none=True)

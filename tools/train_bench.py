@@ -43,7 +43,9 @@ def run(o):
     model.load_state_dict(sd)
     model = model.to(dev).train()
     criterion = criterion.to(dev)
-    model.grad_allreduce = world > 1
+    # SEDT_BENCH_NO_ALLREDUCE=1: the same N-rank step without the gradient exchange (names the exposed all-reduce time by difference)
+    model.grad_allreduce = world > 1 and not os.environ.get("SEDT_BENCH_NO_ALLREDUCE")
+    model.grad_allreduce_overlap = bool(os.environ.get("SEDT_ALLREDUCE_OVERLAP"))
     model.use_cuda_graph = not o.no_graph
     B = o.batch
     x = synth.synth_clips(B, 496, 64, seed=200 + rank).to(dev)
@@ -169,7 +171,10 @@ def run(o):
             ref = run_reference(argparse.Namespace(batch=16, steps=1, warmup=1, gpus=1), emit_line=False)
             extra["cpu_baseline"] = ref["cpu_baseline"]
     return {**_train_line(world, B, o, ms, args), **extra,
-            "cuda_graph": not o.no_graph,
+            "cuda_graph": not o.no_graph, "grad_allreduce": bool(model.grad_allreduce),
+            "allreduce": "none" if not model.grad_allreduce else
+                         ("two buckets inside backward, the non-backbone bucket on a side stream overlapping the backbone backward"
+                          if model.grad_allreduce_overlap else "one all-reduce of the flat gradient buffer after the last backward kernel"),
             "optimizer": ("FusedAdamW (2 groups) with clip 0.1 fused: csrc/optim.cu, table builds = %d" % opt.table_builds)
             if fused_opt else "torch AdamW (2 groups) + clip_grad_norm_ 0.1 (stock PyTorch)",
             "loss": float(loss.detach()), "gpu_launches": int(model.runtime().kernel_launches() - kl0),
