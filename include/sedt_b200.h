@@ -325,9 +325,11 @@ SEDT_API int sedt_op_conv_tc_supported(const sedt_conv_desc* d);
 /* fused encoder self-attention block (csrc/enc_attn_fused.cu; sedt/transformer.py:192-198): in place
  * x[B*S,256] (fp32) += out_proj(MHA(q = k = nap, v = na)), na / nap [B*S,256] bf16 = LN(x) / LN(x)+pos, w_in [768,256] and
  * w_out [256,256] bf16 as nn.MultiheadAttention stores them, b_in [768] / b_out [256] fp32, kpm [B,S] uint8 (1 = padded key)
- * or NULL; S <= 128 tokens per clip, 8 heads of 32 */
+ * or NULL; S <= 128 tokens per clip, 8 heads of 32.  ln_out (bf16 [B*S,256], optional with ln_g / ln_b [256]): LayerNorm of the
+ * updated rows (the layer's norm2, sedt/transformer.py:199) from the same launch */
 SEDT_API int sedt_op_enc_attn(const void* na, const void* nap, const void* w_in, const float* b_in, const void* w_out,
-                              const float* b_out, const uint8_t* kpm, float* x, int B, int S, void* stream);
+                              const float* b_out, const uint8_t* kpm, float* x, int B, int S, const float* ln_g, const float* ln_b,
+                              void* ln_out, void* stream);
 
 SEDT_API int sedt_op_ffn(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual,
                          float* out, int64_t M, int ff, void* stream);

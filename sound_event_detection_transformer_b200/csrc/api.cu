@@ -269,10 +269,11 @@ int sedt_op_ffn(const void* x, const void* w1, const float* b1, const void* w2, 
 }
 
 int sedt_op_enc_attn(const void* na, const void* nap, const void* w_in, const float* b_in, const void* w_out, const float* b_out,
-                     const uint8_t* kpm, float* x, int B, int S, void* stream)
+                     const uint8_t* kpm, float* x, int B, int S, const float* ln_g, const float* ln_b, void* ln_out, void* stream)
 {
     SEDT_REQUIRE(na && nap && w_in && b_in && w_out && b_out && x, "op_enc_attn: null argument");
-    return launch_enc_attn_fused(na, nap, w_in, b_in, w_out, b_out, kpm, x, B, S, 0.17677669529663687f, (cudaStream_t)stream);
+    return launch_enc_attn_fused(na, nap, w_in, b_in, w_out, b_out, kpm, x, B, S, 0.17677669529663687f, (cudaStream_t)stream, ln_g, ln_b,
+                                 ln_out);
 }
 
 int sedt_prepare_clips(const float* raw, const int64_t* offsets, const double* mean, const double* std, float* out, int B, int frames,

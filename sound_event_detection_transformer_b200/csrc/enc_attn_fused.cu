@@ -16,7 +16,9 @@
 //     tcgen05  O_h = P V_h  (A from TMEM)                -> TMEM Otmp[team] (32 columns)
 //     rows     O_h / sum -> bf16 -> TMEM [16h, 16h+16)  (the columns Q_h occupied: dead once S_h has been issued)
 //   tcgen05  Y = O Wo^T  (A = the packed [128 x 256] O in TMEM, Wo streamed)   -> TMEM [128,384)
-//   rows     Y + bo + residual x (TMA-prefetched into bufA/bufB as soon as K / V^T are dead) -> fp32 -> TMA store (S rows only)
+//   rows     Y + bo + residual x (TMA-prefetched into bufA/bufB as soon as K / V are dead) -> fp32 -> TMA store (S rows only)
+//            optionally LayerNorm2 of the new row (two-pass mean / variance like layernorm_kernel; the two teams own half a row each
+//            and exchange partial sums through shared memory) -> bf16 -> global: the FFN's input, without a separate launch
 //
 // Replaces four launches per encoder layer (V projection, Q/K projection, attention_tc_kernel, out_proj + residual: 102 us at
 // B = 256, 11 % of the tensor peak, six HBM round trips of [rows, 256..512] tensors) by one that reads LN(x), LN(x)+pos and x once
@@ -42,7 +44,9 @@ constexpr int EA_BUFB = 65536;
 constexpr int EA_RING = 131072;
 constexpr int EA_BIAS = EA_RING + EA_NSLOTS * EA_SLOT;          // in_proj bias [768] + out_proj bias [256] fp32
 constexpr int EA_MASK = EA_BIAS + 1024 * 4;                     // key validity 0/1 [128], 0/-1e30 [128]
-constexpr int EA_BAR = EA_MASK + 1024;
+constexpr int EA_LN = EA_MASK + 1024;                           // LayerNorm2 gamma [256], beta [256]
+constexpr int EA_STAT = EA_LN + 2048;                           // per-row partial sums of the two teams: [2 passes][2 teams][128]
+constexpr int EA_BAR = EA_STAT + 2048;
 constexpr int EA_NBARS = 2 * EA_NSLOTS + 23;
 constexpr int EA_SMEM = EA_BAR + EA_NBARS * 8 + 16 + 1024;
 static_assert(EA_SMEM <= 232448, "shared memory budget exceeded");
@@ -60,6 +64,9 @@ struct EaParams {
     const uint8_t* kpm;       // [B, S] (1 = padded key) or null
     int B, S;
     float scale;
+    const float* ln_g;        // optional LayerNorm applied to the updated rows (the encoder layer's norm2): gamma / beta [256]
+    const float* ln_b;
+    __nv_bfloat16* ln_out;    // [B*S, 256] bf16 or null
     long long* dbg;           // optional phase timestamps of CTA 0 (SEDT_EA_DEBUG=1, see launch_enc_attn_fused); null in production
 };
 
@@ -105,6 +112,8 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
     float* s_bias = (float*)(smem + EA_BIAS);
     float* s_mask = (float*)(smem + EA_MASK);
     float* s_neg = s_mask + 128;
+    float* s_ln = (float*)(smem + EA_LN);
+    float* s_stat = (float*)(smem + EA_STAT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.S;
@@ -126,6 +135,8 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     for (int i = threadIdx.x; i < 1024; i += EA_THREADS) s_bias[i] = i < 768 ? p.b_in[i] : p.b_out[i - 768];   // weights: not produced by the predecessor
+    if (p.ln_out != nullptr)
+        for (int i = threadIdx.x; i < 512; i += EA_THREADS) s_ln[i] = i < 256 ? p.ln_g[i] : p.ln_b[i - 256];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -505,6 +516,7 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
             uint8_t* stage = team ? bufB : bufA;
             mbar_wait(&res_full[team], par);
             EA_TT(25);
+            float rsum = 0.f;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t acc[32];
@@ -521,8 +533,10 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                     float4* slot = reinterpret_cast<float4*>(rowp + ((j4 ^ (r & 7)) << 4));
                     const float4 r4 = *slot;
                     const float4 b4 = *reinterpret_cast<const float4*>(bo + 4 * j4);
-                    *slot = make_float4(__uint_as_float(acc[4 * j4]) + b4.x + r4.x, __uint_as_float(acc[4 * j4 + 1]) + b4.y + r4.y,
-                                        __uint_as_float(acc[4 * j4 + 2]) + b4.z + r4.z, __uint_as_float(acc[4 * j4 + 3]) + b4.w + r4.w);
+                    const float4 o4 = make_float4(__uint_as_float(acc[4 * j4]) + b4.x + r4.x, __uint_as_float(acc[4 * j4 + 1]) + b4.y + r4.y,
+                                                  __uint_as_float(acc[4 * j4 + 2]) + b4.z + r4.z, __uint_as_float(acc[4 * j4 + 3]) + b4.w + r4.w);
+                    *slot = o4;
+                    rsum += (o4.x + o4.y) + (o4.z + o4.w);
                 }
                 // chunk c leaves through TMA while chunk c + 1 is being computed
                 fence_async_smem();
@@ -531,6 +545,51 @@ enc_attn_fused_kernel(const __grid_constant__ CUtensorMap map_nap, const __grid_
                     tma_store_3d(&map_out, stage + c * EA_SLOT, (4 * team + c) * 32, 0, b);
                     tma_store_commit();
                 }
+            }
+            if (p.ln_out != nullptr) {
+                // LayerNorm2 of the updated row (sedt/transformer.py:199): this thread holds columns [128 team, 128 team + 128) of
+                // row r in the staging tile; mean and centred variance in two passes, the halves meeting in shared memory
+                s_stat[team * 128 + r] = rsum;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float mean = (s_stat[r] + s_stat[128 + r]) * (1.f / 256.f);
+                float q = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const uint8_t* rowp = stage + c * EA_SLOT + r * 128;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 v = *reinterpret_cast<const float4*>(rowp + ((j4 ^ (r & 7)) << 4));
+                        const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+                        q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+                    }
+                }
+                s_stat[256 + team * 128 + r] = q;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float rstd = rsqrtf((s_stat[256 + r] + s_stat[384 + r]) * (1.f / 256.f) + 1e-5f);
+                if (r < S) {
+                    __nv_bfloat16* orow = p.ln_out + ((size_t)b * S + r) * 256 + team * 128;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        const uint8_t* rowp = stage + c * EA_SLOT + r * 128;
+                        const float* g = s_ln + team * 128 + c * 32;
+                        const float* bt = s_ln + 256 + team * 128 + c * 32;
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            const float4 v0 = *reinterpret_cast<const float4*>(rowp + (((2 * j8) ^ (r & 7)) << 4));
+                            const float4 v1 = *reinterpret_cast<const float4*>(rowp + (((2 * j8 + 1) ^ (r & 7)) << 4));
+                            const float4 g0 = *reinterpret_cast<const float4*>(g + 8 * j8), g1 = *reinterpret_cast<const float4*>(g + 8 * j8 + 4);
+                            const float4 b0 = *reinterpret_cast<const float4*>(bt + 8 * j8), b1 = *reinterpret_cast<const float4*>(bt + 8 * j8 + 4);
+                            uint4 o;
+                            o.x = ea_pack2((v0.x - mean) * rstd * g0.x + b0.x, (v0.y - mean) * rstd * g0.y + b0.y);
+                            o.y = ea_pack2((v0.z - mean) * rstd * g0.z + b0.z, (v0.w - mean) * rstd * g0.w + b0.w);
+                            o.z = ea_pack2((v1.x - mean) * rstd * g1.x + b1.x, (v1.y - mean) * rstd * g1.y + b1.y);
+                            o.w = ea_pack2((v1.z - mean) * rstd * g1.z + b1.z, (v1.w - mean) * rstd * g1.w + b1.w);
+                            *reinterpret_cast<uint4*>(orow + c * 32 + j8 * 8) = o;
+                        }
+                    }
+                }
+                // the staging tile has been re-read by every thread of the team: only now may it be handed back to the producer
+                asm volatile("bar.sync %0, 128;" ::"r"(6 + team) : "memory");
             }
             EA_TT(26);
             if ((e & 3) == 0 && lane == 0) {
@@ -569,8 +628,10 @@ bool enc_attn_fused_enabled()
 // x[B*S, 256] (fp32, in place) += out_proj(attention(q = k = nap Wq/Wk^T, v = na Wv^T)); na / nap [B*S, 256] bf16,
 // w_in [768, 256] / w_out [256, 256] bf16 (row-major [out, in] as packed), b_in [768] / b_out [256] fp32, kpm [B, S] or null
 int launch_enc_attn_fused(const void* na, const void* nap, const void* w_in, const float* b_in, const void* w_out, const float* b_out,
-                          const uint8_t* kpm, float* x, int B, int S, float scale, cudaStream_t stream)
+                          const uint8_t* kpm, float* x, int B, int S, float scale, cudaStream_t stream, const float* ln_g,
+                          const float* ln_b, void* ln_out)
 {
+    SEDT_REQUIRE(ln_out == nullptr || (ln_g != nullptr && ln_b != nullptr && ((uintptr_t)ln_out & 15) == 0), "enc_attn_fused: LayerNorm needs gamma, beta and a 16-byte aligned output");
     SEDT_REQUIRE(enc_attn_fused_supported(256, 8, S, na, nap, w_in, w_out, x, DT_BF16), "enc_attn_fused: unsupported shape / alignment");
     SEDT_REQUIRE(B >= 1, "enc_attn_fused: B=%d", B);
     SEDT_TRY(tc_init());
@@ -599,6 +660,7 @@ int launch_enc_attn_fused(const void* na, const void* nap, const void* w_in, con
     }
     EaParams p;
     p.b_in = b_in; p.b_out = b_out; p.kpm = kpm; p.B = B; p.S = S; p.scale = scale; p.dbg = nullptr;
+    p.ln_g = ln_g; p.ln_b = ln_b; p.ln_out = (__nv_bfloat16*)ln_out;
     // SEDT_EA_DEBUG=1 (development only; synchronises): phase timeline of CTA 0's first two clips on stderr, in cycles
     static const bool debug = [] { const char* e = getenv("SEDT_EA_DEBUG"); return e != nullptr && atoi(e) != 0; }();
     long long* dbg_dev = nullptr;

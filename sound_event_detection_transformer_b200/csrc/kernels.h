@@ -223,8 +223,10 @@ int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void*
 bool enc_attn_fused_supported(int d, int nheads, int S, const void* na, const void* nap, const void* w_in, const void* w_out,
                               const float* x, int dt);
 bool enc_attn_fused_enabled();        // SEDT_ENC_ATTN_FUSED (default on)
+// ln_out (optional, bf16 [B*S, 256]): LayerNorm(updated x; ln_g, ln_b) written by the same launch (the layer's norm2)
 int launch_enc_attn_fused(const void* na, const void* nap, const void* w_in, const float* b_in, const void* w_out, const float* b_out,
-                          const uint8_t* kpm, float* x, int B, int S, float scale, cudaStream_t stream);
+                          const uint8_t* kpm, float* x, int B, int S, float scale, cudaStream_t stream, const float* ln_g = nullptr,
+                          const float* ln_b = nullptr, void* ln_out = nullptr);
 
 // ---- matcher.cu
 int launch_matcher(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes,

@@ -479,8 +479,10 @@ int Model::cross_mha(const Mha& A, const void* q_in, const void* Kp, const void*
 }
 
 int Model::mha(const Mha& A, bool self_attn, const void* q_in, const void* k_in, const void* v_in, int64_t B, int Lq, int Lk,
-               const uint8_t* kpm, const float* amask, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry)
+               const uint8_t* kpm, const float* amask, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry,
+               const Norm* post_norm, void* post_norm_out, bool* post_norm_done)
 {
+    if (post_norm_done != nullptr) *post_norm_done = false;
     const int d = cfg_.hidden_dim, dt = act_dt();
     const size_t es = dtype_size(dt);
     const size_t mark = ws.off;
@@ -493,9 +495,15 @@ int Model::mha(const Mha& A, bool self_attn, const void* q_in, const void* k_in,
     if (!dry && self_attn && q_in == k_in && amask == nullptr && Lq == Lk && Lq >= 64 && resid32 == out32 && cfg_.use_tensor_cores &&
         enc_attn_fused_enabled() && !A.in_proj.f32_only &&
         enc_attn_fused_supported(d, cfg_.nheads, Lq, v_in, q_in, packed_ + A.in_proj.off_w, packed_ + A.out_proj.off_w, out32, dt))
+    {
+        // the layer's next LayerNorm (norm2 of the pre-norm encoder layer) rides in the same launch when the caller asks for it
+        const bool ln = post_norm != nullptr && post_norm_out != nullptr && post_norm_done != nullptr;
+        if (ln) *post_norm_done = true;
         return launch_enc_attn_fused(v_in, q_in, packed_ + A.in_proj.off_w, (const float*)(packed_ + A.in_proj.off_b),
                                      packed_ + A.out_proj.off_w, (const float*)(packed_ + A.out_proj.off_b), kpm, out32, (int)B, Lq,
-                                     scale, s);
+                                     scale, s, ln ? (const float*)(packed_ + post_norm->off_g) : nullptr,
+                                     ln ? (const float*)(packed_ + post_norm->off_b) : nullptr, ln ? post_norm_out : nullptr);
+    }
     const void *Qp, *Kp, *Vp; int ldq, ldk;
     void* vbuf = ws.alloc((size_t)B * Lk * d * es);
     SEDT_TRY(linear(A.in_proj, 2 * d, d, v_in, dt, d, B * Lk, nullptr, vbuf, dt, d, 0, s, dry));
@@ -605,13 +613,15 @@ int Model::forward(const float* x, const uint8_t* mask, int B, int T, int F, con
     // ---- encoder (transformer.py:98-111, :177-204)
     void* na = ws.alloc((size_t)rows * d * es);
     void* nap = ws.alloc((size_t)rows * d * es);
+    void* na2 = ws.alloc((size_t)rows * d * es);
     void* ffh = ws.alloc((size_t)rows * ff * es);
     for (auto& e : enc_) {
         if (cfg_.pre_norm) {
             SEDT_TRY(LN(e.n1, x32, pos, pos_rows, na, nap, nullptr, rows));
-            SEDT_TRY(mha(e.attn, true, nap, nap, na, B, S, S, mask_ds, nullptr, x32, x32, ws, s, dry));
-            SEDT_TRY(LN(e.n2, x32, nullptr, 1, na, nullptr, nullptr, rows));
-            SEDT_TRY(ffn(e.lin1, e.lin2, na, rows, ffh, x32));
+            bool ln2_done = false;               // the fused attention block also writes LN2(x) (into na2: na is still being read)
+            SEDT_TRY(mha(e.attn, true, nap, nap, na, B, S, S, mask_ds, nullptr, x32, x32, ws, s, dry, &e.n2, na2, &ln2_done));
+            if (!ln2_done) SEDT_TRY(LN(e.n2, x32, nullptr, 1, na2, nullptr, nullptr, rows));
+            SEDT_TRY(ffn(e.lin1, e.lin2, na2, rows, ffh, x32));
         } else {
             if (!dry) SEDT_TRY(launch_cast_addpos(x32, pos, pos_rows, na, nap, dt, rows, s));
             SEDT_TRY(mha(e.attn, true, nap, nap, na, B, S, S, mask_ds, nullptr, x32, x32, ws, s, dry));

@@ -131,7 +131,8 @@ private:
     int cross_mha(const Mha& A, const void* q_in, const void* Kp, const void* Vp, int ldkv, int64_t B, int Lq, int Lk,
                   const uint8_t* kpm, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry);
     int mha(const Mha& A, bool self_attn, const void* q_in, const void* k_in, const void* v_in, int64_t B, int Lq, int Lk,
-            const uint8_t* kpm, const float* amask, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry);
+            const uint8_t* kpm, const float* amask, float* resid32, float* out32, Arena& ws, cudaStream_t s, bool dry,
+            const Norm* post_norm = nullptr, void* post_norm_out = nullptr, bool* post_norm_done = nullptr);
 
     Config cfg_;
     std::vector<WeightSlot> slots_;

@@ -33,13 +33,17 @@ def reference(na, nap, w_in, b_in, w_out, b_out, kpm, x, B, S):
     return x + o @ r16(w_out).T + b_out
 
 
-def run(na, nap, w_in, b_in, w_out, b_out, kpm, x, B, S):
+def run(na, nap, w_in, b_in, w_out, b_out, kpm, x, B, S, ln=None):
+    """ln = (gamma, beta): also returns LayerNorm(updated x) as the kernel's bf16 side output (the layer's norm2)."""
     lib = _lib.load()
     y = x.clone()
+    ln_out = torch.full((B * S, 256), float("nan"), dtype=torch.bfloat16, device="cuda") if ln is not None else None
     _lib.check(lib.sedt_op_enc_attn(na.data_ptr(), nap.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), w_out.data_ptr(),
-                                    b_out.data_ptr(), _lib.ptr(kpm) or None, y.data_ptr(), B, S, _lib.current_stream()))
+                                    b_out.data_ptr(), _lib.ptr(kpm) or None, y.data_ptr(), B, S,
+                                    ln[0].data_ptr() if ln is not None else None, ln[1].data_ptr() if ln is not None else None,
+                                    _lib.ptr(ln_out) or None, _lib.current_stream()))
     torch.cuda.synchronize()
-    return y
+    return y if ln is None else (y, ln_out)
 
 
 def make(B, S, seed, masked):
@@ -76,6 +80,25 @@ def test_enc_attn_fused_matches_torch(B, S, masked):
     assert err < 1e-3 and upd.item() < 4e-3 and worst < 2e-2
 
 
+@pytest.mark.parametrize("B,S,masked", [(3, 124, False), (5, 128, True), (200, 77, False), (2, 64, True)])
+def test_enc_attn_fused_layernorm_side_output(B, S, masked):
+    """The optional norm2 output: LayerNorm (eps 1e-5, two-pass statistics like layernorm_kernel) of the rows the same launch
+    wrote, rounded to bf16; the main output must not change."""
+    args = make(B, S, 300 + B + S, masked)
+    g = torch.Generator(device="cuda").manual_seed(B * S)
+    gamma = 1.0 + 0.2 * torch.randn(256, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(256, generator=g, device="cuda")
+    y0 = run(*args, B, S)
+    y, ln = run(*args, B, S, ln=(gamma, beta))
+    assert torch.equal(y, y0)
+    want = r16(torch.nn.functional.layer_norm(y, (256,), gamma, beta, 1e-5))
+    got = ln.float()
+    assert torch.isfinite(got).all()
+    err = ((got - want).norm() / want.norm()).item()
+    print(f"enc_attn_fused LN side output B={B} S={S}: rel-L2 {err:.2e}, max abs {(got - want).abs().max().item():.2e}")
+    assert err < 2e-3 and (got - want).abs().max().item() < 6e-2          # bf16 rounding flips of 1 ulp at |y| ~ 4
+
+
 def test_enc_attn_fused_is_deterministic_and_touches_only_its_rows():
     B, S = 150, 124                               # 150 clips on 148 SMs: two CTAs take a second clip
     args = make(B, S, 7, False)
@@ -90,6 +113,6 @@ def test_enc_attn_fused_is_deterministic_and_touches_only_its_rows():
     na, nap, w_in, b_in, w_out, b_out, kpm, _ = args
     na_p, nap_p = (torch.cat([t, torch.zeros(64, 256, dtype=t.dtype, device="cuda")]) for t in (na, nap))
     _lib.check(lib.sedt_op_enc_attn(na_p.data_ptr(), nap_p.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), w_out.data_ptr(),
-                                    b_out.data_ptr(), None, big.data_ptr(), B, S, _lib.current_stream()))
+                                    b_out.data_ptr(), None, big.data_ptr(), B, S, None, None, None, _lib.current_stream()))
     torch.cuda.synchronize()
     assert torch.equal(big[:B * S], a) and bool((big[B * S:] == 7.0).all())
