@@ -497,7 +497,11 @@ int Model::mha(const Mha& A, bool self_attn, const void* q_in, const void* k_in,
         enc_attn_fused_supported(d, cfg_.nheads, Lq, v_in, q_in, packed_ + A.in_proj.off_w, packed_ + A.out_proj.off_w, out32, dt))
     {
         // the layer's next LayerNorm (norm2 of the pre-norm encoder layer) rides in the same launch when the caller asks for it
-        const bool ln = post_norm != nullptr && post_norm_out != nullptr && post_norm_done != nullptr;
+        // (SEDT_ENC_ATTN_LN=1; off by default: measured on B200 at B = 256 the fold makes the forward 40 us SLOWER -- 4.445 vs
+        // 4.405 ms -- although it removes six 14 us launches: the two extra passes over the staging tile and the row-strided
+        // bf16 stores sit on the per-clip critical path between the output stores and the next clip's loads)
+        static const bool ln_on = [] { const char* e = getenv("SEDT_ENC_ATTN_LN"); return e != nullptr && atoi(e) != 0; }();
+        const bool ln = ln_on && post_norm != nullptr && post_norm_out != nullptr && post_norm_done != nullptr;
         if (ln) *post_norm_done = true;
         return launch_enc_attn_fused(v_in, q_in, packed_ + A.in_proj.off_w, (const float*)(packed_ + A.in_proj.off_b),
                                      packed_ + A.out_proj.off_w, (const float*)(packed_ + A.out_proj.off_b), kpm, out32, (int)B, Lq,
