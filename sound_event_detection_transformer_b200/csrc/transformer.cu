@@ -31,10 +31,7 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// ---- LayerNorm: one warp per row, 8 contiguous elements per lane; every warp takes LN_ROWS rows and issues all their loads
-// (and the position rows) before the first reduction, so that 4 KB per warp are in flight instead of 1 KB: the kernel is a pure
-// HBM stream (1 KB in, 0.5-1.5 KB out per row) and ran at 55-60 % of the copy bandwidth with one row per warp ------------------
-constexpr int LN_ROWS = 4;
+// ---- LayerNorm: one warp per row, 8 contiguous elements per lane -------------
 template <typename T, bool kNorm>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -44,45 +41,33 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
-    const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * LN_ROWS;
-    if (row0 >= rows) return;
-    float v[LN_ROWS][8], p[LN_ROWS][8];
-#pragma unroll
-    for (int i = 0; i < LN_ROWS; ++i)
-        if (row0 + i < rows) load8(x + (row0 + i) * D + lane * 8, v[i]);
-    if (ypos != nullptr) {
-#pragma unroll
-        for (int i = 0; i < LN_ROWS; ++i)
-            if (row0 + i < rows) load8(pos + ((row0 + i) % pos_rows) * D + lane * 8, p[i]);
-    }
-    float g[8], bt[8];
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float v[8];
+    load8(x + row * D + lane * 8, v);
     if (kNorm) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[i];
+        const float mean = warp_sum(s) * (1.f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
+        float g[8], bt[8];
         load8(gamma + lane * 8, g);
         load8(beta + lane * 8, bt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * g[i] + bt[i];
     }
+    if (y != nullptr) store8<T>(y + row * D + lane * 8, v);
+    if (y32 != nullptr) store8<float>(y32 + row * D + lane * 8, v);
+    if (ypos != nullptr) {
+        float p[8];
+        load8(pos + (row % pos_rows) * D + lane * 8, p);
 #pragma unroll
-    for (int i = 0; i < LN_ROWS; ++i) {
-        const int64_t row = row0 + i;
-        if (row >= rows) break;
-        if (kNorm) {
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s += v[i][k];
-            const float mean = warp_sum(s) * (1.f / D);
-            float q = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; q = fmaf(d, d, q); }
-            const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[i][k] = (v[i][k] - mean) * rstd * g[k] + bt[k];
-        }
-        if (y != nullptr) store8<T>(y + row * D + lane * 8, v[i]);
-        if (y32 != nullptr) store8<float>(y32 + row * D + lane * 8, v[i]);
-        if (ypos != nullptr) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) p[i][k] += v[i][k];
-            store8<T>(ypos + row * D + lane * 8, p[i]);
-        }
+        for (int i = 0; i < 8; ++i) p[i] += v[i];
+        store8<T>(ypos + row * D + lane * 8, p);
     }
 }
 
@@ -414,7 +399,7 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, cons
                      void* y, void* ypos, float* y32, int dt, int64_t rows, cudaStream_t stream)
 {
     if (rows == 0) return SEDT_OK;
-    dim3 grid((unsigned)ceil_div(rows, 8 * LN_ROWS)), block(256);
+    dim3 grid((unsigned)ceil_div(rows, 8)), block(256);
     ProfScope _prof(PROF_NORM, stream);
     if (dt == DT_F32) SEDT_CHECK_CUDA(launch_pdl(layernorm_kernel<float, true>, grid, block, 0, stream, 1, x, gamma, beta, pos, pos_rows, (float*)y, (float*)ypos, y32, rows));
     else SEDT_CHECK_CUDA(launch_pdl(layernorm_kernel<__nv_bfloat16, true>, grid, block, 0, stream, 1, x, gamma, beta, pos, pos_rows, (__nv_bfloat16*)y, (__nv_bfloat16*)ypos, y32, rows));
@@ -427,7 +412,7 @@ int launch_cast_addpos(const float* x, const float* pos, int64_t pos_rows, void*
                        cudaStream_t stream)
 {
     if (rows == 0) return SEDT_OK;
-    dim3 grid((unsigned)ceil_div(rows, 8 * LN_ROWS)), block(256);
+    dim3 grid((unsigned)ceil_div(rows, 8)), block(256);
     ProfScope _prof(PROF_NORM, stream);
     if (dt == DT_F32) SEDT_CHECK_CUDA(launch_pdl(layernorm_kernel<float, false>, grid, block, 0, stream, 1, x, (const float*)nullptr, (const float*)nullptr, pos, pos_rows, (float*)y, (float*)ypos, (float*)nullptr, rows));
     else SEDT_CHECK_CUDA(launch_pdl(layernorm_kernel<__nv_bfloat16, false>, grid, block, 0, stream, 1, x, (const float*)nullptr, (const float*)nullptr, pos, pos_rows, (__nv_bfloat16*)y, (__nv_bfloat16*)ypos, (float*)nullptr, rows));
