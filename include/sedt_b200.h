@@ -322,6 +322,11 @@ SEDT_API int sedt_op_conv_wgrad(const void* x, const void* dy, float* dw, int B,
 SEDT_API int sedt_op_conv_tc_supported(const sedt_conv_desc* d);
 /* Fused transformer FFN of the eval forward (sedt/transformer.py:202-203): out[M,256] fp32 = residual + relu(x W1^T + b1) W2^T + b2,
  * x [M,256] bf16, W1 [ff,256] / W2 [256,ff] bf16 (nn.Linear layout), ff % 256 == 0; the [M,ff] hidden activation never leaves the SM. */
+/* fused tail of a layer1 bottleneck (csrc/bneck_fused.cu; torchvision resnet.py:150-161): out[B,H,W,256] (bf16 NHWC) =
+ * relu(conv1x1(relu(conv3x3(h1, w2) + bias2), w3) + bias3 + residual); h1 [B,H,W,64] bf16, w2 [64][3][3][64] / w3 [256][64] bf16
+ * with the FrozenBN scale folded in, fp32 biases, residual [B,H,W,256] bf16.  Exported for its parity test. */
+SEDT_API int sedt_op_bneck_tail(const void* h1, const void* w2, const float* bias2, const void* w3, const float* bias3,
+                                const void* residual, void* out, int B, int H, int W, void* stream);
 /* fused encoder self-attention block (csrc/enc_attn_fused.cu; sedt/transformer.py:192-198): in place
  * x[B*S,256] (fp32) += out_proj(MHA(q = k = nap, v = na)), na / nap [B*S,256] bf16 = LN(x) / LN(x)+pos, w_in [768,256] and
  * w_out [256,256] bf16 as nn.MultiheadAttention stores them, b_in [768] / b_out [256] fp32, kpm [B,S] uint8 (1 = padded key)

@@ -103,6 +103,7 @@ SIGNATURES = {
     "sedt_op_conv": (_i, [C.POINTER(SedtConvDesc), _i, _vp]),
     "sedt_op_conv_tc_supported": (_i, [C.POINTER(SedtConvDesc)]),
     "sedt_op_ffn": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "sedt_op_bneck_tail": (_i, [_vp] * 7 + [_i, _i, _i, _vp]),
     "sedt_op_enc_attn": (_i, [_vp] * 8 + [_i, _i, _vp, _vp, _vp, _vp]),
     "sedt_op_repack_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sedt_op_upsample2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libsedt_b200.so")
-SOURCES = ["api.cu", "model.cu", "train.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc3.cu", "gemm_tc4.cu", "gemm_wgrad.cu", "backward.cu", "dropout.cu", "attention_tc.cu", "attention_bwd_tc.cu", "conv_simt.cu", "stem.cu", "stem_tc.cu", "pack.cu", "transformer.cu", "matcher.cu", "optim.cu", "decode.cu", "ffn_fused.cu", "enc_attn_fused.cu", "prepare.cu", "augment.cu"]
+SOURCES = ["api.cu", "model.cu", "train.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc3.cu", "gemm_tc4.cu", "gemm_wgrad.cu", "backward.cu", "dropout.cu", "attention_tc.cu", "attention_bwd_tc.cu", "conv_simt.cu", "stem.cu", "stem_tc.cu", "pack.cu", "transformer.cu", "matcher.cu", "optim.cu", "decode.cu", "ffn_fused.cu", "enc_attn_fused.cu", "bneck_fused.cu", "prepare.cu", "augment.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

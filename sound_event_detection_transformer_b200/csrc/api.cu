@@ -268,6 +268,21 @@ int sedt_op_ffn(const void* x, const void* w1, const float* b1, const void* w2, 
     return launch_ffn_fused(x, w1, b1, w2, b2, residual, 256, out, 256, M, ff, (cudaStream_t)stream);
 }
 
+int sedt_op_bneck_tail(const void* h1, const void* w2, const float* bias2, const void* w3, const float* bias3, const void* residual,
+                       void* out, int B, int H, int W, void* stream)
+{
+    SEDT_REQUIRE(h1 && w2 && bias2 && w3 && bias3 && residual && out, "op_bneck_tail: null argument");
+    ConvGemm g2, g3;
+    g2.in = h1; g2.w = w2; g2.bias = bias2; g2.out = nullptr; g2.in_dt = g2.out_dt = DT_BF16;
+    g2.B = B; g2.H = g2.Ho = H; g2.W = g2.Wo = W; g2.Cin = g2.lda = 64; g2.Cout = g2.ldc = g2.ld_res = 64;
+    g2.R = g2.S = 3; g2.stride = 1; g2.dil = 1; g2.pad = 1; g2.relu = 1;
+    g2.out = out;                                   // (placeholder: alignment checks only, never written)
+    g3.in = out; g3.w = w3; g3.bias = bias3; g3.residual = residual; g3.out = out; g3.in_dt = g3.out_dt = DT_BF16;
+    g3.B = B; g3.H = g3.Ho = H; g3.W = g3.Wo = W; g3.Cin = g3.lda = 64; g3.Cout = g3.ldc = g3.ld_res = 256; g3.relu = 1;
+    SEDT_REQUIRE(bneck_tail_supported(g2, g3), "op_bneck_tail: unsupported shape (H x W = %d x %d)", H, W);
+    return launch_bneck_tail(g2, g3, (cudaStream_t)stream);
+}
+
 int sedt_op_enc_attn(const void* na, const void* nap, const void* w_in, const float* b_in, const void* w_out, const float* b_out,
                      const uint8_t* kpm, float* x, int B, int S, const float* ln_g, const float* ln_b, void* ln_out, void* stream)
 {

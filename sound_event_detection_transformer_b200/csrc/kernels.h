@@ -219,6 +219,11 @@ bool ffn_fused_preferred(int64_t M);  // true where the fused kernel beats the t
 int launch_ffn_fused(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual, int ld_res,
                      float* out, int ldo, int64_t M, int ff, cudaStream_t stream);
 
+// ---- bneck_fused.cu: conv2 (3x3, 64 -> 64) + conv3 (1x1, 64 -> 256) + residual + ReLU of a layer1 bottleneck in one launch
+bool bneck_tail_enabled();            // SEDT_BNECK_FUSED (default on)
+bool bneck_tail_supported(const ConvGemm& g2, const ConvGemm& g3);
+int launch_bneck_tail(const ConvGemm& g2, const ConvGemm& g3, cudaStream_t stream);
+
 // ---- enc_attn_fused.cu: x += out_proj(MHA(q = k = nap, v = na)) for one <= 128-token clip per tile, everything on chip
 bool enc_attn_fused_supported(int d, int nheads, int S, const void* na, const void* nap, const void* w_in, const void* w_out,
                               const float* x, int dt);

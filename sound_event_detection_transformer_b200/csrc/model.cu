@@ -323,8 +323,7 @@ int Model::gemm(const ConvGemm& g, cudaStream_t s, bool dry)
 
 static inline int conv_out_dim(int n, int k, int stride, int pad, int dil) { return (n + 2 * pad - dil * (k - 1) - 1) / stride + 1; }
 
-int Model::conv(const ConvLayer& L, const void* in, int N, int H, int W, const void* residual, void* out, int* Ho, int* Wo,
-                cudaStream_t s, bool dry)
+ConvGemm Model::conv_gemm(const ConvLayer& L, const void* in, int N, int H, int W, const void* residual, void* out) const
 {
     ConvGemm g;
     g.in = in; g.w = packed_ + L.off_w; g.scale = fold_scale() ? nullptr : (const float*)(packed_ + L.off_scale);
@@ -334,6 +333,13 @@ int Model::conv(const ConvLayer& L, const void* in, int N, int H, int W, const v
     g.Ho = conv_out_dim(H, L.k, L.stride, L.pad, L.dil); g.Wo = conv_out_dim(W, L.k, L.stride, L.pad, L.dil);
     g.Cout = L.cout; g.ldc = L.cout; g.ld_res = L.cout;
     g.R = g.S = L.k; g.stride = L.stride; g.dil = L.dil; g.pad = L.pad; g.relu = L.relu;
+    return g;
+}
+
+int Model::conv(const ConvLayer& L, const void* in, int N, int H, int W, const void* residual, void* out, int* Ho, int* Wo,
+                cudaStream_t s, bool dry)
+{
+    const ConvGemm g = conv_gemm(L, in, N, H, W, residual, out);
     *Ho = g.Ho; *Wo = g.Wo;
     return gemm(g, s, dry);
 }
@@ -373,14 +379,22 @@ int Model::run_blocks(size_t b0, size_t b1, const void* in, int N, int* H, int* 
         int h1, w1, ho, wo, h3, w3;
         void* dst = (i + 1 == b1 && final_out != nullptr) ? final_out : ping;
         SEDT_TRY(conv(b.c1, cur, N, *H, *W, nullptr, bb.t1, &h1, &w1, s, dry));
-        SEDT_TRY(conv(b.c2, bb.t1, N, *H, *W, nullptr, bb.t2, &ho, &wo, s, dry));
         const void* idn = cur;
         if (b.has_ds) {
             int hd, wd;
             SEDT_TRY(conv(b.ds, cur, N, *H, *W, nullptr, bb.ds, &hd, &wd, s, dry));
             idn = bb.ds;
         }
-        SEDT_TRY(conv(b.c3, bb.t2, N, ho, wo, idn, dst, &h3, &w3, s, dry));
+        // layer1: conv2 + conv3 + residual as one launch, the 64-channel h2 tile never leaves the SM (bneck_fused.cu)
+        const ConvGemm g2 = conv_gemm(b.c2, bb.t1, N, *H, *W, nullptr, bb.t2);
+        const ConvGemm g3 = conv_gemm(b.c3, bb.t2, N, g2.Ho, g2.Wo, idn, dst);
+        if (!dry && cfg_.precision == 1 && cfg_.use_tensor_cores && bneck_tail_enabled() && bneck_tail_supported(g2, g3)) {
+            SEDT_TRY(launch_bneck_tail(g2, g3, s));
+            ho = g2.Ho; wo = g2.Wo;
+        } else {
+            SEDT_TRY(conv(b.c2, bb.t1, N, *H, *W, nullptr, bb.t2, &ho, &wo, s, dry));
+            SEDT_TRY(conv(b.c3, bb.t2, N, ho, wo, idn, dst, &h3, &w3, s, dry));
+        }
         cur = dst;
         std::swap(ping, pong);
         *H = ho; *W = wo;

@@ -117,6 +117,7 @@ private:
     Mha make_mha(const std::string& name);
 
     int gemm(const ConvGemm& g, cudaStream_t s, bool dry);
+    ConvGemm conv_gemm(const ConvLayer& L, const void* in, int N, int H, int W, const void* residual, void* out) const;
     int conv(const ConvLayer& L, const void* in, int N, int H, int W, const void* residual, void* out, int* Ho, int* Wo,
              cudaStream_t s, bool dry);
     // rows x L.in -> rows x L.out.  row0/nrows select a slice of W's rows (packed in_proj).
