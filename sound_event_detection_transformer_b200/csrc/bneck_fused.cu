@@ -53,9 +53,14 @@ constexpr uint32_t TM_ACC3 = 128;      // conv3 accumulator, 256 columns
 struct BfParams {
     const float* bias2;        // [64]  folded bn2 bias
     const float* bias3;        // [256] folded bn3 bias
+    const __nv_bfloat16* residual;   // identity tensor [B, H, W, ld_res] (RES_REG variant: read straight into registers)
+    int ld_res, H, W;
     int bw, bh, tiles_w, tiles_h, total_tiles;
 };
 
+// RES_REG: the identity chunk is not TMA-prefetched into the staging buffer (where its HBM latency sits inside the 3-deep chunk
+// ring) but loaded by the row threads straight into registers at the start of stage 2, one tile ahead of its use
+template <bool RES_REG>
 __global__ void __launch_bounds__(BF_THREADS, 1)
 bneck_tail_kernel(const __grid_constant__ CUtensorMap map_halo, const __grid_constant__ CUtensorMap map_w2,
                   const __grid_constant__ CUtensorMap map_w3, const __grid_constant__ CUtensorMap map_out,
@@ -179,8 +184,12 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap map_halo, const __grid_con
                 int w0, h0, n0;
                 tile_coords(first + (q / BF_NCHUNK) * stride, w0, h0, n0);
                 const int ob = q % BF_OB;
-                mbar_expect_tx(&buf_ready[ob], BF_CHUNK_BYTES);
-                tma_load_4d(&map_res, out_base + ob * BF_CHUNK_BYTES, &buf_ready[ob], (q % BF_NCHUNK) * 64, w0, h0, n0);
+                if constexpr (RES_REG) {
+                    mbar_arrive(&buf_ready[ob]);                         // the staging buffer is free again, nothing to load
+                } else {
+                    mbar_expect_tx(&buf_ready[ob], BF_CHUNK_BYTES);
+                    tma_load_4d(&map_res, out_base + ob * BF_CHUNK_BYTES, &buf_ready[ob], (q % BF_NCHUNK) * 64, w0, h0, n0);
+                }
             };
             for (int q = 0; q < BF_OB && q < nq; ++q) prefetch(q);
             for (int q = 0; q < nq; ++q) {
@@ -231,9 +240,23 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap map_halo, const __grid_con
         // stage 2 of local tile j: conv3 accumulator + bias3 + identity + ReLU -> bf16 staging chunks (this thread: row r, columns
         // [32 half, 32 half + 32) of every 64-column chunk)
         auto stage2 = [&](int j) {
+            uint4 idn[BF_NCHUNK][4];
+            if constexpr (RES_REG) {
+                // identity: this thread's 32 columns of every chunk of row r, straight from global memory (64 contiguous bytes per chunk)
+                int w0, h0, n0;
+                tile_coords(first + j * stride, w0, h0, n0);
+                const int py = h0 + r / p.bw, px = w0 + r % p.bw;
+                const bool valid = py < p.H && px < p.W;
+                const __nv_bfloat16* rrow = p.residual + (((size_t)n0 * p.H + py) * p.W + px) * p.ld_res + half * 32;
+#pragma unroll
+                for (int c = 0; c < BF_NCHUNK; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        idn[c][k] = valid ? __ldg(reinterpret_cast<const uint4*>(rrow + c * 64) + k) : make_uint4(0, 0, 0, 0);
+            }
             mbar_wait(acc3_full, (uint32_t)j & 1);
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < BF_NCHUNK; ++c) {
                 const int q = j * BF_NCHUNK + c, ob = q % BF_OB;
                 uint32_t acc[32];
@@ -243,9 +266,30 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap map_halo, const __grid_con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc3_empty);
                 }
-                mbar_wait(&buf_ready[ob], (uint32_t)(q / BF_OB) & 1);    // staging chunk free and the identity chunk landed
-                epilogue_slab<__nv_bfloat16, BF_CHUNK_BYTES>(acc, half, c * 64 + half * 32, nullptr, p.bias3, true, 1,
-                                                             out_base + ob * BF_CHUNK_BYTES, r, sw);
+                mbar_wait(&buf_ready[ob], (uint32_t)(q / BF_OB) & 1);    // staging chunk free (and, without RES_REG, the identity chunk landed)
+                if constexpr (RES_REG) {
+                    uint8_t* rowp = out_base + ob * BF_CHUNK_BYTES + r * 128;
+                    const float* b3 = p.bias3 + c * 64 + half * 32;
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        const float4 ba = __ldg(reinterpret_cast<const float4*>(b3) + 2 * j8), bb = __ldg(reinterpret_cast<const float4*>(b3) + 2 * j8 + 1);
+                        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                        const uint32_t rw[4] = {idn[c][j8].x, idn[c][j8].y, idn[c][j8].z, idn[c][j8].w};
+                        uint32_t w[4];
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[qq]);
+                            const float a = fmaxf(__uint_as_float(acc[8 * j8 + 2 * qq]) + bv[2 * qq] + __low2float(h), 0.f);
+                            const float b = fmaxf(__uint_as_float(acc[8 * j8 + 2 * qq + 1]) + bv[2 * qq + 1] + __high2float(h), 0.f);
+                            const __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
+                            w[qq] = *reinterpret_cast<const uint32_t*>(&o);
+                        }
+                        *reinterpret_cast<uint4*>(rowp + (((half * 4 + j8) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                } else {
+                    epilogue_slab<__nv_bfloat16, BF_CHUNK_BYTES>(acc, half, c * 64 + half * 32, nullptr, p.bias3, true, 1,
+                                                                 out_base + ob * BF_CHUNK_BYTES, r, sw);
+                }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&buf_full[ob]);
@@ -318,14 +362,21 @@ int launch_bneck_tail(const ConvGemm& g2, const ConvGemm& g3, cudaStream_t strea
     BfParams p;
     p.bias2 = g2.bias; p.bias3 = g3.bias; p.bw = q.bw; p.bh = q.bh; p.tiles_w = q.tiles_w; p.tiles_h = q.tiles_h;
     p.total_tiles = pr.tiles_m;
+    p.residual = (const __nv_bfloat16*)g3.residual; p.ld_res = g3.ld_res; p.H = g3.Ho; p.W = g3.Wo;
+    // SEDT_BNECK_RESREG: 1 = identity through registers, 0 = TMA-prefetched into the staging chunk
+    static const bool res_reg = [] { const char* e = getenv("SEDT_BNECK_RESREG"); return e != nullptr && atoi(e) != 0; }();
     static bool attr_set = false;
     if (!attr_set) {
-        SEDT_CHECK_CUDA(cudaFuncSetAttribute(bneck_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(bneck_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM));
+        SEDT_CHECK_CUDA(cudaFuncSetAttribute(bneck_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM));
         attr_set = true;
     }
     const int grid = std::min(pr.tiles_m, num_sms());
     ProfScope _prof(PROF_GEMM_TC, stream);
-    SEDT_CHECK_CUDA(launch_pdl(bneck_tail_kernel, dim3((unsigned)grid), dim3(BF_THREADS), BF_SMEM, stream, 1, mhalo, pr.map_b, mw3, mo, mr, p));
+    if (res_reg)
+        SEDT_CHECK_CUDA(launch_pdl(bneck_tail_kernel<true>, dim3((unsigned)grid), dim3(BF_THREADS), BF_SMEM, stream, 1, mhalo, pr.map_b, mw3, mo, mr, p));
+    else
+        SEDT_CHECK_CUDA(launch_pdl(bneck_tail_kernel<false>, dim3((unsigned)grid), dim3(BF_THREADS), BF_SMEM, stream, 1, mhalo, pr.map_b, mw3, mo, mr, p));
     SEDT_COUNT_KIND(KK_BOTTLENECK_FUSED);
     SEDT_CHECK_CUDA(cudaGetLastError());
     return SEDT_OK;

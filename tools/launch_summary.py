@@ -25,7 +25,8 @@ def short(name):
 
 
 def klass(name):
-    if "conv_tc" in name or "ffn_fused" in name: return "gemm_tcgen05"
+    if "conv_tc" in name or "ffn_fused" in name or "bneck_tail" in name: return "gemm_tcgen05"
+    if "enc_attn_fused" in name: return "attention"
     if "stem" in name: return "stem"
     if "attention" in name: return "attention"
     if "layernorm" in name or "cast_addpos" in name: return "norm"
