@@ -364,10 +364,14 @@ def main():
         barrier()
         model.use_cuda_graph = False                       # per-kernel events need eager launches
         lib.sedt_profile_enable(1)
+        kinds0 = _lib.kernel_kind_counts()
         for i in range(K):
             model(devx[i % nrot])
         _lib.check(lib.sedt_profile_read(ms_cls, n_cls))
         lib.sedt_profile_enable(0)
+        kinds1 = _lib.kernel_kind_counts()
+    # which of the size-dependent kernels produced these numbers (launches per step of the eager pass = the graph's contents)
+    kernel_kinds = {k: (kinds1[k] - kinds0[k]) / K for k in kinds1 if kinds1[k] != kinds0[k]}
     per_class = {n: {"ms_per_step": ms_cls[i] / K, "launches_per_step": n_cls[i] / K}
                  for i, n in enumerate(_lib.KERNEL_CLASSES) if n_cls[i]}
 
@@ -428,7 +432,8 @@ def main():
         "l2": f"inputs rotate over {nrot} distinct {in_bytes / 2**20:.1f} MiB batches; per-step activation traffic (>1 GB) exceeds the 126 MB L2",
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": eager,
+        "gpu_launches": launches, "kernel_kinds_per_step": kernel_kinds, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_eager_baseline": eager,
     })
     if world > 1:
         dist.destroy_process_group()
