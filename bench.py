@@ -245,6 +245,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("SEDT_BENCH_LANES", "2")),
+                    help="batches in flight per GPU (eval): lane i is its own model copy + CUDA stream (lanes.py); 1 = plain loop")
     ap.add_argument("--mode", default="eval", choices=["eval", "train"],
                     help="eval: the headline metric (configs[1]); train: the config-4 training step (batch 64 per GPU by default)")
     opts = ap.parse_args()
@@ -301,61 +303,106 @@ def main():
     devx = [h.to(dev) for h in host]
     nrot = len(devx)
 
+    from sound_event_detection_transformer_b200.lanes import EvalLanes
+    from sound_event_detection_transformer_b200.prefetch import ClipPrefetcher
+    nl = max(1, opts.lanes)
+    models = [model]
+    for _ in range(nl - 1):                              # every lane: its own module, packed weights, workspace and graph
+        m, _, _ = build_model(args)
+        m.load_state_dict(sd, strict=True)
+        m = m.to(dev).eval()
+        m.use_cuda_graph = model.use_cuda_graph
+        models.append(m)
+
+    def launch_count():
+        return int(lib.sedt_launch_count()) + sum(int(m.runtime().graph_kernel_launches) for m in models)
+
     # ---- (1) device-resident throughput -------------------------------------------------
-    with torch.no_grad():
-        for i in range(W):
-            model(devx[i % nrot])
-        barrier()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-        # keep every GPU under the bench load while nvidia-smi starts sampling (untimed extra warm-up, <= 1 s)
-        t_w = time.perf_counter()
-        while time.perf_counter() - t_w < 1.0 and (time.perf_counter() - t_w < 0.4 or (rank == 0 and len(sampler.rows) < 2)):
-            model(devx[0])
-            torch.cuda.synchronize()
-        sampler.mark()
-        l0 = model.runtime().kernel_launches()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for i in range(K):
-            model(devx[i % nrot])
-        e1.record()
-        barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
-        launches = int(model.runtime().kernel_launches() - l0)
-        clocks = sampler.stop() if rank == 0 else None
-    value = world * B * K / (ms / 1e3)
+    def device_throughput(lanes, sample_clocks):
+        with torch.no_grad():
+            for i in range(max(W, len(lanes))):
+                with lanes.stream(i):
+                    lanes.model(i)(devx[i % nrot])
+            lanes.join()
+            barrier()
+            sampler = ClockSampler(local) if sample_clocks else None
+            if sampler is not None:
+                if rank == 0:
+                    sampler.start()
+                # keep every GPU under the bench load while nvidia-smi starts sampling (untimed extra warm-up, <= 1 s)
+                t_w = time.perf_counter()
+                while time.perf_counter() - t_w < 1.0 and (time.perf_counter() - t_w < 0.4 or (rank == 0 and len(sampler.rows) < 2)):
+                    model(devx[0])
+                    torch.cuda.synchronize()
+                sampler.mark()
+            l0 = launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            lanes.fork()
+            for i in range(K):
+                with lanes.stream(i):
+                    lanes.model(i)(devx[i % nrot])
+            lanes.join()
+            e1.record()
+            barrier()
+            t = max_over_ranks(e0.elapsed_time(e1))
+            n = launch_count() - l0
+            clk = sampler.stop() if (sampler is not None and rank == 0) else None
+        return t, n, clk
 
     # ---- (2) end to end through the public API with host buffers ------------------------
     with torch.no_grad():
         out = model(host[0])
         keys = [k for k in ("pred_logits", "pred_boxes", "at") if k in out]
-        pinned_out = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in keys}
-        d2h = sum(v.numel() * v.element_size() for v in pinned_out.values())
+        d2h = sum(out[k].numel() * out[k].element_size() for k in keys)
+
+    def end_to_end(lanes):
         # the caller-side loop of the reference: batches come from pinned host memory through a side-stream
         # prefetcher (data_utils/DataLoad.py:304-336), the forward runs through the public module call, the
         # results are read back to pinned host memory.  Steady state: the stream of batches is longer than the
         # timed window, so every timed step issues exactly one H2D copy (of a later batch) and one D2H read.
-        from sound_event_detection_transformer_b200.prefetch import ClipPrefetcher
-        pf = ClipPrefetcher((host[i % nrot] for i in range(W + K + 4)), dev)
+        # Every lane owns its prefetcher and its pinned result buffers; all of a batch's work is ordered on its lane.
+        n = len(lanes)
+        with torch.no_grad():
+            pinned = [{k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in keys} for _ in range(n)]
+            pfs = []
+            for j in range(n):
+                with lanes.stream(j):
+                    pfs.append(ClipPrefetcher((host[(j + n * i) % nrot] for i in range((W + K) // n + 6)), dev))
 
-        def e2e_step():
-            xb = pf.next()
-            o = model(xb)
-            for k in keys:
-                pinned_out[k].copy_(o[k], non_blocking=True)
+            def e2e_step(i):
+                with lanes.stream(i):
+                    xb = pfs[i % n].next()
+                    o = lanes.model(i)(xb)
+                    for k in keys:
+                        pinned[i % n][k].copy_(o[k], non_blocking=True)
 
-        for i in range(W):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(K):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            for i in range(max(W, n)):
+                e2e_step(i)
+            lanes.join()
+            barrier()
+            t0 = time.perf_counter()
+            lanes.fork()
+            for i in range(K):
+                e2e_step(max(W, n) + i)
+            lanes.join()
+            torch.cuda.synchronize()
+            return max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+    lanes = EvalLanes(models, dev)
+    ms, launches, clocks = device_throughput(lanes, True)
+    value = world * B * K / (ms / 1e3)
+    e2e_ms = end_to_end(lanes)
     e2e_value = world * B * K / (e2e_ms / 1e3)
+    single = None
+    if nl > 1:                                           # the plain one-batch-at-a-time loop, reported next to the headline
+        one = EvalLanes([model], dev)
+        ms1, _, _ = device_throughput(one, False)
+        e2e_ms1 = end_to_end(one)
+        single = {"value": world * B * K / (ms1 / 1e3), "ms_per_step": ms1 / K, "e2e_value": world * B * K / (e2e_ms1 / 1e3),
+                  "e2e_ms_per_step": e2e_ms1 / K, "unit": UNIT,
+                  "note": "one batch in flight (lanes = 1): also the latency of one 256-clip forward"}
 
     # ---- (3) per-kernel-class durations (profiled pass, same steps) ----------------------
     ms_cls = (C.c_double * len(_lib.KERNEL_CLASSES))()
@@ -429,6 +476,9 @@ def main():
         "dtype": "bf16" if opts.precision == "bf16" else "f32", "data": "synthetic",
         "config": bench_config(B, world),
         "cuda_graph": not opts.no_graph,
+        "lanes": {"n": nl, "what": "batches in flight per GPU: each lane = its own model copy (weights, workspace, CUDA graph) on its own "
+                                   "CUDA stream, batch i on lane i % n; every step is one complete forward of one batch",
+                  "single_lane": single},
         "l2": f"inputs rotate over {nrot} distinct {in_bytes / 2**20:.1f} MiB batches; per-step activation traffic (>1 GB) exceeds the 126 MB L2",
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K},
