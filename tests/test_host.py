@@ -135,3 +135,20 @@ def test_fused_criterion_gate_is_host_logic():
     assert not criterion._fused_ok(out, tg, slice(1, 2), None, False, False)         # strong set not at the front
     assert not criterion._fused_ok(out, tg, slice(2), None, True, False)             # fine_tune
     assert not criterion._fused_ok(out, tg, slice(2), None, False, True)             # normalize
+
+
+def test_eval_lanes_host_logic():
+    """lanes.py: argument checks are host logic; CPU models are refused (no CPU path)."""
+    from sound_event_detection_transformer_b200.lanes import EvalLanes
+    args = spec.config_args("c1")
+    m, _, _ = build_model(args)
+    m.eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        EvalLanes([m])
+    with pytest.raises(ValueError):
+        EvalLanes([m, m])
+    with pytest.raises(ValueError):
+        EvalLanes([])
+    m.train()
+    with pytest.raises(ValueError, match="eval"):
+        EvalLanes([m])
